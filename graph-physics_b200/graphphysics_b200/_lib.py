@@ -1,0 +1,84 @@
+"""ctypes binding of libgp_b200.so (the C ABI declared in include/gp_b200.h).
+
+There is no CPU fallback: importing works without a GPU (so the C-ABI export test can run),
+but every compute call goes to the CUDA library and raises if it is missing or reports an error.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libgp_b200.so")
+
+_lib: Optional[C.CDLL] = None
+
+
+class GpError(RuntimeError):
+    pass
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise GpError(
+                f"{LIB_PATH} is missing: build it with `python __graft_entry__.py` (nvcc, sm_100a). "
+                "graphphysics_b200 has no CPU or PyTorch fallback."
+            )
+        _lib = C.CDLL(LIB_PATH)
+        _lib.gp_last_error.restype = C.c_char_p
+        _lib.gp_version.restype = C.c_int
+    return _lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        raise GpError(f"{what} failed ({rc}): {lib().gp_last_error().decode()}")
+
+
+def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    """Device pointer of a tensor (None -> NULL)."""
+    if t is None:
+        return None
+    assert t.is_cuda, "graphphysics_b200 kernels take CUDA tensors only"
+    return t.data_ptr()
+
+
+def stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+class MlpFwdArgs(C.Structure):
+    _fields_ = [
+        ("rows", C.c_int32),
+        ("a_bf16", C.c_void_p),
+        ("a_f32", C.c_void_p),
+        ("ka", C.c_int32),
+        ("lda", C.c_int32),
+        ("init", C.c_void_p),
+        ("ld_init", C.c_int32),
+        ("init_off0", C.c_int32),
+        ("init_off1", C.c_int32),
+        ("idx0", C.c_void_p),
+        ("idx1", C.c_void_p),
+        ("two_inits", C.c_int32),
+        ("n_layers", C.c_int32),
+        ("w", C.c_void_p * 4),
+        ("bias", C.c_void_p * 4),
+        ("k", C.c_int32 * 4),
+        ("n", C.c_int32 * 4),
+        ("norm_scale", C.c_void_p),
+        ("resid", C.c_void_p),
+        ("y_bf16", C.c_void_p),
+        ("y_f32", C.c_void_p),
+        ("ld_out", C.c_int32),
+        ("n_valid", C.c_int32),
+        ("save_h2", C.c_void_p),
+        ("seg_id", C.c_void_p),
+        ("seg_out", C.c_void_p),
+        ("seg_bnd", C.c_void_p),
+    ]

@@ -1,0 +1,88 @@
+/* gp_b200.h -- C ABI of libgp_b200.so: the B200 (sm_100a) kernels behind the graph-physics
+ * message-passing hot path.
+ *
+ * The reference (DonsetPG/graph-physics) has no FFI of its own: the path sits behind Python
+ * classes and reaches third-party kernels.  Each entry point below names the reference call
+ * site it replaces (file:line under /root/reference).  INTEGRATION.md shows the ctypes binding.
+ *
+ * Conventions
+ *   - every pointer is a caller-owned DEVICE pointer unless stated otherwise; the library never
+ *     allocates or frees user-visible memory;
+ *   - every call is stream-ordered on `stream` (a cudaStream_t passed as void*), no internal sync;
+ *   - return value 0 = ok, <0 = error; gp_last_error() gives the thread-local message;
+ *   - indices are int32, activations bf16 (raw uint16 storage), accumulators/statistics fp32;
+ *   - "packed weight" = bf16 row-major [n_out][k_in] with n_out, k_in padded to multiples of 16.
+ */
+#ifndef GP_B200_H
+#define GP_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef uint16_t gp_bf16; /* raw bfloat16 bits */
+
+int gp_version(void);
+const char* gp_last_error(void);
+/* out[0]=SM count, out[1]=max dynamic smem per block, out[2]=compute capability major*10+minor */
+int gp_device_info(int* out3);
+
+/* ---------------------------------------------------------------------------------------------
+ * Fused row-tile MLP forward (tcgen05).  Replaces the nn.Sequential built by build_mlp
+ * (graphphysics/models/layers.py:163-210) together with what surrounds it in
+ * GraphNetBlock.forward (layers.py:989-1102): the x[col]/x[row] gathers (1016-1018), the concat
+ * (1058), RMSNorm (104-129), the residual (1039-1040) and the PyG sum aggregation at
+ * edge_index[1] (926, 1031-1037).
+ *
+ * For every row r (an edge in receiver-sorted order, or a node):
+ *   z1 = a_in[r] . W0^T  +  init[idx0[r]][off0:] + init[idx1[r]][off1:]  + b0
+ *   h  = relu(z1); ... hidden layers ...; m = h . W_last^T + b_last
+ *   u  = norm_scale ? norm_scale * m / (||m||/sqrt(n) + 1e-8) : m
+ *   y[r] = (resid ? resid[r] : 0) + u                     (bf16 or fp32)
+ *   seg_out[seg_id[r]] += bf16(u)   (rows with equal seg_id are contiguous; no atomics: complete
+ *       segments are stored directly, pieces cut by a sub-tile boundary go to seg_bnd and are
+ *       combined in fixed order by gp_seg_fixup)
+ * --------------------------------------------------------------------------------------------- */
+typedef struct gp_mlp_fwd_args {
+    int32_t rows;
+    /* layer-0 streamed operand: exactly one of a_bf16 / a_f32 (or neither when ka == 0) */
+    const gp_bf16* a_bf16;
+    const float* a_f32;
+    int32_t ka;  /* multiple of 16, <= 128 */
+    int32_t lda; /* row stride in elements */
+    /* optional pre-activation rows added to layer 0 (bf16, ld_init elements per row) */
+    const gp_bf16* init;
+    int32_t ld_init;
+    int32_t init_off0, init_off1;
+    const int32_t* idx0; /* NULL -> row id */
+    const int32_t* idx1; /* used when two_inits */
+    int32_t two_inits;
+    /* layers */
+    int32_t n_layers;    /* 1..4 */
+    const gp_bf16* w[4]; /* packed [n[l]][k[l]] */
+    const float* bias[4];
+    int32_t k[4], n[4];
+    const float* norm_scale; /* NULL -> no RMSNorm */
+    const gp_bf16* resid;    /* NULL -> none; row stride ld_out */
+    gp_bf16* y_bf16;
+    float* y_f32;
+    int32_t ld_out;
+    int32_t n_valid;       /* columns of the last layer actually written */
+    gp_bf16* save_h2;      /* optional [rows][hidden]: output of layer index 1 (after relu) */
+    const int32_t* seg_id; /* optional [rows], non-decreasing */
+    float* seg_out;        /* [num_segments][hidden] */
+    float* seg_bnd;        /* [ceil(rows/sub)][2][hidden], sub = hidden/2 rows */
+} gp_mlp_fwd_args;
+
+int gp_mlp_fwd(const gp_mlp_fwd_args* args, int hidden, void* stream);
+
+/* Combine the boundary pieces left by gp_mlp_fwd's segment sum: for every segment n with rows
+ * [rowptr[n], rowptr[n+1]) that is empty or spans more than one sub-tile, write seg_out[n]. */
+int gp_seg_fixup(const int32_t* rowptr, int32_t num_segments, int32_t hidden, const float* seg_bnd, float* seg_out,
+                 void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GP_B200_H */
