@@ -1,0 +1,478 @@
+// mlp_bwd.cu -- two-layer backward stage of the fused MLP on tcgen05 (gp_mlp_bwd_stage).
+//
+// One persistent CTA of 256 threads per SM.  Resident in shared memory: the two packed weights
+// (each used K-major for the recompute and MN-major for dgrad), a tile of ones (bias gradients
+// as delta^T . 1 on the tensor core) and the activation buffers Ain / Ha / Db / Q of one
+// 128-row tile.  TMEM holds the working accumulator plus the weight-gradient accumulators,
+// which persist across all tiles of the CTA:
+//     cols   0..127  ACC   working accumulator (recompute, dgrad)
+//     cols 128..255  DWB   dWb  [nb x H]
+//     cols 256..383  DWA   dWa  [H x ka]
+//     cols 384..399  DBB   sum delta_b   (16 identical columns)
+//     cols 400..415  DBA   sum delta_a
+//     cols 416..431  DSC   sum du * m/(rms+eps)   (RMSNorm scale gradient)
+// Thread (row = tid & 127, half = tid >> 7) owns row `row` of the tile and one half of its
+// columns, so ReLU masks, the RMSNorm backward and residuals are thread-local apart from one
+// two-float exchange between the halves.
+#include "common.cuh"
+#include "tile_util.cuh"
+
+namespace {
+using namespace gp;
+
+constexpr uint32_t kColAcc = 0, kColDWB = 128, kColDWA = 256, kColDBB = 384, kColDBA = 400, kColDSC = 416;
+
+struct BwdLayout {
+    int off_dwb, off_dwa, off_dbb, off_dba, off_dsc, stride;
+};
+__host__ __device__ inline BwdLayout bwd_layout(int H, int ka, int nb) {
+    BwdLayout L;
+    L.off_dwb = 0;
+    L.off_dwa = nb * H;
+    L.off_dbb = L.off_dwa + H * ka;
+    L.off_dba = L.off_dbb + nb;
+    L.off_dsc = L.off_dba + H;
+    L.stride = L.off_dsc + H;
+    return L;
+}
+
+template <int H>
+__global__ void __launch_bounds__(256, 1) mlp_bwd_kernel(const gp_mlp_bwd_args p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = align1024(smem_raw);
+    __shared__ uint64_t mma_bar;
+    __shared__ uint32_t tmem_slot;
+
+    const int tid = threadIdx.x;
+    const int row = tid & 127, half = tid >> 7;
+    const int ka = p.ka, nb = p.nb;
+    const bool norm = p.mode == 1;
+
+    // ---- carve
+    uint32_t off = 0;
+    uint8_t* wa_t = smem + off;  off += ((ka + 63) >> 6) * H * 128;          // [H rows][ka]
+    uint8_t* wb_t = smem + off;  off += ((H + 63) >> 6) * nb * 128;          // [nb rows][H]
+    uint8_t* ain = smem + off;   off += kBufBytes;
+    uint8_t* ha = smem + off;    off += kBufBytes;
+    uint8_t* db = smem + off;    off += kBufBytes;
+    uint8_t* qb = smem + off;    off += norm ? kBufBytes : 0;
+    uint8_t* ones = smem + off;  off += 128 * 128;
+    float* s_ba = reinterpret_cast<float*>(smem + off);  off += 128 * 4;
+    float* s_bb = reinterpret_cast<float*>(smem + off);  off += 128 * 4;
+    float* s_g = reinterpret_cast<float*>(smem + off);   off += 128 * 4;
+    float* s_red = reinterpret_cast<float*>(smem + off); off += 4 * 128 * 4;   // [2 quantities][2 halves][128]
+    int* sseg = reinterpret_cast<int*>(smem + off);
+
+    // ---- one-time staging
+    stage_weight(wa_t, p.wa, H, ka);
+    stage_weight(wb_t, p.wb, nb, H);
+    cp_async_commit();
+    for (int i = tid; i < 128 * 8; i += 256) {       // ones tile: first 16 columns of every row = 1.0
+        const int r = i >> 3, ch = i & 7;
+        const uint32_t one2 = 0x3F803F80u;
+        *reinterpret_cast<uint4*>(ones + sw128_chunk_off(r, ch)) =
+            ch < 2 ? make_uint4(one2, one2, one2, one2) : make_uint4(0, 0, 0, 0);
+    }
+    for (int i = tid; i < 128; i += 256) {
+        s_ba[i] = (i < H && p.ba) ? p.ba[i] : 0.f;
+        s_bb[i] = (i < nb && p.bb) ? p.bb[i] : 0.f;
+        s_g[i] = (i < H && p.norm_scale) ? p.norm_scale[i] : 1.f;
+    }
+    if (tid == 0) {
+        mbar_init(&mma_bar, 1);
+        fence_mbar_init();
+    }
+    if (tid < 32) tmem_alloc(&tmem_slot, 512);
+    cp_async_wait<0>();
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+
+    const uint32_t tmem = tmem_slot;
+    const uint32_t tlane = tmem_addr(tmem, (row >> 5) * 32, 0);
+    const uint32_t ain_s = smem_u32(ain), ha_s = smem_u32(ha), db_s = smem_u32(db), qb_s = smem_u32(qb);
+    const uint32_t wa_s = smem_u32(wa_t), wb_s = smem_u32(wb_t), ones_s = smem_u32(ones);
+    const uint32_t lbo_h = (H >= 128) ? 16384u : 0u;      // M=128 MN-major A with < 128 valid columns: alias block
+    const uint32_t lbo_nb = (nb >= 128) ? 16384u : 0u;
+    uint32_t phase = 0;
+    const bool has_init = p.init != nullptr;
+    const int n_tiles = (p.rows + 127) >> 7;
+    constexpr int CH = H / 2;                              // columns per thread half
+    const int cb = half * CH, ce = cb + CH;
+
+    auto wait_mma = [&]() {
+        mbar_wait(&mma_bar, phase);
+        phase ^= 1;
+        tc_fence_after();
+    };
+    auto publish = [&]() {   // smem tiles written by threads -> visible to the MMA issuer
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+    };
+
+    bool first = true;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, first = false) {
+        const int R0 = tile << 7;
+        const int grow = R0 + row;
+        const bool valid = grow < p.rows;
+        const int crow = valid ? grow : p.rows - 1;
+        const uint32_t acc_flag = first ? 0u : 1u;
+
+        // ---- P0: stage inputs
+        stage_rows(ain, p.a_bf16, p.a_f32, ka, p.lda, R0, p.rows, tid, 256);
+        if (!norm) {   // delta_b given: zero rows past the end so they add nothing to the weight gradients
+            const int kc = nb >> 3;
+            for (int i = tid; i < 128 * kc; i += 256) {
+                const int r = i / kc, ch = i - r * kc;
+                if (R0 + r < p.rows)
+                    cp_async16(db_s + sw128_off(128, r, ch * 8), p.delta_b + (size_t)(R0 + r) * p.ld_db + ch * 8);
+                else
+                    *reinterpret_cast<uint4*>(db + sw128_off(128, r, ch * 8)) = make_uint4(0, 0, 0, 0);
+            }
+        }
+        cp_async_commit();
+        if (p.seg_id && tid < 128) {
+            sseg[1 + row] = valid ? __ldg(p.seg_id + grow) : -1;
+            if (row == 0) {
+                sseg[0] = R0 > 0 ? __ldg(p.seg_id + R0 - 1) : -1;
+                sseg[129] = (R0 + 128 < p.rows) ? __ldg(p.seg_id + R0 + 128) : -1;
+            }
+        }
+        if (has_init) {
+            const int i0 = p.idx0 ? __ldg(p.idx0 + crow) : crow;
+            const gp_bf16* r0p = p.init + (size_t)i0 * p.ld_init + p.init_off0;
+            const gp_bf16* r1p = nullptr;
+            if (p.two_inits) {
+                const int i1 = p.idx1 ? __ldg(p.idx1 + crow) : crow;
+                r1p = p.init + (size_t)i1 * p.ld_init + p.init_off1;
+            }
+            init_rows_to_tmem(tlane + kColAcc, r0p, r1p, cb, ce);
+        }
+        cp_async_wait<0>();
+        publish();
+
+        // ---- P1: recompute h_a = relu(a_in . Wa^T + init + ba)
+        if (tid == 0) {
+            tc_fence_after();
+            const uint32_t id = idesc_bf16(H, false, false);
+            for (int ks = 0; ks < (ka >> 4); ++ks)
+                mma_ss(tmem + kColAcc, desc_kmajor(ain_s, 128, ks), desc_kmajor(wa_s, H, ks), id,
+                       (ks > 0 || has_init) ? 1u : 0u);
+            mma_commit(&mma_bar);
+        }
+        wait_mma();
+        for (int c0 = cb; c0 < ce; c0 += 16) {
+            uint32_t v[16];
+            tmem_ld16(tlane + kColAcc + c0, v);
+            tmem_ld_wait();
+            float f[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] = fmaxf(__uint_as_float(v[j]) + s_ba[c0 + j], 0.f);
+            *reinterpret_cast<uint4*>(ha + sw128_off(128, row, c0)) = pack8(f);
+            *reinterpret_cast<uint4*>(ha + sw128_off(128, row, c0 + 8)) = pack8(f + 8);
+        }
+        publish();
+
+        // ---- P2 (NORM): m = h_a . Wb^T + bb ; delta_b = dRMSNorm(m) . du ; q = du * m/(rms+eps)
+        if (norm) {
+            if (tid == 0) {
+                tc_fence_after();
+                const uint32_t id = idesc_bf16(H, false, false);
+                for (int ks = 0; ks < (H >> 4); ++ks)
+                    mma_ss(tmem + kColAcc, desc_kmajor(ha_s, 128, ks), desc_kmajor(wb_s, nb, ks), id, ks > 0 ? 1u : 0u);
+                mma_commit(&mma_bar);
+            }
+            wait_mma();
+            auto load_du = [&](int c0, float* du) {
+                if (p.gy_bf16) {
+                    const gp_bf16* gp_ = p.gy_bf16 + (size_t)crow * p.ld_gy + c0;
+                    unpack8(ldg16(gp_), du);
+                    unpack8(ldg16(gp_ + 8), du + 8);
+                } else {
+                    const float4* gp_ = reinterpret_cast<const float4*>(p.gy_f32 + (size_t)crow * p.ld_gy + c0);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float4 t4 = __ldg(gp_ + j);
+                        du[4 * j] = t4.x; du[4 * j + 1] = t4.y; du[4 * j + 2] = t4.z; du[4 * j + 3] = t4.w;
+                    }
+                }
+                if (p.gy_gather) {
+                    const int gi = p.gy_idx ? __ldg(p.gy_idx + crow) : crow;
+                    const float4* ap = reinterpret_cast<const float4*>(p.gy_gather + (size_t)gi * H + c0);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float4 t4 = __ldg(ap + j);
+                        du[4 * j] += t4.x; du[4 * j + 1] += t4.y; du[4 * j + 2] += t4.z; du[4 * j + 3] += t4.w;
+                    }
+                }
+            };
+            float ss = 0.f, dot = 0.f;
+            for (int c0 = cb; c0 < ce; c0 += 16) {
+                uint32_t v[16];
+                tmem_ld16(tlane + kColAcc + c0, v);
+                tmem_ld_wait();
+                float du[16];
+                load_du(c0, du);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const float m = __uint_as_float(v[j]) + s_bb[c0 + j];
+                    ss = fmaf(m, m, ss);
+                    dot = fmaf(du[j] * s_g[c0 + j], m, dot);
+                }
+            }
+            s_red[(0 * 2 + half) * 128 + row] = ss;
+            s_red[(1 * 2 + half) * 128 + row] = dot;
+            __syncthreads();
+            ss = s_red[(0 * 2 + 0) * 128 + row] + s_red[(0 * 2 + 1) * 128 + row];
+            dot = s_red[(1 * 2 + 0) * 128 + row] + s_red[(1 * 2 + 1) * 128 + row];
+            const float rms = sqrtf(ss * (1.f / H));
+            const float s = 1.f / (rms + 1e-8f);
+            const float coef = rms > 0.f ? dot * s * s / (rms * H) : 0.f;
+            for (int c0 = cb; c0 < ce; c0 += 16) {
+                uint32_t v[16];
+                tmem_ld16(tlane + kColAcc + c0, v);
+                tmem_ld_wait();
+                float du[16], dm[16], q[16];
+                load_du(c0, du);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const float m = __uint_as_float(v[j]) + s_bb[c0 + j];
+                    dm[j] = valid ? (s_g[c0 + j] * du[j] * s - coef * m) : 0.f;
+                    q[j] = valid ? du[j] * m * s : 0.f;
+                }
+                *reinterpret_cast<uint4*>(db + sw128_off(128, row, c0)) = pack8(dm);
+                *reinterpret_cast<uint4*>(db + sw128_off(128, row, c0 + 8)) = pack8(dm + 8);
+                *reinterpret_cast<uint4*>(qb + sw128_off(128, row, c0)) = pack8(q);
+                *reinterpret_cast<uint4*>(qb + sw128_off(128, row, c0 + 8)) = pack8(q + 8);
+            }
+            publish();
+        }
+
+        // ---- P3: dWb += delta_b^T h_a ; dbb += delta_b^T 1 ; dscale += q^T 1 ; acc = delta_b . Wb
+        if (tid == 0) {
+            tc_fence_after();
+            const uint32_t id_w = idesc_bf16(H, true, true), id_1 = idesc_bf16(16, true, true);
+            for (int ks = 0; ks < 8; ++ks)
+                mma_ss(tmem + kColDWB, desc_mnmajor(db_s, 128, ks, 0, lbo_nb), desc_mnmajor(ha_s, 128, ks), id_w,
+                       (ks > 0) ? 1u : acc_flag);
+            for (int ks = 0; ks < 8; ++ks)
+                mma_ss(tmem + kColDBB, desc_mnmajor(db_s, 128, ks, 0, lbo_nb), desc_mnmajor(ones_s, 128, ks), id_1,
+                       (ks > 0) ? 1u : acc_flag);
+            if (norm)
+                for (int ks = 0; ks < 8; ++ks)
+                    mma_ss(tmem + kColDSC, desc_mnmajor(qb_s, 128, ks, 0, lbo_h), desc_mnmajor(ones_s, 128, ks), id_1,
+                           (ks > 0) ? 1u : acc_flag);
+            const uint32_t id_d = idesc_bf16(H, false, true);
+            for (int ks = 0; ks < (nb >> 4); ++ks)
+                mma_ss(tmem + kColAcc, desc_kmajor(db_s, 128, ks), desc_mnmajor(wb_s, nb, ks), id_d, ks > 0 ? 1u : 0u);
+            mma_commit(&mma_bar);
+        }
+        wait_mma();
+        // delta_a = acc * (h_a > 0), written in place over h_a (its readers have completed)
+        for (int c0 = cb; c0 < ce; c0 += 16) {
+            uint32_t v[16];
+            tmem_ld16(tlane + kColAcc + c0, v);
+            tmem_ld_wait();
+            uint4* h0 = reinterpret_cast<uint4*>(ha + sw128_off(128, row, c0));
+            uint4* h1 = reinterpret_cast<uint4*>(ha + sw128_off(128, row, c0 + 8));
+            float hv[16], f[16];
+            unpack8(*h0, hv);
+            unpack8(*h1, hv + 8);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] = hv[j] > 0.f ? __uint_as_float(v[j]) : 0.f;
+            *h0 = pack8(f);
+            *h1 = pack8(f + 8);
+        }
+        publish();
+
+        // ---- P4: dWa += delta_a^T a_in ; dba += delta_a^T 1 ; d_in = delta_a . Wa
+        if (tid == 0) {
+            tc_fence_after();
+            const uint32_t id_w = idesc_bf16(ka, true, true), id_1 = idesc_bf16(16, true, true);
+            for (int ks = 0; ks < 8; ++ks)
+                mma_ss(tmem + kColDWA, desc_mnmajor(ha_s, 128, ks, 0, lbo_h), desc_mnmajor(ain_s, 128, ks), id_w,
+                       (ks > 0) ? 1u : acc_flag);
+            for (int ks = 0; ks < 8; ++ks)
+                mma_ss(tmem + kColDBA, desc_mnmajor(ha_s, 128, ks, 0, lbo_h), desc_mnmajor(ones_s, 128, ks), id_1,
+                       (ks > 0) ? 1u : acc_flag);
+            if (p.need_din) {
+                const uint32_t id_d = idesc_bf16(ka, false, true);
+                for (int ks = 0; ks < (H >> 4); ++ks)
+                    mma_ss(tmem + kColAcc, desc_kmajor(ha_s, 128, ks), desc_mnmajor(wa_s, H, ks), id_d, ks > 0 ? 1u : 0u);
+            }
+            mma_commit(&mma_bar);
+        }
+        // while the tensor core runs: delta_a tile -> global, and its segment sum
+        if (p.delta_a_out && valid) {
+            for (int c0 = cb; c0 < ce; c0 += 8)
+                *reinterpret_cast<uint4*>(p.delta_a_out + (size_t)grow * H + c0) =
+                    *reinterpret_cast<const uint4*>(ha + sw128_off(128, row, c0));
+        }
+        if (p.seg_id && tid < 128) tile_segment_sum<H>(ha, sseg, R0, tid, p.seg_out, p.seg_bnd);
+        wait_mma();
+        if (p.need_din) {
+            const int kh = ka >= 32 ? ka / 2 : ka;          // columns per half (half 1 idles when ka < 32)
+            if (ka >= 32 || half == 0) {
+                for (int c0 = half * kh; c0 < half * kh + kh; c0 += 16) {
+                    uint32_t v[16];
+                    tmem_ld16(tlane + kColAcc + c0, v);
+                    tmem_ld_wait();
+                    float f[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+                    if (p.mask_by_ain) {
+                        float av[16];
+                        unpack8(*reinterpret_cast<const uint4*>(ain + sw128_off(128, row, c0)), av);
+                        unpack8(*reinterpret_cast<const uint4*>(ain + sw128_off(128, row, c0 + 8)), av + 8);
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) f[j] = av[j] > 0.f ? f[j] : 0.f;
+                    }
+                    if (valid) {
+                        if (p.out_resid) {
+                            float rv[16];
+                            const gp_bf16* rp = p.out_resid + (size_t)grow * p.ld_out + c0;
+                            unpack8(ldg16(rp), rv);
+                            unpack8(ldg16(rp + 8), rv + 8);
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) f[j] += rv[j];
+                        }
+                        if (p.out_bf16) {
+                            uint4* d = reinterpret_cast<uint4*>(p.out_bf16 + (size_t)grow * p.ld_out + c0);
+                            d[0] = pack8(f);
+                            d[1] = pack8(f + 8);
+                        } else {
+                            float4* d = reinterpret_cast<float4*>(p.out_f32 + (size_t)grow * p.ld_out + c0);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) d[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+                        }
+                    }
+                }
+            }
+        }
+        tc_fence_before();
+        __syncthreads();   // buffers and ACC are free for the next tile
+    }
+
+    // ---- dump the weight-gradient accumulators of this CTA (lane r <-> output row r)
+    tc_fence_after();
+    if (tid < 128) {
+        const BwdLayout L = bwd_layout(H, ka, nb);
+        float* P = p.partials + (size_t)blockIdx.x * L.stride;
+        for (int c0 = 0; c0 < H; c0 += 16) {
+            uint32_t v[16];
+            tmem_ld16(tlane + kColDWB + c0, v);
+            tmem_ld_wait();
+            if (row < nb) {
+                float4* d = reinterpret_cast<float4*>(P + L.off_dwb + (size_t)row * H + c0);
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    d[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                       __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+            }
+        }
+        for (int c0 = 0; c0 < ka; c0 += 16) {
+            uint32_t v[16];
+            tmem_ld16(tlane + kColDWA + c0, v);
+            tmem_ld_wait();
+            if (row < H) {
+                float4* d = reinterpret_cast<float4*>(P + L.off_dwa + (size_t)row * ka + c0);
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    d[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                       __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+            }
+        }
+        uint32_t v8[8];
+        tmem_ld8(tlane + kColDBB, v8);
+        tmem_ld_wait();
+        if (row < nb) P[L.off_dbb + row] = __uint_as_float(v8[0]);
+        tmem_ld8(tlane + kColDBA, v8);
+        tmem_ld_wait();
+        if (row < H) P[L.off_dba + row] = __uint_as_float(v8[0]);
+        if (norm) {
+            tmem_ld8(tlane + kColDSC, v8);
+            tmem_ld_wait();
+            if (row < H) P[L.off_dsc + row] = __uint_as_float(v8[0]);
+        } else if (row < H) {
+            P[L.off_dsc + row] = 0.f;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (tid < 32) tmem_dealloc(tmem, 512);
+}
+
+__global__ void reduce_partials_kernel(const float* __restrict__ partials, int n_parts, int stride, int offset, int rows,
+                                       int cols, int ld_part, float* __restrict__ dst, int ld_dst, int accumulate) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * cols) return;
+    const int r = i / cols, c = i - r * cols;
+    const float* src = partials + offset + (size_t)r * ld_part + c;
+    float acc = 0.f;
+    for (int pi = 0; pi < n_parts; ++pi) acc += src[(size_t)pi * stride];
+    float* d = dst + (size_t)r * ld_dst + c;
+    *d = accumulate ? (*d + acc) : acc;
+}
+
+template <int H>
+int launch_bwd(const gp_mlp_bwd_args& a, int32_t* grid_out, cudaStream_t st) {
+    size_t smem = 1024;
+    smem += (size_t)((a.ka + 63) / 64) * H * 128 + (size_t)((H + 63) / 64) * a.nb * 128;
+    smem += (size_t)(a.mode == 1 ? 4 : 3) * kBufBytes + 128 * 128 + 3 * 128 * 4 + 4 * 128 * 4 + 136 * 4;
+    GP_REQUIRE((int)smem <= gp::max_smem_optin(), "gp_mlp_bwd_stage: needs %zu B of shared memory (> %d)", smem,
+               gp::max_smem_optin());
+    GP_CHECK_CUDA(cudaFuncSetAttribute(mlp_bwd_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int n_tiles = (a.rows + 127) / 128;
+    int grid = n_tiles < gp::sm_count() ? n_tiles : gp::sm_count();
+    mlp_bwd_kernel<H><<<grid, 256, smem, st>>>(a);
+    GP_CHECK_CUDA(cudaGetLastError());
+    if (grid_out) *grid_out = grid;
+    return 0;
+}
+}  // namespace
+
+extern "C" int gp_mlp_bwd_layout(int hidden, int ka, int nb, int32_t* out6) {
+    GP_REQUIRE(out6 != nullptr, "gp_mlp_bwd_layout: null output");
+    const BwdLayout L = bwd_layout(hidden, ka, nb);
+    out6[0] = L.off_dwb; out6[1] = L.off_dwa; out6[2] = L.off_dbb; out6[3] = L.off_dba; out6[4] = L.off_dsc;
+    out6[5] = L.stride;
+    return 0;
+}
+
+extern "C" int gp_mlp_bwd_stage(const gp_mlp_bwd_args* args, int hidden, int32_t* grid_out, void* stream) {
+    GP_REQUIRE(args != nullptr, "gp_mlp_bwd_stage: null args");
+    const gp_mlp_bwd_args& a = *args;
+    GP_REQUIRE(a.rows > 0, "gp_mlp_bwd_stage: rows must be positive");
+    GP_REQUIRE(a.ka > 0 && a.ka % 16 == 0 && a.ka <= 128, "gp_mlp_bwd_stage: bad ka=%d", a.ka);
+    GP_REQUIRE(a.nb > 0 && a.nb % 16 == 0 && a.nb <= 128, "gp_mlp_bwd_stage: bad nb=%d", a.nb);
+    GP_REQUIRE((a.a_bf16 != nullptr) != (a.a_f32 != nullptr), "gp_mlp_bwd_stage: exactly one of a_bf16 / a_f32");
+    GP_REQUIRE(a.wa && a.wb && a.partials, "gp_mlp_bwd_stage: null weights or partials");
+    if (a.mode == 1) {
+        GP_REQUIRE(a.nb == hidden, "gp_mlp_bwd_stage: NORM mode needs nb == hidden");
+        GP_REQUIRE((a.gy_bf16 != nullptr) != (a.gy_f32 != nullptr), "gp_mlp_bwd_stage: exactly one of gy_bf16 / gy_f32");
+    } else {
+        GP_REQUIRE(a.mode == 0 && a.delta_b != nullptr && a.ld_db % 8 == 0, "gp_mlp_bwd_stage: GIVEN mode needs delta_b");
+    }
+    if (a.need_din) GP_REQUIRE((a.out_bf16 != nullptr) != (a.out_f32 != nullptr), "gp_mlp_bwd_stage: need one output");
+    if (a.seg_id) GP_REQUIRE(a.seg_out && a.seg_bnd, "gp_mlp_bwd_stage: segment sum needs outputs");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    switch (hidden) {
+        case 128: return launch_bwd<128>(a, grid_out, st);
+        case 64: return launch_bwd<64>(a, grid_out, st);
+        case 32: return launch_bwd<32>(a, grid_out, st);
+        default: gp::set_error("gp_mlp_bwd_stage: unsupported hidden size %d (32, 64, 128)", hidden); return -1;
+    }
+}
+
+extern "C" int gp_reduce_partials(const float* partials, int32_t n_parts, int32_t stride, int32_t offset, int32_t rows,
+                                  int32_t cols, int32_t ld_part, float* dst, int32_t ld_dst, int32_t accumulate,
+                                  void* stream) {
+    const int total = rows * cols;
+    if (total <= 0) return 0;
+    reduce_partials_kernel<<<(total + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        partials, n_parts, stride, offset, rows, cols, ld_part, dst, ld_dst, accumulate);
+    GP_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}

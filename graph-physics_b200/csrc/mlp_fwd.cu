@@ -11,26 +11,17 @@
 // residual are thread-local.  The receiver-sorted segment sum re-partitions through shared
 // memory (column pairs x sub-tiles of H/2 rows) and uses no atomics.
 #include "common.cuh"
-#include "tc5.cuh"
-#include "../../include/gp_b200.h"
+#include "tile_util.cuh"
 
 namespace {
-using namespace tc5;
+using namespace gp;
 
-constexpr int kBufBytes = 128 * 128 * 2;   // one activation buffer: 128 rows x up to 128 bf16
 constexpr int kBiasStride = 384;
 
 __device__ __forceinline__ void group_sync(int g) { asm volatile("bar.sync %0, 128;" ::"r"(g + 1) : "memory"); }
 
-__device__ __forceinline__ uint4 ldg16(const void* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
 
-__device__ __forceinline__ void unpack8(const uint4& q, float* f) {
-    f[0] = bf16_lo(q.x); f[1] = bf16_hi(q.x); f[2] = bf16_lo(q.y); f[3] = bf16_hi(q.y);
-    f[4] = bf16_lo(q.z); f[5] = bf16_hi(q.z); f[6] = bf16_lo(q.w); f[7] = bf16_hi(q.w);
-}
-__device__ __forceinline__ uint4 pack8(const float* f) {
-    return make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
-}
+
 
 template <int H, int NG>
 __global__ void __launch_bounds__(128 * NG, 1) mlp_fwd_kernel(const gp_mlp_fwd_args p) {

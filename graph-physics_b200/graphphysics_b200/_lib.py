@@ -82,3 +82,45 @@ class MlpFwdArgs(C.Structure):
         ("seg_out", C.c_void_p),
         ("seg_bnd", C.c_void_p),
     ]
+
+
+class MlpBwdArgs(C.Structure):
+    _fields_ = [
+        ("rows", C.c_int32),
+        ("a_bf16", C.c_void_p),
+        ("a_f32", C.c_void_p),
+        ("ka", C.c_int32),
+        ("lda", C.c_int32),
+        ("init", C.c_void_p),
+        ("ld_init", C.c_int32),
+        ("init_off0", C.c_int32),
+        ("init_off1", C.c_int32),
+        ("idx0", C.c_void_p),
+        ("idx1", C.c_void_p),
+        ("two_inits", C.c_int32),
+        ("wa", C.c_void_p),
+        ("ba", C.c_void_p),
+        ("wb", C.c_void_p),
+        ("bb", C.c_void_p),
+        ("nb", C.c_int32),
+        ("mode", C.c_int32),
+        ("delta_b", C.c_void_p),
+        ("ld_db", C.c_int32),
+        ("norm_scale", C.c_void_p),
+        ("gy_bf16", C.c_void_p),
+        ("gy_f32", C.c_void_p),
+        ("ld_gy", C.c_int32),
+        ("gy_gather", C.c_void_p),
+        ("gy_idx", C.c_void_p),
+        ("need_din", C.c_int32),
+        ("mask_by_ain", C.c_int32),
+        ("out_resid", C.c_void_p),
+        ("out_bf16", C.c_void_p),
+        ("out_f32", C.c_void_p),
+        ("ld_out", C.c_int32),
+        ("delta_a_out", C.c_void_p),
+        ("seg_id", C.c_void_p),
+        ("seg_out", C.c_void_p),
+        ("seg_bnd", C.c_void_p),
+        ("partials", C.c_void_p),
+    ]

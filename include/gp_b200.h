@@ -82,6 +82,71 @@ int gp_mlp_fwd(const gp_mlp_fwd_args* args, int hidden, void* stream);
 int gp_seg_fixup(const int32_t* rowptr, int32_t num_segments, int32_t hidden, const float* seg_bnd, float* seg_out,
                  void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Two-layer backward stage of the same MLP (tcgen05): recomputes layer `a` from its streamed
+ * input (gathers are re-done, no per-row activation is read back except the one tensor the
+ * forward saved between layer pairs), then does dgrad and wgrad of layers b and a.
+ * Replaces torch.autograd through build_mlp / RMSNorm / the gathers / scatter_add
+ * (graphphysics/models/layers.py:104-129, 163-210, 1016-1060) for
+ * LightningModule.training_step (graphphysics/training/lightning_module.py:270-342).
+ *
+ *   h_a   = relu(a_in . Wa^T + init rows + ba)                       (recomputed)
+ *   mode 1 (NORM):  m = h_a . Wb^T + bb;  du = gy (+ gy_gather[gy_idx]);  delta_b = d RMSNorm(m)/dm . du
+ *   mode 0 (GIVEN): delta_b read from memory
+ *   dWb += delta_b^T h_a ;  dbb += sum delta_b ;  dscale += sum du * m/(rms+eps)
+ *   delta_a = (delta_b . Wb) * (h_a > 0)
+ *   dWa += delta_a^T a_in ;  dba += sum delta_a
+ *   d_in = delta_a . Wa  [* (a_in > 0)] [+ out_resid]   -> out
+ *   delta_a optionally stored, and segment-summed by seg_id like gp_mlp_fwd.
+ * Weight-gradient sums live in TMEM for the whole launch; each CTA then writes one partial
+ * block (layout from gp_mlp_bwd_layout) and gp_reduce_partials adds them in CTA order.
+ * --------------------------------------------------------------------------------------------- */
+typedef struct gp_mlp_bwd_args {
+    int32_t rows;
+    const gp_bf16* a_bf16;
+    const float* a_f32;
+    int32_t ka, lda;
+    const gp_bf16* init;
+    int32_t ld_init, init_off0, init_off1;
+    const int32_t* idx0;
+    const int32_t* idx1;
+    int32_t two_inits;
+    const gp_bf16* wa; /* packed [hidden][ka] */
+    const float* ba;
+    const gp_bf16* wb; /* packed [nb][hidden] */
+    const float* bb;
+    int32_t nb;
+    int32_t mode; /* 0 GIVEN, 1 NORM */
+    const gp_bf16* delta_b;
+    int32_t ld_db;
+    const float* norm_scale;
+    const gp_bf16* gy_bf16;
+    const float* gy_f32;
+    int32_t ld_gy;
+    const float* gy_gather; /* optional fp32 [.][hidden] rows added to gy */
+    const int32_t* gy_idx;
+    int32_t need_din;
+    int32_t mask_by_ain;
+    const gp_bf16* out_resid;
+    gp_bf16* out_bf16;
+    float* out_f32;
+    int32_t ld_out;
+    gp_bf16* delta_a_out; /* optional [rows][hidden] */
+    const int32_t* seg_id;
+    float* seg_out;
+    float* seg_bnd;
+    float* partials; /* [grid][stride] floats, grid <= SM count */
+} gp_mlp_bwd_args;
+
+/* out6 = {off_dWb, off_dWa, off_dbb, off_dba, off_dscale, stride} in floats.
+ * dWb is [nb][hidden], dWa is [hidden][ka] (row-major, padded shapes). */
+int gp_mlp_bwd_layout(int hidden, int ka, int nb, int32_t* out6);
+/* Launches the stage; *grid_out (host) receives the number of partial blocks written. */
+int gp_mlp_bwd_stage(const gp_mlp_bwd_args* args, int hidden, int32_t* grid_out, void* stream);
+/* dst[r*ld_dst + c] (+)= sum_p partials[p*stride + offset + r*ld_part + c], p ascending. */
+int gp_reduce_partials(const float* partials, int32_t n_parts, int32_t stride, int32_t offset, int32_t rows,
+                       int32_t cols, int32_t ld_part, float* dst, int32_t ld_dst, int32_t accumulate, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

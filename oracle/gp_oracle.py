@@ -71,13 +71,39 @@ def linear(x, w, b, mode):
     """nn.Linear (y = x W^T + b) with bf16 MMA operands in kernel mode; the gradient that
     reaches the product is rounded too (it is the A operand of dgrad and wgrad)."""
     y = F.linear(rnd(x, mode), rnd(w, mode))
-    y = grad_rnd(y, mode)
-    return y if b is None else y + b
+    if b is not None:
+        y = y + b
+    return grad_rnd(y, mode)        # delta (bf16) feeds dgrad, wgrad and the bias gradient alike
 
 
 # --------------------------------------------------------------------------- layers
-def rms_norm(x: torch.Tensor, scale: torch.Tensor, eps: float = 1e-8) -> torch.Tensor:
+class _RmsNormKernel(torch.autograd.Function):
+    """RMSNorm with the kernel's backward arithmetic: the scale gradient is the column sum of
+    bf16(g * x/(rms+eps)) -- that product is staged as a bf16 MMA operand (delta^T . 1)."""
+
+    @staticmethod
+    def forward(ctx, x, scale, eps):
+        d = x.shape[-1]
+        rms = x.norm(2, dim=-1, keepdim=True) / math.sqrt(d)
+        s = 1.0 / (rms + eps)
+        ctx.save_for_backward(x, scale, s, rms)
+        return scale * (x * s)
+
+    @staticmethod
+    def backward(ctx, g):
+        x, scale, s, rms = ctx.saved_tensors
+        d = x.shape[-1]
+        q = (g * x * s).to(torch.bfloat16).to(g.dtype)
+        dscale = q.reshape(-1, d).sum(0)
+        dot = (g * scale * x).sum(-1, keepdim=True)
+        coef = torch.where(rms > 0, dot * s * s / (rms * d), torch.zeros_like(dot))
+        return scale * g * s - coef * x, dscale, None
+
+
+def rms_norm(x: torch.Tensor, scale: torch.Tensor, eps: float = 1e-8, mode: Optional[str] = None) -> torch.Tensor:
     """RMSNorm.forward, full-vector branch (layers.py:104-129): scale * x / (||x||/sqrt(d) + eps)."""
+    if mode == "bf16":
+        return _RmsNormKernel.apply(x, scale, eps)
     d = x.shape[-1]
     rms = x.norm(2, dim=-1, keepdim=True) / math.sqrt(d)
     return scale * (x / (rms + eps))
@@ -87,22 +113,26 @@ _ACT = {"relu": F.relu, "gelu": F.gelu, "silu": F.silu}
 
 
 def mlp(x, sd: Dict[str, torch.Tensor], prefix: str, nb_layers: int = 4, layer_norm: bool = True,
-        act: str = "relu", mode: Optional[str] = None, first_pre: Optional[torch.Tensor] = None):
+        act: str = "relu", mode: Optional[str] = None, first_pre: Optional[torch.Tensor] = None,
+        preacts: Optional[list] = None):
     """build_mlp (layers.py:163-210): Linear,act,[Linear,act]*(nb-2),Linear,[RMSNorm].
     Sequential indices: linear i sits at 2*i, the norm at 2*nb-1.
     ``first_pre`` (kernel mode only) replaces the first layer's product with a precomputed
-    pre-activation (bias excluded)."""
+    pre-activation (bias excluded).  ``preacts``, if a list, receives the ReLU inputs (tests use
+    it to keep inputs away from the kink, where summation order would pick the subgradient)."""
     h = x
     for i in range(nb_layers):
         w, b = sd[f"{prefix}.{2 * i}.weight"], sd[f"{prefix}.{2 * i}.bias"]
         if i == 0 and first_pre is not None:
-            h = first_pre + b
+            h = grad_rnd(first_pre + b, mode)
         else:
             h = linear(h, w, b, mode)
         if i < nb_layers - 1:
+            if preacts is not None:
+                preacts.append(h.detach())
             h = _ACT[act](h)
     if layer_norm:
-        h = rms_norm(h, sd[f"{prefix}.{2 * nb_layers - 1}.scale"])
+        h = rms_norm(h, sd[f"{prefix}.{2 * nb_layers - 1}.scale"], mode=mode)
     return h
 
 
@@ -119,7 +149,7 @@ def graph_net_block(x, e, src, dst, sd, prefix: str, mode: Optional[str] = None)
         ps = rnd(linear(x, w1s, None, mode), mode)
         # delta_1 (the gradient of this sum) is one bf16 tensor in the kernel: it feeds dE,
         # the receiver/sender segment sums and dW1e alike.
-        pre = grad_rnd(F.linear(rnd(e, mode), rnd(w1e, mode)) + pd[dst] + ps[src], mode)
+        pre = F.linear(rnd(e, mode), rnd(w1e, mode)) + pd[dst] + ps[src]
         e_upd = mlp(None, sd, f"{prefix}.edge_block", mode=mode, first_pre=pre)
         agg = torch.zeros_like(x).index_add_(0, dst, rnd(e_upd, mode))   # kernel sums bf16(e_upd) in fp32
     else:

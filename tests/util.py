@@ -28,3 +28,42 @@ def random_sorted_graph(num_nodes: int, num_edges: int, seed: int = 0, max_degre
     dst = np.sort(dst)
     src = rng.integers(0, num_nodes, num_edges)
     return torch.from_numpy(src.astype(np.int64)), torch.from_numpy(dst.astype(np.int64))
+
+
+def check_close(got, ref, name, l2_tol, max_tol, report):
+    """Parity criterion used for kernel-vs-oracle comparisons.
+
+    * l2_tol bounds the norm-relative error  ||got-ref|| / ||ref||  (the north-star's rtol 1e-3
+      is applied here; 2e-3..4e-3 where the result itself is stored as bf16, whose half-ulp is
+      2e-3 relative).
+    * max_tol bounds  max|got-ref| / max|ref|.  It is looser because a ReLU pre-activation that
+      lands within fp32 summation noise of zero can flip between the kernel (fp32, tile order)
+      and the oracle (fp64): that changes one row by O(|dh|*|W|), an outlier, not a drift.
+    """
+    l2, mx = l2_rel(got, ref), rel_err(got, ref)
+    ok = (l2 <= l2_tol) and (mx <= max_tol)
+    report.append(f"{'ok ' if ok else 'BAD'} {name:24s} l2_rel={l2:.2e} (tol {l2_tol:.0e})  max_rel={mx:.2e} (tol {max_tol:.0e})")
+    return ok
+
+
+def condition_rows(draw_rows, preacts_of_rows, num_rows: int, tau: float = 1e-4, max_iter: int = 50):
+    """Re-draw input rows until no ReLU pre-activation lies within `tau` of zero.
+
+    A kernel sums in fp32 and tile order, the oracle in fp64: a pre-activation closer to the
+    kink than that noise (~1e-6) can fall on either side, and both ReLU masks are valid
+    subgradients but give different gradients for that row.  Unit-level gradient parity is
+    therefore tested on inputs conditioned away from the kink (margin 1e-4); model-level tests,
+    where this is not possible, use norm-wise tolerances instead.
+
+    draw_rows(idx) -> new rows for the row indices `idx`;  preacts_of_rows(idx) -> list of
+    pre-activation tensors for those rows (after the rows were updated)."""
+    idx = torch.arange(num_rows)
+    for _ in range(max_iter):
+        if idx.numel() == 0:
+            return
+        draw_rows(idx)
+        bad = torch.zeros(idx.numel(), dtype=torch.bool)
+        for z in preacts_of_rows(idx):
+            bad |= (z.abs() < tau).any(dim=1)
+        idx = idx[bad]
+    raise RuntimeError("could not condition the test inputs away from the ReLU kink")
