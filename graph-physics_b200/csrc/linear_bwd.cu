@@ -1,0 +1,212 @@
+// linear_bwd.cu -- backward of the bias-free per-node projection  P = x . Wp^T  (gp_linear_bwd).
+//
+// P holds the node-side halves of the first edge-MLP layer and of the first node-MLP layer
+// (W1 = [W1e | W1d | W1s] of layers.py:1058 splits by linearity; see gp_b200.h).  Its gradient
+// arrives in up to three `hidden`-wide pieces (receiver sums, sender sums, node-MLP delta).
+// Per 128-row tile, for each piece s:   dX += dP_s . Wp_s      (dgrad, accumulated in TMEM)
+//                                       dWp_s += dP_s^T . x    (wgrad, TMEM-resident per CTA)
+#include "common.cuh"
+#include "tile_util.cuh"
+
+namespace {
+using namespace gp;
+
+template <int H>
+__global__ void __launch_bounds__(256, 1) linear_bwd_kernel(const gp_linear_bwd_args p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = align1024(smem_raw);
+    __shared__ uint64_t mma_bar;
+    __shared__ uint32_t tmem_slot;
+
+    const int tid = threadIdx.x, row = tid & 127, half = tid >> 7;
+    const int S = p.n_src;
+    const int wrows = S * H;
+    uint32_t off = 0;
+    uint8_t* w_t = smem + off;  off += ((H + 63) >> 6) * wrows * 128;
+    uint8_t* abuf = smem + off; off += kBufBytes;
+    uint8_t* xbuf = smem + off;
+
+    stage_weight(w_t, p.w, wrows, H);
+    cp_async_commit();
+    if (tid == 0) {
+        mbar_init(&mma_bar, 1);
+        fence_mbar_init();
+    }
+    if (tid < 32) tmem_alloc(&tmem_slot, 512);
+    cp_async_wait<0>();
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+
+    const uint32_t tmem = tmem_slot;
+    const uint32_t tlane = tmem_addr(tmem, (row >> 5) * 32, 0);
+    const uint32_t a_s = smem_u32(abuf), x_s = smem_u32(xbuf), w_s = smem_u32(w_t);
+    const uint32_t lbo_h = (H >= 128) ? 16384u : 0u;
+    uint32_t phase = 0;
+    const int n_tiles = (p.rows + 127) >> 7;
+    constexpr int CH = H / 2;
+    bool first = true;
+
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, first = false) {
+        const int R0 = tile << 7, grow = R0 + row;
+        const bool valid = grow < p.rows;
+        stage_rows(xbuf, p.x, nullptr, H, p.ldx, R0, p.rows, tid, 256);
+        cp_async_commit();
+        for (int s = 0; s < S; ++s) {
+            // gradient piece s -> abuf (bf16), rows past the end zeroed
+            const int kc = H >> 3;
+            for (int i = tid; i < 128 * kc; i += 256) {
+                const int r = i / kc, ch = i - r * kc;
+                uint4 pk = make_uint4(0, 0, 0, 0);
+                if (R0 + r < p.rows) {
+                    if (p.src_f32[s]) {
+                        const float4* sp = reinterpret_cast<const float4*>(p.src_f32[s] + (size_t)(R0 + r) * p.ld_src[s] + ch * 8);
+                        const float4 u0 = __ldg(sp), u1 = __ldg(sp + 1);
+                        pk = make_uint4(pack_bf16(u0.x, u0.y), pack_bf16(u0.z, u0.w), pack_bf16(u1.x, u1.y), pack_bf16(u1.z, u1.w));
+                    } else {
+                        pk = ldg16(p.src_bf16[s] + (size_t)(R0 + r) * p.ld_src[s] + ch * 8);
+                    }
+                }
+                *reinterpret_cast<uint4*>(abuf + sw128_off(128, r, ch * 8)) = pk;
+            }
+            cp_async_wait<0>();
+            fence_async_smem();
+            tc_fence_before();
+            __syncthreads();
+            if (tid == 0) {
+                tc_fence_after();
+                const uint32_t id_w = idesc_bf16(H, true, true), id_d = idesc_bf16(H, false, true);
+                for (int ks = 0; ks < 8; ++ks)
+                    mma_ss(tmem + 128 * (1 + s), desc_mnmajor(a_s, 128, ks, 0, lbo_h), desc_mnmajor(x_s, 128, ks), id_w,
+                           (ks > 0) ? 1u : (first ? 0u : 1u));
+                for (int ks = 0; ks < (H >> 4); ++ks)
+                    mma_ss(tmem, desc_kmajor(a_s, 128, ks), desc_mnmajor(w_s + s * H * 128, wrows, ks), id_d,
+                           (s > 0 || ks > 0) ? 1u : 0u);
+                mma_commit(&mma_bar);
+            }
+            mbar_wait(&mma_bar, phase);
+            phase ^= 1;
+            tc_fence_after();
+        }
+        for (int c0 = half * CH; c0 < half * CH + CH; c0 += 16) {
+            uint32_t v[16];
+            tmem_ld16(tlane + c0, v);
+            tmem_ld_wait();
+            if (valid) {
+                float f[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+                if (p.dx_in) {
+                    const float4* ip = reinterpret_cast<const float4*>(p.dx_in + (size_t)grow * H + c0);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float4 t4 = __ldg(ip + j);
+                        f[4 * j] += t4.x; f[4 * j + 1] += t4.y; f[4 * j + 2] += t4.z; f[4 * j + 3] += t4.w;
+                    }
+                }
+                float4* d = reinterpret_cast<float4*>(p.dx_out + (size_t)grow * H + c0);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) d[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+            }
+        }
+        tc_fence_before();
+        __syncthreads();
+    }
+
+    tc_fence_after();
+    if (tid < 128) {
+        float* P = p.partials + (size_t)blockIdx.x * S * H * H;
+        for (int s = 0; s < S; ++s)
+            for (int c0 = 0; c0 < H; c0 += 16) {
+                uint32_t v[16];
+                tmem_ld16(tlane + 128 * (1 + s) + c0, v);
+                tmem_ld_wait();
+                if (row < H) {
+                    float4* d = reinterpret_cast<float4*>(P + ((size_t)s * H + row) * H + c0);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        d[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                           __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+                }
+            }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (tid < 32) tmem_dealloc(tmem, 512);
+}
+
+template <int H>
+int launch(const gp_linear_bwd_args& a, int32_t* grid_out, cudaStream_t st) {
+    const size_t smem = 1024 + (size_t)((H + 63) / 64) * a.n_src * H * 128 + 2 * kBufBytes;
+    GP_CHECK_CUDA(cudaFuncSetAttribute(linear_bwd_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int n_tiles = (a.rows + 127) / 128;
+    const int grid = n_tiles < gp::sm_count() ? n_tiles : gp::sm_count();
+    linear_bwd_kernel<H><<<grid, 256, smem, st>>>(a);
+    GP_CHECK_CUDA(cudaGetLastError());
+    if (grid_out) *grid_out = grid;
+    return 0;
+}
+
+// out[n][:] = sum over j in [rowptr[n], rowptr[n+1]) of src[perm[j]][:]   (bf16 rows, fp32 sum, fixed order)
+template <int VPT>
+__global__ void segsum_gather_kernel(const gp_bf16* __restrict__ src, int ld, const int32_t* __restrict__ perm,
+                                     const int32_t* __restrict__ rowptr, int num_segments, float* __restrict__ out) {
+    const int seg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (seg >= num_segments) return;
+    const int b = rowptr[seg], e = rowptr[seg + 1];
+    float acc[VPT];
+#pragma unroll
+    for (int i = 0; i < VPT; ++i) acc[i] = 0.f;
+    for (int j = b; j < e; ++j) {
+        const int r = perm ? __ldg(perm + j) : j;
+        const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(src) + (size_t)r * ld + lane * VPT;
+        if constexpr (VPT == 4) {
+            const uint2 q = __ldg(reinterpret_cast<const uint2*>(rp));
+            acc[0] += bf16_lo(q.x); acc[1] += bf16_hi(q.x); acc[2] += bf16_lo(q.y); acc[3] += bf16_hi(q.y);
+        } else if constexpr (VPT == 2) {
+            const uint32_t q = __ldg(reinterpret_cast<const uint32_t*>(rp));
+            acc[0] += bf16_lo(q); acc[1] += bf16_hi(q);
+        } else {
+            acc[0] += __bfloat162float(rp[0]);
+        }
+    }
+    float* o = out + (size_t)seg * (32 * VPT) + lane * VPT;
+#pragma unroll
+    for (int i = 0; i < VPT; ++i) o[i] = acc[i];
+}
+}  // namespace
+
+extern "C" int gp_linear_bwd(const gp_linear_bwd_args* args, int hidden, int32_t* grid_out, void* stream) {
+    GP_REQUIRE(args != nullptr, "gp_linear_bwd: null args");
+    const gp_linear_bwd_args& a = *args;
+    GP_REQUIRE(a.rows > 0 && a.n_src >= 1 && a.n_src <= 3, "gp_linear_bwd: bad rows / n_src");
+    for (int s = 0; s < a.n_src; ++s)
+        GP_REQUIRE((a.src_f32[s] != nullptr) != (a.src_bf16[s] != nullptr) && a.ld_src[s] % 8 == 0,
+                   "gp_linear_bwd: source %d needs exactly one pointer and an aligned stride", s);
+    GP_REQUIRE(a.w && a.x && a.dx_out && a.partials, "gp_linear_bwd: null pointer");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    switch (hidden) {
+        case 128: return launch<128>(a, grid_out, st);
+        case 64: return launch<64>(a, grid_out, st);
+        case 32: return launch<32>(a, grid_out, st);
+        default: gp::set_error("gp_linear_bwd: unsupported hidden size %d", hidden); return -1;
+    }
+}
+
+extern "C" int gp_segsum_gather(const gp_bf16* src, int32_t ld, const int32_t* perm, const int32_t* rowptr,
+                                int32_t num_segments, int32_t hidden, float* out, void* stream) {
+    if (num_segments <= 0) return 0;
+    const int threads = 256;
+    const int blocks = (int)(((size_t)num_segments * 32 + threads - 1) / threads);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    switch (hidden) {
+        case 128: segsum_gather_kernel<4><<<blocks, threads, 0, st>>>(src, ld, perm, rowptr, num_segments, out); break;
+        case 64: segsum_gather_kernel<2><<<blocks, threads, 0, st>>>(src, ld, perm, rowptr, num_segments, out); break;
+        case 32: segsum_gather_kernel<1><<<blocks, threads, 0, st>>>(src, ld, perm, rowptr, num_segments, out); break;
+        default: gp::set_error("gp_segsum_gather: unsupported hidden size %d", hidden); return -1;
+    }
+    GP_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}

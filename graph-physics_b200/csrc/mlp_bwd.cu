@@ -190,6 +190,9 @@ __global__ void __launch_bounds__(256, 1) mlp_bwd_kernel(const gp_mlp_bwd_args p
                     const gp_bf16* gp_ = p.gy_bf16 + (size_t)crow * p.ld_gy + c0;
                     unpack8(ldg16(gp_), du);
                     unpack8(ldg16(gp_ + 8), du + 8);
+                } else if (!p.gy_f32) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) du[j] = 0.f;
                 } else {
                     const float4* gp_ = reinterpret_cast<const float4*>(p.gy_f32 + (size_t)crow * p.ld_gy + c0);
 #pragma unroll
@@ -416,6 +419,23 @@ __global__ void reduce_partials_kernel(const float* __restrict__ partials, int n
     *d = accumulate ? (*d + acc) : acc;
 }
 
+struct ReduceSegs {
+    gp_reduce_seg s[8];
+    int n;
+};
+__global__ void reduce_multi_kernel(const float* __restrict__ partials, int n_parts, int stride, ReduceSegs segs) {
+    const gp_reduce_seg sg = segs.s[blockIdx.y];
+    const int total = sg.rows * sg.cols;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int r = i / sg.cols, c = i - r * sg.cols;
+        const float* src = partials + sg.offset + (size_t)r * sg.ld_part + c;
+        float acc = 0.f;
+        for (int pi = 0; pi < n_parts; ++pi) acc += src[(size_t)pi * stride];
+        float* d = sg.dst + (size_t)r * sg.ld_dst + c;
+        *d = sg.accumulate ? (*d + acc) : acc;
+    }
+}
+
 template <int H>
 int launch_bwd(const gp_mlp_bwd_args& a, int32_t* grid_out, cudaStream_t st) {
     size_t smem = 1024;
@@ -451,7 +471,8 @@ extern "C" int gp_mlp_bwd_stage(const gp_mlp_bwd_args* args, int hidden, int32_t
     GP_REQUIRE(a.wa && a.wb && a.partials, "gp_mlp_bwd_stage: null weights or partials");
     if (a.mode == 1) {
         GP_REQUIRE(a.nb == hidden, "gp_mlp_bwd_stage: NORM mode needs nb == hidden");
-        GP_REQUIRE((a.gy_bf16 != nullptr) != (a.gy_f32 != nullptr), "gp_mlp_bwd_stage: exactly one of gy_bf16 / gy_f32");
+        GP_REQUIRE(!(a.gy_bf16 && a.gy_f32) && (a.gy_bf16 || a.gy_f32 || a.gy_gather),
+                   "gp_mlp_bwd_stage: NORM mode needs gy_bf16 or gy_f32 (not both), or at least gy_gather");
     } else {
         GP_REQUIRE(a.mode == 0 && a.delta_b != nullptr && a.ld_db % 8 == 0, "gp_mlp_bwd_stage: GIVEN mode needs delta_b");
     }
@@ -473,6 +494,27 @@ extern "C" int gp_reduce_partials(const float* partials, int32_t n_parts, int32_
     if (total <= 0) return 0;
     reduce_partials_kernel<<<(total + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(
         partials, n_parts, stride, offset, rows, cols, ld_part, dst, ld_dst, accumulate);
+    GP_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int gp_reduce_partials_multi(const float* partials, int32_t n_parts, int32_t stride,
+                                        const gp_reduce_seg* segs_host, int32_t n_segs, void* stream) {
+    GP_REQUIRE(n_segs >= 0 && n_segs <= 8, "gp_reduce_partials_multi: at most 8 segments");
+    if (n_segs == 0) return 0;
+    ReduceSegs segs;
+    segs.n = n_segs;
+    int max_total = 0;
+    for (int i = 0; i < n_segs; ++i) {
+        segs.s[i] = segs_host[i];
+        const int t = segs_host[i].rows * segs_host[i].cols;
+        if (t > max_total) max_total = t;
+    }
+    int bx = (max_total + 255) / 256;
+    if (bx > 64) bx = 64;
+    if (bx < 1) bx = 1;
+    dim3 grid(bx, n_segs);
+    reduce_multi_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(partials, n_parts, stride, segs);
     GP_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

@@ -1,0 +1,158 @@
+// train_ops.cu -- the small, bandwidth-trivial pieces of the training step, kept on the device and
+// deterministic: masked L2 loss + gradient, global gradient norm, clip + AdamW on the flat
+// parameter buffer, and the fp32 -> packed-bf16 weight refresh.
+#include "common.cuh"
+#include "../../include/gp_b200.h"
+#include <cuda_bf16.h>
+
+namespace {
+
+__device__ __forceinline__ float block_sum(float v, float* sh) {
+    // fixed-shape tree: warp shuffle then one warp over the per-warp sums (deterministic)
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    __syncthreads();
+    if (l == 0) sh[w] = v;
+    __syncthreads();
+    v = (threadIdx.x < (blockDim.x >> 5)) ? sh[threadIdx.x] : 0.f;
+    if (w == 0)
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (threadIdx.x == 0) sh[0] = v;
+    __syncthreads();
+    return sh[0];
+}
+
+// L2Loss.forward (graphphysics/utils/loss.py:45-75): mean over masked rows x D of (out-target)^2,
+// and its gradient.  One block: the tensors are N x output_size (a few hundred KB).
+__global__ void __launch_bounds__(1024, 1) masked_mse_kernel(const float* __restrict__ out, const float* __restrict__ tgt,
+                                                             const uint8_t* __restrict__ mask, int n, int d,
+                                                             float* __restrict__ loss, float* __restrict__ grad,
+                                                             float grad_scale) {
+    __shared__ float sh[32];
+    float se = 0.f, cnt = 0.f;
+    for (int i = threadIdx.x; i < n * d; i += blockDim.x) {
+        const int r = i / d;
+        if (mask[r]) {
+            const float e = out[i] - tgt[i];
+            se = fmaf(e, e, se);
+        }
+    }
+    for (int r = threadIdx.x; r < n; r += blockDim.x) cnt += mask[r] ? 1.f : 0.f;
+    se = block_sum(se, sh);
+    cnt = block_sum(cnt, sh);
+    const float denom = cnt * d;
+    if (threadIdx.x == 0) loss[0] = se / denom;      // 0/0 -> NaN like torch.mean of an empty selection
+    if (grad) {
+        const float k = 2.f * grad_scale / denom;
+        for (int i = threadIdx.x; i < n * d; i += blockDim.x) grad[i] = mask[i / d] ? k * (out[i] - tgt[i]) : 0.f;
+    }
+}
+
+__global__ void sqnorm_partial_kernel(const float* __restrict__ g, size_t n, float* __restrict__ partial) {
+    __shared__ float sh[32];
+    float s = 0.f;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        s = fmaf(g[i], g[i], s);
+    s = block_sum(s, sh);
+    if (threadIdx.x == 0) partial[blockIdx.x] = s;
+}
+__global__ void sqnorm_final_kernel(const float* __restrict__ partial, int n, float* __restrict__ out) {
+    __shared__ float sh[32];
+    float s = 0.f;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) s += partial[i];
+    s = block_sum(s, sh);
+    if (threadIdx.x == 0) out[0] = s;
+}
+
+// clip_grad_norm_(max_norm) followed by torch.optim.AdamW (lightning_module.py:494-511,
+// train.py:288 gradient_clip_val=1.0).
+__global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                             float* __restrict__ v, size_t n, float lr, float b1, float b2, float eps, float wd,
+                             float bc1, float bc2, float max_norm, const float* __restrict__ sqnorm) {
+    float coef = 1.f;
+    if (max_norm > 0.f) {
+        const float nrm = sqrtf(sqnorm[0]);
+        coef = fminf(max_norm / (nrm + 1e-6f), 1.f);
+    }
+    const float step = lr / bc1, rs = rsqrtf(bc2);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float gi = g[i] * coef;
+        float pi = p[i] * (1.f - lr * wd);
+        const float mi = b1 * m[i] + (1.f - b1) * gi;
+        const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+        pi -= step * mi / (sqrtf(vi) * rs + eps);
+        p[i] = pi; m[i] = mi; v[i] = vi;
+    }
+}
+
+// fp32 master weights -> packed bf16 operands.  One table entry per matrix; blockIdx.y = entry.
+__global__ void pack_weights_kernel(const float* __restrict__ params, __nv_bfloat16* __restrict__ packed,
+                                    const gp_pack_entry* __restrict__ table) {
+    const gp_pack_entry e = table[blockIdx.y];
+    const int total = e.n * e.k;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int r = i / e.k, c = i - r * e.k;
+        packed[(size_t)e.dst_off + (size_t)(e.dst_row0 + r) * e.ld_dst + e.dst_col0 + c] =
+            __float2bfloat16(params[(size_t)e.src_off + (size_t)r * e.ld_src + e.src_col0 + c]);
+    }
+}
+
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ s, __nv_bfloat16* __restrict__ d, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        d[i] = __float2bfloat16(s[i]);
+}
+}  // namespace
+
+extern "C" int gp_masked_mse(const float* out, const float* target, const uint8_t* mask, int32_t n, int32_t d,
+                             float* loss, float* grad, float grad_scale, void* stream) {
+    GP_REQUIRE(out && target && mask && loss && n > 0 && d > 0, "gp_masked_mse: bad arguments");
+    masked_mse_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(out, target, mask, n, d, loss, grad, grad_scale);
+    GP_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int gp_sqnorm(const float* g, int64_t n, float* workspace, float* out, void* stream) {
+    GP_REQUIRE(g && workspace && out && n > 0, "gp_sqnorm: bad arguments");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int blocks = 256;
+    sqnorm_partial_kernel<<<blocks, 256, 0, st>>>(g, (size_t)n, workspace);
+    sqnorm_final_kernel<<<1, 256, 0, st>>>(workspace, blocks, out);
+    GP_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int gp_adamw(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                        float beta1, float beta2, float eps, float weight_decay, int32_t step, float max_norm,
+                        const float* sqnorm, void* stream) {
+    GP_REQUIRE(params && grads && exp_avg && exp_avg_sq && n > 0 && step >= 1, "gp_adamw: bad arguments");
+    GP_REQUIRE(max_norm <= 0.f || sqnorm != nullptr, "gp_adamw: clipping needs the squared gradient norm");
+    const float bc1 = 1.f - powf(beta1, (float)step), bc2 = 1.f - powf(beta2, (float)step);
+    int blocks = (int)((n + 255) / 256);
+    if (blocks > gp::sm_count() * 8) blocks = gp::sm_count() * 8;
+    adamw_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(params, grads, exp_avg, exp_avg_sq, (size_t)n, lr,
+                                                                         beta1, beta2, eps, weight_decay, bc1, bc2,
+                                                                         max_norm, sqnorm);
+    GP_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int gp_pack_weights(const float* params, gp_bf16* packed, const gp_pack_entry* table, int32_t n_entries,
+                               void* stream) {
+    if (n_entries <= 0) return 0;
+    GP_REQUIRE(params && packed && table, "gp_pack_weights: null pointer");
+    dim3 grid(16, n_entries);
+    pack_weights_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        params, reinterpret_cast<__nv_bfloat16*>(packed), table);
+    GP_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int gp_cast_bf16(const float* src, gp_bf16* dst, int64_t n, void* stream) {
+    if (n <= 0) return 0;
+    int blocks = (int)((n + 255) / 256);
+    if (blocks > gp::sm_count() * 8) blocks = gp::sm_count() * 8;
+    cast_f32_bf16_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(src, reinterpret_cast<__nv_bfloat16*>(dst),
+                                                                                 (size_t)n);
+    GP_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}

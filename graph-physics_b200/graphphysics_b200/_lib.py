@@ -124,3 +124,45 @@ class MlpBwdArgs(C.Structure):
         ("seg_bnd", C.c_void_p),
         ("partials", C.c_void_p),
     ]
+
+
+class LinearBwdArgs(C.Structure):
+    _fields_ = [
+        ("rows", C.c_int32),
+        ("n_src", C.c_int32),
+        ("src_f32", C.c_void_p * 3),
+        ("src_bf16", C.c_void_p * 3),
+        ("ld_src", C.c_int32 * 3),
+        ("w", C.c_void_p),
+        ("x", C.c_void_p),
+        ("ldx", C.c_int32),
+        ("dx_in", C.c_void_p),
+        ("dx_out", C.c_void_p),
+        ("partials", C.c_void_p),
+    ]
+
+
+class PackEntry(C.Structure):
+    _fields_ = [
+        ("src_off", C.c_int64),
+        ("ld_src", C.c_int32),
+        ("src_col0", C.c_int32),
+        ("n", C.c_int32),
+        ("k", C.c_int32),
+        ("dst_off", C.c_int64),
+        ("ld_dst", C.c_int32),
+        ("dst_row0", C.c_int32),
+        ("dst_col0", C.c_int32),
+    ]
+
+
+class ReduceSeg(C.Structure):
+    _fields_ = [
+        ("offset", C.c_int32),
+        ("rows", C.c_int32),
+        ("cols", C.c_int32),
+        ("ld_part", C.c_int32),
+        ("dst", C.c_void_p),
+        ("ld_dst", C.c_int32),
+        ("accumulate", C.c_int32),
+    ]

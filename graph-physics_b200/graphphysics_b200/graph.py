@@ -1,0 +1,100 @@
+"""Graph containers for the kernels: a PyG-like attribute bag and the receiver-sorted CSR layout.
+
+The reference hands edge lists sorted by sender (PyG coalesce) and aggregates at the receiver
+(`edge_index[1]`, graphphysics/models/layers.py:926, 1031-1037).  The kernels want every
+receiver's edges contiguous, so a topology is converted once into `GraphCSR` and cached.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+
+class Data:
+    """Minimal stand-in for torch_geometric.data.Data: an attribute bag where a missing attribute
+    reads as None (the behaviour graphphysics/models/simulator.py:169-174 and
+    processors.py:187 rely on).  A real PyG Data works everywhere this does."""
+
+    def __init__(self, **kwargs):
+        for k, v in kwargs.items():
+            setattr(self, k, v)
+
+    def __getattr__(self, name):
+        if name.startswith("__"):
+            raise AttributeError(name)
+        return None
+
+    def clone(self) -> "Data":
+        return Data(**{k: (v.clone() if torch.is_tensor(v) else v) for k, v in self.__dict__.items()})
+
+    def to(self, device, non_blocking: bool = False) -> "Data":
+        return Data(**{k: (v.to(device, non_blocking=non_blocking) if torch.is_tensor(v) else v)
+                       for k, v in self.__dict__.items()})
+
+    @property
+    def num_nodes(self) -> int:
+        return int(self.x.shape[0])
+
+
+Batch = Data
+
+
+class GraphCSR:
+    """Receiver-sorted edge layout of one topology (all int32, on the device of edge_index).
+
+    perm_dst      : sorted position -> original edge id (stable sort by receiver)
+    src, dst      : endpoints in sorted order
+    rowptr_dst    : [N+1] receiver segments of the sorted list
+    perm_src      : positions of the sorted list, stable-sorted by sender
+    rowptr_src    : [N+1] sender segments of perm_src
+    """
+
+    def __init__(self, edge_index: torch.Tensor, num_nodes: int):
+        assert edge_index.dim() == 2 and edge_index.shape[0] == 2
+        src, dst = edge_index[0].long(), edge_index[1].long()
+        self.num_nodes = int(num_nodes)
+        self.num_edges = int(src.numel())
+        perm = torch.sort(dst, stable=True).indices
+        src_s, dst_s = src[perm], dst[perm]
+        self.perm_dst64 = perm
+        self.perm_dst = perm.int()
+        self.src, self.dst = src_s.int(), dst_s.int()
+        self.rowptr_dst = self._rowptr(dst_s, num_nodes)
+        self.perm_src = torch.sort(src_s, stable=True).indices.int()
+        self.rowptr_src = self._rowptr(src_s, num_nodes)
+        self._inv_perm: Optional[torch.Tensor] = None
+
+    @staticmethod
+    def _rowptr(ids: torch.Tensor, n: int) -> torch.Tensor:
+        rp = torch.zeros(n + 1, dtype=torch.int32, device=ids.device)
+        if ids.numel():
+            rp[1:] = torch.cumsum(torch.bincount(ids, minlength=n), 0).int()
+        return rp
+
+    @property
+    def inv_perm_dst64(self) -> torch.Tensor:
+        """original edge id -> sorted position."""
+        if self._inv_perm is None:
+            inv = torch.empty_like(self.perm_dst64)
+            inv[self.perm_dst64] = torch.arange(self.num_edges, device=inv.device)
+            self._inv_perm = inv
+        return self._inv_perm
+
+
+_CACHE: dict = {}
+
+
+def get_csr(edge_index: torch.Tensor, num_nodes: int) -> GraphCSR:
+    """GraphCSR of `edge_index`, cached on (storage pointer, version, shape) so a static topology
+    (roll-outs, repeated batches) is sorted once."""
+    key = (edge_index.data_ptr(), edge_index._version, tuple(edge_index.shape), int(num_nodes), str(edge_index.device))
+    g = _CACHE.get(key)
+    if g is None:
+        if len(_CACHE) > 64:
+            _CACHE.clear()
+        g = GraphCSR(edge_index, num_nodes)
+        # keep the tensor alive so the pointer cannot be recycled for a different graph
+        g._keepalive = edge_index
+        _CACHE[key] = g
+    return g

@@ -1,0 +1,57 @@
+"""Encode-process-decode model with the reference's constructor, forward signature and
+state_dict keys (graphphysics/models/processors.py:57-215), executed by EPDEngine on the
+sm_100a kernels.  `graph` is any object with `.x`, `.edge_index`, `.edge_attr` (a PyG Data or
+graphphysics_b200.graph.Data)."""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from ..graph import get_csr
+from .layers import GraphNetBlock, build_mlp
+
+
+class EncodeProcessDecode(nn.Module):
+    def __init__(self, message_passing_num: int, node_input_size: int, edge_input_size: int, output_size: int,
+                 hidden_size: int = 128, only_processor: bool = False, use_rope_embeddings: bool = False,
+                 use_gated_attention: bool = False, use_gated_mlp: bool = False, rope_pos_dimension: int = 3,
+                 rope_base: float = 10000.0, use_temporal_block: bool = False):
+        super().__init__()
+        if use_temporal_block:
+            raise NotImplementedError("use_temporal_block is not implemented on the sm_100a path (SURVEY §8f N3)")
+        self.only_processor = only_processor
+        self.hidden_size = hidden_size
+        self.d = output_size
+        self.use_temporal_block = use_temporal_block
+        self.use_gated_mlp = use_gated_mlp
+        self.use_rope = use_rope_embeddings
+        self.use_gate = use_gated_attention
+        self.rope_axes, self.rope_base = rope_pos_dimension, rope_base
+        if not only_processor:
+            self.nodes_encoder = build_mlp(node_input_size, hidden_size, hidden_size)
+            self.edges_encoder = build_mlp(edge_input_size, hidden_size, hidden_size)
+            self.decode_module = build_mlp(hidden_size, hidden_size, output_size, layer_norm=False)
+        self.processor_list = nn.ModuleList([
+            GraphNetBlock(hidden_size=hidden_size, use_gated_mlp=use_gated_mlp, use_rope=use_rope_embeddings,
+                          rope_axes=rope_pos_dimension, rope_base=rope_base, use_gate=use_gated_attention)
+            for _ in range(message_passing_num)])
+        self._engine = None
+
+    @property
+    def engine(self):
+        from ..engine import EPDEngine
+        if self._engine is None or not self._engine.is_bound():
+            self._engine = EPDEngine(self)
+        return self._engine
+
+    def forward(self, graph) -> torch.Tensor:
+        from ..engine import BlockFunction, EPDFunction
+        eng = self.engine
+        x, edge_attr = graph.x, graph.edge_attr
+        g = get_csr(graph.edge_index, x.shape[0])
+        if torch.is_grad_enabled():
+            if self.only_processor:
+                return BlockFunction.apply(eng.flat, x, edge_attr, eng, g)[0]
+            return EPDFunction.apply(eng.flat, x, edge_attr, eng, g)
+        out, _, _ = eng.forward(x, edge_attr, g, save=False)
+        return out.float()

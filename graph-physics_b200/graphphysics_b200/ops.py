@@ -179,15 +179,16 @@ def mlp_bwd_stage(
     args.wa, args.ba, args.wb, args.bb = ptr(wa), ptr(ba), ptr(wb), ptr(bb)
     args.nb = wb.shape[0]
     assert wa.shape == (hidden, ka) and wb.shape[1] == hidden
-    if gy is not None:
+    if delta_b is None:
         args.mode = 1
         args.norm_scale = ptr(norm_scale)
-        if gy.dtype == torch.bfloat16:
-            args.gy_bf16 = ptr(gy)
-        else:
-            assert gy.dtype == torch.float32
-            args.gy_f32 = ptr(gy)
-        args.ld_gy = gy.stride(0)
+        if gy is not None:
+            if gy.dtype == torch.bfloat16:
+                args.gy_bf16 = ptr(gy)
+            else:
+                assert gy.dtype == torch.float32
+                args.gy_f32 = ptr(gy)
+            args.ld_gy = gy.stride(0)
         args.gy_gather, args.gy_idx = ptr(gy_gather), ptr(gy_idx)
     else:
         args.mode = 0
@@ -221,3 +222,77 @@ def reduce_partials(partials: torch.Tensor, n_parts: int, stride: int, offset: i
                                  C.c_void_p(ptr(dst)), ld_dst, 1 if accumulate else 0, C.c_void_p(stream_ptr())),
         "gp_reduce_partials",
     )
+
+
+from ._lib import LinearBwdArgs, PackEntry, ReduceSeg  # noqa: E402
+
+
+def linear_bwd(rows: int, hidden: int, srcs: Sequence[torch.Tensor], w: torch.Tensor, x: torch.Tensor,
+               dx_in: Optional[torch.Tensor], dx_out: torch.Tensor, partials: torch.Tensor) -> int:
+    """gp_linear_bwd: dx_out = dx_in + sum_s srcs[s] . W_s ;  per-CTA dW partials."""
+    args = LinearBwdArgs()
+    args.rows, args.n_src = rows, len(srcs)
+    for s, t in enumerate(srcs):
+        if t.dtype == torch.float32:
+            args.src_f32[s] = ptr(t)
+        else:
+            assert t.dtype == torch.bfloat16
+            args.src_bf16[s] = ptr(t)
+        args.ld_src[s] = t.stride(0)
+    args.w, args.x, args.ldx = ptr(w), ptr(x), x.stride(0)
+    args.dx_in, args.dx_out, args.partials = ptr(dx_in), ptr(dx_out), ptr(partials)
+    grid = C.c_int32(0)
+    check(lib().gp_linear_bwd(C.byref(args), C.c_int(hidden), C.byref(grid), C.c_void_p(stream_ptr())), "gp_linear_bwd")
+    return int(grid.value)
+
+
+def segsum_gather(src: torch.Tensor, perm: Optional[torch.Tensor], rowptr: torch.Tensor, hidden: int,
+                  out: torch.Tensor) -> None:
+    check(
+        lib().gp_segsum_gather(C.c_void_p(ptr(src)), C.c_int32(src.stride(0)), C.c_void_p(ptr(perm)),
+                               C.c_void_p(ptr(rowptr)), C.c_int32(rowptr.numel() - 1), C.c_int32(hidden),
+                               C.c_void_p(ptr(out)), C.c_void_p(stream_ptr())),
+        "gp_segsum_gather",
+    )
+
+
+def reduce_multi(partials: torch.Tensor, n_parts: int, stride: int, segs) -> None:
+    """segs: list of (offset, rows, cols, ld_part, dst_ptr(int), ld_dst, accumulate)."""
+    arr = (ReduceSeg * len(segs))()
+    for i, (off, rows, cols, ldp, dst, ldd, acc) in enumerate(segs):
+        arr[i].offset, arr[i].rows, arr[i].cols, arr[i].ld_part = off, rows, cols, ldp
+        arr[i].dst, arr[i].ld_dst, arr[i].accumulate = dst, ldd, 1 if acc else 0
+    check(lib().gp_reduce_partials_multi(C.c_void_p(ptr(partials)), n_parts, stride, arr, len(segs),
+                                         C.c_void_p(stream_ptr())), "gp_reduce_partials_multi")
+
+
+def masked_mse(out: torch.Tensor, target: torch.Tensor, mask_u8: torch.Tensor, loss: torch.Tensor,
+               grad: Optional[torch.Tensor], grad_scale: float = 1.0) -> None:
+    n, d = out.shape
+    assert out.is_contiguous() and target.is_contiguous() and mask_u8.dtype == torch.uint8
+    check(lib().gp_masked_mse(C.c_void_p(ptr(out)), C.c_void_p(ptr(target)), C.c_void_p(ptr(mask_u8)), n, d,
+                              C.c_void_p(ptr(loss)), C.c_void_p(ptr(grad)), C.c_float(grad_scale),
+                              C.c_void_p(stream_ptr())), "gp_masked_mse")
+
+
+def sqnorm(g: torch.Tensor, workspace: torch.Tensor, out: torch.Tensor) -> None:
+    check(lib().gp_sqnorm(C.c_void_p(ptr(g)), C.c_int64(g.numel()), C.c_void_p(ptr(workspace)), C.c_void_p(ptr(out)),
+                          C.c_void_p(stream_ptr())), "gp_sqnorm")
+
+
+def adamw(params, grads, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_decay, step, max_norm, sqnorm_t) -> None:
+    check(lib().gp_adamw(C.c_void_p(ptr(params)), C.c_void_p(ptr(grads)), C.c_void_p(ptr(exp_avg)),
+                         C.c_void_p(ptr(exp_avg_sq)), C.c_int64(params.numel()), C.c_float(lr), C.c_float(beta1),
+                         C.c_float(beta2), C.c_float(eps), C.c_float(weight_decay), C.c_int32(step), C.c_float(max_norm),
+                         C.c_void_p(ptr(sqnorm_t)), C.c_void_p(stream_ptr())), "gp_adamw")
+
+
+def pack_weights(params: torch.Tensor, packed: torch.Tensor, table_dev: torch.Tensor, n_entries: int) -> None:
+    check(lib().gp_pack_weights(C.c_void_p(ptr(params)), C.c_void_p(ptr(packed)), C.c_void_p(ptr(table_dev)),
+                                C.c_int32(n_entries), C.c_void_p(stream_ptr())), "gp_pack_weights")
+
+
+def cast_bf16(src: torch.Tensor, dst: torch.Tensor) -> None:
+    assert src.dtype == torch.float32 and dst.dtype == torch.bfloat16 and src.numel() == dst.numel()
+    check(lib().gp_cast_bf16(C.c_void_p(ptr(src)), C.c_void_p(ptr(dst)), C.c_int64(src.numel()),
+                             C.c_void_p(stream_ptr())), "gp_cast_bf16")

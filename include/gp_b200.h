@@ -147,6 +147,70 @@ int gp_mlp_bwd_stage(const gp_mlp_bwd_args* args, int hidden, int32_t* grid_out,
 int gp_reduce_partials(const float* partials, int32_t n_parts, int32_t stride, int32_t offset, int32_t rows,
                        int32_t cols, int32_t ld_part, float* dst, int32_t ld_dst, int32_t accumulate, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Backward of the bias-free per-node projection P = x . Wp^T (tcgen05).  W1 of the edge MLP is
+ * [W1e | W1d | W1s] over the concat [e, x[dst], x[src]] (layers.py:1016-1018, 1058) and W1 of the
+ * node MLP is [W1x | W1a] over [x, agg] (layers.py:1100-1102); by linearity the x-dependent
+ * column blocks are applied once per node (Wp = [W1d; W1s; W1x], P = x.Wp^T) and P's rows are
+ * gathered into the fused kernels as pre-activations.  This entry point is autograd through that
+ * projection:  dx_out = dx_in + sum_s src_s . Wp_s ;  dWp_s = src_s^T . x  (per-CTA partials,
+ * [grid][n_src*hidden*hidden] floats, reduce with gp_reduce_partials).
+ * --------------------------------------------------------------------------------------------- */
+typedef struct gp_linear_bwd_args {
+    int32_t rows;
+    int32_t n_src;
+    const float* src_f32[3];
+    const gp_bf16* src_bf16[3];
+    int32_t ld_src[3];
+    const gp_bf16* w; /* packed [n_src*hidden][hidden] */
+    const gp_bf16* x; /* [rows][ldx] */
+    int32_t ldx;
+    const float* dx_in; /* optional [rows][hidden] */
+    float* dx_out;      /* [rows][hidden] */
+    float* partials;
+} gp_linear_bwd_args;
+int gp_linear_bwd(const gp_linear_bwd_args* args, int hidden, int32_t* grid_out, void* stream);
+
+/* out[n][:] = sum_{j in [rowptr[n], rowptr[n+1])} src[perm[j]][:]  -- the sender-side sum of the
+ * edge gradients (the transpose of the x[row] gather, layers.py:1018), fixed order, no atomics.
+ * perm may be NULL (identity). */
+int gp_segsum_gather(const gp_bf16* src, int32_t ld, const int32_t* perm, const int32_t* rowptr, int32_t num_segments,
+                     int32_t hidden, float* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Training-step glue (graphphysics/training/lightning_module.py:270-342, 494-511;
+ * graphphysics/utils/loss.py:19-75; train.py:276-290).
+ * --------------------------------------------------------------------------------------------- */
+/* loss[0] = mean over rows with mask!=0 and all d columns of (out-target)^2; grad (optional) =
+ * grad_scale * dloss/dout. */
+int gp_masked_mse(const float* out, const float* target, const uint8_t* mask, int32_t n, int32_t d, float* loss,
+                  float* grad, float grad_scale, void* stream);
+/* out[0] = sum g[i]^2 (two fixed-shape passes; workspace >= 256 floats). */
+int gp_sqnorm(const float* g, int64_t n, float* workspace, float* out, void* stream);
+/* clip-by-global-norm (max_norm <= 0 disables; sqnorm = device scalar from gp_sqnorm) + AdamW. */
+int gp_adamw(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
+             float beta2, float eps, float weight_decay, int32_t step, float max_norm, const float* sqnorm, void* stream);
+/* fp32 master matrices -> packed bf16 operands, one launch for the whole model. */
+typedef struct gp_pack_entry {
+    int64_t src_off; /* floats into params */
+    int32_t ld_src, src_col0;
+    int32_t n, k; /* block copied: n rows x k columns */
+    int64_t dst_off; /* elements into packed */
+    int32_t ld_dst, dst_row0, dst_col0;
+} gp_pack_entry;
+int gp_pack_weights(const float* params, gp_bf16* packed, const gp_pack_entry* table, int32_t n_entries, void* stream);
+int gp_cast_bf16(const float* src, gp_bf16* dst, int64_t n, void* stream);
+
+/* One launch for all gradient pieces of a stage: for each segment s,
+ * dst_s[r*ld_dst + c] (+)= sum_p partials[p*stride + offset_s + r*ld_part_s + c]. */
+typedef struct gp_reduce_seg {
+    int32_t offset, rows, cols, ld_part;
+    float* dst;
+    int32_t ld_dst, accumulate;
+} gp_reduce_seg;
+int gp_reduce_partials_multi(const float* partials, int32_t n_parts, int32_t stride, const gp_reduce_seg* segs_host,
+                             int32_t n_segs, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

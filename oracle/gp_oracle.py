@@ -152,10 +152,15 @@ def graph_net_block(x, e, src, dst, sd, prefix: str, mode: Optional[str] = None)
         pre = F.linear(rnd(e, mode), rnd(w1e, mode)) + pd[dst] + ps[src]
         e_upd = mlp(None, sd, f"{prefix}.edge_block", mode=mode, first_pre=pre)
         agg = torch.zeros_like(x).index_add_(0, dst, rnd(e_upd, mode))   # kernel sums bf16(e_upd) in fp32
+        # node MLP, first layer split the same way: W1 = [W1x | W1a] over [x, agg]
+        wn = sd[f"{prefix}.node_block.0.weight"]
+        q = rnd(linear(x, wn[:, :H], None, mode), mode)
+        pre_n = F.linear(rnd(agg, mode), rnd(wn[:, H:], mode)) + q
+        x_upd = mlp(None, sd, f"{prefix}.node_block", mode=mode, first_pre=pre_n)
     else:
         e_upd = mlp(torch.cat([e, x[dst], x[src]], dim=-1), sd, f"{prefix}.edge_block")
         agg = torch.zeros_like(x).index_add_(0, dst, e_upd)
-    x_upd = mlp(torch.cat([x, agg], dim=-1), sd, f"{prefix}.node_block", mode=mode)
+        x_upd = mlp(torch.cat([x, agg], dim=-1), sd, f"{prefix}.node_block")
     return rnd(x + x_upd, mode), rnd(e + e_upd, mode)
 
 
