@@ -1,0 +1,249 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200-native graph-physics hot path.
+
+Workload (BASELINE.json configs[1]): CylinderFlow-shaped synthetic meshes (~1.9k nodes, ~11k
+directed edges each), EncodeProcessDecode with 15 message-passing layers, hidden 128, batch 32
+graphs per GPU, data-parallel over --gpus ranks (weak scaling).  One step = one full training
+step (Simulator forward, masked L2, backward, gradient all-reduce, clip, AdamW, LR schedule).
+
+Metric: edges/s per message-passing layer (fwd+bwd) = directed edges in the global batch x MP
+layers / step time.  `value` is measured with the batch resident in HBM; `e2e` goes through the
+public Trainer.training_step with the batch in pinned host memory (H2D copy every step, loss
+read back every step).
+
+    python bench.py --gpus 1 --steps 20 --warmup 5
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference      # reference algorithm on the host CPU cores
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "graph-physics_b200"))
+
+import torch  # noqa: E402
+
+CONFIG = {
+    "model": {"type": "epd", "message_passing_num": 15, "hidden_size": 128, "node_input_size": 2, "output_size": 2,
+              "edge_input_size": 3},
+    "index": {"feature_index_start": 0, "feature_index_end": 2, "output_index_start": 0, "output_index_end": 2,
+              "node_type_index": 2},
+}
+BATCH = 32
+METRIC = "edges/sec per MP layer (fwd+bwd)"
+UNIT = "edges/s"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops_sustained", 1400.0), "measured"
+    return 6650.0, 1400.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clocks / throttle reasons with nvidia-smi while the timed region runs."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self._stop_evt = index, [], set(), threading.Event()
+        self.sm_max = None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                f = [s.strip() for s in out.split(",")]
+                self.samples.append(float(f[0]))
+                self.sm_max = float(f[1])
+                for n, v in zip(names, f[2:6]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=5)
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons)}
+
+
+def run_reference(args, sample_graphs: int = 1):
+    """The reference algorithm (oracle port of the PyTorch path) on the host CPU cores, on a
+    bounded sample of the workload: `sample_graphs` of the 32 graphs of one rank's batch."""
+    from oracle.cpu_train import CpuTrainer, default_state_dict
+    from graphphysics_b200.synthetic import cylinder_flow_batch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    m, idx = CONFIG["model"], CONFIG["index"]
+    b = cylinder_flow_batch(sample_graphs, seed=0)
+    sd = default_state_dict(m["message_passing_num"], m["node_input_size"] + 9, m["edge_input_size"], m["output_size"],
+                            m["hidden_size"])
+    tr = CpuTrainer(sd, m["message_passing_num"], idx, m["output_size"], m["node_input_size"] + 9, m["edge_input_size"],
+                    lr=1e-4, num_steps=1000, warmup=10)
+    E = b.edge_index.shape[1]
+    for _ in range(max(args.warmup_ref, 1)):
+        tr.training_step(b.x, b.y, b.edge_attr, b.edge_index)
+    t0 = time.perf_counter()
+    for _ in range(args.steps_ref):
+        tr.training_step(b.x, b.y, b.edge_attr, b.edge_index)
+    dt = (time.perf_counter() - t0) / args.steps_ref
+    value = E * m["message_passing_num"] / dt
+    return {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{sample_graphs} of the {BATCH} graphs of one batch ({b.x.shape[0]} nodes, {E} directed edges), "
+                      f"full train step, fp32, {args.steps_ref} steps after {max(args.warmup_ref, 1)} warm-up",
+            "ms_per_step": dt * 1e3}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--steps-ref", dest="steps_ref", type=int, default=None)
+    ap.add_argument("--warmup-ref", dest="warmup_ref", type=int, default=1)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    workload = (f"CylinderFlow-shape synthetic mesh x{BATCH} graphs per GPU, EPD 15 MP layers, hidden 128 "
+                f"(BASELINE.json configs[1])")
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        if args.steps_ref is None:
+            args.steps_ref = min(args.steps, 5)
+        cb = run_reference(args)
+        line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
+                "steps": args.steps_ref, "warmup": max(args.warmup_ref, 1), "ms_per_step": cb["ms_per_step"],
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": workload, "sample": cb["sample"]},
+                "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    if args.steps_ref is None:
+        args.steps_ref = 3
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    pg = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+        pg = dist.group.WORLD
+
+    from graphphysics_b200 import ops
+    from graphphysics_b200.synthetic import cylinder_flow_batch
+    from graphphysics_b200.training.loop import Trainer
+
+    host = cylinder_flow_batch(BATCH, seed=rank, pin=True)
+    N, E = host.x.shape[0], host.edge_index.shape[1]
+    L, H = CONFIG["model"]["message_passing_num"], CONFIG["model"]["hidden_size"]
+    tr = Trainer(CONFIG, learning_rate=1e-4, num_steps=100000, warmup=1000, device=dev, process_group=pg, seed=0)
+    resident = host.to(dev)
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def timed(step_fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step_fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
+        return float(ms.item())
+
+    def step_resident():
+        tr.training_step(resident)
+
+    loss_host = []
+
+    def step_e2e():
+        b = host.to(dev, non_blocking=True)          # pinned host -> device, every step
+        loss_host.append(tr.training_step(b).item())  # loss read back, every step
+
+    for _ in range(args.warmup):
+        step_e2e()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ops.PROFILE.reset(tags=("edge_fwd", "edge_bwd_B", "edge_bwd_A"))
+    ops.COUNTERS["launches"] = 0
+    ms_res = timed(step_resident, args.steps)
+    launches = ops.COUNTERS["launches"] // args.steps
+    prof = ops.PROFILE.summary()
+    ops.PROFILE.reset(tags=())
+    ms_e2e = timed(step_e2e, args.steps)
+    clocks = sampler.stop()
+
+    total_edges = E * world            # every rank holds a batch of the same shape
+    value = total_edges * L * args.steps / (ms_res * 1e-3)
+    e2e_value = total_edges * L * args.steps / (ms_e2e * 1e-3)
+    h2d = sum(v.numel() * v.element_size() for v in (host.x, host.y, host.pos, host.edge_index, host.edge_attr))
+
+    # roofline of the dominant kernel (SURVEY §8d algorithmic bytes, bf16 storage)
+    hbm_peak, tf_peak, peak_src = peaks()
+    alg_bytes = {"edge_fwd": E * (8 * H + 8) + 4 * N * H, "edge_bwd_B": E * (6 * H) + 4 * N * H,
+                 "edge_bwd_A": E * (10 * H + 8) + 4 * N * H}
+    alg_flops = {"edge_fwd": E * 8 * H * H, "edge_bwd_B": E * 12 * H * H, "edge_bwd_A": E * 10 * H * H}
+    roof = None
+    if prof:
+        top = max(prof, key=lambda k: prof[k]["total_ms"])
+        avg_ms = prof[top]["total_ms"] / max(prof[top]["calls"], 1)
+        ach = alg_bytes[top] / (avg_ms * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": top, "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+                "traffic": None, "peak_source": peak_src, "avg_launch_ms": avg_ms,
+                "share_of_step": prof[top]["total_ms"] / ms_res,
+                "tensor": {"achieved_tflops": alg_flops[top] / (avg_ms * 1e-3) / 1e12, "peak_tflops": tf_peak,
+                           "frac": alg_flops[top] / (avg_ms * 1e-3) / 1e12 / tf_peak},
+                "kernels_ms_per_step": {k: v["total_ms"] / args.steps for k, v in prof.items()}}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_res / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": workload, "nodes_per_gpu": N, "directed_edges_per_gpu": E, "mp_layers": L,
+                           "hidden": H, "parallelism": f"dp{world}",
+                           "timing": "inputs (activations ~4 GB per step) larger than L2; no explicit flush"},
+                "train_steps_per_s": args.steps / (ms_res * 1e-3),
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                        "ms_per_step": ms_e2e / args.steps, "train_steps_per_s": args.steps / (ms_e2e * 1e-3)},
+                "gpu_launches": launches, "clocks": clocks, "roofline": roof, "loss_last": loss_host[-1]}
+        if world == 1 and not args.no_cpu_baseline:
+            cb = run_reference(args)
+            line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        print(json.dumps(line))
+    if world > 1:
+        torch.distributed.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -185,7 +185,7 @@ class EPDEngine:
         agg = torch.empty((N, H), dtype=torch.float32, device=dev)
         h2e = torch.empty((E, H), dtype=bf, device=dev) if save else None
         self._mlp(self.edge[l], E, e, H, e2, H, save_h2=h2e, resid=e, init=P, init_off0=0, init_off1=H,
-                  idx0=g.dst, idx1=g.src, two_inits=True, seg_id=g.dst, seg_out=agg, seg_bnd=bnd)
+                  idx0=g.dst, idx1=g.src, two_inits=True, seg_id=g.dst, seg_out=agg, seg_bnd=bnd, tag="edge_fwd")
         ops.seg_fixup(g.rowptr_dst, H, bnd, agg)
         x2 = torch.empty((N, H), dtype=bf, device=dev)
         h2n = torch.empty((N, H), dtype=bf, device=dev) if save else None
@@ -248,20 +248,21 @@ class EPDEngine:
         ops.reduce_multi(self.partials, grid, stride, segs)
 
     def _mlp_backward(self, s: _MLPSlots, rows, *, a_in, ka, h2, top, first=None, out=None, out_resid=None,
-                      delta_a_out=None, seg=None):
+                      delta_a_out=None, seg=None, tag=None):
         """Backward through the 4-layer MLP `s`: stage B over layers (2,3), stage A over (0,1).
         top = dict(gy=..., gy_gather=..., gy_idx=...) for a normalised MLP, or dict(delta_b=...)."""
         H, dev = self.H, self.device
         delta2 = torch.empty((rows, H), dtype=torch.bfloat16, device=dev)
         gridB = ops.mlp_bwd_stage(rows, H, a=h2, ka=H, wa=s.packed[2], ba=s.bias[2], wb=s.packed[3], bb=s.bias[3],
-                                  partials=self.partials, norm_scale=s.scale, out=delta2, mask_by_ain=True, **top)
+                                  partials=self.partials, norm_scale=s.scale, out=delta2, mask_by_ain=True,
+                                  tag=(tag + "_B") if tag else None, **top)
         self._reduce_stage(gridB, H, s.packed[3].shape[0], s, 2, 3, s.scale is not None)
         kw = dict(first or {})
         if seg is not None:
             kw.update(seg_id=seg[0], seg_out=seg[1], seg_bnd=seg[2])
         gridA = ops.mlp_bwd_stage(rows, H, a=a_in, ka=ka, wa=s.packed[0], ba=s.bias[0], wb=s.packed[1], bb=s.bias[1],
                                   partials=self.partials, delta_b=delta2, out=out, out_resid=out_resid,
-                                  delta_a_out=delta_a_out, **kw)
+                                  delta_a_out=delta_a_out, tag=(tag + "_A") if tag else None, **kw)
         self._reduce_stage(gridA, ka, H, s, 0, 1, False)
 
     def backward(self, ctx, d_out: torch.Tensor, dE_sorted: Optional[torch.Tensor] = None):
@@ -296,7 +297,8 @@ class EPDEngine:
             dPd = torch.empty((N, H), dtype=torch.float32, device=dev)
             self._mlp_backward(self.edge[l], E, a_in=e, ka=H, h2=h2e, top=dict(gy=dE, gy_gather=dagg, gy_idx=g.dst),
                                out=dE_new, out_resid=dE, delta_a_out=d1, seg=(g.dst, dPd, bnd),
-                               first=dict(init=P, init_off0=0, init_off1=H, idx0=g.dst, idx1=g.src, two_inits=True))
+                               first=dict(init=P, init_off0=0, init_off1=H, idx0=g.dst, idx1=g.src, two_inits=True),
+                               tag="edge_bwd")
             ops.seg_fixup(g.rowptr_dst, H, bnd, dPd)
             dPs = torch.empty((N, H), dtype=torch.float32, device=dev)
             ops.segsum_gather(d1, g.perm_src, g.rowptr_src, H, dPs)

@@ -14,6 +14,45 @@ from . import _lib
 from ._lib import MlpFwdArgs, check, lib, ptr, stream_ptr
 
 
+COUNTERS = {"launches": 0}      # kernels of libgp_b200.so launched through these wrappers
+
+
+class _Profile:
+    """Opt-in CUDA-event timing of selected kernel tags on the launching stream (bench.py)."""
+
+    def __init__(self):
+        self.tags, self.records = (), {}
+
+    def reset(self, tags=()):
+        self.tags, self.records = tuple(tags), {t: [] for t in tags}
+
+    def begin(self, tag):
+        if tag is None or tag not in self.tags:
+            return None
+        e0 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        return e0
+
+    def end(self, tag, e0):
+        if e0 is None:
+            return
+        e1 = torch.cuda.Event(enable_timing=True)
+        e1.record()
+        self.records[tag].append((e0, e1))
+
+    def summary(self):
+        torch.cuda.synchronize()
+        return {t: {"total_ms": sum(a.elapsed_time(b) for a, b in r), "calls": len(r)}
+                for t, r in self.records.items() if r}
+
+
+PROFILE = _Profile()
+
+
+def _launched(n: int = 1) -> None:
+    COUNTERS["launches"] += n
+
+
 def pad16(v: int) -> int:
     return (v + 15) // 16 * 16
 
@@ -62,6 +101,7 @@ def mlp_fwd(
     seg_id: Optional[torch.Tensor] = None,
     seg_out: Optional[torch.Tensor] = None,
     seg_bnd: Optional[torch.Tensor] = None,
+    tag: Optional[str] = None,
 ) -> torch.Tensor:
     """gp_mlp_fwd (include/gp_b200.h).  `weights` are packed bf16 [n][k]; `a` is [rows, >=ka]
     bf16 or fp32 with unit column stride; `out` is [rows, ld] bf16 or fp32."""
@@ -97,7 +137,10 @@ def mlp_fwd(
     args.n_valid = n_valid
     args.save_h2 = ptr(save_h2)
     args.seg_id, args.seg_out, args.seg_bnd = ptr(seg_id), ptr(seg_out), ptr(seg_bnd)
+    ev = PROFILE.begin(tag)
     check(lib().gp_mlp_fwd(C.byref(args), C.c_int(hidden), C.c_void_p(stream_ptr())), "gp_mlp_fwd")
+    PROFILE.end(tag, ev)
+    _launched()
     return out
 
 
@@ -108,6 +151,7 @@ def seg_fixup(rowptr: torch.Tensor, hidden: int, seg_bnd: torch.Tensor, seg_out:
                            C.c_void_p(ptr(seg_bnd)), C.c_void_p(ptr(seg_out)), C.c_void_p(stream_ptr())),
         "gp_seg_fixup",
     )
+    _launched()
 
 
 from ._lib import MlpBwdArgs  # noqa: E402
@@ -160,6 +204,7 @@ def mlp_bwd_stage(
     seg_id: Optional[torch.Tensor] = None,
     seg_out: Optional[torch.Tensor] = None,
     seg_bnd: Optional[torch.Tensor] = None,
+    tag: Optional[str] = None,
 ) -> int:
     """gp_mlp_bwd_stage (include/gp_b200.h).  NORM mode when `gy` is given, GIVEN mode when
     `delta_b` is given.  Returns the number of partial blocks written to `partials`."""
@@ -210,8 +255,11 @@ def mlp_bwd_stage(
     assert partials.dtype == torch.float32 and partials.numel() >= stride * min(sm_count(), (rows + 127) // 128)
     args.partials = ptr(partials)
     grid = C.c_int32(0)
+    ev = PROFILE.begin(tag)
     check(lib().gp_mlp_bwd_stage(C.byref(args), C.c_int(hidden), C.byref(grid), C.c_void_p(stream_ptr())),
           "gp_mlp_bwd_stage")
+    PROFILE.end(tag, ev)
+    _launched()
     return int(grid.value)
 
 
@@ -222,6 +270,7 @@ def reduce_partials(partials: torch.Tensor, n_parts: int, stride: int, offset: i
                                  C.c_void_p(ptr(dst)), ld_dst, 1 if accumulate else 0, C.c_void_p(stream_ptr())),
         "gp_reduce_partials",
     )
+    _launched()
 
 
 from ._lib import LinearBwdArgs, PackEntry, ReduceSeg  # noqa: E402
@@ -243,6 +292,7 @@ def linear_bwd(rows: int, hidden: int, srcs: Sequence[torch.Tensor], w: torch.Te
     args.dx_in, args.dx_out, args.partials = ptr(dx_in), ptr(dx_out), ptr(partials)
     grid = C.c_int32(0)
     check(lib().gp_linear_bwd(C.byref(args), C.c_int(hidden), C.byref(grid), C.c_void_p(stream_ptr())), "gp_linear_bwd")
+    _launched()
     return int(grid.value)
 
 
@@ -254,6 +304,7 @@ def segsum_gather(src: torch.Tensor, perm: Optional[torch.Tensor], rowptr: torch
                                C.c_void_p(ptr(out)), C.c_void_p(stream_ptr())),
         "gp_segsum_gather",
     )
+    _launched()
 
 
 def reduce_multi(partials: torch.Tensor, n_parts: int, stride: int, segs) -> None:
@@ -264,6 +315,7 @@ def reduce_multi(partials: torch.Tensor, n_parts: int, stride: int, segs) -> Non
         arr[i].dst, arr[i].ld_dst, arr[i].accumulate = dst, ldd, 1 if acc else 0
     check(lib().gp_reduce_partials_multi(C.c_void_p(ptr(partials)), n_parts, stride, arr, len(segs),
                                          C.c_void_p(stream_ptr())), "gp_reduce_partials_multi")
+    _launched()
 
 
 def masked_mse(out: torch.Tensor, target: torch.Tensor, mask_u8: torch.Tensor, loss: torch.Tensor,
@@ -273,11 +325,13 @@ def masked_mse(out: torch.Tensor, target: torch.Tensor, mask_u8: torch.Tensor, l
     check(lib().gp_masked_mse(C.c_void_p(ptr(out)), C.c_void_p(ptr(target)), C.c_void_p(ptr(mask_u8)), n, d,
                               C.c_void_p(ptr(loss)), C.c_void_p(ptr(grad)), C.c_float(grad_scale),
                               C.c_void_p(stream_ptr())), "gp_masked_mse")
+    _launched()
 
 
 def sqnorm(g: torch.Tensor, workspace: torch.Tensor, out: torch.Tensor) -> None:
     check(lib().gp_sqnorm(C.c_void_p(ptr(g)), C.c_int64(g.numel()), C.c_void_p(ptr(workspace)), C.c_void_p(ptr(out)),
                           C.c_void_p(stream_ptr())), "gp_sqnorm")
+    _launched(2)
 
 
 def adamw(params, grads, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_decay, step, max_norm, sqnorm_t) -> None:
@@ -285,14 +339,17 @@ def adamw(params, grads, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_deca
                          C.c_void_p(ptr(exp_avg_sq)), C.c_int64(params.numel()), C.c_float(lr), C.c_float(beta1),
                          C.c_float(beta2), C.c_float(eps), C.c_float(weight_decay), C.c_int32(step), C.c_float(max_norm),
                          C.c_void_p(ptr(sqnorm_t)), C.c_void_p(stream_ptr())), "gp_adamw")
+    _launched()
 
 
 def pack_weights(params: torch.Tensor, packed: torch.Tensor, table_dev: torch.Tensor, n_entries: int) -> None:
     check(lib().gp_pack_weights(C.c_void_p(ptr(params)), C.c_void_p(ptr(packed)), C.c_void_p(ptr(table_dev)),
                                 C.c_int32(n_entries), C.c_void_p(stream_ptr())), "gp_pack_weights")
+    _launched()
 
 
 def cast_bf16(src: torch.Tensor, dst: torch.Tensor) -> None:
     assert src.dtype == torch.float32 and dst.dtype == torch.bfloat16 and src.numel() == dst.numel()
     check(lib().gp_cast_bf16(C.c_void_p(ptr(src)), C.c_void_p(ptr(dst)), C.c_int64(src.numel()),
                              C.c_void_p(stream_ptr())), "gp_cast_bf16")
+    _launched()

@@ -1,0 +1,120 @@
+"""Training step and autoregressive roll-out (graphphysics/training/lightning_module.py:270-342,
+375-492, 494-511; Trainer knobs of graphphysics/train.py:276-290) as a plain loop around the
+CUDA engine -- no Lightning.
+
+One step = Simulator forward (normalise, one-hot, model) -> masked L2 -> backward -> optional
+gradient all-reduce -> clip-by-global-norm 1.0 -> AdamW(wd 1e-4, betas (0.9, 0.95)) -> cosine
+warm-up LR.  The model forward/backward call the engine directly (no autograd tape); the
+optimizer works on the engine's flat fp32 parameter/gradient buffers.
+"""
+from __future__ import annotations
+
+from typing import Any, Dict, List, Optional, Sequence
+
+import torch
+
+from .. import ops
+from ..graph import get_csr
+from ..utils.loss import prepare_mask
+from ..utils.nodetype import NodeType
+from ..utils.scheduler import lr_factor
+from .parse_parameters import get_model, get_simulator
+
+
+def build_mask(param: Dict[str, Any], graph) -> torch.Tensor:
+    """True where the node is NOT NORMAL / OUTFLOW (lightning_module.py:27-35)."""
+    x = graph.x
+    nt = x[:, 0, param["index"]["node_type_index"]] if x.dim() > 2 else x[:, param["index"]["node_type_index"]]
+    return ~((nt == NodeType.NORMAL) | (nt == NodeType.OUTFLOW))
+
+
+class Trainer:
+    def __init__(self, parameters: Dict[str, Any], learning_rate: float, num_steps: int, warmup: int,
+                 device: torch.device, masks: Sequence[int] = (NodeType.NORMAL, NodeType.OUTFLOW),
+                 gradient_clip_val: float = 1.0, weight_decay: float = 1e-4, betas=(0.9, 0.95), eps: float = 1e-8,
+                 process_group=None, seed: Optional[int] = None):
+        if seed is not None:
+            torch.manual_seed(seed)
+        self.param = parameters
+        self.device = device
+        model = get_model(parameters)
+        self.model = get_simulator(parameters, model, device)       # the reference calls the Simulator `model`
+        self.processor = self.model.model
+        self.learning_rate, self.num_steps, self.warmup = learning_rate, num_steps, warmup
+        self.loss_masks = list(masks)
+        self.clip, self.wd, self.betas, self.eps = gradient_clip_val, weight_decay, betas, eps
+        self.pg = process_group
+        self.step_index = 0
+        eng = self.processor.engine
+        self.exp_avg = torch.zeros_like(eng.flat.data)
+        self.exp_avg_sq = torch.zeros_like(eng.flat.data)
+        self._loss = torch.zeros(1, dtype=torch.float32, device=device)
+        if self.pg is not None:
+            import torch.distributed as dist
+            dist.broadcast(eng.flat.data, src=0, group=self.pg)
+
+    @property
+    def engine(self):
+        return self.processor.engine
+
+    def current_lr(self) -> float:
+        """LR used by the next optimizer step (CosineWarmupScheduler, scheduler.py:51-67)."""
+        return self.learning_rate * lr_factor(self.step_index - 1, self.warmup, self.num_steps)
+
+    def training_step(self, batch) -> torch.Tensor:
+        """lightning_module.py:270-342 + the optimizer step Lightning does afterwards.
+        Returns the loss as a device scalar (no host sync here)."""
+        sim, eng = self.model, self.engine
+        sim.train()
+        if not batch.x.is_cuda:
+            batch = batch.to(self.device, non_blocking=True)
+        node_type = batch.x[:, sim.node_type_index]
+        graph, target = sim._build_input_graph(batch, True)
+        g = get_csr(graph.edge_index, graph.x.shape[0])
+        out, _, ctx = eng.forward(graph.x, graph.edge_attr, g, save=True)
+        d_out = torch.empty_like(out)
+        ops.masked_mse(out, target.contiguous(), prepare_mask(node_type, self.loss_masks), self._loss, d_out)
+        eng.backward(ctx, d_out)
+        if self.pg is not None:
+            import torch.distributed as dist
+            dist.all_reduce(eng.gflat, group=self.pg)
+            eng.gflat.mul_(1.0 / dist.get_world_size(self.pg))
+        self.optimizer_step()
+        return self._loss[0]
+
+    def optimizer_step(self):
+        eng = self.engine
+        self.step_index += 1
+        lr = self.current_lr()
+        sq = eng.grad_sqnorm() if self.clip and self.clip > 0 else None
+        ops.adamw(eng.flat.data, eng.gflat, self.exp_avg, self.exp_avg_sq, lr, self.betas[0], self.betas[1], self.eps,
+                  self.wd, self.step_index, float(self.clip or 0.0), sq)
+
+    # ------------------------------------------------------------------ roll-out
+    @torch.no_grad()
+    def make_prediction(self, batch, last_prediction):
+        """_make_prediction (lightning_module.py:375-409), `use_previous_data` off."""
+        sim = self.model
+        sim.eval()
+        batch = batch.clone()
+        if last_prediction is not None:
+            batch.x[:, sim.output_index_start:sim.output_index_end] = last_prediction
+        mask = build_mask(self.param, batch)
+        _, _, predicted = sim(batch)
+        predicted[mask] = batch.y[mask]
+        return batch, predicted
+
+    @torch.no_grad()
+    def rollout(self, frames: List[Any]) -> Dict[str, Any]:
+        """Autoregressive roll-out over the frames of one trajectory; returns predictions and the
+        reference's two metrics (lightning_module.py:451-489)."""
+        last, preds, targets = None, [], []
+        for fr in frames:
+            fr = fr.to(self.device) if not fr.x.is_cuda else fr
+            _, last = self.make_prediction(fr, last)
+            preds.append(last)
+            targets.append(fr.y)
+        p, t = torch.cat(preds), torch.cat(targets)
+        return {"predictions": preds,
+                "val_1step_rmse": torch.sqrt(((preds[0] - targets[0]) ** 2).mean()).item(),
+                "val_all_rollout_rmse": torch.sqrt(((p - t) ** 2).mean()).item()}
