@@ -27,8 +27,9 @@ int max_smem_optin();
         }                              \
     } while (0)
 
-__device__ __forceinline__ uint8_t* align1024(uint8_t* p) {
-    return reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(p) + 1023) & ~uintptr_t(1023));
-}
+// 1024-byte aligned view of the dynamic shared memory array.  Written as an offset from the
+// __shared__ symbol (not an integer round-trip) so the compiler keeps the shared address space and
+// emits LDS/STS instead of generic LD/ST for everything carved out of it.
+#define GP_SMEM_ALIGNED(raw) ((raw) + ((1024u - (static_cast<uint32_t>(__cvta_generic_to_shared(raw)) & 1023u)) & 1023u))
 
 }  // namespace gp

@@ -14,7 +14,7 @@ using namespace gp;
 template <int H>
 __global__ void __launch_bounds__(256, 1) linear_bwd_kernel(const gp_linear_bwd_args p) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = align1024(smem_raw);
+    uint8_t* smem = GP_SMEM_ALIGNED(smem_raw);
     __shared__ uint64_t mma_bar;
     __shared__ uint32_t tmem_slot;
 

@@ -39,7 +39,7 @@ __host__ __device__ inline BwdLayout bwd_layout(int H, int ka, int nb) {
 template <int H>
 __global__ void __launch_bounds__(256, 1) mlp_bwd_kernel(const gp_mlp_bwd_args p) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = align1024(smem_raw);
+    uint8_t* smem = GP_SMEM_ALIGNED(smem_raw);
     __shared__ uint64_t mma_bar;
     __shared__ uint32_t tmem_slot;
 
@@ -134,10 +134,10 @@ __global__ void __launch_bounds__(256, 1) mlp_bwd_kernel(const gp_mlp_bwd_args p
         }
         cp_async_commit();
         if (p.seg_id && tid < 128) {
-            sseg[1 + row] = valid ? __ldg(p.seg_id + grow) : -1;
+            sseg[4 + row] = valid ? __ldg(p.seg_id + grow) : -1;
             if (row == 0) {
-                sseg[0] = R0 > 0 ? __ldg(p.seg_id + R0 - 1) : -1;
-                sseg[129] = (R0 + 128 < p.rows) ? __ldg(p.seg_id + R0 + 128) : -1;
+                sseg[3] = R0 > 0 ? __ldg(p.seg_id + R0 - 1) : -1;
+                sseg[132] = (R0 + 128 < p.rows) ? __ldg(p.seg_id + R0 + 128) : -1;
             }
         }
         if (has_init) {
@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(256, 1) mlp_bwd_kernel(const gp_mlp_bwd_args p
                 const int i1 = p.idx1 ? __ldg(p.idx1 + crow) : crow;
                 r1p = p.init + (size_t)i1 * p.ld_init + p.init_off1;
             }
-            init_rows_to_tmem(tlane + kColAcc, r0p, r1p, cb, ce);
+            init_rows_to_tmem<CH>(tlane + kColAcc + cb, r0p + cb, r1p ? r1p + cb : nullptr);
         }
         cp_async_wait<0>();
         publish();
@@ -313,7 +313,7 @@ __global__ void __launch_bounds__(256, 1) mlp_bwd_kernel(const gp_mlp_bwd_args p
                 *reinterpret_cast<uint4*>(p.delta_a_out + (size_t)grow * H + c0) =
                     *reinterpret_cast<const uint4*>(ha + sw128_off(128, row, c0));
         }
-        if (p.seg_id && tid < 128) tile_segment_sum<H>(ha, sseg, R0, tid, p.seg_out, p.seg_bnd);
+        if (p.seg_id) tile_segment_sum<H, 256>(ha, sseg, R0, tid, p.seg_out, p.seg_bnd);
         wait_mma();
         if (p.need_din) {
             const int kh = ka >= 32 ? ka / 2 : ka;          // columns per half (half 1 idles when ka < 32)
@@ -423,16 +423,34 @@ struct ReduceSegs {
     gp_reduce_seg s[8];
     int n;
 };
-__global__ void reduce_multi_kernel(const float* __restrict__ partials, int n_parts, int stride, ReduceSegs segs) {
+// Block = 32 elements x 8 partial-groups: thread (tx, ty) adds the partial blocks p = ty, ty+8, ...
+// in ascending order, then the 8 group sums are added in fixed order -> bit-reproducible.
+__global__ void __launch_bounds__(256) reduce_multi_kernel(const float* __restrict__ partials, int n_parts, int stride,
+                                                           ReduceSegs segs) {
+    __shared__ float sh[8][33];
     const gp_reduce_seg sg = segs.s[blockIdx.y];
     const int total = sg.rows * sg.cols;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-        const int r = i / sg.cols, c = i - r * sg.cols;
-        const float* src = partials + sg.offset + (size_t)r * sg.ld_part + c;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int base = blockIdx.x * 32; base < total; base += gridDim.x * 32) {
+        const int i = base + tx;
         float acc = 0.f;
-        for (int pi = 0; pi < n_parts; ++pi) acc += src[(size_t)pi * stride];
-        float* d = sg.dst + (size_t)r * sg.ld_dst + c;
-        *d = sg.accumulate ? (*d + acc) : acc;
+        int r = 0, c = 0;
+        if (i < total) {
+            r = i / sg.cols;
+            c = i - r * sg.cols;
+            const float* src = partials + sg.offset + (size_t)r * sg.ld_part + c;
+            for (int pi = ty; pi < n_parts; pi += 8) acc += src[(size_t)pi * stride];
+        }
+        sh[ty][tx] = acc;
+        __syncthreads();
+        if (ty == 0 && i < total) {
+            float t = sh[0][tx];
+#pragma unroll
+            for (int k = 1; k < 8; ++k) t += sh[k][tx];
+            float* d = sg.dst + (size_t)r * sg.ld_dst + c;
+            *d = sg.accumulate ? (*d + t) : t;
+        }
+        __syncthreads();
     }
 }
 
@@ -440,7 +458,7 @@ template <int H>
 int launch_bwd(const gp_mlp_bwd_args& a, int32_t* grid_out, cudaStream_t st) {
     size_t smem = 1024;
     smem += (size_t)((a.ka + 63) / 64) * H * 128 + (size_t)((H + 63) / 64) * a.nb * 128;
-    smem += (size_t)(a.mode == 1 ? 4 : 3) * kBufBytes + 128 * 128 + 3 * 128 * 4 + 4 * 128 * 4 + 136 * 4;
+    smem += (size_t)(a.mode == 1 ? 4 : 3) * kBufBytes + 128 * 128 + 3 * 128 * 4 + 4 * 128 * 4 + 144 * 4;
     GP_REQUIRE((int)smem <= gp::max_smem_optin(), "gp_mlp_bwd_stage: needs %zu B of shared memory (> %d)", smem,
                gp::max_smem_optin());
     GP_CHECK_CUDA(cudaFuncSetAttribute(mlp_bwd_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -510,8 +528,8 @@ extern "C" int gp_reduce_partials_multi(const float* partials, int32_t n_parts, 
         const int t = segs_host[i].rows * segs_host[i].cols;
         if (t > max_total) max_total = t;
     }
-    int bx = (max_total + 255) / 256;
-    if (bx > 64) bx = 64;
+    int bx = (max_total + 31) / 32;
+    if (bx > 512) bx = 512;
     if (bx < 1) bx = 1;
     dim3 grid(bx, n_segs);
     reduce_multi_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(partials, n_parts, stride, segs);

@@ -1,15 +1,21 @@
 // mlp_fwd.cu -- fused row-tile MLP forward on tcgen05 (see include/gp_b200.h, gp_mlp_fwd).
 //
 // Persistent kernel, one CTA per SM.  The packed bf16 weights of all layers stay resident in
-// shared memory (SW128 row tiles) for the whole launch.  A CTA runs NG independent worker
-// groups of 128 threads; each group owns one 128-row activation buffer, one 128-column fp32
-// accumulator in TMEM and one mbarrier, and walks its own tiles.  Inside a group the flow is
-// bulk-synchronous (stage -> MMA -> epilogue per layer); the two groups run out of phase, so
-// one group's tcgen05.mma overlaps the other group's TMEM epilogue.
+// shared memory (SW128 row tiles) for the whole launch.  A CTA runs NG independent tile slots of
+// 256 threads; each slot owns one 128-row activation buffer, one 128-column fp32 accumulator in
+// TMEM and one mbarrier, and walks its own tiles.  Inside a slot the flow is bulk-synchronous
+// (stage -> MMA -> epilogue per layer); the slots run out of phase, so one slot's tcgen05.mma
+// and global-memory latency overlap the other slot's TMEM epilogue (16 resident warps per SM).
 //
-// Thread r of a group owns row r of the tile == TMEM lane r: bias, ReLU, RMSNorm and the
-// residual are thread-local.  The receiver-sorted segment sum re-partitions through shared
-// memory (column pairs x sub-tiles of H/2 rows) and uses no atomics.
+// Thread (row = t & 127, half = t >> 7) of a slot owns row `row` of the tile (== TMEM lane) and
+// one half of its columns: bias, ReLU and RMSNorm are thread-local apart from one float
+// exchanged between the halves.  Everything that goes to or comes from global memory as a tile
+// (layer-0 operand, saved activation, output + residual) moves in row-major 16-byte chunks, one
+// chunk per lane, so a warp touches 4 cache lines per instruction instead of 32; the tile is
+// transposed between the two mappings through the swizzled shared-memory buffer.  The copy-out
+// of the saved activation runs while the next layer's MMA is in flight.
+// The receiver-sorted segment sum re-partitions through shared memory (column pairs x sub-tiles
+// of H/4 rows) and uses no atomics.
 #include "common.cuh"
 #include "tile_util.cuh"
 
@@ -17,23 +23,27 @@ namespace {
 using namespace gp;
 
 constexpr int kBiasStride = 384;
+constexpr int kSlotThreads = 256;
 
-__device__ __forceinline__ void group_sync(int g) { asm volatile("bar.sync %0, 128;" ::"r"(g + 1) : "memory"); }
-
-
-
+__device__ __forceinline__ void slot_sync(int g) { asm volatile("bar.sync %0, 256;" ::"r"(g + 1) : "memory"); }
 
 template <int H, int NG>
-__global__ void __launch_bounds__(128 * NG, 1) mlp_fwd_kernel(const gp_mlp_fwd_args p) {
+__global__ void __launch_bounds__(kSlotThreads * NG, 1) mlp_fwd_kernel(const gp_mlp_fwd_args p) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = gp::align1024(smem_raw);
+    uint8_t* smem = GP_SMEM_ALIGNED(smem_raw);
     __shared__ uint64_t mma_bar[NG];
     __shared__ uint32_t tmem_slot;
 
     const int tid = threadIdx.x;
-    const int g = tid >> 7;           // worker group
-    const int row = tid & 127;        // row in tile == TMEM lane
+    const int g = tid / kSlotThreads;        // tile slot
+    const int t = tid - g * kSlotThreads;    // thread in slot
+    const int row = t & 127;                 // row in tile == TMEM lane
+    const int half = t >> 7;                 // column half
     const int L = p.n_layers;
+    constexpr int CH = H / 2;                // columns per thread in H-wide layers
+    constexpr int KC = H / 8;                // 16-byte chunks per H-wide row
+    constexpr int CPT = 128 * KC / kSlotThreads;   // chunks per thread in a row-major tile copy
+    const int cb = half * CH;
 
     // ---- carve shared memory (all offsets uniform across the CTA)
     uint32_t w_off[4];
@@ -49,16 +59,13 @@ __global__ void __launch_bounds__(128 * NG, 1) mlp_fwd_kernel(const gp_mlp_fwd_a
     off += 4 * kBiasStride * 4;
     float* sscale = reinterpret_cast<float*>(smem + off);
     off += 128 * 4;
-    int* sseg = reinterpret_cast<int*>(smem + off) + g * 136;
+    float* sred = reinterpret_cast<float*>(smem + off) + g * 256;   // [2 halves][128 rows]
+    off += NG * 256 * 4;
+    int* sseg = reinterpret_cast<int*>(smem + off) + g * 144;       // 16-byte aligned, ids at [4..131]
 
     // ---- one-time staging: weights, biases, barriers, TMEM
     for (int l = 0; l < L; ++l) {
-        const int kc = p.k[l] >> 3, total = p.n[l] * kc;
-        const uint32_t ws = smem_u32(smem + w_off[l]);
-        for (int i = tid; i < total; i += blockDim.x) {
-            const int r = i / kc, ch = i - r * kc;
-            cp_async16(ws + sw128_off(p.n[l], r, ch * 8), p.w[l] + (size_t)r * p.k[l] + ch * 8);
-        }
+        stage_weight(smem + w_off[l], p.w[l], p.n[l], p.k[l]);
         for (int i = tid; i < p.n[l]; i += blockDim.x) sbias[l * kBiasStride + i] = p.bias[l] ? p.bias[l][i] : 0.f;
     }
     cp_async_commit();
@@ -68,7 +75,8 @@ __global__ void __launch_bounds__(128 * NG, 1) mlp_fwd_kernel(const gp_mlp_fwd_a
         for (int i = 0; i < NG; ++i) mbar_init(&mma_bar[i], 1);
         fence_mbar_init();
     }
-    if (tid < 32) tmem_alloc(&tmem_slot, NG * 128);
+    constexpr uint32_t kTmemCols = NG * 128 < 32 ? 32 : NG * 128;
+    if (tid < 32) tmem_alloc(&tmem_slot, kTmemCols);
     cp_async_wait<0>();
     fence_async_smem();
     tc_fence_before();
@@ -82,76 +90,95 @@ __global__ void __launch_bounds__(128 * NG, 1) mlp_fwd_kernel(const gp_mlp_fwd_a
     uint32_t phase = 0;
     const bool has_init = p.init != nullptr;
     const int n_tiles = (p.rows + 127) >> 7;
+    const int tile_stride = gridDim.x * NG;
 
-    for (int tile = blockIdx.x * NG + g; tile < n_tiles; tile += gridDim.x * NG) {
+    const bool prof = p.prof != nullptr && t == 0;
+    long long tk = 0;
+    auto tick = [&](int slot) {   // accumulate cycles since the previous tick into counter `slot`
+        if (prof) {
+            const long long now = clock64();
+            atomicAdd(p.prof + slot, (unsigned long long)(now - tk));
+            tk = now;
+        }
+    };
+    // the MMA issuer adds (byte offset >> 4) to descriptor templates built once
+    const uint64_t adesc0 = desc_kmajor(buf_s, 128, 0);
+
+    // gather indices of a tile for this thread's row (prefetched one tile ahead)
+    int i0n = 0, i1n = 0;
+    auto load_idx = [&](int tile_) {
+        const int r = min((tile_ << 7) + row, p.rows - 1);
+        i0n = p.idx0 ? __ldg(p.idx0 + r) : r;
+        i1n = (p.two_inits && p.idx1) ? __ldg(p.idx1 + r) : r;   // only used to prefetch the row into L2
+    };
+    const int tile0 = blockIdx.x * NG + g;
+    if (has_init && tile0 < n_tiles) load_idx(tile0);
+
+    for (int tile = tile0; tile < n_tiles; tile += tile_stride) {
+        if (prof) tk = clock64();
         const int R0 = tile << 7;
         const int grow = R0 + row;
         const bool valid = grow < p.rows;
-        const int crow = valid ? grow : p.rows - 1;
 
-        // (a) streamed layer-0 operand -> buf (rows past the end replicate the last row; their
-        //     results are never stored)
-        {
-            const int kc = p.ka >> 3;
-            if (p.a_bf16) {
-                for (int i = row; i < 128 * kc; i += 128) {
-                    const int r = i / kc, ch = i - r * kc;
-                    const int gr = min(R0 + r, p.rows - 1);
-                    cp_async16(buf_s + sw128_off(128, r, ch * 8), p.a_bf16 + (size_t)gr * p.lda + ch * 8);
-                }
-            } else if (p.a_f32) {
-                for (int i = row; i < 128 * kc; i += 128) {
-                    const int r = i / kc, ch = i - r * kc;
-                    const int gr = min(R0 + r, p.rows - 1);
-                    const float4* s = reinterpret_cast<const float4*>(p.a_f32 + (size_t)gr * p.lda + ch * 8);
-                    const float4 u0 = __ldg(s), u1 = __ldg(s + 1);
-                    const uint4 pk = make_uint4(pack_bf16(u0.x, u0.y), pack_bf16(u0.z, u0.w), pack_bf16(u1.x, u1.y),
-                                                pack_bf16(u1.z, u1.w));
-                    *reinterpret_cast<uint4*>(buf + sw128_off(128, r, ch * 8)) = pk;
-                }
+        // (a) segment ids of the tile (+ one row of context on each side): requested now, stored
+        //     to shared memory later so their latency is not exposed
+        int sid_me = -1, sid_prev = -1, sid_next = -1;
+        if (p.seg_id && t < 128) {
+            if (valid) sid_me = __ldg(p.seg_id + grow);
+            if (row == 0) {
+                if (R0 > 0) sid_prev = __ldg(p.seg_id + R0 - 1);
+                if (R0 + 128 < p.rows) sid_next = __ldg(p.seg_id + R0 + 128);
+            }
+        }
+        // (b) accumulator pre-load = fp32 sum of the gathered pre-activation rows.  The randomly
+        //     indexed source (senders; or the node's own row) is gathered into buf with 16-byte
+        //     chunks in row-major order -- 8 lanes per cache line, so the LSU sees ~1/8 of the
+        //     wavefronts a row-per-thread load would cost -- and read back row-wise; the
+        //     receiver-indexed source is sorted, its row-per-thread loads already coalesce.
+        if (has_init) {
+            const bool stage1 = p.two_inits != 0;           // which source goes through buf
+            const int32_t* sidx = stage1 ? p.idx1 : p.idx0;
+            const int soff = stage1 ? p.init_off1 : p.init_off0;
+#pragma unroll
+            for (int j = 0; j < CPT; ++j) {
+                const int i = t + j * kSlotThreads;
+                const int r = i / KC, ch = i % KC;
+                const int gr = min(R0 + r, p.rows - 1);
+                const int ridx = sidx ? __ldg(sidx + gr) : gr;
+                cp_async16(buf_s + sw128_off(128, r, ch * 8), p.init + (size_t)ridx * p.ld_init + soff + ch * 8);
             }
             cp_async_commit();
-        }
-        // (b) segment ids of the tile (+ one row of context on each side)
-        if (p.seg_id) {
-            sseg[1 + row] = valid ? __ldg(p.seg_id + grow) : -1;
-            if (row == 0) {
-                sseg[0] = R0 > 0 ? __ldg(p.seg_id + R0 - 1) : -1;
-                sseg[129] = (R0 + 128 < p.rows) ? __ldg(p.seg_id + R0 + 128) : -1;
-            }
-        }
-        // (c) accumulator pre-load: gathered pre-activation rows (fp32 sum of bf16 rows)
-        if (has_init) {
-            const int i0 = p.idx0 ? __ldg(p.idx0 + crow) : crow;
-            const gp_bf16* r0p = p.init + (size_t)i0 * p.ld_init + p.init_off0;
-            const gp_bf16* r1p = nullptr;
-            if (p.two_inits) {
-                const int i1 = p.idx1 ? __ldg(p.idx1 + crow) : crow;
-                r1p = p.init + (size_t)i1 * p.ld_init + p.init_off1;
-            }
-#pragma unroll 2
-            for (int c = 0; c < H; c += 16) {
-                float f[16];
-                unpack8(ldg16(r0p + c), f);
-                unpack8(ldg16(r0p + c + 8), f + 8);
-                if (r1p) {
-                    float h[16];
-                    unpack8(ldg16(r1p + c), h);
-                    unpack8(ldg16(r1p + c + 8), h + 8);
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) f[j] += h[j];
+            // L2 prefetch of the layer-0 operand tile, which is staged right after
+            if (p.a_bf16 && (t & 7) == 0) {
+                const int kc0 = p.ka >> 3;
+                for (int i = t; i < 128 * kc0; i += kSlotThreads) {
+                    const int r = i / kc0, ch = i - r * kc0;
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(p.a_bf16 + (size_t)min(R0 + r, p.rows - 1) * p.lda + ch * 8));
                 }
-                uint32_t v[16];
-#pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(f[j]);
-                tmem_st16(tacc + c, v);
             }
-            tmem_st_wait();
+            cp_async_wait<0>();
+            slot_sync(g);
+            const gp_bf16* dp = stage1 ? p.init + (size_t)i0n * p.ld_init + p.init_off0 + cb : nullptr;
+            init_staged_to_tmem<CH>(tacc + cb, buf, row, cb, dp);
+            slot_sync(g);            // buf is free for the layer-0 operand
         }
+        if (p.seg_id && t < 128) {
+            sseg[4 + row] = sid_me;
+            if (row == 0) {
+                sseg[3] = sid_prev;
+                sseg[132] = sid_next;
+            }
+        }
+        // (c) streamed layer-0 operand -> buf (rows past the end replicate the last row; their
+        //     results are never stored)
+        stage_rows(buf, p.a_bf16, p.a_f32, p.ka, p.lda, R0, p.rows, t, kSlotThreads);
+        cp_async_commit();
+        tick(0);                 // issue of loads + gathers + TMEM pre-load (this thread)
         cp_async_wait<0>();
         fence_async_smem();
         tc_fence_before();
-        group_sync(g);
+        slot_sync(g);
+        tick(1);                 // waiting for the tile's loads / the slowest thread
 
         // (d) layers
         for (int l = 0; l < L; ++l) {
@@ -161,153 +188,172 @@ __global__ void __launch_bounds__(128 * NG, 1) mlp_fwd_kernel(const gp_mlp_fwd_a
             const float* bl = sbias + l * kBiasStride;
             for (int nc = 0; nc < Nl; nc += 128) {
                 const int ncols = min(128, Nl - nc);
-                if (row == 0) {
+                if (t == 0) {
                     tc_fence_after();
                     const uint32_t idesc = idesc_bf16(ncols, false, false);
-                    const uint32_t ws = smem_u32(smem + w_off[l]) + nc * 128;
-                    for (int ks = 0; ks < (K >> 4); ++ks)
-                        mma_ss(tacc_mma, desc_kmajor(buf_s, 128, ks), desc_kmajor(ws, Nl, ks), idesc,
-                               (ks > 0 || (l == 0 && has_init)) ? 1u : 0u);
+                    const uint64_t bdesc0 = desc_kmajor(smem_u32(smem + w_off[l]) + nc * 128, Nl, 0);
+                    const uint32_t bblk = (uint32_t)(Nl * 128) >> 4;     // next 64-column block of W, in 16-B units
+                    const int nks = K >> 4;
+                    for (int ks = 0; ks < nks; ++ks) {
+                        const uint32_t ko = (ks & 3) * 2;                // 32 bytes per k-step inside a block
+                        mma_ss(tacc_mma, adesc0 + (uint64_t)((ks >> 2) * 1024u + ko), bdesc0 + (uint64_t)((ks >> 2) * bblk + ko),
+                               idesc, (ks > 0 || (l == 0 && has_init)) ? 1u : 0u);
+                    }
                     mma_commit(&mma_bar[g]);
+                }
+                tick(8);         // MMA issue (thread 0 of the slot)
+                // while the first MMA runs: indices of this slot's next tile, and its gathered rows
+                // into L2, so the next tile's pre-load does not start with two dependent misses
+                if (l == 0 && nc == 0 && has_init && tile + tile_stride < n_tiles) {
+                    load_idx(tile + tile_stride);
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(p.init + (size_t)i0n * p.ld_init + p.init_off0 + cb));
+                    if (p.two_inits)
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(p.init + (size_t)i1n * p.ld_init + p.init_off1 + cb));
+                }
+                // while the MMA of layer 2 runs: copy the saved activation (layer-1 output, still
+                // intact in buf as this MMA's A operand) to global memory, row-major chunks
+                if (l == 2 && nc == 0 && p.save_h2) {
+#pragma unroll
+                    for (int j = 0; j < CPT; ++j) {
+                        const int i = t + j * kSlotThreads;
+                        const int r = i / KC, ch = i % KC;
+                        if (R0 + r < p.rows)
+                            *reinterpret_cast<uint4*>(p.save_h2 + (size_t)(R0 + r) * H + ch * 8) =
+                                *reinterpret_cast<const uint4*>(buf + sw128_off(128, r, ch * 8));
+                    }
+                    slot_sync(g);    // every chunk is out before any thread overwrites buf in the epilogue
                 }
                 mbar_wait(&mma_bar[g], phase);
                 phase ^= 1;
                 tc_fence_after();
+                tick(2);         // MMA issue + wait (+ overlapped copy-out)
 
                 if (!last) {
                     // hidden layer: relu(acc + b) -> bf16 -> next A operand (in place over buf)
-                    for (int c0 = 0; c0 < H; c0 += 16) {
-                        uint32_t v[16];
-                        tmem_ld16(tacc + c0, v);
-                        tmem_ld_wait();
-                        float f[16];
+                    uint32_t v[CH];
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) f[j] = fmaxf(__uint_as_float(v[j]) + bl[c0 + j], 0.f);
-                        const uint4 q0 = pack8(f), q1 = pack8(f + 8);
-                        *reinterpret_cast<uint4*>(buf + sw128_off(128, row, c0)) = q0;
-                        *reinterpret_cast<uint4*>(buf + sw128_off(128, row, c0 + 8)) = q1;
-                        if (l == 1 && p.save_h2 && valid) {
-                            uint4* d = reinterpret_cast<uint4*>(p.save_h2 + (size_t)grow * H + c0);
-                            d[0] = q0;
-                            d[1] = q1;
-                        }
+                    for (int c = 0; c < CH; c += 16) tmem_ld16(tacc + cb + c, *reinterpret_cast<uint32_t(*)[16]>(&v[c]));
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int c = 0; c < CH; c += 8) {
+                        float f[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) f[j] = fmaxf(__uint_as_float(v[c + j]) + bl[cb + c + j], 0.f);
+                        *reinterpret_cast<uint4*>(buf + sw128_off(128, row, cb + c)) = pack8(f);
                     }
                     fence_async_smem();
+                    tick(3);
                 } else if (p.norm_scale) {
-                    // RMSNorm (layers.py:104-129) + residual + optional segment-sum staging
+                    // RMSNorm (layers.py:104-129): u = scale * m / (||m||/sqrt(H) + 1e-8), rounded to
+                    // bf16 once; that value feeds the segment sum and the residual alike.
+                    uint32_t v[CH];
+#pragma unroll
+                    for (int c = 0; c < CH; c += 16) tmem_ld16(tacc + cb + c, *reinterpret_cast<uint32_t(*)[16]>(&v[c]));
+                    tmem_ld_wait();
                     float ss = 0.f;
-                    for (int c0 = 0; c0 < H; c0 += 16) {
-                        uint32_t v[16];
-                        tmem_ld16(tacc + c0, v);
-                        tmem_ld_wait();
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            const float m = __uint_as_float(v[j]) + bl[c0 + j];
-                            ss = fmaf(m, m, ss);
-                        }
+                    for (int c = 0; c < CH; ++c) {
+                        const float m = __uint_as_float(v[c]) + bl[cb + c];
+                        v[c] = __float_as_uint(m);
+                        ss = fmaf(m, m, ss);
                     }
+                    sred[half * 128 + row] = ss;
+                    slot_sync(g);
+                    ss = sred[row] + sred[128 + row];
                     const float rinv = 1.f / (sqrtf(ss * (1.f / H)) + 1e-8f);
-                    for (int c0 = 0; c0 < H; c0 += 16) {
-                        uint32_t v[16];
-                        tmem_ld16(tacc + c0, v);
-                        tmem_ld_wait();
-                        float u[16];
 #pragma unroll
-                        for (int j = 0; j < 16; ++j)
-                            u[j] = sscale[c0 + j] * ((__uint_as_float(v[j]) + bl[c0 + j]) * rinv);
-                        if (p.seg_id) {
-                            *reinterpret_cast<uint4*>(buf + sw128_off(128, row, c0)) = pack8(u);
-                            *reinterpret_cast<uint4*>(buf + sw128_off(128, row, c0 + 8)) = pack8(u + 8);
-                        }
-                        if (valid) {
-                            if (p.resid) {
-                                float e[16];
-                                const gp_bf16* rp = p.resid + (size_t)grow * p.ld_out + c0;
-                                unpack8(ldg16(rp), e);
-                                unpack8(ldg16(rp + 8), e + 8);
+                    for (int c = 0; c < CH; c += 8) {
+                        float u[8];
 #pragma unroll
-                                for (int j = 0; j < 16; ++j) u[j] += e[j];
-                            }
-                            if (p.y_bf16) {
-                                uint4* d = reinterpret_cast<uint4*>(p.y_bf16 + (size_t)grow * p.ld_out + c0);
-                                d[0] = pack8(u);
-                                d[1] = pack8(u + 8);
-                            } else {
-                                float4* d = reinterpret_cast<float4*>(p.y_f32 + (size_t)grow * p.ld_out + c0);
-#pragma unroll
-                                for (int j = 0; j < 4; ++j) d[j] = make_float4(u[4 * j], u[4 * j + 1], u[4 * j + 2], u[4 * j + 3]);
-                            }
-                        }
+                        for (int j = 0; j < 8; ++j) u[j] = sscale[cb + c + j] * (__uint_as_float(v[c + j]) * rinv);
+                        *reinterpret_cast<uint4*>(buf + sw128_off(128, row, cb + c)) = pack8(u);
                     }
+                    tick(4);
                 } else {
                     // plain last layer (decoder / projection): acc + b, first n_valid columns
-                    for (int c0 = 0; c0 < ncols; c0 += 16) {
-                        uint32_t v[16];
-                        tmem_ld16(tacc + c0, v);
-                        tmem_ld_wait();
-                        float u[16];
+                    const int chh = ncols >= 32 ? ncols / 2 : ncols;      // half 1 idles on narrow outputs
+                    if (ncols >= 32 || half == 0) {
+                        for (int c0 = half * chh; c0 < half * chh + chh; c0 += 16) {
+                            uint32_t v[16];
+                            tmem_ld16(tacc + c0, v);
+                            tmem_ld_wait();
+                            float u[16];
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) u[j] = __uint_as_float(v[j]) + bl[nc + c0 + j];
-                        if (valid) {
-                            const int cg = nc + c0;
-                            if (p.y_bf16 && cg + 16 <= p.n_valid) {
-                                uint4* d = reinterpret_cast<uint4*>(p.y_bf16 + (size_t)grow * p.ld_out + cg);
-                                d[0] = pack8(u);
-                                d[1] = pack8(u + 8);
-                            } else {
+                            for (int j = 0; j < 16; ++j) u[j] = __uint_as_float(v[j]) + bl[nc + c0 + j];
+                            if (valid) {
+                                const int cg = nc + c0;
+                                if (p.y_bf16 && cg + 16 <= p.n_valid) {
+                                    uint4* d = reinterpret_cast<uint4*>(p.y_bf16 + (size_t)grow * p.ld_out + cg);
+                                    d[0] = pack8(u);
+                                    d[1] = pack8(u + 8);
+                                } else {
 #pragma unroll
-                                for (int j = 0; j < 16; ++j)
-                                    if (cg + j < p.n_valid) {
-                                        if (p.y_bf16)
-                                            reinterpret_cast<__nv_bfloat16*>(p.y_bf16)[(size_t)grow * p.ld_out + cg + j] =
-                                                __float2bfloat16(u[j]);
-                                        else
-                                            p.y_f32[(size_t)grow * p.ld_out + cg + j] = u[j];
-                                    }
+                                    for (int j = 0; j < 16; ++j)
+                                        if (cg + j < p.n_valid) {
+                                            if (p.y_bf16)
+                                                reinterpret_cast<__nv_bfloat16*>(p.y_bf16)[(size_t)grow * p.ld_out + cg + j] =
+                                                    __float2bfloat16(u[j]);
+                                            else
+                                                p.y_f32[(size_t)grow * p.ld_out + cg + j] = u[j];
+                                        }
+                                }
                             }
                         }
                     }
+                    tick(4);
                 }
                 tc_fence_before();
-                group_sync(g);
+                slot_sync(g);
+                tick(5);         // waiting for the slowest thread of the slot
             }
         }
 
-        // (e) receiver-sorted segment sum of bf16(u) (fp32 accumulate, fixed order, no atomics)
-        if (p.seg_id) {
-            constexpr int SUB = H / 2;             // rows per sub-tile == column pairs
-            const int part = row / SUB, cp = row - part * SUB;
-            const int rb = part * SUB, re = rb + SUB;
-            const int c = cp * 2;
-            const size_t sub_index = (size_t)(R0 + rb) / SUB;
-            auto flush = [&](int seg, int a, int b, float s0, float s1) {
-                if (seg < 0) return;
-                const bool before = (a == rb) && (sseg[a] == seg);          // sseg[a] is row a-1
-                const bool after = (b == re) && (sseg[1 + b] == seg);
-                float* d = (!before && !after) ? p.seg_out + (size_t)seg * H + c
-                                               : p.seg_bnd + (sub_index * 2 + (before ? 0 : 1)) * H + c;
-                *reinterpret_cast<float2*>(d) = make_float2(s0, s1);
-            };
-            int cur = sseg[1 + rb], a = rb;
-            float s0 = 0.f, s1 = 0.f;
-            for (int r = rb; r < re; ++r) {
-                const int s = sseg[1 + r];
-                if (s != cur) {
-                    flush(cur, a, r, s0, s1);
-                    cur = s; a = r; s0 = 0.f; s1 = 0.f;
+        if (p.norm_scale) {
+            // (e) output: y = resid + bf16(u), row-major chunks.  The residual chunks are requested
+            //     first and consumed after the segment walk, which hides their latency.
+            uint4 rq[CPT];
+            if (p.resid) {
+#pragma unroll
+                for (int j = 0; j < CPT; ++j) {
+                    const int i = t + j * kSlotThreads;
+                    const int r = i / KC, ch = i % KC;
+                    rq[j] = ldg16(p.resid + (size_t)min(R0 + r, p.rows - 1) * p.ld_out + ch * 8);
                 }
-                const uint32_t w = *reinterpret_cast<const uint32_t*>(buf + sw128_off(128, r, c & ~7) + (c & 7) * 2);
-                s0 += bf16_lo(w);
-                s1 += bf16_hi(w);
             }
-            flush(cur, a, re, s0, s1);
-            group_sync(g);
+            // (f) receiver-sorted segment sum of bf16(u) (fp32 accumulate, fixed order, no atomics)
+            if (p.seg_id) tile_segment_sum<H, kSlotThreads>(buf, sseg, R0, t, p.seg_out, p.seg_bnd);
+            tick(6);
+#pragma unroll
+            for (int j = 0; j < CPT; ++j) {
+                const int i = t + j * kSlotThreads;
+                const int r = i / KC, ch = i % KC;
+                if (R0 + r < p.rows) {
+                    float u[8];
+                    unpack8(*reinterpret_cast<const uint4*>(buf + sw128_off(128, r, ch * 8)), u);
+                    if (p.resid) {
+                        float e[8];
+                        unpack8(rq[j], e);
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) u[q] += e[q];
+                    }
+                    if (p.y_bf16) {
+                        *reinterpret_cast<uint4*>(p.y_bf16 + (size_t)(R0 + r) * p.ld_out + ch * 8) = pack8(u);
+                    } else {
+                        float4* d = reinterpret_cast<float4*>(p.y_f32 + (size_t)(R0 + r) * p.ld_out + ch * 8);
+                        d[0] = make_float4(u[0], u[1], u[2], u[3]);
+                        d[1] = make_float4(u[4], u[5], u[6], u[7]);
+                    }
+                }
+            }
+            slot_sync(g);        // buf and sseg are free for the next tile
+            tick(7);
         }
+        if (prof) atomicAdd(p.prof + 15, 1ull);
     }
 
     tc_fence_before();
     __syncthreads();
-    if (tid < 32) tmem_dealloc(tmem_base, NG * 128);
+    if (tid < 32) tmem_dealloc(tmem_base, kTmemCols);
 }
 
 __global__ void seg_fixup_kernel(const int32_t* __restrict__ rowptr, int num_segments, int H, int SUB,
@@ -334,7 +380,7 @@ template <int H, int NG>
 int launch_fwd(const gp_mlp_fwd_args& a, cudaStream_t st) {
     size_t smem = 1024;
     for (int l = 0; l < a.n_layers; ++l) smem += (size_t)((a.k[l] + 63) / 64) * a.n[l] * 128;
-    smem += (size_t)NG * kBufBytes + 4 * kBiasStride * 4 + 128 * 4 + NG * 136 * 4;
+    smem += (size_t)NG * kBufBytes + 4 * kBiasStride * 4 + 128 * 4 + NG * 256 * 4 + NG * 144 * 4;
     GP_REQUIRE((int)smem <= gp::max_smem_optin(), "gp_mlp_fwd: needs %zu B of shared memory (> %d)", smem,
                gp::max_smem_optin());
     GP_CHECK_CUDA(cudaFuncSetAttribute(mlp_fwd_kernel<H, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -342,7 +388,7 @@ int launch_fwd(const gp_mlp_fwd_args& a, cudaStream_t st) {
     int grid = (n_tiles + NG - 1) / NG;
     if (grid > gp::sm_count()) grid = gp::sm_count();
     if (grid < 1) grid = 1;
-    mlp_fwd_kernel<H, NG><<<grid, 128 * NG, smem, st>>>(a);
+    mlp_fwd_kernel<H, NG><<<grid, kSlotThreads * NG, smem, st>>>(a);
     GP_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -367,8 +413,9 @@ extern "C" int gp_mlp_fwd(const gp_mlp_fwd_args* args, int hidden, void* stream)
                            "gp_mlp_fwd: init rows need n[0]==hidden and 16-byte aligned offsets");
     if (a.norm_scale) GP_REQUIRE(a.n[a.n_layers - 1] == hidden, "gp_mlp_fwd: RMSNorm needs n_last == hidden");
     if (a.seg_id) GP_REQUIRE(a.norm_scale && a.seg_out && a.seg_bnd, "gp_mlp_fwd: segment sum needs norm + outputs");
+    if (a.save_h2) GP_REQUIRE(a.n_layers >= 3, "gp_mlp_fwd: save_h2 needs at least 3 layers");
     GP_REQUIRE((a.y_bf16 != nullptr) != (a.y_f32 != nullptr), "gp_mlp_fwd: exactly one of y_bf16 / y_f32");
-    GP_REQUIRE(a.ld_out % 8 == 0 || !a.y_bf16 || !a.norm_scale, "gp_mlp_fwd: ld_out must be a multiple of 8");
+    if (a.norm_scale) GP_REQUIRE(a.ld_out % 8 == 0, "gp_mlp_fwd: ld_out must be a multiple of 8 with RMSNorm");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     switch (hidden) {
         case 128: return launch_fwd<128, 2>(a, st);
@@ -383,7 +430,7 @@ extern "C" int gp_seg_fixup(const int32_t* rowptr, int32_t num_segments, int32_t
     if (num_segments <= 0) return 0;
     const int threads = 256;
     const int blocks = (int)(((size_t)num_segments * 32 + threads - 1) / threads);
-    seg_fixup_kernel<<<blocks, threads, 0, static_cast<cudaStream_t>(stream)>>>(rowptr, num_segments, hidden, hidden / 2,
+    seg_fixup_kernel<<<blocks, threads, 0, static_cast<cudaStream_t>(stream)>>>(rowptr, num_segments, hidden, hidden / 4,
                                                                                  seg_bnd, seg_out);
     GP_CHECK_CUDA(cudaGetLastError());
     return 0;

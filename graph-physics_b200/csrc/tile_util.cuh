@@ -32,17 +32,18 @@ __device__ __forceinline__ void stage_weight(uint8_t* tile, const gp_bf16* w, in
 // fly) into an SW128 row tile.  Rows past `rows` replicate the last valid row.
 __device__ __forceinline__ void stage_rows(uint8_t* buf, const gp_bf16* a_bf16, const float* a_f32, int ka, int lda,
                                            int R0, int rows, int t, int nthreads) {
-    const int kc = ka >> 3;
+    const int kc = ka >> 3;                       // 16-byte chunks per row: 2, 4, 8 or 16
+    const int sh = 31 - __clz(kc);
     const uint32_t buf_s = smem_u32(buf);
     if (a_bf16) {
         for (int i = t; i < 128 * kc; i += nthreads) {
-            const int r = i / kc, ch = i - r * kc;
+            const int r = i >> sh, ch = i & (kc - 1);
             const int gr = min(R0 + r, rows - 1);
             cp_async16(buf_s + sw128_off(128, r, ch * 8), a_bf16 + (size_t)gr * lda + ch * 8);
         }
     } else if (a_f32) {
         for (int i = t; i < 128 * kc; i += nthreads) {
-            const int r = i / kc, ch = i - r * kc;
+            const int r = i >> sh, ch = i & (kc - 1);
             const int gr = min(R0 + r, rows - 1);
             const float4* s = reinterpret_cast<const float4*>(a_f32 + (size_t)gr * lda + ch * 8);
             const float4 u0 = __ldg(s), u1 = __ldg(s + 1);
@@ -52,17 +53,26 @@ __device__ __forceinline__ void stage_rows(uint8_t* buf, const gp_bf16* a_bf16, 
     }
 }
 
-// Accumulator pre-load: fp32 sum of one or two gathered bf16 rows -> TMEM columns [c_begin, c_end).
-__device__ __forceinline__ void init_rows_to_tmem(uint32_t tacc, const gp_bf16* r0p, const gp_bf16* r1p, int c_begin,
-                                                  int c_end) {
-    for (int c = c_begin; c < c_end; c += 16) {
+// Accumulator pre-load: fp32 sum of one or two gathered bf16 rows -> NC TMEM columns starting at
+// `tacc`.  All row loads are issued before the first use so one memory round trip covers them.
+template <int NC>
+__device__ __forceinline__ void init_rows_to_tmem(uint32_t tacc, const gp_bf16* r0p, const gp_bf16* r1p) {
+    uint4 q0[NC / 8], q1[NC / 8];
+#pragma unroll
+    for (int i = 0; i < NC / 8; ++i) q0[i] = ldg16(r0p + i * 8);
+    if (r1p) {
+#pragma unroll
+        for (int i = 0; i < NC / 8; ++i) q1[i] = ldg16(r1p + i * 8);
+    }
+#pragma unroll
+    for (int c = 0; c < NC; c += 16) {
         float f[16];
-        unpack8(ldg16(r0p + c), f);
-        unpack8(ldg16(r0p + c + 8), f + 8);
+        unpack8(q0[c / 8], f);
+        unpack8(q0[c / 8 + 1], f + 8);
         if (r1p) {
             float h[16];
-            unpack8(ldg16(r1p + c), h);
-            unpack8(ldg16(r1p + c + 8), h + 8);
+            unpack8(q1[c / 8], h);
+            unpack8(q1[c / 8 + 1], h + 8);
 #pragma unroll
             for (int j = 0; j < 16; ++j) f[j] += h[j];
         }
@@ -74,38 +84,87 @@ __device__ __forceinline__ void init_rows_to_tmem(uint32_t tacc, const gp_bf16* 
     tmem_st_wait();
 }
 
-// Segment sum over the rows of one 128-row tile held in `buf` (bf16, SW128 layout, H columns).
-// sseg[0] = segment of the row before the tile, sseg[1..128] = rows, sseg[129] = row after;
-// -1 marks "no row".  Threads t in [0,128) take part.  See gp_mlp_fwd in gp_b200.h.
-template <int H>
+// Same pre-load, but one of the two sources has already been gathered into the SW128 tile `buf`
+// (row-major 16-byte chunks, one cache line per 8 lanes) and is read back row-wise from there;
+// `dp` (may be null) is this thread's part of the directly loaded row.  Columns [c0, c0+NC).
+template <int NC>
+__device__ __forceinline__ void init_staged_to_tmem(uint32_t tacc, const uint8_t* buf, int row, int c0,
+                                                    const gp_bf16* dp) {
+    uint4 q1[NC / 8];
+    if (dp) {
+#pragma unroll
+        for (int i = 0; i < NC / 8; ++i) q1[i] = ldg16(dp + i * 8);
+    }
+#pragma unroll
+    for (int c = 0; c < NC; c += 16) {
+        float f[16];
+        unpack8(*reinterpret_cast<const uint4*>(buf + sw128_off(128, row, c0 + c)), f);
+        unpack8(*reinterpret_cast<const uint4*>(buf + sw128_off(128, row, c0 + c + 8)), f + 8);
+        if (dp) {
+            float h[16];
+            unpack8(q1[c / 8], h);
+            unpack8(q1[c / 8 + 1], h + 8);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] += h[j];
+        }
+        uint32_t v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(f[j]);
+        tmem_st16(tacc + c, v);
+    }
+    tmem_st_wait();
+}
+
+// Segment sum over the rows of one 128-row tile held in `buf` (bf16, SW128 layout, H columns),
+// by NT threads: thread t owns column pair (t % (H/2)) of the sub-tile of SUB = 64*H/NT rows
+// number t / (H/2).  sseg[3] = segment id of the row before the tile, sseg[4..131] = rows,
+// sseg[132] = row after; -1 marks "no row".  A piece that neither continues from the previous
+// sub-tile nor into the next one is a complete segment and goes to seg_out; other pieces go to
+// seg_bnd[sub-tile][0 = continues from before | 1 = continues after] for gp_seg_fixup.
+template <int H, int NT>
 __device__ __forceinline__ void tile_segment_sum(const uint8_t* buf, const int* sseg, int R0, int t, float* seg_out,
                                                  float* seg_bnd) {
-    constexpr int SUB = H / 2;   // rows per sub-tile == number of column pairs
-    const int part = t / SUB, cp = t - part * SUB;
-    const int rb = part * SUB, re = rb + SUB;
+    constexpr int NP = H / 2;            // column pairs
+    constexpr int SUB = 128 * NP / NT;   // rows per sub-tile
+    static_assert(SUB % 8 == 0, "sub-tile must be a multiple of 8 rows");
+    const int part = t / NP, cp = t - part * NP;
+    const int rb = part * SUB;
     const int c = cp * 2;
     const size_t sub_index = (size_t)(R0 + rb) / SUB;
-    auto flush = [&](int seg, int a, int b, float s0, float s1) {
-        if (seg < 0) return;
-        const bool before = (a == rb) && (sseg[a] == seg);   // sseg[a] is row a-1
-        const bool after = (b == re) && (sseg[1 + b] == seg);
-        float* d = (!before && !after) ? seg_out + (size_t)seg * H + c
-                                       : seg_bnd + (sub_index * 2 + (before ? 0 : 1)) * H + c;
-        *reinterpret_cast<float2*>(d) = make_float2(s0, s1);
-    };
-    int cur = sseg[1 + rb], a = rb;
+    const uint32_t chunk = (c & 63) >> 3;
+    const uint8_t* colbase = buf + (c >> 6) * (128 * 128) + (c & 7) * 2;
+    const int seg_prev = sseg[3 + rb], seg_next = sseg[4 + rb + SUB];
+    int cur = sseg[4 + rb];
+    bool first_piece = true;
     float s0 = 0.f, s1 = 0.f;
-    for (int r = rb; r < re; ++r) {
-        const int s = sseg[1 + r];
-        if (s != cur) {
-            flush(cur, a, r, s0, s1);
-            cur = s; a = r; s0 = 0.f; s1 = 0.f;
+    auto flush = [&](int seg, bool last_piece) {
+        if (seg >= 0) {
+            const bool before = first_piece && (seg_prev == seg);
+            const bool after = last_piece && (seg_next == seg);
+            float* d = (!before && !after) ? seg_out + (size_t)seg * H + c
+                                           : seg_bnd + (sub_index * 2 + (before ? 0 : 1)) * H + c;
+            *reinterpret_cast<float2*>(d) = make_float2(s0, s1);
         }
-        const uint32_t w = *reinterpret_cast<const uint32_t*>(buf + sw128_off(128, r, c & ~7) + (c & 7) * 2);
-        s0 += bf16_lo(w);
-        s1 += bf16_hi(w);
+        first_piece = false;
+    };
+#pragma unroll 1
+    for (int r8 = rb; r8 < rb + SUB; r8 += 8) {
+        const int4 sa = *reinterpret_cast<const int4*>(sseg + 4 + r8);
+        const int4 sb = *reinterpret_cast<const int4*>(sseg + 8 + r8);
+        const int sid[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
+        const uint8_t* rowbase = colbase + r8 * 128;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (sid[j] != cur) {
+                flush(cur, false);
+                cur = sid[j]; s0 = 0.f; s1 = 0.f;
+            }
+            const uint32_t w = *reinterpret_cast<const uint32_t*>(rowbase + j * 128 + ((chunk ^ j) << 4));
+            s0 += bf16_lo(w);
+            s1 += bf16_hi(w);
+        }
     }
-    flush(cur, a, re, s0, s1);
+    flush(cur, true);
 }
 
 }  // namespace gp

@@ -23,29 +23,46 @@ __device__ __forceinline__ float block_sum(float v, float* sh) {
 }
 
 // L2Loss.forward (graphphysics/utils/loss.py:45-75): mean over masked rows x D of (out-target)^2,
-// and its gradient.  One block: the tensors are N x output_size (a few hundred KB).
-__global__ void __launch_bounds__(1024, 1) masked_mse_kernel(const float* __restrict__ out, const float* __restrict__ tgt,
-                                                             const uint8_t* __restrict__ mask, int n, int d,
-                                                             float* __restrict__ loss, float* __restrict__ grad,
-                                                             float grad_scale) {
+// and its gradient.  Three small launches: per-block partial sums, fixed-order final sum, gradient.
+constexpr int kMseBlocks = 128;
+__global__ void masked_mse_partial_kernel(const float* __restrict__ out, const float* __restrict__ tgt,
+                                          const uint8_t* __restrict__ mask, int n, int d, float* __restrict__ ws) {
     __shared__ float sh[32];
     float se = 0.f, cnt = 0.f;
-    for (int i = threadIdx.x; i < n * d; i += blockDim.x) {
-        const int r = i / d;
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
         if (mask[r]) {
-            const float e = out[i] - tgt[i];
-            se = fmaf(e, e, se);
+            cnt += 1.f;
+            for (int c = 0; c < d; ++c) {
+                const float e = out[(size_t)r * d + c] - tgt[(size_t)r * d + c];
+                se = fmaf(e, e, se);
+            }
         }
     }
-    for (int r = threadIdx.x; r < n; r += blockDim.x) cnt += mask[r] ? 1.f : 0.f;
     se = block_sum(se, sh);
     cnt = block_sum(cnt, sh);
-    const float denom = cnt * d;
-    if (threadIdx.x == 0) loss[0] = se / denom;      // 0/0 -> NaN like torch.mean of an empty selection
-    if (grad) {
-        const float k = 2.f * grad_scale / denom;
-        for (int i = threadIdx.x; i < n * d; i += blockDim.x) grad[i] = mask[i / d] ? k * (out[i] - tgt[i]) : 0.f;
+    if (threadIdx.x == 0) {
+        ws[blockIdx.x] = se;
+        ws[kMseBlocks + blockIdx.x] = cnt;
     }
+}
+__global__ void masked_mse_final_kernel(float* __restrict__ ws, int d, float* __restrict__ loss) {
+    __shared__ float sh[32];
+    float se = threadIdx.x < kMseBlocks ? ws[threadIdx.x] : 0.f;
+    float cnt = threadIdx.x < kMseBlocks ? ws[kMseBlocks + threadIdx.x] : 0.f;
+    se = block_sum(se, sh);
+    cnt = block_sum(cnt, sh);
+    if (threadIdx.x == 0) {
+        const float denom = cnt * d;
+        loss[0] = se / denom;          // 0/0 -> NaN like torch.mean of an empty selection
+        ws[2 * kMseBlocks] = denom;
+    }
+}
+__global__ void masked_mse_grad_kernel(const float* __restrict__ out, const float* __restrict__ tgt,
+                                       const uint8_t* __restrict__ mask, int n, int d, const float* __restrict__ ws,
+                                       float* __restrict__ grad, float grad_scale) {
+    const float k = 2.f * grad_scale / ws[2 * kMseBlocks];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n * d; i += gridDim.x * blockDim.x)
+        grad[i] = mask[i / d] ? k * (out[i] - tgt[i]) : 0.f;
 }
 
 __global__ void sqnorm_partial_kernel(const float* __restrict__ g, size_t n, float* __restrict__ partial) {
@@ -104,9 +121,13 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ s, __nv_bfloat16*
 }  // namespace
 
 extern "C" int gp_masked_mse(const float* out, const float* target, const uint8_t* mask, int32_t n, int32_t d,
-                             float* loss, float* grad, float grad_scale, void* stream) {
+                             float* loss, float* grad, float grad_scale, float* workspace, void* stream) {
     GP_REQUIRE(out && target && mask && loss && n > 0 && d > 0, "gp_masked_mse: bad arguments");
-    masked_mse_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(out, target, mask, n, d, loss, grad, grad_scale);
+    GP_REQUIRE(workspace != nullptr, "gp_masked_mse: workspace of 260 floats required");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    masked_mse_partial_kernel<<<kMseBlocks, 256, 0, st>>>(out, target, mask, n, d, workspace);
+    masked_mse_final_kernel<<<1, 128, 0, st>>>(workspace, d, loss);
+    if (grad) masked_mse_grad_kernel<<<256, 256, 0, st>>>(out, target, mask, n, d, workspace, grad, grad_scale);
     GP_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

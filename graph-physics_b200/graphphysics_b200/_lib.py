@@ -81,6 +81,7 @@ class MlpFwdArgs(C.Structure):
         ("seg_id", C.c_void_p),
         ("seg_out", C.c_void_p),
         ("seg_bnd", C.c_void_p),
+        ("prof", C.c_void_p),
     ]
 
 

@@ -75,7 +75,7 @@ def pack_bias(b: Optional[torch.Tensor], n_pad: int, device) -> torch.Tensor:
 
 
 def seg_bnd_size(rows: int, hidden: int) -> int:
-    sub = hidden // 2
+    sub = hidden // 4            # rows per sub-tile of the kernels' segment walk (256 threads)
     return ((rows + sub - 1) // sub) * 2 * hidden
 
 
@@ -102,6 +102,7 @@ def mlp_fwd(
     seg_out: Optional[torch.Tensor] = None,
     seg_bnd: Optional[torch.Tensor] = None,
     tag: Optional[str] = None,
+    prof: Optional[torch.Tensor] = None,
 ) -> torch.Tensor:
     """gp_mlp_fwd (include/gp_b200.h).  `weights` are packed bf16 [n][k]; `a` is [rows, >=ka]
     bf16 or fp32 with unit column stride; `out` is [rows, ld] bf16 or fp32."""
@@ -137,6 +138,7 @@ def mlp_fwd(
     args.n_valid = n_valid
     args.save_h2 = ptr(save_h2)
     args.seg_id, args.seg_out, args.seg_bnd = ptr(seg_id), ptr(seg_out), ptr(seg_bnd)
+    args.prof = ptr(prof)
     ev = PROFILE.begin(tag)
     check(lib().gp_mlp_fwd(C.byref(args), C.c_int(hidden), C.c_void_p(stream_ptr())), "gp_mlp_fwd")
     PROFILE.end(tag, ev)
@@ -318,14 +320,20 @@ def reduce_multi(partials: torch.Tensor, n_parts: int, stride: int, segs) -> Non
     _launched()
 
 
+_MSE_WS: dict = {}
+
+
 def masked_mse(out: torch.Tensor, target: torch.Tensor, mask_u8: torch.Tensor, loss: torch.Tensor,
                grad: Optional[torch.Tensor], grad_scale: float = 1.0) -> None:
     n, d = out.shape
     assert out.is_contiguous() and target.is_contiguous() and mask_u8.dtype == torch.uint8
+    ws = _MSE_WS.get(out.device)
+    if ws is None:
+        ws = _MSE_WS[out.device] = torch.empty(260, dtype=torch.float32, device=out.device)
     check(lib().gp_masked_mse(C.c_void_p(ptr(out)), C.c_void_p(ptr(target)), C.c_void_p(ptr(mask_u8)), n, d,
                               C.c_void_p(ptr(loss)), C.c_void_p(ptr(grad)), C.c_float(grad_scale),
-                              C.c_void_p(stream_ptr())), "gp_masked_mse")
-    _launched()
+                              C.c_void_p(ptr(ws)), C.c_void_p(stream_ptr())), "gp_masked_mse")
+    _launched(3 if grad is not None else 2)
 
 
 def sqnorm(g: torch.Tensor, workspace: torch.Tensor, out: torch.Tensor) -> None:

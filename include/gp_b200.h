@@ -72,7 +72,8 @@ typedef struct gp_mlp_fwd_args {
     gp_bf16* save_h2;      /* optional [rows][hidden]: output of layer index 1 (after relu) */
     const int32_t* seg_id; /* optional [rows], non-decreasing */
     float* seg_out;        /* [num_segments][hidden] */
-    float* seg_bnd;        /* [ceil(rows/sub)][2][hidden], sub = hidden/2 rows */
+    float* seg_bnd;        /* [ceil(rows/sub)][2][hidden], sub = hidden/4 rows */
+    unsigned long long* prof; /* optional [16] device counters: SM cycles per phase, summed over tiles (tuning aid) */
 } gp_mlp_fwd_args;
 
 int gp_mlp_fwd(const gp_mlp_fwd_args* args, int hidden, void* stream);
@@ -182,9 +183,9 @@ int gp_segsum_gather(const gp_bf16* src, int32_t ld, const int32_t* perm, const 
  * graphphysics/utils/loss.py:19-75; train.py:276-290).
  * --------------------------------------------------------------------------------------------- */
 /* loss[0] = mean over rows with mask!=0 and all d columns of (out-target)^2; grad (optional) =
- * grad_scale * dloss/dout. */
+ * grad_scale * dloss/dout.  workspace: 260 floats. */
 int gp_masked_mse(const float* out, const float* target, const uint8_t* mask, int32_t n, int32_t d, float* loss,
-                  float* grad, float grad_scale, void* stream);
+                  float* grad, float grad_scale, float* workspace, void* stream);
 /* out[0] = sum g[i]^2 (two fixed-shape passes; workspace >= 256 floats). */
 int gp_sqnorm(const float* g, int64_t n, float* workspace, float* out, void* stream);
 /* clip-by-global-norm (max_norm <= 0 disables; sqnorm = device scalar from gp_sqnorm) + AdamW. */

@@ -161,7 +161,8 @@ def graph_net_block(x, e, src, dst, sd, prefix: str, mode: Optional[str] = None)
         e_upd = mlp(torch.cat([e, x[dst], x[src]], dim=-1), sd, f"{prefix}.edge_block")
         agg = torch.zeros_like(x).index_add_(0, dst, e_upd)
         x_upd = mlp(torch.cat([x, agg], dim=-1), sd, f"{prefix}.node_block")
-    return rnd(x + x_upd, mode), rnd(e + e_upd, mode)
+    # the kernels round the normalised update to bf16 once; that value feeds agg and the residual
+    return rnd(x + rnd(x_upd, mode), mode), rnd(e + rnd(e_upd, mode), mode)
 
 
 def epd_forward(sd, x_in, edge_attr, edge_index, num_layers: int, mode: Optional[str] = None,

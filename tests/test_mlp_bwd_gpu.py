@@ -91,7 +91,7 @@ def test_edge_block_backward(hidden):
     pre = (torch.nn.functional.linear(e64, O.rnd(sd64["m.0.weight"], "bf16"))
            + P64[dst, :hidden] + P64[src, hidden:2 * hidden])
     upd = O.mlp(None, sd64, "m", mode="bf16", first_pre=pre)
-    e_new = O.rnd(e64 + upd, "bf16")
+    e_new = O.rnd(e64 + O.rnd(upd, "bf16"), "bf16")
     agg = torch.zeros(N, hidden, dtype=torch.float64).index_add_(0, dst, O.rnd(upd, "bf16"))
     ((e_new * G1.double()).sum() + (agg * G2.double()).sum()).backward()
 

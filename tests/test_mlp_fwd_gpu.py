@@ -50,7 +50,9 @@ def test_plain_mlp_norm(hidden, rows):
     ops.mlp_fwd(rows, hidden, ws, bs, a=x.to(dev).to(torch.bfloat16), ka=hidden,
                 norm_scale=sd["m.7.scale"].to(dev), out=out, n_valid=hidden)
     torch.cuda.synchronize()
-    assert rel_err(out, ref) < 1e-3
+    # a normalised output leaves the kernel through a bf16 tile (it is rounded once, before the
+    # residual / segment sum), so fp32 storage still carries bf16 resolution: one ulp = 4e-3
+    assert rel_err(out, bf16_round(ref.float()).double()) < 4e-3
 
 
 @pytest.mark.parametrize("hidden", [128, 32])
@@ -115,7 +117,7 @@ def test_edge_mode_gather_residual_segment_sum(hidden):
     pre = (F_linear(e.double(), bf16_round(sd["m.0.weight"]).double())
            + P[dst, :hidden].double() + P[src, hidden:2 * hidden].double())
     upd = O.mlp(None, sd64, "m", mode="bf16", first_pre=pre)
-    ref_e = e.double() + upd
+    ref_e = e.double() + bf16_round(upd.float()).double()
     ref_agg = torch.zeros(N, hidden, dtype=torch.float64).index_add_(0, dst, bf16_round(upd.float()).double())
 
     ws, bs = _pack(sd, dev)
@@ -152,7 +154,7 @@ def test_node_mode_fp32_operand_direct_init():
     P = bf16_round(torch.randn(N, 3 * hidden, generator=g))
     pre = F_linear(bf16_round(agg).double(), bf16_round(sd["m.0.weight"]).double()) + P[:, 2 * hidden:].double()
     upd = O.mlp(None, {k: v.double() for k, v in sd.items()}, "m", mode="bf16", first_pre=pre)
-    ref = x.double() + upd
+    ref = x.double() + bf16_round(upd.float()).double()
     ws, bs = _pack(sd, dev)
     out = torch.empty((N, hidden), dtype=torch.bfloat16, device=dev)
     h2 = torch.empty((N, hidden), dtype=torch.bfloat16, device=dev)
