@@ -60,7 +60,7 @@ class CpuTrainer:
         loss.backward()
         torch.nn.utils.clip_grad_norm_(list(self.params.values()), 1.0)
         for gpar in self.opt.param_groups:
-            gpar["lr"] = self.base_lr * O.cosine_warmup_factor(self.step_index - 1 + 1 - 1, self.warmup, self.num_steps)
+            gpar["lr"] = self.base_lr * O.cosine_warmup_factor(self.step_index, self.warmup, self.num_steps)
         self.opt.step()
         self.step_index += 1
-        return float(loss)
+        return float(loss.detach())

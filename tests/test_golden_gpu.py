@@ -1,0 +1,81 @@
+"""GPU: the CUDA path against golden vectors of the UNMODIFIED reference (fp32 PyTorch) on the
+reference's own weights.  This is the end-to-end parity statement; the tolerance is the drift of
+bf16 kernel arithmetic from exact arithmetic (tests/test_host_cpu.py::test_spec_drift...), i.e.
+norm-relative 2e-2 on outputs and 1e-2 on the loss over three optimizer steps."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from tests.util import l2_rel
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.mark.parametrize("name,hidden", [("epd_l2_h32.npz", 32), ("epd_l2_h64.npz", 64)])
+def test_epd_against_reference_golden(name, hidden):
+    from graphphysics_b200.graph import Data
+    from graphphysics_b200.models.processors import EncodeProcessDecode
+    dev = torch.device("cuda:0")
+    z = np.load(os.path.join(G, name))
+    sd = {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd/")}
+    m = EncodeProcessDecode(int(z["L"]), 11, 3, 2, hidden_size=hidden)
+    m.load_state_dict(sd)                       # reference checkpoint loads 1:1
+    m = m.to(dev)
+    graph = Data(x=torch.from_numpy(z["x"]).to(dev), edge_index=torch.from_numpy(z["edge_index"]).to(dev),
+                 edge_attr=torch.from_numpy(z["edge_attr"]).to(dev))
+    out = m(graph)
+    assert l2_rel(out, torch.from_numpy(z["out"])) < 2e-2
+    (out * torch.from_numpy(z["G"]).to(dev)).sum().backward()
+    grads = m.engine.grads_by_name()
+    # Gradients versus exact arithmetic are a sanity bound only: a forward that differs by ~1 % (bf16)
+    # flips the ReLU mask of the ~1 % of units whose pre-activation is that close to zero, and each
+    # flipped unit changes its gradient contribution by 100 %, i.e. ~sqrt(0.01) = 10 % in l2 per
+    # ReLU layer.  The CPU oracle in kernel-arithmetic mode shows the same 16-23 % against its own
+    # exact mode on these fixtures; kernel-vs-oracle gradient parity is tight (test_mlp_bwd_gpu.py).
+    ref = {k: torch.from_numpy(z["grad/" + k]).double() for k in sd}
+    got = {k: grads[k].detach().double().cpu() for k in sd}
+    num = sum(float((got[k] - ref[k]).pow(2).sum()) for k in sd) ** 0.5
+    den = sum(float(ref[k].pow(2).sum()) for k in sd) ** 0.5
+    assert num / den < 0.35, num / den
+    biggest = max(float(ref[k].norm()) for k in sd)
+    per = {k: float((got[k] - ref[k]).norm()) / biggest for k in sd}
+    worst = max(per, key=per.get)
+    print(f"global grad l2_rel {num / den:.3e}; worst tensor {worst}: {per[worst]:.3e} of the largest gradient norm")
+    assert per[worst] < 0.15, (worst, per[worst])
+
+
+def test_three_training_steps_against_reference_golden():
+    from graphphysics_b200.graph import Data
+    from graphphysics_b200.training.loop import Trainer
+    dev = torch.device("cuda:0")
+    z = np.load(os.path.join(G, "train_steps.npz"))
+    cfg = {"model": {"type": "epd", "message_passing_num": 2, "hidden_size": 32, "node_input_size": 2, "output_size": 2,
+                     "edge_input_size": 3},
+           "index": {"feature_index_start": 0, "feature_index_end": 2, "output_index_start": 0, "output_index_end": 2,
+                     "node_type_index": 2}}
+    tr = Trainer(cfg, learning_rate=1e-3, num_steps=10, warmup=2, device=dev)
+    sd0 = {k[4:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd0/")}
+    tr.processor.load_state_dict(sd0)
+    ei, ea, pos = (torch.from_numpy(z[k]).to(dev) for k in ("edge_index", "edge_attr", "pos"))
+    frames, ys = torch.from_numpy(z["frames"]).to(dev), torch.from_numpy(z["ys"]).to(dev)
+    for s in range(3):
+        loss = float(tr.training_step(Data(x=frames[s], y=ys[s], pos=pos, edge_index=ei, edge_attr=ea)))
+        assert tr.current_lr() == pytest.approx(float(z["lrs"][s]), rel=1e-9)
+        assert abs(loss - z["losses"][s]) < 1e-2 * abs(z["losses"][s]), (s, loss, float(z["losses"][s]))
+    # normaliser statistics are exact sums of the same inputs
+    sdn = tr.model.state_dict()
+    for k in ("_node_normalizer._acc_sum", "_output_normalizer._acc_sum_squared", "_edge_normalizer._acc_count"):
+        assert torch.allclose(sdn[k].cpu(), torch.from_numpy(z["sd3/" + k]), rtol=1e-5)
+    # parameters after three AdamW steps stay close to the reference's
+    ref3 = {k[len("sd3/model."):]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd3/model.")}
+    mine = {k: v.detach().cpu() for k, v in tr.processor.state_dict().items()}
+    assert max(l2_rel(mine[k], ref3[k]) for k in ref3 if ref3[k].numel() > 64) < 2e-2
+    # eval step: de-normalised outputs
+    tr.model.eval()
+    with torch.no_grad():
+        net, tgt, outp = tr.model(Data(x=frames[3], y=ys[3], pos=pos, edge_index=ei, edge_attr=ea))
+    assert l2_rel(tgt, torch.from_numpy(z["eval_target"])) < 1e-4
+    assert l2_rel(outp, torch.from_numpy(z["eval_outputs"])) < 2e-2

@@ -1,0 +1,111 @@
+"""CPU: the oracle (oracle/gp_oracle.py, exact mode) against golden vectors produced by the
+UNMODIFIED reference modules (oracle/make_golden.py, committed under tests/golden/), and against
+the integer facts the reference's own tests pin."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import gp_oracle as O
+from oracle.cpu_train import CpuTrainer
+
+G = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _load(name):
+    z = np.load(os.path.join(G, name))
+    sd = {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd/")}
+    return z, sd
+
+
+@pytest.mark.parametrize("name", ["epd_l2_h32.npz", "epd_l2_h64.npz"])
+def test_epd_forward_and_gradients_match_reference(name):
+    z, sd = _load(name)
+    sd = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    out = O.epd_forward(sd, torch.from_numpy(z["x"]), torch.from_numpy(z["edge_attr"]), torch.from_numpy(z["edge_index"]),
+                        int(z["L"]))
+    np.testing.assert_allclose(out.detach().numpy(), z["out"], rtol=1e-4, atol=1e-5)
+    (out * torch.from_numpy(z["G"])).sum().backward()
+    for k, p in sd.items():
+        np.testing.assert_allclose(p.grad.numpy(), z["grad/" + k], rtol=2e-3, atol=2e-5, err_msg=k)
+
+
+def test_graphnet_block_matches_reference():
+    z, sd = _load("graphnet_block_h32.npz")
+    sd = {"b." + k: v for k, v in sd.items()}
+    ei = torch.from_numpy(z["edge_index"])
+    ox, oe = O.graph_net_block(torch.from_numpy(z["x"]), torch.from_numpy(z["e"]), ei[0], ei[1], sd, "b")
+    np.testing.assert_allclose(ox.numpy(), z["out_x"], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(oe.numpy(), z["out_e"], rtol=1e-4, atol=1e-5)
+
+
+def test_transformer_forward_and_gradients_match_reference():
+    z, sd = _load("transformer_l2_h64.npz")
+    sd = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    out = O.etd_forward(sd, torch.from_numpy(z["x"]), torch.from_numpy(z["edge_index"]), 2, 4)
+    np.testing.assert_allclose(out.detach().numpy(), z["out"], rtol=1e-4, atol=1e-5)
+    (out * torch.from_numpy(z["G"])).sum().backward()
+    for k, p in sd.items():
+        if p.grad is None:          # rope_inv_freq etc. are buffers, not in named_parameters
+            continue
+        np.testing.assert_allclose(p.grad.numpy(), z["grad/" + k], rtol=2e-3, atol=2e-5, err_msg=k)
+
+
+def test_training_steps_match_reference():
+    """Simulator (normalisers, one-hot, target delta) + L2Loss + clip + AdamW + cosine warm-up."""
+    z = np.load(os.path.join(G, "train_steps.npz"))
+    sd0 = {k[4:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd0/")}
+    index = dict(feature_index_start=0, feature_index_end=2, output_index_start=0, output_index_end=2, node_type_index=2)
+    tr = CpuTrainer(sd0, 2, index, 2, 11, 3, lr=1e-3, num_steps=10, warmup=2)
+    ei, ea = torch.from_numpy(z["edge_index"]), torch.from_numpy(z["edge_attr"])
+    frames, ys = torch.from_numpy(z["frames"]), torch.from_numpy(z["ys"])
+    for s in range(3):
+        loss = tr.training_step(frames[s], ys[s], ea, ei)
+        assert abs(loss - z["losses"][s]) <= 2e-5 * max(1.0, abs(z["losses"][s])), (s, loss, z["losses"][s])
+        assert abs(tr.opt.param_groups[0]["lr"] - z["lrs"][s]) < 1e-12
+    for k, p in tr.params.items():
+        np.testing.assert_allclose(p.detach().numpy(), z["sd3/model." + k], rtol=2e-3, atol=2e-6, err_msg=k)
+    np.testing.assert_allclose(tr.norms["node"].acc_sum.numpy(), z["sd3/_node_normalizer._acc_sum"], rtol=1e-5)
+    np.testing.assert_allclose(tr.norms["output"].acc_sum_sq.numpy(), z["sd3/_output_normalizer._acc_sum_squared"], rtol=1e-5)
+    with torch.no_grad():
+        net, tgt, outp = tr.forward(frames[3], ys[3], ea, ei, training=False)
+    np.testing.assert_allclose(net.numpy(), z["eval_net"], rtol=5e-3, atol=5e-5)
+    np.testing.assert_allclose(tgt.numpy(), z["eval_target"], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(outp.numpy(), z["eval_outputs"], rtol=5e-3, atol=5e-5)
+
+
+def test_small_ops_match_reference():
+    z = np.load(os.path.join(G, "small_ops.npz"))
+    np.testing.assert_allclose(O.rms_norm(torch.from_numpy(z["rms_x"]), torch.ones(16)).numpy(), z["rms_out"], rtol=1e-6)
+    nz = O.Normalizer(5)
+    n1 = nz(torch.from_numpy(z["norm_d1"]))
+    n2 = nz(torch.from_numpy(z["norm_d2"]))
+    np.testing.assert_allclose(n1.numpy(), z["norm_n1"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(n2.numpy(), z["norm_n2"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(nz.inverse(n2).numpy(), z["norm_inv"], rtol=1e-5, atol=1e-6)   # test_layers.py:92-100
+    np.testing.assert_allclose([O.cosine_warmup_factor(e, 2, 10) for e in range(12)], z["sched"], rtol=1e-12)
+
+
+def test_integer_goldens_of_the_reference_tests():
+    """tests/graphphysics/dataset/test_xdmfdataset.py:31,46,189-191,247-249 of the reference."""
+    c = np.load(os.path.join(G, "cylinder_mesh.npz"))
+    assert c["points"].shape == (1923, 3) and c["triangles"].shape == (3612, 3)
+    ei = O.face_to_edge(c["triangles"], 1923)
+    assert ei.shape == (2, 11070)
+    assert O.edge_features(c["points"], ei).shape == (11070, 4)
+    assert O.khop_edges(ei, 1923, 2).shape == (2, 32638)
+    assert (np.diff(ei[0] * 1923 + ei[1]) > 0).all()            # coalesced: sorted by (row, col), unique
+    rev = np.stack([ei[1], ei[0]])
+    assert set(map(tuple, rev.T)) == set(map(tuple, ei.T))      # symmetric
+    a = np.load(os.path.join(G, "aneurysm_mesh.npz"))
+    assert a["points"].shape == (22535, 3) and a["tets"].shape == (115275, 4)
+    assert O.face_to_edge(O.tetra_to_faces(a["tets"]), 22535).shape == (2, 291144)
+
+
+def test_l2_loss_masking():
+    """tests/graphphysics/utils/test_loss.py:58-123 of the reference: only NORMAL/OUTFLOW rows count."""
+    out, tgt = torch.tensor([[1.0, 2.0], [3.0, 4.0], [5.0, 6.0]]), torch.zeros(3, 2)
+    nt = torch.tensor([0.0, 6.0, 5.0])
+    assert float(O.l2_loss(tgt, out, nt)) == pytest.approx((1 + 4 + 25 + 36) / 4)
+    assert bool(O.boundary_mask(nt).tolist() == [False, True, False])
