@@ -167,3 +167,15 @@ class ReduceSeg(C.Structure):
         ("ld_dst", C.c_int32),
         ("accumulate", C.c_int32),
     ]
+
+
+class AttentionArgs(C.Structure):
+    _fields_ = [
+        ("n", C.c_int32), ("hidden", C.c_int32), ("num_heads", C.c_int32),
+        ("q", C.c_void_p), ("k", C.c_void_p), ("v", C.c_void_p),
+        ("rowptr", C.c_void_p), ("col", C.c_void_p),
+        ("y", C.c_void_p), ("lse", C.c_void_p),
+        ("dy", C.c_void_p), ("pos", C.c_void_p), ("colptr", C.c_void_p), ("row", C.c_void_p),
+        ("dq", C.c_void_p), ("dk", C.c_void_p), ("dv", C.c_void_p),
+        ("edge_a", C.c_void_p), ("edge_ds", C.c_void_p),
+    ]

@@ -64,6 +64,9 @@ class GraphCSR:
         self.perm_src = torch.sort(src_s, stable=True).indices.int()
         self.rowptr_src = self._rowptr(src_s, num_nodes)
         self._inv_perm: Optional[torch.Tensor] = None
+        # attention view: rows = senders (edge_index[0]); the row-sorted entry p is entry perm_src[p] of
+        # the receiver-sorted list, so its column is dst[perm_src[p]]
+        self.att_col = self.dst[self.perm_src.long()].contiguous()
 
     @staticmethod
     def _rowptr(ids: torch.Tensor, n: int) -> torch.Tensor:

@@ -185,3 +185,92 @@ class GraphNetBlock(nn.Module):
         eng = self._get_engine()
         g = get_csr(edge_index, x.shape[0])
         return BlockFunction.apply(eng.flat, x, edge_attr, eng, g)
+
+
+# --------------------------------------------------------------------------------------------------
+# Graph Transformer block (layers.py:213-278, 564-819 of the reference)
+# --------------------------------------------------------------------------------------------------
+class GatedMLP(nn.Module):
+    """GELU(W1 x) * (W2 x)  (layers.py:213-249)."""
+
+    def __init__(self, in_size: int, hidden_size: int, expansion_factor: int):
+        super().__init__()
+        if use_silu_activation():
+            raise NotImplementedError("SiLU gating is not implemented on the sm_100a path (SURVEY §8f N3)")
+        self.linear1 = nn.Linear(in_size, expansion_factor * hidden_size)
+        self.linear2 = nn.Linear(in_size, expansion_factor * hidden_size)
+        self.activation = nn.GELU()
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        return self.activation(self.linear1(x)) * self.linear2(x)
+
+
+def build_gated_mlp(in_size: int, hidden_size: int, out_size: int, expansion_factor: int = 3) -> nn.Module:
+    """RMSNorm -> GatedMLP -> Linear (layers.py:252-278); keys `0.scale`, `1.linear{1,2}.*`, `2.*`."""
+    return nn.Sequential(RMSNorm(in_size), GatedMLP(in_size, hidden_size, expansion_factor),
+                         nn.Linear(hidden_size * expansion_factor, out_size))
+
+
+class Attention(nn.Module):
+    """Multi-head attention masked by the mesh adjacency (layers.py:564-697).  The projections are
+    plain dense layers (library GEMMs); scores, row softmax and the weighted sum -- the part the
+    reference sends to dgl.sparse bsddmm / softmax / bspmm -- run in the CSR attention kernels of
+    libgp_b200.so.  `adj` is the graph: a GraphCSR, or an edge_index tensor (2, E)."""
+
+    def __init__(self, input_dim=512, output_dim=512, num_heads=4, pos_dimension: int = 3, use_proj_bias: bool = True,
+                 use_separate_proj_weight: bool = True, use_rope_embeddings: bool = False,
+                 use_gated_attention: bool = False, rope_base: float = 10000.0):
+        super().__init__()
+        assert output_dim % num_heads == 0, "Output dimension must be divisible by number of heads."
+        if use_rope_embeddings or use_gated_attention:
+            raise NotImplementedError("RoPE / gated attention are not implemented on the sm_100a path (SURVEY §8f N3)")
+        self.hidden_size, self.num_heads, self.head_dim = output_dim, num_heads, output_dim // num_heads
+        self.use_rope_embeddings, self.use_gated_attention = use_rope_embeddings, use_gated_attention
+        self.pos_dimension, self.rope_base = pos_dimension, rope_base
+        self.q_proj = nn.Linear(input_dim, output_dim, bias=use_proj_bias)
+        self.k_proj = nn.Linear(input_dim, output_dim, bias=use_proj_bias)
+        self.v_proj = nn.Linear(input_dim, output_dim, bias=use_proj_bias)
+        self.proj = nn.Linear(output_dim, output_dim, bias=use_proj_bias)
+        self.m = 0
+        self.register_buffer("rope_inv_freq", torch.empty(0, dtype=torch.float32), persistent=False)
+        self.gate_proj = None
+        if not use_separate_proj_weight:
+            with torch.no_grad():
+                self.k_proj.weight = self.q_proj.weight
+                self.v_proj.weight = self.q_proj.weight
+
+    def forward(self, x: torch.Tensor, adj, pos: Optional[torch.Tensor] = None, return_attention: bool = False):
+        from ..graph import GraphCSR
+        from ..ops import CSRAttention
+        if return_attention:
+            raise NotImplementedError("return_attention=True is not supported (attention weights are never materialised)")
+        if adj is None:
+            raise ValueError("Attention needs the mesh adjacency (a GraphCSR or an edge_index tensor)")
+        g = adj if isinstance(adj, GraphCSR) else get_csr(adj, x.shape[0])
+        q, k, v = self.q_proj(x), self.k_proj(x), self.v_proj(x)
+        y = CSRAttention.apply(q, k, v, g, self.num_heads)
+        return self.proj(y)
+
+
+class Transformer(nn.Module):
+    """x += Attention(norm1(x));  x += gated_mlp(norm2(x))   (layers.py:700-819)."""
+
+    def __init__(self, input_dim: int, output_dim: int, num_heads: int, activation_layer=nn.ReLU, use_proj_bias: bool = True,
+                 use_separate_proj_weight: bool = True, use_rope_embeddings: bool = False,
+                 use_gated_attention: bool = False, pos_dimension: int = 3, rope_base: float = 10000.0):
+        super().__init__()
+        self.use_rope_embeddings, self.use_gated_attention, self.pos_dimension = (use_rope_embeddings, use_gated_attention,
+                                                                                pos_dimension)
+        self.attention = Attention(input_dim=input_dim, output_dim=output_dim, num_heads=num_heads,
+                                   pos_dimension=pos_dimension, use_proj_bias=use_proj_bias,
+                                   use_separate_proj_weight=use_separate_proj_weight,
+                                   use_rope_embeddings=use_rope_embeddings, use_gated_attention=use_gated_attention,
+                                   rope_base=rope_base)
+        self.activation = activation_layer()        # constructed but unused, as in the reference (layers.py:757)
+        self.norm1, self.norm2 = RMSNorm(output_dim), RMSNorm(output_dim)
+        self.gated_mlp = build_gated_mlp(in_size=output_dim, hidden_size=output_dim, out_size=output_dim)
+        self.use_adjacency = True
+
+    def forward(self, x: torch.Tensor, adj, pos: Optional[torch.Tensor] = None, return_attention: bool = False):
+        x = x + self.attention(self.norm1(x), adj, pos=pos, return_attention=return_attention)
+        return x + self.gated_mlp(self.norm2(x))

@@ -55,3 +55,43 @@ class EncodeProcessDecode(nn.Module):
             return EPDFunction.apply(eng.flat, x, edge_attr, eng, g)
         out, _, _ = eng.forward(x, edge_attr, g, save=False)
         return out.float()
+
+
+class EncodeTransformDecode(nn.Module):
+    """Encoder MLP, L graph-Transformer blocks over the mesh adjacency, decoder MLP
+    (graphphysics/models/processors.py:218-384, the DGL branch).  Same constructor and state_dict
+    keys.  The adjacency-masked attention runs in the CSR kernels of libgp_b200.so; encoder, decoder,
+    projections and the gated MLP are dense layers executed as library GEMMs in fp32."""
+
+    def __init__(self, message_passing_num: int, node_input_size: int, output_size: int, hidden_size: int = 128,
+                 num_heads: int = 4, only_processor: bool = False, use_proj_bias: bool = True,
+                 use_separate_proj_weight: bool = True, use_rope_embeddings: bool = False,
+                 use_gated_attention: bool = False, rope_pos_dimension: int = 3, rope_base: float = 10000.0,
+                 use_temporal_block: bool = False):
+        super().__init__()
+        from .layers import Transformer
+        if use_temporal_block:
+            raise NotImplementedError("use_temporal_block is not implemented on the sm_100a path (SURVEY §8f N3)")
+        self.hidden_size, self.only_processor, self.d = hidden_size, only_processor, output_size
+        self.use_rope_embeddings, self.use_gated_attention = use_rope_embeddings, use_gated_attention
+        self.use_temporal_block = use_temporal_block
+        if not only_processor:
+            self.nodes_encoder = build_mlp(node_input_size, hidden_size, hidden_size)
+            self.decode_module = build_mlp(hidden_size, hidden_size, output_size, layer_norm=False)
+        self.processor_list = nn.ModuleList([
+            Transformer(input_dim=hidden_size, output_dim=hidden_size, num_heads=num_heads, use_proj_bias=use_proj_bias,
+                        use_separate_proj_weight=use_separate_proj_weight, use_rope_embeddings=use_rope_embeddings,
+                        use_gated_attention=use_gated_attention, pos_dimension=rope_pos_dimension, rope_base=rope_base)
+            for _ in range(message_passing_num)])
+        self.temporal_block = None
+
+    def forward(self, graph) -> torch.Tensor:
+        x = graph.x
+        if x.device.type != "cuda":
+            raise RuntimeError("graphphysics_b200 runs on CUDA devices only (there is no CPU fallback)")
+        g = get_csr(graph.edge_index, x.shape[0])          # processors.py:366: rows edge_index[0], cols edge_index[1]
+        if not self.only_processor:
+            x = self.nodes_encoder(x)
+        for block in self.processor_list:
+            x = block(x, g, pos=getattr(graph, "pos", None))
+        return x if self.only_processor else self.decode_module(x)

@@ -361,3 +361,47 @@ def cast_bf16(src: torch.Tensor, dst: torch.Tensor) -> None:
     check(lib().gp_cast_bf16(C.c_void_p(ptr(src)), C.c_void_p(ptr(dst)), C.c_int64(src.numel()),
                              C.c_void_p(stream_ptr())), "gp_cast_bf16")
     _launched()
+
+
+from ._lib import AttentionArgs  # noqa: E402
+
+
+class CSRAttention(torch.autograd.Function):
+    """y = masked multi-head attention(q, k, v) over the adjacency of `g` (rows = edge_index[0],
+    columns = edge_index[1]); gp_csr_attention_fwd / _bwd.  q, k, v: fp32 [N, H] contiguous."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, g, num_heads: int):
+        q, k, v = q.contiguous().float(), k.contiguous().float(), v.contiguous().float()
+        n, h = q.shape
+        a = AttentionArgs()
+        a.n, a.hidden, a.num_heads = n, h, num_heads
+        a.q, a.k, a.v = ptr(q), ptr(k), ptr(v)
+        a.rowptr, a.col = ptr(g.rowptr_src), ptr(g.att_col)
+        y = torch.empty_like(q)
+        lse = torch.empty((n, num_heads), dtype=torch.float32, device=q.device)
+        a.y, a.lse = ptr(y), ptr(lse)
+        check(lib().gp_csr_attention_fwd(C.byref(a), C.c_void_p(stream_ptr())), "gp_csr_attention_fwd")
+        _launched()
+        ctx.save_for_backward(q, k, v, y, lse)
+        ctx.g, ctx.num_heads = g, num_heads
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        q, k, v, y, lse = ctx.saved_tensors
+        g, nh = ctx.g, ctx.num_heads
+        n, h = q.shape
+        dy = dy.contiguous().float()
+        a = AttentionArgs()
+        a.n, a.hidden, a.num_heads = n, h, nh
+        a.q, a.k, a.v, a.y, a.lse, a.dy = ptr(q), ptr(k), ptr(v), ptr(y), ptr(lse), ptr(dy)
+        a.rowptr, a.col, a.pos = ptr(g.rowptr_src), ptr(g.att_col), ptr(g.perm_src)
+        a.colptr, a.row = ptr(g.rowptr_dst), ptr(g.src)
+        dq, dk, dv = torch.empty_like(q), torch.empty_like(q), torch.empty_like(q)
+        ea = torch.empty((g.num_edges, nh), dtype=torch.float32, device=q.device)
+        eds = torch.empty_like(ea)
+        a.dq, a.dk, a.dv, a.edge_a, a.edge_ds = ptr(dq), ptr(dk), ptr(dv), ptr(ea), ptr(eds)
+        check(lib().gp_csr_attention_bwd(C.byref(a), C.c_void_p(stream_ptr())), "gp_csr_attention_bwd")
+        _launched(2)
+        return dq, dk, dv, None, None

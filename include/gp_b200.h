@@ -212,6 +212,40 @@ typedef struct gp_reduce_seg {
 int gp_reduce_partials_multi(const float* partials, int32_t n_parts, int32_t stride, const gp_reduce_seg* segs_host,
                              int32_t n_segs, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Adjacency-masked multi-head attention over a CSR graph: the DGL-sparse path of
+ * graphphysics/models/layers.py:493-561 (bsddmm, row softmax, bspmm) as used by Attention.forward
+ * (layers.py:637-697).  q, k, v, y, dy, dq, dk, dv are fp32 [n][hidden] with the reference's head
+ * layout (channel c = d_idx*num_heads + h).  Rows are edge_index[0], columns edge_index[1].
+ *   rowptr/col : the entries sorted by row (CSR);      pos[p] = index of row-sorted entry p in the
+ *   colptr/row : the entries sorted by column (CSC);             column-sorted list
+ *   lse        : [n][num_heads] log-sum-exp saved by the forward
+ *   edge_a/ds  : [nnz][num_heads] scratch written by the backward (column-sorted order)
+ * Forward and backward are gather-only (no atomics) and bit-reproducible.
+ * --------------------------------------------------------------------------------------------- */
+typedef struct gp_attention_args {
+    int32_t n, hidden, num_heads;
+    const float* q;
+    const float* k;
+    const float* v;
+    const int32_t* rowptr;
+    const int32_t* col;
+    float* y;
+    float* lse;
+    /* backward only */
+    const float* dy;
+    const int32_t* pos;
+    const int32_t* colptr;
+    const int32_t* row;
+    float* dq;
+    float* dk;
+    float* dv;
+    float* edge_a;
+    float* edge_ds;
+} gp_attention_args;
+int gp_csr_attention_fwd(const gp_attention_args* args, void* stream);
+int gp_csr_attention_bwd(const gp_attention_args* args, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
