@@ -1,0 +1,51 @@
+"""Data-parallel glue: one process per GPU, batches of independent graphs per rank.
+
+The reference is single-device (`devices: 1`, graphphysics/train.py:276-279); the equivalent of its
+result on N GPUs is "one device with the N-times larger batch", so after the backward the flat
+gradient buffer is averaged over ranks with ONE all-reduce (NCCL on GPUs, gloo in the CPU tests), and
+the online normalisers (graphphysics/models/layers.py:331-377) accumulate the statistics of the
+global batch so every rank normalises identically.  Works on any backend / device."""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+def broadcast_(flat: torch.Tensor, group=None, src: int = 0) -> None:
+    dist.broadcast(flat, src=src, group=group)
+
+
+def allreduce_mean_(flat_grad: torch.Tensor, group=None) -> None:
+    """flat_grad <- mean over ranks (sum all-reduce, then scale)."""
+    dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM, group=group)
+    flat_grad.mul_(1.0 / dist.get_world_size(group))
+
+
+def _accumulate_global(norm, data: torch.Tensor, group) -> None:
+    """Normalizer._accumulate (layers.py:363-377) with the sums taken over all ranks."""
+    if norm is None:
+        return
+    if norm._host_calls is None:
+        norm._host_calls = int(norm._num_accumulations.item())
+    if norm._host_calls >= norm._max_accumulations:
+        return
+    d = data.detach()
+    stats = torch.cat([d.sum(0), (d ** 2).sum(0), d.new_tensor([float(d.shape[0])])])
+    dist.all_reduce(stats, op=dist.ReduceOp.SUM, group=group)
+    k = d.shape[1]
+    norm._acc_sum += stats[:k][None]
+    norm._acc_sum_squared += stats[k:2 * k][None]
+    norm._acc_count += stats[2 * k]
+    norm._num_accumulations += 1
+    norm._host_calls += 1
+
+
+def accumulate_normalizers_globally(sim, batch, group=None) -> None:
+    """What Simulator._build_input_graph(is_training=True) accumulates (simulator.py:145-167), over the
+    global batch.  Call before building the input graph with accumulate=False."""
+    pre = batch.x[:, sim.output_index_start:sim.output_index_end]
+    _accumulate_global(sim._output_normalizer, batch.y - pre, group)
+    nf = sim._build_node_features(batch, sim._get_one_hot_type(batch)).float()
+    _accumulate_global(sim._node_normalizer, nf, group)
+    if sim._edge_normalizer is not None:
+        _accumulate_global(sim._edge_normalizer, batch.edge_attr, group)

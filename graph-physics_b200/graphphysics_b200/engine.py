@@ -192,9 +192,11 @@ class EPDEngine:
         self._mlp(self.node[l], N, agg, H, x2, H, save_h2=h2n, resid=x, init=P, init_off0=2 * H)
         return x2, e2, ((x, e, P, agg, h2e, h2n) if save else None)
 
-    def forward(self, x_in: torch.Tensor, edge_attr: torch.Tensor, g: GraphCSR, save: bool):
+    def forward(self, x_in: torch.Tensor, edge_attr: torch.Tensor, g: GraphCSR, save: bool, after_block=None):
         """x_in [N, node_in] / edge_attr [E, edge_in] fp32 in the caller's edge order (latent
-        [N,H] / [E,H] when only_processor).  Returns (out, e_last_sorted, ctx)."""
+        [N,H] / [E,H] when only_processor).  Returns (out, e_last_sorted, ctx).
+        `after_block(x)` (optional) runs on the node latent after the encoder and after every block
+        -- the halo exchange of the node-partitioned mode (dist/partitioned.py)."""
         H, dev = self.H, self.device
         N, E = g.num_nodes, g.num_edges
         bf = torch.bfloat16
@@ -217,6 +219,8 @@ class EPDEngine:
         bnd = torch.empty(ops.seg_bnd_size(E, H), dtype=torch.float32, device=dev)
         for l in range(self.L):
             x2, e2, saved = self.run_block(l, x, e, g, bnd, save)
+            if after_block is not None:
+                after_block(x2)
             if save:
                 ctx["layers"].append(saved)
             x, e = x2, e2
@@ -319,6 +323,40 @@ class EPDEngine:
         return None, None
 
     # ------------------------------------------------------------------ optimizer helpers
+    def grad_sqnorm(self) -> torch.Tensor:
+        ops.sqnorm(self.gflat, self._sq_ws, self.sqnorm)
+        return self.sqnorm
+
+
+class FlatParams:
+    """Flat fp32 parameter / gradient buffers for a model that runs under torch autograd (the
+    Transformer path): every nn.Parameter becomes a view of `flat`, every `.grad` a view of `gflat`,
+    so clip + AdamW run as the same two kernels (gp_sqnorm, gp_adamw) as on the EPD engine."""
+
+    def __init__(self, model: nn.Module):
+        params = [p for p in model.parameters() if p.requires_grad]
+        uniq, seen = [], set()
+        for p in params:                      # shared weights (use_separate_proj_weight=False) appear once
+            if id(p) not in seen:
+                seen.add(id(p))
+                uniq.append(p)
+        self.device = uniq[0].device
+        total = sum((p.numel() + 15) // 16 * 16 for p in uniq)
+        self.flat = torch.zeros(total, dtype=torch.float32, device=self.device)
+        self.gflat = torch.zeros_like(self.flat)
+        off = 0
+        for p in uniq:
+            n = p.numel()
+            self.flat[off:off + n].copy_(p.data.reshape(-1))
+            p.data = self.flat[off:off + n].view(p.shape)
+            p.grad = self.gflat[off:off + n].view(p.shape)
+            off += (n + 15) // 16 * 16
+        self._sq_ws = torch.empty(256, dtype=torch.float32, device=self.device)
+        self.sqnorm = torch.zeros(1, dtype=torch.float32, device=self.device)
+
+    def zero_grad(self):
+        self.gflat.zero_()
+
     def grad_sqnorm(self) -> torch.Tensor:
         ops.sqnorm(self.gflat, self._sq_ws, self.sqnorm)
         return self.sqnorm

@@ -45,17 +45,23 @@ class Trainer:
         self.clip, self.wd, self.betas, self.eps = gradient_clip_val, weight_decay, betas, eps
         self.pg = process_group
         self.step_index = 0
-        eng = self.processor.engine
+        self.fused = hasattr(self.processor, "engine")      # EPD: engine-driven forward/backward, no autograd tape
+        self._flat = None if self.fused else None
+        if not self.fused:
+            from ..engine import FlatParams
+            self._flat = FlatParams(self.processor)
+        eng = self.engine
         self.exp_avg = torch.zeros_like(eng.flat.data)
         self.exp_avg_sq = torch.zeros_like(eng.flat.data)
         self._loss = torch.zeros(1, dtype=torch.float32, device=device)
         if self.pg is not None:
-            import torch.distributed as dist
-            dist.broadcast(eng.flat.data, src=0, group=self.pg)
+            from ..dist.ddp import broadcast_
+            broadcast_(eng.flat.data, self.pg)
 
     @property
     def engine(self):
-        return self.processor.engine
+        """Owner of the flat parameter / gradient buffers (EPDEngine, or FlatParams for autograd models)."""
+        return self.processor.engine if self.fused else self._flat
 
     def current_lr(self) -> float:
         """LR used by the next optimizer step (CosineWarmupScheduler, scheduler.py:51-67)."""
@@ -69,16 +75,28 @@ class Trainer:
         if not batch.x.is_cuda:
             batch = batch.to(self.device, non_blocking=True)
         node_type = batch.x[:, sim.node_type_index]
-        graph, target = sim._build_input_graph(batch, True)
-        g = get_csr(graph.edge_index, graph.x.shape[0])
-        out, _, ctx = eng.forward(graph.x, graph.edge_attr, g, save=True)
-        d_out = torch.empty_like(out)
-        ops.masked_mse(out, target.contiguous(), prepare_mask(node_type, self.loss_masks), self._loss, d_out)
-        eng.backward(ctx, d_out)
         if self.pg is not None:
-            import torch.distributed as dist
-            dist.all_reduce(eng.gflat, group=self.pg)
-            eng.gflat.mul_(1.0 / dist.get_world_size(self.pg))
+            from ..dist.ddp import accumulate_normalizers_globally
+            accumulate_normalizers_globally(sim, batch, self.pg)       # ranks keep identical statistics
+            graph, target = sim._build_input_graph(batch, False)
+        else:
+            graph, target = sim._build_input_graph(batch, True)
+        mask = prepare_mask(node_type, self.loss_masks)
+        if self.fused:
+            g = get_csr(graph.edge_index, graph.x.shape[0])
+            out, _, ctx = eng.forward(graph.x, graph.edge_attr, g, save=True)
+            d_out = torch.empty_like(out)
+            ops.masked_mse(out, target.contiguous(), mask, self._loss, d_out)
+            eng.backward(ctx, d_out)
+        else:
+            eng.zero_grad()
+            out = self.processor(graph)
+            d_out = torch.empty_like(out)
+            ops.masked_mse(out.detach().contiguous(), target.contiguous(), mask, self._loss, d_out)
+            out.backward(d_out)                                        # gradients land in the flat buffer
+        if self.pg is not None:
+            from ..dist.ddp import allreduce_mean_
+            allreduce_mean_(eng.gflat, self.pg)
         self.optimizer_step()
         return self._loss[0]
 

@@ -140,6 +140,11 @@ def main():
     np.savez_compressed(f"{OUT}/small_ops.npz", rms_x=xx.numpy(), rms_out=rn(xx).detach().numpy(), norm_d1=d1.numpy(),
                         norm_d2=d2.numpy(), norm_n1=n1.numpy(), norm_n2=n2.numpy(), norm_inv=nz.inverse(n2).numpy(),
                         sched=np.array([sched_m.CosineWarmupScheduler.get_lr_factor(sch, e) for e in range(12)]))
+    # 6) the `model` / `index` / `training` sections of the shipped training configs, verbatim
+    import json
+    cfgs = {n: {k: json.load(open(f"{REF}/training_config/{n}.json"))[k] for k in ("model", "index", "training")}
+            for n in ("cylinder", "plate", "coarse-aneurysm")}
+    json.dump(cfgs, open(f"{OUT}/training_configs.json", "w"), indent=1)
     print("golden fixtures written to", OUT)
     for f in sorted(os.listdir(OUT)):
         print(f"  {f:32s} {os.path.getsize(os.path.join(OUT, f)) / 1024:8.1f} KiB")

@@ -147,3 +147,27 @@ def test_spec_drift_vs_exact_arithmetic_is_bounded():
     exact = O.epd_forward(sd, x, ea, ei, 5, mode=None)
     spec = O.epd_forward(sd, x, ea, ei, 5, mode="bf16")
     assert float((spec - exact).norm() / exact.norm()) < 2e-2
+
+
+def test_shipped_training_configs_parse_verbatim():
+    """get_model / get_simulator read the `model` / `index` / `training` sections of the reference's
+    training_config/*.json unchanged (parse_parameters.py:81-190); plate.json is a transformer."""
+    import json
+    from graphphysics_b200.models.processors import EncodeProcessDecode, EncodeTransformDecode
+    from graphphysics_b200.training.parse_parameters import get_model, get_simulator
+    cfgs = json.load(open(os.path.join(ROOT, "tests", "golden", "training_configs.json")))
+    m = get_model(cfgs["cylinder"])
+    assert isinstance(m, EncodeProcessDecode) and len(m.processor_list) == 5 and m.hidden_size == 32
+    assert m.nodes_encoder[0].in_features == 2 + 9 and m.edges_encoder[0].in_features == 3
+    for name, nin in (("plate", 6), ("coarse-aneurysm", 14)):
+        t = get_model(cfgs[name])
+        assert isinstance(t, EncodeTransformDecode) and len(t.processor_list) == 10
+        assert t.nodes_encoder[0].in_features == nin + 9 and t.decode_module[6].out_features == 3
+        sim = get_simulator(cfgs[name], t, torch.device("cpu"))
+        assert sim._edge_normalizer is None and sim.node_input_size == nin + 9
+    with pytest.raises(ValueError):
+        get_model({"model": {"type": "nope", "node_input_size": 1}})
+    bad = json.loads(json.dumps(cfgs["cylinder"]))
+    bad["model"]["use_silu_activation"] = True
+    with pytest.raises(NotImplementedError):
+        get_model(bad)
