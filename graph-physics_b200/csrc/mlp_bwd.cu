@@ -11,7 +11,7 @@
 //     cols 384..399  DBB   sum delta_b   (16 identical columns)
 //     cols 400..415  DBA   sum delta_a
 //     cols 416..431  DSC   sum du * m/(rms+eps)   (RMSNorm scale gradient)
-// Thread (row = tid & 127, half = tid >> 7) owns row `row` of the tile and one half of its
+// Thread (row = tid & 127, part = tid >> 7) owns row `row` of the tile and one part (1/2 or 1/4) of its
 // columns, so ReLU masks, the RMSNorm backward and residuals are thread-local apart from one
 // two-float exchange between the halves.
 #include "common.cuh"
@@ -36,15 +36,25 @@ __host__ __device__ inline BwdLayout bwd_layout(int H, int ka, int nb) {
     return L;
 }
 
+// Threads per CTA: 128 rows x NPART column parts (4 parts = 16 warps at H = 128, where the epilogues are
+// latency-bound and need the extra warps; 2 parts for narrower layers).
 template <int H>
-__global__ void __launch_bounds__(256, 1) mlp_bwd_kernel(const gp_mlp_bwd_args p) {
+struct BwdCfg {
+    static constexpr int NPART = H >= 128 ? 4 : 2;
+    static constexpr int NT = 128 * NPART;
+};
+
+template <int H>
+__global__ void __launch_bounds__(BwdCfg<H>::NT, 1) mlp_bwd_kernel(const gp_mlp_bwd_args p) {
+    constexpr int NPART = BwdCfg<H>::NPART;
+    constexpr int NT = BwdCfg<H>::NT;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = GP_SMEM_ALIGNED(smem_raw);
     __shared__ uint64_t mma_bar;
     __shared__ uint32_t tmem_slot;
 
     const int tid = threadIdx.x;
-    const int row = tid & 127, half = tid >> 7;
+    const int row = tid & 127, part = tid >> 7;
     const int ka = p.ka, nb = p.nb;
     const bool norm = p.mode == 1;
 
@@ -60,20 +70,20 @@ __global__ void __launch_bounds__(256, 1) mlp_bwd_kernel(const gp_mlp_bwd_args p
     float* s_ba = reinterpret_cast<float*>(smem + off);  off += 128 * 4;
     float* s_bb = reinterpret_cast<float*>(smem + off);  off += 128 * 4;
     float* s_g = reinterpret_cast<float*>(smem + off);   off += 128 * 4;
-    float* s_red = reinterpret_cast<float*>(smem + off); off += 4 * 128 * 4;   // [2 quantities][2 halves][128]
+    float* s_red = reinterpret_cast<float*>(smem + off); off += 2 * NPART * 128 * 4;   // [2 quantities][NPART][128]
     int* sseg = reinterpret_cast<int*>(smem + off);
 
     // ---- one-time staging
     stage_weight(wa_t, p.wa, H, ka);
     stage_weight(wb_t, p.wb, nb, H);
     cp_async_commit();
-    for (int i = tid; i < 128 * 8; i += 256) {       // ones tile: first 16 columns of every row = 1.0
+    for (int i = tid; i < 128 * 8; i += NT) {       // ones tile: first 16 columns of every row = 1.0
         const int r = i >> 3, ch = i & 7;
         const uint32_t one2 = 0x3F803F80u;
         *reinterpret_cast<uint4*>(ones + sw128_chunk_off(r, ch)) =
             ch < 2 ? make_uint4(one2, one2, one2, one2) : make_uint4(0, 0, 0, 0);
     }
-    for (int i = tid; i < 128; i += 256) {
+    for (int i = tid; i < 128; i += NT) {
         s_ba[i] = (i < H && p.ba) ? p.ba[i] : 0.f;
         s_bb[i] = (i < nb && p.bb) ? p.bb[i] : 0.f;
         s_g[i] = (i < H && p.norm_scale) ? p.norm_scale[i] : 1.f;
@@ -98,8 +108,8 @@ __global__ void __launch_bounds__(256, 1) mlp_bwd_kernel(const gp_mlp_bwd_args p
     uint32_t phase = 0;
     const bool has_init = p.init != nullptr;
     const int n_tiles = (p.rows + 127) >> 7;
-    constexpr int CH = H / 2;                              // columns per thread half
-    const int cb = half * CH, ce = cb + CH;
+    constexpr int CH = H / NPART;                          // columns per thread
+    const int cb = part * CH;
 
     auto wait_mma = [&]() {
         mbar_wait(&mma_bar, phase);
@@ -112,19 +122,53 @@ __global__ void __launch_bounds__(256, 1) mlp_bwd_kernel(const gp_mlp_bwd_args p
         __syncthreads();
     };
 
+    constexpr int KC = H / 8;                 // 16-byte chunks per H-wide row
+    constexpr int CPT = 128 * KC / NT;       // chunks per thread in a row-major tile copy
+    const bool stage1 = p.two_inits != 0;     // which pre-activation source is gathered through shared memory
+    const int32_t* sidx = stage1 ? p.idx1 : p.idx0;
+    const int soff = stage1 ? p.init_off1 : p.init_off0;
+    const bool du_smem = norm && p.gy_bf16 != nullptr;     // upstream gradient tile staged in qb (+ gathered rows in db)
+
+    const bool prof = p.prof != nullptr && tid == 0;
+    long long tk = 0;
+    auto tick = [&](int slot) {
+        if (prof) {
+            const long long now = clock64();
+            atomicAdd(p.prof + slot, (unsigned long long)(now - tk));
+            tk = now;
+        }
+    };
+    // indices of a tile, prefetched one tile ahead so P0 starts with the rows, not with their ids
+    int ridx[CPT], gidx[CPT], i0n = 0;
+    auto load_idx = [&](int tile_) {
+        const int R0_ = tile_ << 7;
+#pragma unroll
+        for (int j = 0; j < CPT; ++j) {
+            const int gr = min(R0_ + (tid + j * NT) / KC, p.rows - 1);
+            ridx[j] = (has_init && sidx) ? __ldg(sidx + gr) : gr;
+            gidx[j] = (du_smem && p.gy_gather && p.gy_idx) ? __ldg(p.gy_idx + gr) : gr;
+        }
+        if (has_init && stage1) {
+            const int r = min(R0_ + row, p.rows - 1);
+            i0n = p.idx0 ? __ldg(p.idx0 + r) : r;
+        }
+    };
+    if ((int)blockIdx.x < n_tiles) load_idx(blockIdx.x);
     bool first = true;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, first = false) {
+        if (prof) { tk = clock64(); atomicAdd(p.prof + 15, 1ull); }
         const int R0 = tile << 7;
         const int grow = R0 + row;
         const bool valid = grow < p.rows;
         const int crow = valid ? grow : p.rows - 1;
         const uint32_t acc_flag = first ? 0u : 1u;
 
-        // ---- P0: stage inputs
-        stage_rows(ain, p.a_bf16, p.a_f32, ka, p.lda, R0, p.rows, tid, 256);
+        // ---- P0: stage inputs.  Every tile-shaped transfer uses row-major 16-byte chunks (8 lanes per
+        //      cache line); tiles are transposed to the row-per-thread mapping through shared memory.
+        stage_rows(ain, p.a_bf16, p.a_f32, ka, p.lda, R0, p.rows, tid, NT);
         if (!norm) {   // delta_b given: zero rows past the end so they add nothing to the weight gradients
             const int kc = nb >> 3;
-            for (int i = tid; i < 128 * kc; i += 256) {
+            for (int i = tid; i < 128 * kc; i += NT) {
                 const int r = i / kc, ch = i - r * kc;
                 if (R0 + r < p.rows)
                     cp_async16(db_s + sw128_off(128, r, ch * 8), p.delta_b + (size_t)(R0 + r) * p.ld_db + ch * 8);
@@ -132,26 +176,91 @@ __global__ void __launch_bounds__(256, 1) mlp_bwd_kernel(const gp_mlp_bwd_args p
                     *reinterpret_cast<uint4*>(db + sw128_off(128, r, ch * 8)) = make_uint4(0, 0, 0, 0);
             }
         }
+        if (du_smem) {
+#pragma unroll
+            for (int j = 0; j < CPT; ++j) {
+                const int i = tid + j * NT;
+                const int r = i / KC, ch = i % KC;
+                cp_async16(qb_s + sw128_off(128, r, ch * 8), p.gy_bf16 + (size_t)min(R0 + r, p.rows - 1) * p.ld_gy + ch * 8);
+            }
+        }
+        if (has_init) {   // gathered pre-activation rows of the randomly indexed source -> ha
+#pragma unroll
+            for (int j = 0; j < CPT; ++j) {
+                const int i = tid + j * NT;
+                const int r = i / KC, ch = i % KC;
+                cp_async16(ha_s + sw128_off(128, r, ch * 8), p.init + (size_t)ridx[j] * p.ld_init + soff + ch * 8);
+            }
+        }
+        if (du_smem && p.gy_gather) {   // receiver-indexed fp32 rows, rounded to bf16 into db; loads batched by 4 chunks
+#pragma unroll
+            for (int j0 = 0; j0 < CPT; j0 += 4) {
+                float4 u[8];
+#pragma unroll
+                for (int j = 0; j < 4 && j0 + j < CPT; ++j) {
+                    const int ch = (tid + (j0 + j) * NT) % KC;
+                    const float4* sp = reinterpret_cast<const float4*>(p.gy_gather + (size_t)gidx[j0 + j] * H + ch * 8);
+                    u[2 * j] = __ldg(sp);
+                    u[2 * j + 1] = __ldg(sp + 1);
+                }
+#pragma unroll
+                for (int j = 0; j < 4 && j0 + j < CPT; ++j) {
+                    const int i = tid + (j0 + j) * NT;
+                    const int r = i / KC, ch = i % KC;
+                    *reinterpret_cast<uint4*>(db + sw128_off(128, r, ch * 8)) =
+                        make_uint4(pack_bf16(u[2 * j].x, u[2 * j].y), pack_bf16(u[2 * j].z, u[2 * j].w),
+                                   pack_bf16(u[2 * j + 1].x, u[2 * j + 1].y), pack_bf16(u[2 * j + 1].z, u[2 * j + 1].w));
+                }
+            }
+        }
         cp_async_commit();
+        int sid_me = -1, sid_prev = -1, sid_next = -1;
         if (p.seg_id && tid < 128) {
-            sseg[4 + row] = valid ? __ldg(p.seg_id + grow) : -1;
+            if (valid) sid_me = __ldg(p.seg_id + grow);
             if (row == 0) {
-                sseg[3] = R0 > 0 ? __ldg(p.seg_id + R0 - 1) : -1;
-                sseg[132] = (R0 + 128 < p.rows) ? __ldg(p.seg_id + R0 + 128) : -1;
+                if (R0 > 0) sid_prev = __ldg(p.seg_id + R0 - 1);
+                if (R0 + 128 < p.rows) sid_next = __ldg(p.seg_id + R0 + 128);
             }
         }
-        if (has_init) {
-            const int i0 = p.idx0 ? __ldg(p.idx0 + crow) : crow;
-            const gp_bf16* r0p = p.init + (size_t)i0 * p.ld_init + p.init_off0;
-            const gp_bf16* r1p = nullptr;
-            if (p.two_inits) {
-                const int i1 = p.idx1 ? __ldg(p.idx1 + crow) : crow;
-                r1p = p.init + (size_t)i1 * p.ld_init + p.init_off1;
-            }
-            init_rows_to_tmem<CH>(tlane + kColAcc + cb, r0p + cb, r1p ? r1p + cb : nullptr);
+        uint4 dq[CH / 8];                                   // this thread's part of the receiver-indexed row
+        if (has_init && stage1) {
+            const gp_bf16* dp = p.init + (size_t)i0n * p.ld_init + p.init_off0 + cb;
+#pragma unroll
+            for (int i = 0; i < CH / 8; ++i) dq[i] = ldg16(dp + i * 8);
         }
+        tick(0);      // P0 issue
         cp_async_wait<0>();
+        __syncthreads();
+        tick(1);      // P0 wait
+        if (has_init) {
+#pragma unroll
+            for (int c = 0; c < CH; c += 16) {
+                float f[16];
+                unpack8(*reinterpret_cast<const uint4*>(ha + sw128_off(128, row, cb + c)), f);
+                unpack8(*reinterpret_cast<const uint4*>(ha + sw128_off(128, row, cb + c + 8)), f + 8);
+                if (stage1) {
+                    float h[16];
+                    unpack8(dq[c / 8], h);
+                    unpack8(dq[c / 8 + 1], h + 8);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) f[j] += h[j];
+                }
+                uint32_t v[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(f[j]);
+                tmem_st16(tlane + kColAcc + cb + c, v);
+            }
+            tmem_st_wait();
+        }
+        if (p.seg_id && tid < 128) {
+            sseg[4 + row] = sid_me;
+            if (row == 0) {
+                sseg[3] = sid_prev;
+                sseg[132] = sid_next;
+            }
+        }
         publish();
+        tick(2);      // gather combine + publish
 
         // ---- P1: recompute h_a = relu(a_in . Wa^T + init + ba)
         if (tid == 0) {
@@ -162,18 +271,24 @@ __global__ void __launch_bounds__(256, 1) mlp_bwd_kernel(const gp_mlp_bwd_args p
                        (ks > 0 || has_init) ? 1u : 0u);
             mma_commit(&mma_bar);
         }
+        if (tile + (int)gridDim.x < n_tiles) load_idx(tile + gridDim.x);
         wait_mma();
-        for (int c0 = cb; c0 < ce; c0 += 16) {
-            uint32_t v[16];
-            tmem_ld16(tlane + kColAcc + c0, v);
-            tmem_ld_wait();
-            float f[16];
+        tick(3);      // P1 MMA
+        {
+            uint32_t v[CH];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) f[j] = fmaxf(__uint_as_float(v[j]) + s_ba[c0 + j], 0.f);
-            *reinterpret_cast<uint4*>(ha + sw128_off(128, row, c0)) = pack8(f);
-            *reinterpret_cast<uint4*>(ha + sw128_off(128, row, c0 + 8)) = pack8(f + 8);
+            for (int c = 0; c < CH; c += 16) tmem_ld16(tlane + kColAcc + cb + c, *reinterpret_cast<uint32_t(*)[16]>(&v[c]));
+            tmem_ld_wait();
+#pragma unroll
+            for (int c = 0; c < CH; c += 8) {
+                float f[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] = fmaxf(__uint_as_float(v[c + j]) + s_ba[cb + c + j], 0.f);
+                *reinterpret_cast<uint4*>(ha + sw128_off(128, row, cb + c)) = pack8(f);
+            }
         }
         publish();
+        tick(4);      // E1
 
         // ---- P2 (NORM): m = h_a . Wb^T + bb ; delta_b = dRMSNorm(m) . du ; q = du * m/(rms+eps)
         if (norm) {
@@ -185,72 +300,81 @@ __global__ void __launch_bounds__(256, 1) mlp_bwd_kernel(const gp_mlp_bwd_args p
                 mma_commit(&mma_bar);
             }
             wait_mma();
+            tick(5);  // P2 MMA
+            // du for 8 columns of this thread's row: staged bf16 tiles, or fp32 rows read directly
             auto load_du = [&](int c0, float* du) {
-                if (p.gy_bf16) {
-                    const gp_bf16* gp_ = p.gy_bf16 + (size_t)crow * p.ld_gy + c0;
-                    unpack8(ldg16(gp_), du);
-                    unpack8(ldg16(gp_ + 8), du + 8);
-                } else if (!p.gy_f32) {
+                if (du_smem) {
+                    unpack8(*reinterpret_cast<const uint4*>(qb + sw128_off(128, row, c0)), du);
+                    if (p.gy_gather) {
+                        float g8[8];
+                        unpack8(*reinterpret_cast<const uint4*>(db + sw128_off(128, row, c0)), g8);
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) du[j] = 0.f;
-                } else {
-                    const float4* gp_ = reinterpret_cast<const float4*>(p.gy_f32 + (size_t)crow * p.ld_gy + c0);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const float4 t4 = __ldg(gp_ + j);
-                        du[4 * j] = t4.x; du[4 * j + 1] = t4.y; du[4 * j + 2] = t4.z; du[4 * j + 3] = t4.w;
+                        for (int j = 0; j < 8; ++j) du[j] += g8[j];
                     }
-                }
-                if (p.gy_gather) {
-                    const int gi = p.gy_idx ? __ldg(p.gy_idx + crow) : crow;
-                    const float4* ap = reinterpret_cast<const float4*>(p.gy_gather + (size_t)gi * H + c0);
+                } else {
+                    if (p.gy_f32) {
+                        const float4* gp_ = reinterpret_cast<const float4*>(p.gy_f32 + (size_t)crow * p.ld_gy + c0);
+                        const float4 t0 = __ldg(gp_), t1 = __ldg(gp_ + 1);
+                        du[0] = t0.x; du[1] = t0.y; du[2] = t0.z; du[3] = t0.w;
+                        du[4] = t1.x; du[5] = t1.y; du[6] = t1.z; du[7] = t1.w;
+                    } else {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const float4 t4 = __ldg(ap + j);
-                        du[4 * j] += t4.x; du[4 * j + 1] += t4.y; du[4 * j + 2] += t4.z; du[4 * j + 3] += t4.w;
+                        for (int j = 0; j < 8; ++j) du[j] = 0.f;
+                    }
+                    if (p.gy_gather) {
+                        const int gi = p.gy_idx ? __ldg(p.gy_idx + crow) : crow;
+                        const float4* ap = reinterpret_cast<const float4*>(p.gy_gather + (size_t)gi * H + c0);
+                        const float4 t0 = __ldg(ap), t1 = __ldg(ap + 1);
+                        du[0] += t0.x; du[1] += t0.y; du[2] += t0.z; du[3] += t0.w;
+                        du[4] += t1.x; du[5] += t1.y; du[6] += t1.z; du[7] += t1.w;
                     }
                 }
             };
-            float ss = 0.f, dot = 0.f;
-            for (int c0 = cb; c0 < ce; c0 += 16) {
-                uint32_t v[16];
-                tmem_ld16(tlane + kColAcc + c0, v);
-                tmem_ld_wait();
-                float du[16];
-                load_du(c0, du);
+            uint32_t v[CH];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const float m = __uint_as_float(v[j]) + s_bb[c0 + j];
+            for (int c = 0; c < CH; c += 16) tmem_ld16(tlane + kColAcc + cb + c, *reinterpret_cast<uint32_t(*)[16]>(&v[c]));
+            tmem_ld_wait();
+            float ss = 0.f, dot = 0.f;
+#pragma unroll
+            for (int c = 0; c < CH; c += 8) {
+                float du[8];
+                load_du(cb + c, du);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float m = __uint_as_float(v[c + j]) + s_bb[cb + c + j];
+                    v[c + j] = __float_as_uint(m);
                     ss = fmaf(m, m, ss);
-                    dot = fmaf(du[j] * s_g[c0 + j], m, dot);
+                    dot = fmaf(du[j] * s_g[cb + c + j], m, dot);
                 }
             }
-            s_red[(0 * 2 + half) * 128 + row] = ss;
-            s_red[(1 * 2 + half) * 128 + row] = dot;
+            s_red[(0 * NPART + part) * 128 + row] = ss;
+            s_red[(1 * NPART + part) * 128 + row] = dot;
             __syncthreads();
-            ss = s_red[(0 * 2 + 0) * 128 + row] + s_red[(0 * 2 + 1) * 128 + row];
-            dot = s_red[(1 * 2 + 0) * 128 + row] + s_red[(1 * 2 + 1) * 128 + row];
+            ss = 0.f;
+            dot = 0.f;
+#pragma unroll
+            for (int q = 0; q < NPART; ++q) {       // fixed order: every part of the row gets the same sums
+                ss += s_red[(0 * NPART + q) * 128 + row];
+                dot += s_red[(1 * NPART + q) * 128 + row];
+            }
             const float rms = sqrtf(ss * (1.f / H));
             const float s = 1.f / (rms + 1e-8f);
             const float coef = rms > 0.f ? dot * s * s / (rms * H) : 0.f;
-            for (int c0 = cb; c0 < ce; c0 += 16) {
-                uint32_t v[16];
-                tmem_ld16(tlane + kColAcc + c0, v);
-                tmem_ld_wait();
-                float du[16], dm[16], q[16];
-                load_du(c0, du);
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const float m = __uint_as_float(v[j]) + s_bb[c0 + j];
-                    dm[j] = valid ? (s_g[c0 + j] * du[j] * s - coef * m) : 0.f;
+            for (int c = 0; c < CH; c += 8) {
+                float du[8], dm[8], q[8];
+                load_du(cb + c, du);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float m = __uint_as_float(v[c + j]);
+                    dm[j] = valid ? (s_g[cb + c + j] * du[j] * s - coef * m) : 0.f;
                     q[j] = valid ? du[j] * m * s : 0.f;
                 }
-                *reinterpret_cast<uint4*>(db + sw128_off(128, row, c0)) = pack8(dm);
-                *reinterpret_cast<uint4*>(db + sw128_off(128, row, c0 + 8)) = pack8(dm + 8);
-                *reinterpret_cast<uint4*>(qb + sw128_off(128, row, c0)) = pack8(q);
-                *reinterpret_cast<uint4*>(qb + sw128_off(128, row, c0 + 8)) = pack8(q + 8);
+                *reinterpret_cast<uint4*>(db + sw128_off(128, row, cb + c)) = pack8(dm);
+                *reinterpret_cast<uint4*>(qb + sw128_off(128, row, cb + c)) = pack8(q);
             }
             publish();
+            tick(6);  // E2 (norm backward)
         }
 
         // ---- P3: dWb += delta_b^T h_a ; dbb += delta_b^T 1 ; dscale += q^T 1 ; acc = delta_b . Wb
@@ -273,22 +397,25 @@ __global__ void __launch_bounds__(256, 1) mlp_bwd_kernel(const gp_mlp_bwd_args p
             mma_commit(&mma_bar);
         }
         wait_mma();
+        tick(7);      // P3 MMAs
         // delta_a = acc * (h_a > 0), written in place over h_a (its readers have completed)
-        for (int c0 = cb; c0 < ce; c0 += 16) {
-            uint32_t v[16];
-            tmem_ld16(tlane + kColAcc + c0, v);
-            tmem_ld_wait();
-            uint4* h0 = reinterpret_cast<uint4*>(ha + sw128_off(128, row, c0));
-            uint4* h1 = reinterpret_cast<uint4*>(ha + sw128_off(128, row, c0 + 8));
-            float hv[16], f[16];
-            unpack8(*h0, hv);
-            unpack8(*h1, hv + 8);
+        {
+            uint32_t v[CH];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) f[j] = hv[j] > 0.f ? __uint_as_float(v[j]) : 0.f;
-            *h0 = pack8(f);
-            *h1 = pack8(f + 8);
+            for (int c = 0; c < CH; c += 16) tmem_ld16(tlane + kColAcc + cb + c, *reinterpret_cast<uint32_t(*)[16]>(&v[c]));
+            tmem_ld_wait();
+#pragma unroll
+            for (int c = 0; c < CH; c += 8) {
+                uint4* hp = reinterpret_cast<uint4*>(ha + sw128_off(128, row, cb + c));
+                float hv[8], f[8];
+                unpack8(*hp, hv);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] = hv[j] > 0.f ? __uint_as_float(v[c + j]) : 0.f;
+                *hp = pack8(f);
+            }
         }
         publish();
+        tick(8);      // E3
 
         // ---- P4: dWa += delta_a^T a_in ; dba += delta_a^T 1 ; d_in = delta_a . Wa
         if (tid == 0) {
@@ -307,18 +434,27 @@ __global__ void __launch_bounds__(256, 1) mlp_bwd_kernel(const gp_mlp_bwd_args p
             }
             mma_commit(&mma_bar);
         }
-        // while the tensor core runs: delta_a tile -> global, and its segment sum
-        if (p.delta_a_out && valid) {
-            for (int c0 = cb; c0 < ce; c0 += 8)
-                *reinterpret_cast<uint4*>(p.delta_a_out + (size_t)grow * H + c0) =
-                    *reinterpret_cast<const uint4*>(ha + sw128_off(128, row, c0));
+        // while the tensor core runs: delta_a tile -> global (row-major chunks), and its segment sum
+        if (p.delta_a_out) {
+#pragma unroll
+            for (int j = 0; j < CPT; ++j) {
+                const int i = tid + j * NT;
+                const int r = i / KC, ch = i % KC;
+                if (R0 + r < p.rows)
+                    *reinterpret_cast<uint4*>(p.delta_a_out + (size_t)(R0 + r) * H + ch * 8) =
+                        *reinterpret_cast<const uint4*>(ha + sw128_off(128, r, ch * 8));
+            }
         }
-        if (p.seg_id) tile_segment_sum<H, 256>(ha, sseg, R0, tid, p.seg_out, p.seg_bnd);
+        if (p.seg_id) tile_segment_sum<H, NT>(ha, sseg, R0, tid, p.seg_out, p.seg_bnd);
+        tick(9);      // P4 issue + copy-out + segment walk
         wait_mma();
+        tick(10);     // P4 MMA wait
         if (p.need_din) {
-            const int kh = ka >= 32 ? ka / 2 : ka;          // columns per half (half 1 idles when ka < 32)
-            if (ka >= 32 || half == 0) {
-                for (int c0 = half * kh; c0 < half * kh + kh; c0 += 16) {
+            const bool via_smem = p.out_bf16 != nullptr && ka == H;     // bf16 tile output: transpose through db
+            const int nsplit = (ka >= 16 * NPART) ? NPART : (ka >= 32 ? 2 : 1);   // column parts that take part
+            const int kh = ka / nsplit;
+            if (part < nsplit) {
+                for (int c0 = part * kh; c0 < part * kh + kh; c0 += 16) {
                     uint32_t v[16];
                     tmem_ld16(tlane + kColAcc + c0, v);
                     tmem_ld_wait();
@@ -332,7 +468,10 @@ __global__ void __launch_bounds__(256, 1) mlp_bwd_kernel(const gp_mlp_bwd_args p
 #pragma unroll
                         for (int j = 0; j < 16; ++j) f[j] = av[j] > 0.f ? f[j] : 0.f;
                     }
-                    if (valid) {
+                    if (via_smem) {
+                        *reinterpret_cast<uint4*>(db + sw128_off(128, row, c0)) = pack8(f);
+                        *reinterpret_cast<uint4*>(db + sw128_off(128, row, c0 + 8)) = pack8(f + 8);
+                    } else if (valid) {
                         if (p.out_resid) {
                             float rv[16];
                             const gp_bf16* rp = p.out_resid + (size_t)grow * p.ld_out + c0;
@@ -353,9 +492,38 @@ __global__ void __launch_bounds__(256, 1) mlp_bwd_kernel(const gp_mlp_bwd_args p
                     }
                 }
             }
+            if (via_smem) {
+                uint4 rq[CPT];
+                if (p.out_resid) {       // residual chunks requested together, before the barrier
+#pragma unroll
+                    for (int j = 0; j < CPT; ++j) {
+                        const int i = tid + j * NT;
+                        rq[j] = ldg16(p.out_resid + (size_t)min(R0 + i / KC, p.rows - 1) * p.ld_out + (i % KC) * 8);
+                    }
+                }
+                __syncthreads();
+#pragma unroll
+                for (int j = 0; j < CPT; ++j) {
+                    const int i = tid + j * NT;
+                    const int r = i / KC, ch = i % KC;
+                    if (R0 + r < p.rows) {
+                        uint4 q = *reinterpret_cast<const uint4*>(db + sw128_off(128, r, ch * 8));
+                        if (p.out_resid) {
+                            float f[8], rv[8];
+                            unpack8(q, f);
+                            unpack8(rq[j], rv);
+#pragma unroll
+                            for (int u = 0; u < 8; ++u) f[u] += rv[u];
+                            q = pack8(f);
+                        }
+                        *reinterpret_cast<uint4*>(p.out_bf16 + (size_t)(R0 + r) * p.ld_out + ch * 8) = q;
+                    }
+                }
+            }
         }
         tc_fence_before();
         __syncthreads();   // buffers and ACC are free for the next tile
+        tick(11);     // E4 + output
     }
 
     // ---- dump the weight-gradient accumulators of this CTA (lane r <-> output row r)
@@ -458,13 +626,13 @@ template <int H>
 int launch_bwd(const gp_mlp_bwd_args& a, int32_t* grid_out, cudaStream_t st) {
     size_t smem = 1024;
     smem += (size_t)((a.ka + 63) / 64) * H * 128 + (size_t)((H + 63) / 64) * a.nb * 128;
-    smem += (size_t)(a.mode == 1 ? 4 : 3) * kBufBytes + 128 * 128 + 3 * 128 * 4 + 4 * 128 * 4 + 144 * 4;
+    smem += (size_t)(a.mode == 1 ? 4 : 3) * kBufBytes + 128 * 128 + 3 * 128 * 4 + 2 * BwdCfg<H>::NPART * 128 * 4 + 144 * 4;
     GP_REQUIRE((int)smem <= gp::max_smem_optin(), "gp_mlp_bwd_stage: needs %zu B of shared memory (> %d)", smem,
                gp::max_smem_optin());
     GP_CHECK_CUDA(cudaFuncSetAttribute(mlp_bwd_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int n_tiles = (a.rows + 127) / 128;
     int grid = n_tiles < gp::sm_count() ? n_tiles : gp::sm_count();
-    mlp_bwd_kernel<H><<<grid, 256, smem, st>>>(a);
+    mlp_bwd_kernel<H><<<grid, BwdCfg<H>::NT, smem, st>>>(a);
     GP_CHECK_CUDA(cudaGetLastError());
     if (grid_out) *grid_out = grid;
     return 0;

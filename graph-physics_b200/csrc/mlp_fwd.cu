@@ -104,12 +104,20 @@ __global__ void __launch_bounds__(kSlotThreads * NG, 1) mlp_fwd_kernel(const gp_
     // the MMA issuer adds (byte offset >> 4) to descriptor templates built once
     const uint64_t adesc0 = desc_kmajor(buf_s, 128, 0);
 
-    // gather indices of a tile for this thread's row (prefetched one tile ahead)
-    int i0n = 0, i1n = 0;
+    // gather indices of a tile (prefetched one tile ahead): i0n = this thread's row in the directly
+    // loaded source; ridx[] = rows of the chunks this thread copies for the staged source
+    const bool stage1 = p.two_inits != 0;           // which source goes through buf
+    const int32_t* sidx = stage1 ? p.idx1 : p.idx0;
+    const int soff = stage1 ? p.init_off1 : p.init_off0;
+    int i0n = 0, ridx[CPT];
     auto load_idx = [&](int tile_) {
         const int r = min((tile_ << 7) + row, p.rows - 1);
         i0n = p.idx0 ? __ldg(p.idx0 + r) : r;
-        i1n = (p.two_inits && p.idx1) ? __ldg(p.idx1 + r) : r;   // only used to prefetch the row into L2
+#pragma unroll
+        for (int j = 0; j < CPT; ++j) {
+            const int gr = min((tile_ << 7) + (t + j * kSlotThreads) / KC, p.rows - 1);
+            ridx[j] = sidx ? __ldg(sidx + gr) : gr;
+        }
     };
     const int tile0 = blockIdx.x * NG + g;
     if (has_init && tile0 < n_tiles) load_idx(tile0);
@@ -136,18 +144,20 @@ __global__ void __launch_bounds__(kSlotThreads * NG, 1) mlp_fwd_kernel(const gp_
         //     wavefronts a row-per-thread load would cost -- and read back row-wise; the
         //     receiver-indexed source is sorted, its row-per-thread loads already coalesce.
         if (has_init) {
-            const bool stage1 = p.two_inits != 0;           // which source goes through buf
-            const int32_t* sidx = stage1 ? p.idx1 : p.idx0;
-            const int soff = stage1 ? p.init_off1 : p.init_off0;
 #pragma unroll
             for (int j = 0; j < CPT; ++j) {
                 const int i = t + j * kSlotThreads;
                 const int r = i / KC, ch = i % KC;
-                const int gr = min(R0 + r, p.rows - 1);
-                const int ridx = sidx ? __ldg(sidx + gr) : gr;
-                cp_async16(buf_s + sw128_off(128, r, ch * 8), p.init + (size_t)ridx * p.ld_init + soff + ch * 8);
+                cp_async16(buf_s + sw128_off(128, r, ch * 8), p.init + (size_t)ridx[j] * p.ld_init + soff + ch * 8);
             }
             cp_async_commit();
+            // this thread's part of the directly loaded (receiver-indexed) row: requested before the wait
+            uint4 dq[CH / 8];
+            if (stage1) {
+                const gp_bf16* dp = p.init + (size_t)i0n * p.ld_init + p.init_off0 + cb;
+#pragma unroll
+                for (int i = 0; i < CH / 8; ++i) dq[i] = ldg16(dp + i * 8);
+            }
             // L2 prefetch of the layer-0 operand tile, which is staged right after
             if (p.a_bf16 && (t & 7) == 0) {
                 const int kc0 = p.ka >> 3;
@@ -158,8 +168,24 @@ __global__ void __launch_bounds__(kSlotThreads * NG, 1) mlp_fwd_kernel(const gp_
             }
             cp_async_wait<0>();
             slot_sync(g);
-            const gp_bf16* dp = stage1 ? p.init + (size_t)i0n * p.ld_init + p.init_off0 + cb : nullptr;
-            init_staged_to_tmem<CH>(tacc + cb, buf, row, cb, dp);
+#pragma unroll
+            for (int c = 0; c < CH; c += 16) {
+                float f[16];
+                unpack8(*reinterpret_cast<const uint4*>(buf + sw128_off(128, row, cb + c)), f);
+                unpack8(*reinterpret_cast<const uint4*>(buf + sw128_off(128, row, cb + c + 8)), f + 8);
+                if (stage1) {
+                    float h[16];
+                    unpack8(dq[c / 8], h);
+                    unpack8(dq[c / 8 + 1], h + 8);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) f[j] += h[j];
+                }
+                uint32_t v[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(f[j]);
+                tmem_st16(tacc + cb + c, v);
+            }
+            tmem_st_wait();
             slot_sync(g);            // buf is free for the layer-0 operand
         }
         if (p.seg_id && t < 128) {
@@ -204,11 +230,13 @@ __global__ void __launch_bounds__(kSlotThreads * NG, 1) mlp_fwd_kernel(const gp_
                 tick(8);         // MMA issue (thread 0 of the slot)
                 // while the first MMA runs: indices of this slot's next tile, and its gathered rows
                 // into L2, so the next tile's pre-load does not start with two dependent misses
-                if (l == 0 && nc == 0 && has_init && tile + tile_stride < n_tiles) {
-                    load_idx(tile + tile_stride);
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(p.init + (size_t)i0n * p.ld_init + p.init_off0 + cb));
-                    if (p.two_inits)
-                        asm volatile("prefetch.global.L2 [%0];" ::"l"(p.init + (size_t)i1n * p.ld_init + p.init_off1 + cb));
+                if (l == 0 && nc == 0 && has_init && tile + tile_stride < n_tiles) load_idx(tile + tile_stride);
+                if (l == 1 && nc == 0 && has_init && tile + tile_stride < n_tiles) {
+#pragma unroll
+                    for (int j = 0; j < CPT; ++j)
+                        if (((t + j * kSlotThreads) & 7) == 0)     // one prefetch per 128-byte line of the staged rows
+                            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.init + (size_t)ridx[j] * p.ld_init + soff +
+                                                                         ((t + j * kSlotThreads) % KC) * 8));
                 }
                 // while the MMA of layer 2 runs: copy the saved activation (layer-1 output, still
                 // intact in buf as this MMA's A operand) to global memory, row-major chunks
@@ -425,12 +453,18 @@ extern "C" int gp_mlp_fwd(const gp_mlp_fwd_args* args, int hidden, void* stream)
     }
 }
 
-extern "C" int gp_seg_fixup(const int32_t* rowptr, int32_t num_segments, int32_t hidden, const float* seg_bnd,
-                            float* seg_out, void* stream) {
+extern "C" int gp_seg_sub_rows(int32_t hidden, int32_t backward) {
+    // rows per sub-tile = 64 * hidden / (threads walking a tile): forward 256 threads, backward 512 at hidden 128
+    return (backward && hidden >= 128) ? hidden / 8 : hidden / 4;
+}
+
+extern "C" int gp_seg_fixup(const int32_t* rowptr, int32_t num_segments, int32_t hidden, int32_t sub_rows,
+                            const float* seg_bnd, float* seg_out, void* stream) {
     if (num_segments <= 0) return 0;
+    GP_REQUIRE(sub_rows > 0, "gp_seg_fixup: sub_rows must be positive");
     const int threads = 256;
     const int blocks = (int)(((size_t)num_segments * 32 + threads - 1) / threads);
-    seg_fixup_kernel<<<blocks, threads, 0, static_cast<cudaStream_t>(stream)>>>(rowptr, num_segments, hidden, hidden / 4,
+    seg_fixup_kernel<<<blocks, threads, 0, static_cast<cudaStream_t>(stream)>>>(rowptr, num_segments, hidden, sub_rows,
                                                                                  seg_bnd, seg_out);
     GP_CHECK_CUDA(cudaGetLastError());
     return 0;

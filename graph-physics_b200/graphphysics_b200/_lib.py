@@ -124,6 +124,7 @@ class MlpBwdArgs(C.Structure):
         ("seg_out", C.c_void_p),
         ("seg_bnd", C.c_void_p),
         ("partials", C.c_void_p),
+        ("prof", C.c_void_p),
     ]
 
 
@@ -140,6 +141,7 @@ class LinearBwdArgs(C.Structure):
         ("dx_in", C.c_void_p),
         ("dx_out", C.c_void_p),
         ("partials", C.c_void_p),
+        ("prof", C.c_void_p),
     ]
 
 

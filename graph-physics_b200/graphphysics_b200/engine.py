@@ -286,7 +286,7 @@ class EPDEngine:
             dX = torch.empty((N, H), dtype=torch.float32, device=dev)
             self._mlp_backward(self.dec, N, a_in=ctx["x_last"], ka=H, h2=ctx["h2d"], top=dict(delta_b=Gp), out=dX)
         dE = dE_sorted
-        bnd = torch.empty(ops.seg_bnd_size(E, H), dtype=torch.float32, device=dev)
+        bnd = torch.empty(ops.seg_bnd_size(E, H, backward=True), dtype=torch.float32, device=dev)
         gp = self.gflat.data_ptr()
         for l in reversed(range(self.L)):
             x, e, P, agg, h2e, h2n = ctx["layers"][l]
@@ -303,7 +303,7 @@ class EPDEngine:
                                out=dE_new, out_resid=dE, delta_a_out=d1, seg=(g.dst, dPd, bnd),
                                first=dict(init=P, init_off0=0, init_off1=H, idx0=g.dst, idx1=g.src, two_inits=True),
                                tag="edge_bwd")
-            ops.seg_fixup(g.rowptr_dst, H, bnd, dPd)
+            ops.seg_fixup(g.rowptr_dst, H, bnd, dPd, backward=True)
             dPs = torch.empty((N, H), dtype=torch.float32, device=dev)
             ops.segsum_gather(d1, g.perm_src, g.rowptr_src, H, dPs)
             # projection P = x . Wp^T, plus the residual path of x

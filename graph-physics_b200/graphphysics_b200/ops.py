@@ -74,8 +74,13 @@ def pack_bias(b: Optional[torch.Tensor], n_pad: int, device) -> torch.Tensor:
     return out
 
 
-def seg_bnd_size(rows: int, hidden: int) -> int:
-    sub = hidden // 4            # rows per sub-tile of the kernels' segment walk (256 threads)
+def seg_sub_rows(hidden: int, backward: bool = False) -> int:
+    """Rows per sub-tile of a kernel's segment walk (gp_seg_sub_rows)."""
+    return int(lib().gp_seg_sub_rows(C.c_int32(hidden), C.c_int32(1 if backward else 0)))
+
+
+def seg_bnd_size(rows: int, hidden: int, backward: bool = False) -> int:
+    sub = seg_sub_rows(hidden, backward)
     return ((rows + sub - 1) // sub) * 2 * hidden
 
 
@@ -146,11 +151,13 @@ def mlp_fwd(
     return out
 
 
-def seg_fixup(rowptr: torch.Tensor, hidden: int, seg_bnd: torch.Tensor, seg_out: torch.Tensor) -> None:
+def seg_fixup(rowptr: torch.Tensor, hidden: int, seg_bnd: torch.Tensor, seg_out: torch.Tensor,
+              backward: bool = False) -> None:
     assert rowptr.dtype == torch.int32
     check(
         lib().gp_seg_fixup(C.c_void_p(ptr(rowptr)), C.c_int32(rowptr.numel() - 1), C.c_int32(hidden),
-                           C.c_void_p(ptr(seg_bnd)), C.c_void_p(ptr(seg_out)), C.c_void_p(stream_ptr())),
+                           C.c_int32(seg_sub_rows(hidden, backward)), C.c_void_p(ptr(seg_bnd)), C.c_void_p(ptr(seg_out)),
+                           C.c_void_p(stream_ptr())),
         "gp_seg_fixup",
     )
     _launched()
@@ -207,6 +214,7 @@ def mlp_bwd_stage(
     seg_out: Optional[torch.Tensor] = None,
     seg_bnd: Optional[torch.Tensor] = None,
     tag: Optional[str] = None,
+    prof: Optional[torch.Tensor] = None,
 ) -> int:
     """gp_mlp_bwd_stage (include/gp_b200.h).  NORM mode when `gy` is given, GIVEN mode when
     `delta_b` is given.  Returns the number of partial blocks written to `partials`."""
@@ -256,6 +264,7 @@ def mlp_bwd_stage(
     stride = bwd_layout(hidden, ka, args.nb)[5]
     assert partials.dtype == torch.float32 and partials.numel() >= stride * min(sm_count(), (rows + 127) // 128)
     args.partials = ptr(partials)
+    args.prof = ptr(prof)
     grid = C.c_int32(0)
     ev = PROFILE.begin(tag)
     check(lib().gp_mlp_bwd_stage(C.byref(args), C.c_int(hidden), C.byref(grid), C.c_void_p(stream_ptr())),

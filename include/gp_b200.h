@@ -72,16 +72,19 @@ typedef struct gp_mlp_fwd_args {
     gp_bf16* save_h2;      /* optional [rows][hidden]: output of layer index 1 (after relu) */
     const int32_t* seg_id; /* optional [rows], non-decreasing */
     float* seg_out;        /* [num_segments][hidden] */
-    float* seg_bnd;        /* [ceil(rows/sub)][2][hidden], sub = hidden/4 rows */
+    float* seg_bnd;        /* [ceil(rows/sub)][2][hidden], sub = gp_seg_sub_rows(hidden, 0) */
     unsigned long long* prof; /* optional [16] device counters: SM cycles per phase, summed over tiles (tuning aid) */
 } gp_mlp_fwd_args;
 
 int gp_mlp_fwd(const gp_mlp_fwd_args* args, int hidden, void* stream);
 
-/* Combine the boundary pieces left by gp_mlp_fwd's segment sum: for every segment n with rows
- * [rowptr[n], rowptr[n+1]) that is empty or spans more than one sub-tile, write seg_out[n]. */
-int gp_seg_fixup(const int32_t* rowptr, int32_t num_segments, int32_t hidden, const float* seg_bnd, float* seg_out,
-                 void* stream);
+/* Combine the boundary pieces left by a kernel's segment sum: for every segment n with rows
+ * [rowptr[n], rowptr[n+1]) that is empty or spans more than one sub-tile, write seg_out[n].
+ * sub_rows = rows per sub-tile of the producing kernel: hidden/4 for gp_mlp_fwd, hidden/4 or hidden/8
+ * (hidden = 128) for gp_mlp_bwd_stage -- gp_seg_sub_rows() tells. */
+int gp_seg_sub_rows(int32_t hidden, int32_t backward);
+int gp_seg_fixup(const int32_t* rowptr, int32_t num_segments, int32_t hidden, int32_t sub_rows, const float* seg_bnd,
+                 float* seg_out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Two-layer backward stage of the same MLP (tcgen05): recomputes layer `a` from its streamed
@@ -137,6 +140,7 @@ typedef struct gp_mlp_bwd_args {
     float* seg_out;
     float* seg_bnd;
     float* partials; /* [grid][stride] floats, grid <= SM count */
+    unsigned long long* prof; /* optional [16] device counters: SM cycles per phase (tuning aid) */
 } gp_mlp_bwd_args;
 
 /* out6 = {off_dWb, off_dWa, off_dbb, off_dba, off_dscale, stride} in floats.

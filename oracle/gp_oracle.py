@@ -151,7 +151,8 @@ def graph_net_block(x, e, src, dst, sd, prefix: str, mode: Optional[str] = None)
         # the receiver/sender segment sums and dW1e alike.
         pre = F.linear(rnd(e, mode), rnd(w1e, mode)) + pd[dst] + ps[src]
         e_upd = mlp(None, sd, f"{prefix}.edge_block", mode=mode, first_pre=pre)
-        agg = torch.zeros_like(x).index_add_(0, dst, rnd(e_upd, mode))   # kernel sums bf16(e_upd) in fp32
+        # kernel sums bf16(e_upd) in fp32; in the backward the gathered d agg rows are staged as bf16
+        agg = torch.zeros_like(x).index_add_(0, dst, grad_rnd(rnd(e_upd, mode), mode))
         # node MLP, first layer split the same way: W1 = [W1x | W1a] over [x, agg]
         wn = sd[f"{prefix}.node_block.0.weight"]
         q = rnd(linear(x, wn[:, :H], None, mode), mode)

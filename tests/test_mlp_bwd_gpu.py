@@ -92,7 +92,7 @@ def test_edge_block_backward(hidden):
            + P64[dst, :hidden] + P64[src, hidden:2 * hidden])
     upd = O.mlp(None, sd64, "m", mode="bf16", first_pre=pre)
     e_new = O.rnd(e64 + O.rnd(upd, "bf16"), "bf16")
-    agg = torch.zeros(N, hidden, dtype=torch.float64).index_add_(0, dst, O.rnd(upd, "bf16"))
+    agg = torch.zeros(N, hidden, dtype=torch.float64).index_add_(0, dst, O.grad_rnd(O.rnd(upd, "bf16"), "bf16"))
     ((e_new * G1.double()).sum() + (agg * G2.double()).sum()).backward()
 
     # ---- kernels
@@ -118,7 +118,7 @@ def test_edge_block_backward(hidden):
     dE = torch.empty((E, hidden), dtype=torch.bfloat16, device=dev)
     delta1 = torch.empty((E, hidden), dtype=torch.bfloat16, device=dev)
     dPd = torch.full((N, hidden), float("nan"), device=dev)
-    bnd2 = torch.zeros((ops.seg_bnd_size(E, hidden),), device=dev)
+    bnd2 = torch.zeros((ops.seg_bnd_size(E, hidden, backward=True),), device=dev)
     gridA = ops.mlp_bwd_stage(E, hidden, a=e_d, ka=hidden, wa=ws[0], ba=bs[0], wb=ws[1], bb=bs[1], partials=part,
                               init=P_d, init_off0=0, init_off1=hidden, idx0=dst32, idx1=src32, two_inits=True,
                               delta_b=delta2, out=dE, out_resid=G1_d, delta_a_out=delta1, seg_id=dst32, seg_out=dPd,
@@ -126,7 +126,7 @@ def test_edge_block_backward(hidden):
     dW1, dW0, db1, db0, _ = _collect(ops, part, gridA, hidden, hidden, hidden, dev)
     rowptr = torch.zeros(N + 1, dtype=torch.int32)
     rowptr[1:] = torch.cumsum(torch.bincount(dst, minlength=N), 0)
-    ops.seg_fixup(rowptr.to(dev), hidden, bnd2, dPd)
+    ops.seg_fixup(rowptr.to(dev), hidden, bnd2, dPd, backward=True)
     torch.cuda.synchronize()
 
     rep, ok = [], True
