@@ -139,7 +139,11 @@ __global__ void __launch_bounds__(256, 1) linear_bwd_kernel(const gp_linear_bwd_
 template <int H>
 int launch(const gp_linear_bwd_args& a, int32_t* grid_out, cudaStream_t st) {
     const size_t smem = 1024 + (size_t)((H + 63) / 64) * a.n_src * H * 128 + 2 * kBufBytes;
-    GP_CHECK_CUDA(cudaFuncSetAttribute(linear_bwd_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static int smem_set = 0;      // raised once per instantiation (and never inside a stream capture twice)
+    if ((int)smem > smem_set) {
+        GP_CHECK_CUDA(cudaFuncSetAttribute(linear_bwd_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_set = (int)smem;
+    }
     const int n_tiles = (a.rows + 127) / 128;
     const int grid = n_tiles < gp::sm_count() ? n_tiles : gp::sm_count();
     linear_bwd_kernel<H><<<grid, 256, smem, st>>>(a);

@@ -629,7 +629,11 @@ int launch_bwd(const gp_mlp_bwd_args& a, int32_t* grid_out, cudaStream_t st) {
     smem += (size_t)(a.mode == 1 ? 4 : 3) * kBufBytes + 128 * 128 + 3 * 128 * 4 + 2 * BwdCfg<H>::NPART * 128 * 4 + 144 * 4;
     GP_REQUIRE((int)smem <= gp::max_smem_optin(), "gp_mlp_bwd_stage: needs %zu B of shared memory (> %d)", smem,
                gp::max_smem_optin());
-    GP_CHECK_CUDA(cudaFuncSetAttribute(mlp_bwd_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static int smem_set = 0;      // raised once per instantiation (and never inside a stream capture twice)
+    if ((int)smem > smem_set) {
+        GP_CHECK_CUDA(cudaFuncSetAttribute(mlp_bwd_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_set = (int)smem;
+    }
     const int n_tiles = (a.rows + 127) / 128;
     int grid = n_tiles < gp::sm_count() ? n_tiles : gp::sm_count();
     mlp_bwd_kernel<H><<<grid, BwdCfg<H>::NT, smem, st>>>(a);

@@ -411,7 +411,11 @@ int launch_fwd(const gp_mlp_fwd_args& a, cudaStream_t st) {
     smem += (size_t)NG * kBufBytes + 4 * kBiasStride * 4 + 128 * 4 + NG * 256 * 4 + NG * 144 * 4;
     GP_REQUIRE((int)smem <= gp::max_smem_optin(), "gp_mlp_fwd: needs %zu B of shared memory (> %d)", smem,
                gp::max_smem_optin());
-    GP_CHECK_CUDA(cudaFuncSetAttribute(mlp_fwd_kernel<H, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static int smem_set = 0;      // raised once per instantiation (and never inside a stream capture twice)
+    if ((int)smem > smem_set) {
+        GP_CHECK_CUDA(cudaFuncSetAttribute(mlp_fwd_kernel<H, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_set = (int)smem;
+    }
     const int n_tiles = (a.rows + 127) / 128;
     int grid = (n_tiles + NG - 1) / NG;
     if (grid > gp::sm_count()) grid = gp::sm_count();

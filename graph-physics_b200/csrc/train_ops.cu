@@ -102,6 +102,33 @@ __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
     }
 }
 
+// Same update with the step-dependent scalars taken from device memory, so the whole training step
+// can be captured once in a CUDA graph and replayed: state[0] = number of optimizer steps done so
+// far.  The learning rate is base_lr * CosineWarmupScheduler.get_lr_factor(last_epoch = state[0])
+// (graphphysics/utils/scheduler.py:51-67).
+__global__ void adamw_sched_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                   float* __restrict__ v, size_t n, const int* __restrict__ state, float base_lr,
+                                   int warmup, int max_iters, float min_factor, float b1, float b2, float eps, float wd,
+                                   float max_norm, const float* __restrict__ sqnorm) {
+    const int t = state[0] + 1;
+    float f = 0.5f * (1.f + cospif((float)t / (float)max_iters));
+    if (t <= warmup) f *= (float)t / (float)warmup;
+    const float lr = base_lr * fmaxf(f, min_factor);
+    const float bc1 = 1.f - powf(b1, (float)t), bc2 = 1.f - powf(b2, (float)t);
+    float coef = 1.f;
+    if (max_norm > 0.f) coef = fminf(max_norm / (sqrtf(sqnorm[0]) + 1e-6f), 1.f);
+    const float step = lr / bc1, rs = rsqrtf(bc2);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float gi = g[i] * coef;
+        float pi = p[i] * (1.f - lr * wd);
+        const float mi = b1 * m[i] + (1.f - b1) * gi;
+        const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+        pi -= step * mi / (sqrtf(vi) * rs + eps);
+        p[i] = pi; m[i] = mi; v[i] = vi;
+    }
+}
+__global__ void advance_step_kernel(int* state) { state[0] += 1; }
+
 // fp32 master weights -> packed bf16 operands.  One table entry per matrix; blockIdx.y = entry.
 __global__ void pack_weights_kernel(const float* __restrict__ params, __nv_bfloat16* __restrict__ packed,
                                     const gp_pack_entry* __restrict__ table) {
@@ -153,6 +180,22 @@ extern "C" int gp_adamw(float* params, const float* grads, float* exp_avg, float
     adamw_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(params, grads, exp_avg, exp_avg_sq, (size_t)n, lr,
                                                                          beta1, beta2, eps, weight_decay, bc1, bc2,
                                                                          max_norm, sqnorm);
+    GP_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int gp_adamw_sched(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                              int32_t* state, float base_lr, int32_t warmup, int32_t max_iters, float min_lr_factor,
+                              float beta1, float beta2, float eps, float weight_decay, float max_norm,
+                              const float* sqnorm, void* stream) {
+    GP_REQUIRE(params && grads && exp_avg && exp_avg_sq && state && n > 0 && max_iters > 0, "gp_adamw_sched: bad arguments");
+    GP_REQUIRE(max_norm <= 0.f || sqnorm != nullptr, "gp_adamw_sched: clipping needs the squared gradient norm");
+    int blocks = (int)((n + 255) / 256);
+    if (blocks > gp::sm_count() * 8) blocks = gp::sm_count() * 8;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    adamw_sched_kernel<<<blocks, 256, 0, st>>>(params, grads, exp_avg, exp_avg_sq, (size_t)n, state, base_lr, warmup,
+                                               max_iters, min_lr_factor, beta1, beta2, eps, weight_decay, max_norm, sqnorm);
+    advance_step_kernel<<<1, 1, 0, st>>>(state);
     GP_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

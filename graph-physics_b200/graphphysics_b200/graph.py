@@ -61,19 +61,20 @@ class GraphCSR:
         self.perm_dst = perm.int()
         self.src, self.dst = src_s.int(), dst_s.int()
         self.rowptr_dst = self._rowptr(dst_s, num_nodes)
-        self.perm_src = torch.sort(src_s, stable=True).indices.int()
-        self.rowptr_src = self._rowptr(src_s, num_nodes)
+        src_sorted, perm_src = torch.sort(src_s, stable=True)
+        self.perm_src = perm_src.int()
+        self.rowptr_src = self._rowptr(src_sorted, num_nodes)
         self._inv_perm: Optional[torch.Tensor] = None
         # attention view: rows = senders (edge_index[0]); the row-sorted entry p is entry perm_src[p] of
         # the receiver-sorted list, so its column is dst[perm_src[p]]
         self.att_col = self.dst[self.perm_src.long()].contiguous()
 
     @staticmethod
-    def _rowptr(ids: torch.Tensor, n: int) -> torch.Tensor:
-        rp = torch.zeros(n + 1, dtype=torch.int32, device=ids.device)
-        if ids.numel():
-            rp[1:] = torch.cumsum(torch.bincount(ids, minlength=n), 0).int()
-        return rp
+    def _rowptr(sorted_ids: torch.Tensor, n: int) -> torch.Tensor:
+        """rowptr[k] = number of ids < k, for ids already sorted.  searchsorted needs no host
+        round trip (bincount does), so the layout can be rebuilt inside a CUDA graph."""
+        bounds = torch.arange(n + 1, device=sorted_ids.device, dtype=sorted_ids.dtype)
+        return torch.searchsorted(sorted_ids, bounds, right=False).int()
 
     @property
     def inv_perm_dst64(self) -> torch.Tensor:
@@ -88,9 +89,26 @@ class GraphCSR:
 _CACHE: dict = {}
 
 
+_CACHE_ENABLED = [True]
+
+
+class no_csr_cache:
+    """Inside this context every get_csr call re-sorts (used while a CUDA graph is being captured, so
+    the replay recomputes the layout from the current contents of the static input buffers)."""
+
+    def __enter__(self):
+        self.old = _CACHE_ENABLED[0]
+        _CACHE_ENABLED[0] = False
+
+    def __exit__(self, *a):
+        _CACHE_ENABLED[0] = self.old
+
+
 def get_csr(edge_index: torch.Tensor, num_nodes: int) -> GraphCSR:
     """GraphCSR of `edge_index`, cached on (storage pointer, version, shape) so a static topology
     (roll-outs, repeated batches) is sorted once."""
+    if not _CACHE_ENABLED[0]:
+        return GraphCSR(edge_index, num_nodes)
     key = (edge_index.data_ptr(), edge_index._version, tuple(edge_index.shape), int(num_nodes), str(edge_index.device))
     g = _CACHE.get(key)
     if g is None:

@@ -359,6 +359,16 @@ def adamw(params, grads, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_deca
     _launched()
 
 
+def adamw_sched(params, grads, exp_avg, exp_avg_sq, state, base_lr, warmup, max_iters, min_lr_factor, beta1, beta2, eps,
+                weight_decay, max_norm, sqnorm_t) -> None:
+    check(lib().gp_adamw_sched(C.c_void_p(ptr(params)), C.c_void_p(ptr(grads)), C.c_void_p(ptr(exp_avg)),
+                               C.c_void_p(ptr(exp_avg_sq)), C.c_int64(params.numel()), C.c_void_p(ptr(state)),
+                               C.c_float(base_lr), C.c_int32(warmup), C.c_int32(max_iters), C.c_float(min_lr_factor),
+                               C.c_float(beta1), C.c_float(beta2), C.c_float(eps), C.c_float(weight_decay),
+                               C.c_float(max_norm), C.c_void_p(ptr(sqnorm_t)), C.c_void_p(stream_ptr())), "gp_adamw_sched")
+    _launched(2)
+
+
 def pack_weights(params: torch.Tensor, packed: torch.Tensor, table_dev: torch.Tensor, n_entries: int) -> None:
     check(lib().gp_pack_weights(C.c_void_p(ptr(params)), C.c_void_p(ptr(packed)), C.c_void_p(ptr(table_dev)),
                                 C.c_int32(n_entries), C.c_void_p(stream_ptr())), "gp_pack_weights")

@@ -54,6 +54,9 @@ class Trainer:
         self.exp_avg = torch.zeros_like(eng.flat.data)
         self.exp_avg_sq = torch.zeros_like(eng.flat.data)
         self._loss = torch.zeros(1, dtype=torch.float32, device=device)
+        self._opt_state = torch.zeros(1, dtype=torch.int32, device=device)     # optimizer steps done (device copy)
+        self._graphs = {}            # input shapes -> (CUDAGraph, static batch)
+        self.use_cuda_graph = False
         if self.pg is not None:
             from ..dist.ddp import broadcast_
             broadcast_(eng.flat.data, self.pg)
@@ -67,9 +70,43 @@ class Trainer:
         """LR used by the next optimizer step (CosineWarmupScheduler, scheduler.py:51-67)."""
         return self.learning_rate * lr_factor(self.step_index - 1, self.warmup, self.num_steps)
 
+    def enable_cuda_graph(self, enabled: bool = True) -> None:
+        """Capture the whole step (CSR build, forward, loss, backward, clip, AdamW, schedule) once per
+        input shape and replay it afterwards.  Valid while the batch SHAPES repeat (fixed-size meshes,
+        the synthetic benchmark); contents -- including the topology -- may change freely.  Not combined
+        with data parallelism in this round."""
+        if enabled and self.pg is not None:
+            raise NotImplementedError("CUDA-graph replay of the step is single-GPU in this round")
+        self.use_cuda_graph = bool(enabled)
+
     def training_step(self, batch) -> torch.Tensor:
         """lightning_module.py:270-342 + the optimizer step Lightning does afterwards.
         Returns the loss as a device scalar (no host sync here)."""
+        if not self.use_cuda_graph:
+            return self._training_step_eager(batch)
+        from ..graph import Data, no_csr_cache
+        fields = [k for k in ("x", "y", "pos", "edge_index", "edge_attr") if getattr(batch, k) is not None]
+        key = tuple((k, tuple(getattr(batch, k).shape), getattr(batch, k).dtype) for k in fields)
+        entry = self._graphs.get(key)
+        if entry is None:
+            static = Data(**{k: torch.empty_like(getattr(batch, k), device=self.device) for k in fields})
+            for k in fields:
+                getattr(static, k).copy_(getattr(batch, k), non_blocking=True)
+            self._training_step_eager(static)          # first step of this shape runs eagerly (allocations, smem attributes)
+            graph = torch.cuda.CUDAGraph()
+            with no_csr_cache(), torch.cuda.graph(graph):
+                self._training_step_eager(static)
+            self.step_index -= 1                        # the capture pass enqueued nothing; undo its host-side count
+            self._graphs[key] = (graph, static, fields)
+            return self._loss[0]
+        graph, static, fields = entry
+        for k in fields:
+            getattr(static, k).copy_(getattr(batch, k), non_blocking=True)
+        graph.replay()
+        self.step_index += 1
+        return self._loss[0]
+
+    def _training_step_eager(self, batch) -> torch.Tensor:
         sim, eng = self.model, self.engine
         sim.train()
         if not batch.x.is_cuda:
@@ -103,10 +140,10 @@ class Trainer:
     def optimizer_step(self):
         eng = self.engine
         self.step_index += 1
-        lr = self.current_lr()
         sq = eng.grad_sqnorm() if self.clip and self.clip > 0 else None
-        ops.adamw(eng.flat.data, eng.gflat, self.exp_avg, self.exp_avg_sq, lr, self.betas[0], self.betas[1], self.eps,
-                  self.wd, self.step_index, float(self.clip or 0.0), sq)
+        ops.adamw_sched(eng.flat.data, eng.gflat, self.exp_avg, self.exp_avg_sq, self._opt_state, self.learning_rate,
+                        self.warmup, self.num_steps, 1e-3, self.betas[0], self.betas[1], self.eps, self.wd,
+                        float(self.clip or 0.0), sq)
 
     # ------------------------------------------------------------------ roll-out
     @torch.no_grad()

@@ -195,6 +195,12 @@ int gp_sqnorm(const float* g, int64_t n, float* workspace, float* out, void* str
 /* clip-by-global-norm (max_norm <= 0 disables; sqnorm = device scalar from gp_sqnorm) + AdamW. */
 int gp_adamw(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
              float beta2, float eps, float weight_decay, int32_t step, float max_norm, const float* sqnorm, void* stream);
+/* Same, with the step counter on the device (state[0] = optimizer steps done; incremented here) and the
+ * cosine-warm-up factor of graphphysics/utils/scheduler.py:51-67 computed on the device: no host value
+ * changes between steps, so a whole training step can be replayed as a CUDA graph. */
+int gp_adamw_sched(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, int32_t* state,
+                   float base_lr, int32_t warmup, int32_t max_iters, float min_lr_factor, float beta1, float beta2,
+                   float eps, float weight_decay, float max_norm, const float* sqnorm, void* stream);
 /* fp32 master matrices -> packed bf16 operands, one launch for the whole model. */
 typedef struct gp_pack_entry {
     int64_t src_off; /* floats into params */
