@@ -1,5 +1,6 @@
 // common.cuh -- host-side error plumbing and small device helpers shared by the kernels.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -9,6 +10,13 @@ namespace gp {
 void set_error(const char* fmt, ...);
 int sm_count();
 int max_smem_optin();
+
+// TMA descriptor of a row-major bf16 matrix [rows x cols] with leading dimension `ld` (elements):
+// box = 64 columns x 128 rows, SWIZZLE_128B, i.e. one instruction moves one 64-column block of an
+// SW128 row tile; out-of-range rows / columns read as zero and are clipped on store.  Returns
+// false (map untouched) when the tensor cannot be described (alignment) -- callers then use
+// their per-thread copy path.
+bool tma_map_2d(CUtensorMap* map, const void* base, long long rows, int cols, long long ld);
 
 #define GP_CHECK_CUDA(expr)                                                                    \
     do {                                                                                       \

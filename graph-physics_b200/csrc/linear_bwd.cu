@@ -19,6 +19,7 @@ __global__ void __launch_bounds__(256, 1) linear_bwd_kernel(const gp_linear_bwd_
     __shared__ uint32_t tmem_slot;
 
     const int tid = threadIdx.x, row = tid & 127, half = tid >> 7;
+    const int warp = warp_uniform(tid >> 5);
     const int S = p.n_src;
     const int wrows = S * H;
     uint32_t off = 0;
@@ -74,7 +75,7 @@ __global__ void __launch_bounds__(256, 1) linear_bwd_kernel(const gp_linear_bwd_
             fence_async_smem();
             tc_fence_before();
             __syncthreads();
-            if (tid == 0) {
+            if (warp == 0 && elect_one()) {
                 tc_fence_after();
                 const uint32_t id_w = idesc_bf16(H, true, true), id_d = idesc_bf16(H, false, true);
                 for (int ks = 0; ks < 8; ++ks)
@@ -168,10 +169,10 @@ __global__ void segsum_gather_kernel(const gp_bf16* __restrict__ src, int ld, co
         const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(src) + (size_t)r * ld + lane * VPT;
         if constexpr (VPT == 4) {
             const uint2 q = __ldg(reinterpret_cast<const uint2*>(rp));
-            acc[0] += bf16_lo(q.x); acc[1] += bf16_hi(q.x); acc[2] += bf16_lo(q.y); acc[3] += bf16_hi(q.y);
+            acc[0] = add_bf16_lo(q.x, acc[0]); acc[1] = add_bf16_hi(q.x, acc[1]); acc[2] = add_bf16_lo(q.y, acc[2]); acc[3] = add_bf16_hi(q.y, acc[3]);
         } else if constexpr (VPT == 2) {
             const uint32_t q = __ldg(reinterpret_cast<const uint32_t*>(rp));
-            acc[0] += bf16_lo(q); acc[1] += bf16_hi(q);
+            acc[0] = add_bf16_lo(q, acc[0]); acc[1] = add_bf16_hi(q, acc[1]);
         } else {
             acc[0] += __bfloat162float(rp[0]);
         }

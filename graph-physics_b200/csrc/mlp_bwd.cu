@@ -14,6 +14,9 @@
 // Thread (row = tid & 127, part = tid >> 7) owns row `row` of the tile and one part (1/2 or 1/4) of its
 // columns, so ReLU masks, the RMSNorm backward and residuals are thread-local apart from one
 // two-float exchange between the halves.
+#include <stdlib.h>
+#include <string.h>
+
 #include "common.cuh"
 #include "tile_util.cuh"
 
@@ -36,6 +39,15 @@ __host__ __device__ inline BwdLayout bwd_layout(int H, int ka, int nb) {
     return L;
 }
 
+// Tile-shaped global tensors that meet the TMA alignment rules are moved by the copy engine (one
+// elected thread, 16 KB per instruction, straight into / out of the SW128 layout); the flags say
+// which descriptors are valid, everything else falls back to per-thread 16-byte copies.
+struct BwdMaps {
+    CUtensorMap ain, db, gy, resid, da_out, out;
+    uint32_t use;
+};
+enum : uint32_t { kMapAin = 1, kMapDb = 2, kMapGy = 4, kMapResid = 8, kMapDaOut = 16, kMapOut = 32 };
+
 // Threads per CTA: 128 rows x NPART column parts (4 parts = 16 warps at H = 128, where the epilogues are
 // latency-bound and need the extra warps; 2 parts for narrower layers).
 template <int H>
@@ -45,16 +57,20 @@ struct BwdCfg {
 };
 
 template <int H>
-__global__ void __launch_bounds__(BwdCfg<H>::NT, 1) mlp_bwd_kernel(const gp_mlp_bwd_args p) {
+__global__ void __launch_bounds__(BwdCfg<H>::NT, 1) mlp_bwd_kernel(const gp_mlp_bwd_args p,
+                                                                     const __grid_constant__ BwdMaps maps) {
     constexpr int NPART = BwdCfg<H>::NPART;
     constexpr int NT = BwdCfg<H>::NT;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = GP_SMEM_ALIGNED(smem_raw);
-    __shared__ uint64_t mma_bar;
+    __shared__ uint64_t mma_bar, tma_bar;
     __shared__ uint32_t tmem_slot;
 
     const int tid = threadIdx.x;
     const int row = tid & 127, part = tid >> 7;
+    const bool t_ain = maps.use & kMapAin, t_db = maps.use & kMapDb, t_gy = maps.use & kMapGy;
+    const bool t_res = maps.use & kMapResid, t_da = maps.use & kMapDaOut, t_out = maps.use & kMapOut;
+    const int warp = warp_uniform(tid >> 5);
     const int ka = p.ka, nb = p.nb;
     const bool norm = p.mode == 1;
 
@@ -65,7 +81,7 @@ __global__ void __launch_bounds__(BwdCfg<H>::NT, 1) mlp_bwd_kernel(const gp_mlp_
     uint8_t* ain = smem + off;   off += kBufBytes;
     uint8_t* ha = smem + off;    off += kBufBytes;
     uint8_t* db = smem + off;    off += kBufBytes;
-    uint8_t* qb = smem + off;    off += norm ? kBufBytes : 0;
+    uint8_t* qb = smem + off;    off += (norm || t_res) ? kBufBytes : 0;      // NORM: du / q tile; else residual tile
     uint8_t* ones = smem + off;  off += 128 * 128;
     float* s_ba = reinterpret_cast<float*>(smem + off);  off += 128 * 4;
     float* s_bb = reinterpret_cast<float*>(smem + off);  off += 128 * 4;
@@ -90,6 +106,7 @@ __global__ void __launch_bounds__(BwdCfg<H>::NT, 1) mlp_bwd_kernel(const gp_mlp_
     }
     if (tid == 0) {
         mbar_init(&mma_bar, 1);
+        mbar_init(&tma_bar, 1);
         fence_mbar_init();
     }
     if (tid < 32) tmem_alloc(&tmem_slot, 512);
@@ -105,7 +122,7 @@ __global__ void __launch_bounds__(BwdCfg<H>::NT, 1) mlp_bwd_kernel(const gp_mlp_
     const uint32_t wa_s = smem_u32(wa_t), wb_s = smem_u32(wb_t), ones_s = smem_u32(ones);
     const uint32_t lbo_h = (H >= 128) ? 16384u : 0u;      // M=128 MN-major A with < 128 valid columns: alias block
     const uint32_t lbo_nb = (nb >= 128) ? 16384u : 0u;
-    uint32_t phase = 0;
+    uint32_t phase = 0, tphase = 0;
     const bool has_init = p.init != nullptr;
     const int n_tiles = (p.rows + 127) >> 7;
     constexpr int CH = H / NPART;                          // columns per thread
@@ -165,8 +182,24 @@ __global__ void __launch_bounds__(BwdCfg<H>::NT, 1) mlp_bwd_kernel(const gp_mlp_
 
         // ---- P0: stage inputs.  Every tile-shaped transfer uses row-major 16-byte chunks (8 lanes per
         //      cache line); tiles are transposed to the row-per-thread mapping through shared memory.
-        stage_rows(ain, p.a_bf16, p.a_f32, ka, p.lda, R0, p.rows, tid, NT);
-        if (!norm) {   // delta_b given: zero rows past the end so they add nothing to the weight gradients
+        const uint32_t tma_blocks = (t_ain ? (ka + 63) >> 6 : 0) + (t_db ? (nb + 63) >> 6 : 0) + (t_gy ? (H + 63) >> 6 : 0) +
+                                    (t_res ? (ka + 63) >> 6 : 0);
+        if (tma_blocks && warp == 0 && elect_one()) {
+            // the bulk stores of the previous tile have read their shared-memory sources (the output
+            // staging buffer is only ever refilled by this thread's own loads below)
+            tma_store_wait_read<0>();
+            mbar_arrive_expect_tx(&tma_bar, tma_blocks * 16384u);
+            if (t_ain)
+                for (int b = 0; b < (ka + 63) >> 6; ++b) tma_load_2d(ain_s + b * 16384, &maps.ain, b * 64, R0, &tma_bar);
+            if (t_db)    // rows past the end arrive as zeros, so they add nothing to the weight gradients
+                for (int b = 0; b < (nb + 63) >> 6; ++b) tma_load_2d(db_s + b * 16384, &maps.db, b * 64, R0, &tma_bar);
+            if (t_gy)
+                for (int b = 0; b < (H + 63) >> 6; ++b) tma_load_2d(qb_s + b * 16384, &maps.gy, b * 64, R0, &tma_bar);
+            if (t_res)
+                for (int b = 0; b < (ka + 63) >> 6; ++b) tma_load_2d(qb_s + b * 16384, &maps.resid, b * 64, R0, &tma_bar);
+        }
+        if (!t_ain) stage_rows(ain, p.a_bf16, p.a_f32, ka, p.lda, R0, p.rows, tid, NT);
+        if (!norm && !t_db) {   // delta_b given: zero rows past the end so they add nothing to the weight gradients
             const int kc = nb >> 3;
             for (int i = tid; i < 128 * kc; i += NT) {
                 const int r = i / kc, ch = i - r * kc;
@@ -176,7 +209,7 @@ __global__ void __launch_bounds__(BwdCfg<H>::NT, 1) mlp_bwd_kernel(const gp_mlp_
                     *reinterpret_cast<uint4*>(db + sw128_off(128, r, ch * 8)) = make_uint4(0, 0, 0, 0);
             }
         }
-        if (du_smem) {
+        if (du_smem && !t_gy) {
 #pragma unroll
             for (int j = 0; j < CPT; ++j) {
                 const int i = tid + j * NT;
@@ -230,28 +263,32 @@ __global__ void __launch_bounds__(BwdCfg<H>::NT, 1) mlp_bwd_kernel(const gp_mlp_
         }
         tick(0);      // P0 issue
         cp_async_wait<0>();
+        if (tma_blocks) {
+            mbar_wait(&tma_bar, tphase);
+            tphase ^= 1;
+        }
         __syncthreads();
         tick(1);      // P0 wait
-        if (has_init) {
+        // accumulator pre-load: bias ba (+ the gathered pre-activation rows), so E1 adds nothing
 #pragma unroll
-            for (int c = 0; c < CH; c += 16) {
-                float f[16];
-                unpack8(*reinterpret_cast<const uint4*>(ha + sw128_off(128, row, cb + c)), f);
-                unpack8(*reinterpret_cast<const uint4*>(ha + sw128_off(128, row, cb + c + 8)), f + 8);
+        for (int c = 0; c < CH; c += 16) {
+            float f[16];
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(f + j) = *reinterpret_cast<const float4*>(s_ba + cb + c + j);
+            if (has_init) {
+                acc8(*reinterpret_cast<const uint4*>(ha + sw128_off(128, row, cb + c)), f);
+                acc8(*reinterpret_cast<const uint4*>(ha + sw128_off(128, row, cb + c + 8)), f + 8);
                 if (stage1) {
-                    float h[16];
-                    unpack8(dq[c / 8], h);
-                    unpack8(dq[c / 8 + 1], h + 8);
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) f[j] += h[j];
+                    acc8(dq[c / 8], f);
+                    acc8(dq[c / 8 + 1], f + 8);
                 }
-                uint32_t v[16];
-#pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(f[j]);
-                tmem_st16(tlane + kColAcc + cb + c, v);
             }
-            tmem_st_wait();
+            uint32_t v[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(f[j]);
+            tmem_st16(tlane + kColAcc + cb + c, v);
         }
+        tmem_st_wait();
         if (p.seg_id && tid < 128) {
             sseg[4 + row] = sid_me;
             if (row == 0) {
@@ -263,12 +300,11 @@ __global__ void __launch_bounds__(BwdCfg<H>::NT, 1) mlp_bwd_kernel(const gp_mlp_
         tick(2);      // gather combine + publish
 
         // ---- P1: recompute h_a = relu(a_in . Wa^T + init + ba)
-        if (tid == 0) {
+        if (warp == 0 && elect_one()) {
             tc_fence_after();
             const uint32_t id = idesc_bf16(H, false, false);
             for (int ks = 0; ks < (ka >> 4); ++ks)
-                mma_ss(tmem + kColAcc, desc_kmajor(ain_s, 128, ks), desc_kmajor(wa_s, H, ks), id,
-                       (ks > 0 || has_init) ? 1u : 0u);
+                mma_ss(tmem + kColAcc, desc_kmajor(ain_s, 128, ks), desc_kmajor(wa_s, H, ks), id, 1u);
             mma_commit(&mma_bar);
         }
         if (tile + (int)gridDim.x < n_tiles) load_idx(tile + gridDim.x);
@@ -279,24 +315,33 @@ __global__ void __launch_bounds__(BwdCfg<H>::NT, 1) mlp_bwd_kernel(const gp_mlp_
 #pragma unroll
             for (int c = 0; c < CH; c += 16) tmem_ld16(tlane + kColAcc + cb + c, *reinterpret_cast<uint32_t(*)[16]>(&v[c]));
             tmem_ld_wait();
+            if (norm) {      // P2 accumulates onto bb
 #pragma unroll
-            for (int c = 0; c < CH; c += 8) {
-                float f[8];
+                for (int c = 0; c < CH; c += 16) {
+                    uint32_t b16[16];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) f[j] = fmaxf(__uint_as_float(v[c + j]) + s_ba[cb + c + j], 0.f);
-                *reinterpret_cast<uint4*>(ha + sw128_off(128, row, cb + c)) = pack8(f);
+                    for (int j = 0; j < 16; j += 4) {
+                        const uint4 q = *reinterpret_cast<const uint4*>(s_bb + cb + c + j);
+                        b16[j] = q.x; b16[j + 1] = q.y; b16[j + 2] = q.z; b16[j + 3] = q.w;
+                    }
+                    tmem_st16(tlane + kColAcc + cb + c, b16);
+                }
             }
+#pragma unroll
+            for (int c = 0; c < CH; c += 8)
+                *reinterpret_cast<uint4*>(ha + sw128_off(128, row, cb + c)) = pack8_relu(reinterpret_cast<const float*>(&v[c]));
+            tmem_st_wait();
         }
         publish();
         tick(4);      // E1
 
         // ---- P2 (NORM): m = h_a . Wb^T + bb ; delta_b = dRMSNorm(m) . du ; q = du * m/(rms+eps)
         if (norm) {
-            if (tid == 0) {
+            if (warp == 0 && elect_one()) {
                 tc_fence_after();
                 const uint32_t id = idesc_bf16(H, false, false);
                 for (int ks = 0; ks < (H >> 4); ++ks)
-                    mma_ss(tmem + kColAcc, desc_kmajor(ha_s, 128, ks), desc_kmajor(wb_s, nb, ks), id, ks > 0 ? 1u : 0u);
+                    mma_ss(tmem + kColAcc, desc_kmajor(ha_s, 128, ks), desc_kmajor(wb_s, nb, ks), id, 1u);
                 mma_commit(&mma_bar);
             }
             wait_mma();
@@ -305,12 +350,7 @@ __global__ void __launch_bounds__(BwdCfg<H>::NT, 1) mlp_bwd_kernel(const gp_mlp_
             auto load_du = [&](int c0, float* du) {
                 if (du_smem) {
                     unpack8(*reinterpret_cast<const uint4*>(qb + sw128_off(128, row, c0)), du);
-                    if (p.gy_gather) {
-                        float g8[8];
-                        unpack8(*reinterpret_cast<const uint4*>(db + sw128_off(128, row, c0)), g8);
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) du[j] += g8[j];
-                    }
+                    if (p.gy_gather) acc8(*reinterpret_cast<const uint4*>(db + sw128_off(128, row, c0)), du);
                 } else {
                     if (p.gy_f32) {
                         const float4* gp_ = reinterpret_cast<const float4*>(p.gy_f32 + (size_t)crow * p.ld_gy + c0);
@@ -341,8 +381,7 @@ __global__ void __launch_bounds__(BwdCfg<H>::NT, 1) mlp_bwd_kernel(const gp_mlp_
                 load_du(cb + c, du);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    const float m = __uint_as_float(v[c + j]) + s_bb[cb + c + j];
-                    v[c + j] = __float_as_uint(m);
+                    const float m = __uint_as_float(v[c + j]);
                     ss = fmaf(m, m, ss);
                     dot = fmaf(du[j] * s_g[cb + c + j], m, dot);
                 }
@@ -358,8 +397,10 @@ __global__ void __launch_bounds__(BwdCfg<H>::NT, 1) mlp_bwd_kernel(const gp_mlp_
                 dot += s_red[(1 * NPART + q) * 128 + row];
             }
             const float rms = sqrtf(ss * (1.f / H));
-            const float s = 1.f / (rms + 1e-8f);
-            const float coef = rms > 0.f ? dot * s * s / (rms * H) : 0.f;
+            const float s1 = 1.f / (rms + 1e-8f);
+            // rows past the end get s = coef = 0, i.e. delta_b = q = 0 (their du / m are finite)
+            const float s = valid ? s1 : 0.f;
+            const float coef = (valid && rms > 0.f) ? dot * s1 * s1 / (rms * H) : 0.f;
 #pragma unroll
             for (int c = 0; c < CH; c += 8) {
                 float du[8], dm[8], q[8];
@@ -367,8 +408,8 @@ __global__ void __launch_bounds__(BwdCfg<H>::NT, 1) mlp_bwd_kernel(const gp_mlp_
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const float m = __uint_as_float(v[c + j]);
-                    dm[j] = valid ? (s_g[cb + c + j] * du[j] * s - coef * m) : 0.f;
-                    q[j] = valid ? du[j] * m * s : 0.f;
+                    dm[j] = fmaf(s_g[cb + c + j] * du[j], s, -(coef * m));
+                    q[j] = (du[j] * m) * s;
                 }
                 *reinterpret_cast<uint4*>(db + sw128_off(128, row, cb + c)) = pack8(dm);
                 *reinterpret_cast<uint4*>(qb + sw128_off(128, row, cb + c)) = pack8(q);
@@ -378,7 +419,7 @@ __global__ void __launch_bounds__(BwdCfg<H>::NT, 1) mlp_bwd_kernel(const gp_mlp_
         }
 
         // ---- P3: dWb += delta_b^T h_a ; dbb += delta_b^T 1 ; dscale += q^T 1 ; acc = delta_b . Wb
-        if (tid == 0) {
+        if (warp == 0 && elect_one()) {
             tc_fence_after();
             const uint32_t id_w = idesc_bf16(H, true, true), id_1 = idesc_bf16(16, true, true);
             for (int ks = 0; ks < 8; ++ks)
@@ -407,18 +448,14 @@ __global__ void __launch_bounds__(BwdCfg<H>::NT, 1) mlp_bwd_kernel(const gp_mlp_
 #pragma unroll
             for (int c = 0; c < CH; c += 8) {
                 uint4* hp = reinterpret_cast<uint4*>(ha + sw128_off(128, row, cb + c));
-                float hv[8], f[8];
-                unpack8(*hp, hv);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) f[j] = hv[j] > 0.f ? __uint_as_float(v[c + j]) : 0.f;
-                *hp = pack8(f);
+                *hp = mask8_pos(pack8(reinterpret_cast<const float*>(&v[c])), *hp);
             }
         }
         publish();
         tick(8);      // E3
 
         // ---- P4: dWa += delta_a^T a_in ; dba += delta_a^T 1 ; d_in = delta_a . Wa
-        if (tid == 0) {
+        if (warp == 0 && elect_one()) {
             tc_fence_after();
             const uint32_t id_w = idesc_bf16(ka, true, true), id_1 = idesc_bf16(16, true, true);
             for (int ks = 0; ks < 8; ++ks)
@@ -435,7 +472,12 @@ __global__ void __launch_bounds__(BwdCfg<H>::NT, 1) mlp_bwd_kernel(const gp_mlp_
             mma_commit(&mma_bar);
         }
         // while the tensor core runs: delta_a tile -> global (row-major chunks), and its segment sum
-        if (p.delta_a_out) {
+        if (p.delta_a_out && t_da) {
+            if (warp == 0 && elect_one()) {
+                for (int b = 0; b < (H + 63) >> 6; ++b) tma_store_2d(&maps.da_out, b * 64, R0, ha_s + b * 16384);
+                tma_store_commit();
+            }
+        } else if (p.delta_a_out) {
 #pragma unroll
             for (int j = 0; j < CPT; ++j) {
                 const int i = tid + j * NT;
@@ -450,7 +492,8 @@ __global__ void __launch_bounds__(BwdCfg<H>::NT, 1) mlp_bwd_kernel(const gp_mlp_
         wait_mma();
         tick(10);     // P4 MMA wait
         if (p.need_din) {
-            const bool via_smem = p.out_bf16 != nullptr && ka == H;     // bf16 tile output: transpose through db
+            const bool via_smem = p.out_bf16 != nullptr && ka == H;     // bf16 tile output: transpose through shared memory
+            uint8_t* ob = (t_out && norm) ? qb : db;                    // staging tile (free since P3)
             const int nsplit = (ka >= 16 * NPART) ? NPART : (ka >= 32 ? 2 : 1);   // column parts that take part
             const int kh = ka / nsplit;
             if (part < nsplit) {
@@ -461,6 +504,20 @@ __global__ void __launch_bounds__(BwdCfg<H>::NT, 1) mlp_bwd_kernel(const gp_mlp_
                     float f[16];
 #pragma unroll
                     for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+                    if (via_smem) {
+                        uint4 q0 = pack8(f), q1 = pack8(f + 8);
+                        if (p.mask_by_ain) {
+                            q0 = mask8_pos(q0, *reinterpret_cast<const uint4*>(ain + sw128_off(128, row, c0)));
+                            q1 = mask8_pos(q1, *reinterpret_cast<const uint4*>(ain + sw128_off(128, row, c0 + 8)));
+                        }
+                        if (t_out && t_res) {     // residual tile already in shared memory (bulk-loaded in P0)
+                            q0 = add8_bf16(q0, *reinterpret_cast<const uint4*>(qb + sw128_off(128, row, c0)));
+                            q1 = add8_bf16(q1, *reinterpret_cast<const uint4*>(qb + sw128_off(128, row, c0 + 8)));
+                        }
+                        *reinterpret_cast<uint4*>(ob + sw128_off(128, row, c0)) = q0;
+                        *reinterpret_cast<uint4*>(ob + sw128_off(128, row, c0 + 8)) = q1;
+                        continue;
+                    }
                     if (p.mask_by_ain) {
                         float av[16];
                         unpack8(*reinterpret_cast<const uint4*>(ain + sw128_off(128, row, c0)), av);
@@ -468,10 +525,7 @@ __global__ void __launch_bounds__(BwdCfg<H>::NT, 1) mlp_bwd_kernel(const gp_mlp_
 #pragma unroll
                         for (int j = 0; j < 16; ++j) f[j] = av[j] > 0.f ? f[j] : 0.f;
                     }
-                    if (via_smem) {
-                        *reinterpret_cast<uint4*>(db + sw128_off(128, row, c0)) = pack8(f);
-                        *reinterpret_cast<uint4*>(db + sw128_off(128, row, c0 + 8)) = pack8(f + 8);
-                    } else if (valid) {
+                    if (valid) {
                         if (p.out_resid) {
                             float rv[16];
                             const gp_bf16* rp = p.out_resid + (size_t)grow * p.ld_out + c0;
@@ -492,7 +546,15 @@ __global__ void __launch_bounds__(BwdCfg<H>::NT, 1) mlp_bwd_kernel(const gp_mlp_
                     }
                 }
             }
-            if (via_smem) {
+            if (via_smem && t_out) {
+                fence_async_smem();
+                __syncthreads();
+                if (warp == 0 && elect_one()) {
+                    for (int b = 0; b < (ka + 63) >> 6; ++b)
+                        tma_store_2d(&maps.out, b * 64, R0, smem_u32(ob) + b * 16384);
+                    tma_store_commit();
+                }
+            } else if (via_smem) {
                 uint4 rq[CPT];
                 if (p.out_resid) {       // residual chunks requested together, before the barrier
 #pragma unroll
@@ -509,23 +571,27 @@ __global__ void __launch_bounds__(BwdCfg<H>::NT, 1) mlp_bwd_kernel(const gp_mlp_
                     if (R0 + r < p.rows) {
                         uint4 q = *reinterpret_cast<const uint4*>(db + sw128_off(128, r, ch * 8));
                         if (p.out_resid) {
-                            float f[8], rv[8];
-                            unpack8(q, f);
-                            unpack8(rq[j], rv);
-#pragma unroll
-                            for (int u = 0; u < 8; ++u) f[u] += rv[u];
-                            q = pack8(f);
+                            q = add8_bf16(q, rq[j]);
                         }
                         *reinterpret_cast<uint4*>(p.out_bf16 + (size_t)(R0 + r) * p.ld_out + ch * 8) = q;
                     }
                 }
             }
         }
+        // bulk stores still reading a buffer that the next tile refills with per-thread copies must
+        // finish their reads first; the output staging tile is refilled by the elected thread's own
+        // bulk loads (after its wait in P0), so the newest store group may stay in flight then
+        if ((t_da || t_out) && warp == 0 && elect_one()) {
+            const bool ob_refilled_by_tma = norm ? t_gy : t_db;
+            if (t_out && ob_refilled_by_tma) tma_store_wait_read<1>(); else tma_store_wait_read<0>();
+        }
+        fence_async_smem();
         tc_fence_before();
         __syncthreads();   // buffers and ACC are free for the next tile
         tick(11);     // E4 + output
     }
 
+    if ((t_da || t_out) && warp == 0 && elect_one()) tma_store_wait_all();
     // ---- dump the weight-gradient accumulators of this CTA (lane r <-> output row r)
     tc_fence_after();
     if (tid < 128) {
@@ -626,7 +692,25 @@ template <int H>
 int launch_bwd(const gp_mlp_bwd_args& a, int32_t* grid_out, cudaStream_t st) {
     size_t smem = 1024;
     smem += (size_t)((a.ka + 63) / 64) * H * 128 + (size_t)((H + 63) / 64) * a.nb * 128;
-    smem += (size_t)(a.mode == 1 ? 4 : 3) * kBufBytes + 128 * 128 + 3 * 128 * 4 + 2 * BwdCfg<H>::NPART * 128 * 4 + 144 * 4;
+    BwdMaps maps;
+    memset(&maps, 0, sizeof(maps));
+    static const bool no_tma = getenv("GP_NO_TMA") != nullptr;
+    if (!no_tma) {
+        uint32_t use = 0;
+        if (a.a_bf16 && gp::tma_map_2d(&maps.ain, a.a_bf16, a.rows, a.ka, a.lda)) use |= kMapAin;
+        if (a.mode == 0 && gp::tma_map_2d(&maps.db, a.delta_b, a.rows, a.nb, a.ld_db)) use |= kMapDb;
+        if (a.mode == 1 && a.gy_bf16 && gp::tma_map_2d(&maps.gy, a.gy_bf16, a.rows, H, a.ld_gy)) use |= kMapGy;
+        if (a.delta_a_out && gp::tma_map_2d(&maps.da_out, a.delta_a_out, a.rows, H, H)) use |= kMapDaOut;
+        if (a.need_din && a.out_bf16 && a.ka == H && gp::tma_map_2d(&maps.out, a.out_bf16, a.rows, a.ka, a.ld_out)) {
+            // the residual rides through the spare tile buffer; GIVEN mode only (NORM keeps du / q there)
+            if (!a.out_resid)
+                use |= kMapOut;
+            else if (a.mode == 0 && gp::tma_map_2d(&maps.resid, a.out_resid, a.rows, a.ka, a.ld_out))
+                use |= kMapOut | kMapResid;
+        }
+        maps.use = use;
+    }
+    smem += (size_t)((a.mode == 1 || (maps.use & kMapResid)) ? 4 : 3) * kBufBytes + 128 * 128 + 3 * 128 * 4 + 2 * BwdCfg<H>::NPART * 128 * 4 + 144 * 4;
     GP_REQUIRE((int)smem <= gp::max_smem_optin(), "gp_mlp_bwd_stage: needs %zu B of shared memory (> %d)", smem,
                gp::max_smem_optin());
     static int smem_set = 0;      // raised once per instantiation (and never inside a stream capture twice)
@@ -636,7 +720,7 @@ int launch_bwd(const gp_mlp_bwd_args& a, int32_t* grid_out, cudaStream_t st) {
     }
     const int n_tiles = (a.rows + 127) / 128;
     int grid = n_tiles < gp::sm_count() ? n_tiles : gp::sm_count();
-    mlp_bwd_kernel<H><<<grid, BwdCfg<H>::NT, smem, st>>>(a);
+    mlp_bwd_kernel<H><<<grid, BwdCfg<H>::NT, smem, st>>>(a, maps);
     GP_CHECK_CUDA(cudaGetLastError());
     if (grid_out) *grid_out = grid;
     return 0;

@@ -16,6 +16,9 @@
 // of the saved activation runs while the next layer's MMA is in flight.
 // The receiver-sorted segment sum re-partitions through shared memory (column pairs x sub-tiles
 // of H/4 rows) and uses no atomics.
+#include <stdlib.h>
+#include <string.h>
+
 #include "common.cuh"
 #include "tile_util.cuh"
 
@@ -25,18 +28,34 @@ using namespace gp;
 constexpr int kBiasStride = 384;
 constexpr int kSlotThreads = 256;
 
+// TMA descriptors of the tile-shaped global tensors (valid ones flagged in `use`): the layer-0
+// operand is bulk-loaded and the saved activation bulk-stored by one elected thread per slot.
+struct FwdMaps {
+    CUtensorMap a, h2;
+    uint32_t use;
+};
+enum : uint32_t { kMapA = 1, kMapH2 = 2 };
+
 __device__ __forceinline__ void slot_sync(int g) { asm volatile("bar.sync %0, 256;" ::"r"(g + 1) : "memory"); }
 
 template <int H, int NG>
-__global__ void __launch_bounds__(kSlotThreads * NG, 1) mlp_fwd_kernel(const gp_mlp_fwd_args p) {
+__global__ void __launch_bounds__(kSlotThreads * NG, 1) mlp_fwd_kernel(const gp_mlp_fwd_args p,
+                                                                       const __grid_constant__ FwdMaps maps) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = GP_SMEM_ALIGNED(smem_raw);
-    __shared__ uint64_t mma_bar[NG];
+    __shared__ uint64_t mma_bar[NG], tma_bar[NG];
+    const bool t_a = maps.use & kMapA, t_h2 = maps.use & kMapH2;
     __shared__ uint32_t tmem_slot;
 
     const int tid = threadIdx.x;
     const int g = tid / kSlotThreads;        // tile slot
     const int t = tid - g * kSlotThreads;    // thread in slot
+    // The same slot / warp numbers taken from lane 0, which the compiler can prove warp-uniform; only
+    // the single-thread issue blocks (tcgen05.mma, TMA) use them, so that their descriptors live in
+    // uniform registers.  (Using them for the per-thread addressing as well measured 7% slower.)
+    const int warp_u = warp_uniform(tid >> 5);
+    const int g_u = warp_u / (kSlotThreads / 32);
+    const int wis = warp_u - g_u * (kSlotThreads / 32);    // warp in slot
     const int row = t & 127;                 // row in tile == TMEM lane
     const int half = t >> 7;                 // column half
     const int L = p.n_layers;
@@ -53,6 +72,7 @@ __global__ void __launch_bounds__(kSlotThreads * NG, 1) mlp_fwd_kernel(const gp_
         w_off[l] = off;
         if (l < L) off += ((p.k[l] + 63) >> 6) * p.n[l] * 128;
     }
+    const uint32_t buf_u = smem_u32(smem + off) + g_u * kBufBytes;      // slot buffer, uniform copy of its address
     uint8_t* buf = smem + off + g * kBufBytes;
     off += NG * kBufBytes;
     float* sbias = reinterpret_cast<float*>(smem + off);
@@ -66,13 +86,17 @@ __global__ void __launch_bounds__(kSlotThreads * NG, 1) mlp_fwd_kernel(const gp_
     // ---- one-time staging: weights, biases, barriers, TMEM
     for (int l = 0; l < L; ++l) {
         stage_weight(smem + w_off[l], p.w[l], p.n[l], p.k[l]);
-        for (int i = tid; i < p.n[l]; i += blockDim.x) sbias[l * kBiasStride + i] = p.bias[l] ? p.bias[l][i] : 0.f;
+        for (int i = tid; i < kBiasStride; i += blockDim.x)
+            sbias[l * kBiasStride + i] = (p.bias[l] && i < p.n[l]) ? p.bias[l][i] : 0.f;
     }
     cp_async_commit();
     if (p.norm_scale)
         for (int i = tid; i < H; i += blockDim.x) sscale[i] = p.norm_scale[i];
     if (tid == 0) {
-        for (int i = 0; i < NG; ++i) mbar_init(&mma_bar[i], 1);
+        for (int i = 0; i < NG; ++i) {
+            mbar_init(&mma_bar[i], 1);
+            mbar_init(&tma_bar[i], 1);
+        }
         fence_mbar_init();
     }
     constexpr uint32_t kTmemCols = NG * 128 < 32 ? 32 : NG * 128;
@@ -84,10 +108,10 @@ __global__ void __launch_bounds__(kSlotThreads * NG, 1) mlp_fwd_kernel(const gp_
     tc_fence_after();
 
     const uint32_t tmem_base = tmem_slot;
-    const uint32_t tacc_mma = tmem_base + g * 128;                               // D operand (lane 0)
+    const uint32_t tacc_mma = tmem_base + g_u * 128;                             // D operand (lane 0)
     const uint32_t tacc = tmem_addr(tmem_base, (row >> 5) * 32, g * 128);         // this warp's lanes
     const uint32_t buf_s = smem_u32(buf);
-    uint32_t phase = 0;
+    uint32_t phase = 0, tphase = 0;
     const bool has_init = p.init != nullptr;
     const int n_tiles = (p.rows + 127) >> 7;
     const int tile_stride = gridDim.x * NG;
@@ -102,7 +126,7 @@ __global__ void __launch_bounds__(kSlotThreads * NG, 1) mlp_fwd_kernel(const gp_
         }
     };
     // the MMA issuer adds (byte offset >> 4) to descriptor templates built once
-    const uint64_t adesc0 = desc_kmajor(buf_s, 128, 0);
+    const uint64_t adesc0 = desc_kmajor(buf_u, 128, 0);
 
     // gather indices of a tile (prefetched one tile ahead): i0n = this thread's row in the directly
     // loaded source; ridx[] = rows of the chunks this thread copies for the staged source
@@ -117,6 +141,27 @@ __global__ void __launch_bounds__(kSlotThreads * NG, 1) mlp_fwd_kernel(const gp_
         for (int j = 0; j < CPT; ++j) {
             const int gr = min((tile_ << 7) + (t + j * kSlotThreads) / KC, p.rows - 1);
             ridx[j] = sidx ? __ldg(sidx + gr) : gr;
+        }
+    };
+    // The accumulator always starts from the bias, so the epilogues never add it: before the MMAs of
+    // (layer l, column chunk nc) are issued, bias[l][nc + c] is stored to column c of every lane.
+    // A thread only overwrites columns it has itself just read: its CH columns of an H-wide
+    // accumulator (`wide` = false), or its 64 of a full 128-column chunk (`wide` = true).
+    auto prestore_bias = [&](int l, int nc, bool wide) {
+        const int c0 = wide ? half * 64 : cb;
+        const float* b = sbias + l * kBiasStride + nc + c0;
+        const uint32_t ta = tmem_addr(tmem_base, (row >> 5) * 32, g * 128) + c0;
+#pragma unroll
+        for (int c = 0; c < 64; c += 16) {
+            if (c < CH || wide) {
+                uint32_t v[16];
+#pragma unroll
+                for (int j = 0; j < 16; j += 4) {
+                    const uint4 q = *reinterpret_cast<const uint4*>(b + c + j);
+                    v[j] = q.x; v[j + 1] = q.y; v[j + 2] = q.z; v[j + 3] = q.w;
+                }
+                tmem_st16(ta + c, v);
+            }
         }
     };
     const int tile0 = blockIdx.x * NG + g;
@@ -159,26 +204,23 @@ __global__ void __launch_bounds__(kSlotThreads * NG, 1) mlp_fwd_kernel(const gp_
                 for (int i = 0; i < CH / 8; ++i) dq[i] = ldg16(dp + i * 8);
             }
             // L2 prefetch of the layer-0 operand tile, which is staged right after
-            if (p.a_bf16 && (t & 7) == 0) {
-                const int kc0 = p.ka >> 3;
-                for (int i = t; i < 128 * kc0; i += kSlotThreads) {
-                    const int r = i / kc0, ch = i - r * kc0;
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(p.a_bf16 + (size_t)min(R0 + r, p.rows - 1) * p.lda + ch * 8));
-                }
+            if (p.a_bf16 && t < 128) {
+                const gp_bf16* rp = p.a_bf16 + (size_t)min(grow, p.rows - 1) * p.lda;
+                for (int c = 0; c < p.ka; c += 64) asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + c));
             }
             cp_async_wait<0>();
             slot_sync(g);
 #pragma unroll
             for (int c = 0; c < CH; c += 16) {
                 float f[16];
-                unpack8(*reinterpret_cast<const uint4*>(buf + sw128_off(128, row, cb + c)), f);
-                unpack8(*reinterpret_cast<const uint4*>(buf + sw128_off(128, row, cb + c + 8)), f + 8);
-                if (stage1) {
-                    float h[16];
-                    unpack8(dq[c / 8], h);
-                    unpack8(dq[c / 8 + 1], h + 8);
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) f[j] += h[j];
+                for (int j = 0; j < 16; j += 4)
+                    *reinterpret_cast<float4*>(f + j) = *reinterpret_cast<const float4*>(sbias + cb + c + j);
+                acc8(*reinterpret_cast<const uint4*>(buf + sw128_off(128, row, cb + c)), f);
+                acc8(*reinterpret_cast<const uint4*>(buf + sw128_off(128, row, cb + c + 8)), f + 8);
+                if (stage1) {
+                    acc8(dq[c / 8], f);
+                    acc8(dq[c / 8 + 1], f + 8);
                 }
                 uint32_t v[16];
 #pragma unroll
@@ -186,7 +228,10 @@ __global__ void __launch_bounds__(kSlotThreads * NG, 1) mlp_fwd_kernel(const gp_
                 tmem_st16(tacc + cb + c, v);
             }
             tmem_st_wait();
+            fence_async_smem();
             slot_sync(g);            // buf is free for the layer-0 operand
+        } else {
+            prestore_bias(0, 0, true);
         }
         if (p.seg_id && t < 128) {
             sseg[4 + row] = sid_me;
@@ -196,11 +241,24 @@ __global__ void __launch_bounds__(kSlotThreads * NG, 1) mlp_fwd_kernel(const gp_
             }
         }
         // (c) streamed layer-0 operand -> buf (rows past the end replicate the last row; their
-        //     results are never stored)
-        stage_rows(buf, p.a_bf16, p.a_f32, p.ka, p.lda, R0, p.rows, t, kSlotThreads);
-        cp_async_commit();
+        //     results are never stored); bulk-loaded when a descriptor exists (rows past the end = 0)
+        if (t_a) {
+            if (wis == 0 && elect_one()) {
+                const int nblk = (p.ka + 63) >> 6;
+                mbar_arrive_expect_tx(&tma_bar[g_u], nblk * 16384u);
+                for (int b = 0; b < nblk; ++b) tma_load_2d(buf_u + b * 16384, &maps.a, b * 64, R0, &tma_bar[g_u]);
+            }
+        } else {
+            stage_rows(buf, p.a_bf16, p.a_f32, p.ka, p.lda, R0, p.rows, t, kSlotThreads);
+            cp_async_commit();
+        }
         tick(0);                 // issue of loads + gathers + TMEM pre-load (this thread)
+        tmem_st_wait();
         cp_async_wait<0>();
+        if (t_a) {
+            mbar_wait(&tma_bar[g], tphase);
+            tphase ^= 1;
+        }
         fence_async_smem();
         tc_fence_before();
         slot_sync(g);
@@ -211,10 +269,9 @@ __global__ void __launch_bounds__(kSlotThreads * NG, 1) mlp_fwd_kernel(const gp_
             const int K = p.k[l];
             const int Nl = p.n[l];
             const bool last = (l == L - 1);
-            const float* bl = sbias + l * kBiasStride;
             for (int nc = 0; nc < Nl; nc += 128) {
                 const int ncols = min(128, Nl - nc);
-                if (t == 0) {
+                if (wis == 0 && elect_one()) {
                     tc_fence_after();
                     const uint32_t idesc = idesc_bf16(ncols, false, false);
                     const uint64_t bdesc0 = desc_kmajor(smem_u32(smem + w_off[l]) + nc * 128, Nl, 0);
@@ -223,9 +280,9 @@ __global__ void __launch_bounds__(kSlotThreads * NG, 1) mlp_fwd_kernel(const gp_
                     for (int ks = 0; ks < nks; ++ks) {
                         const uint32_t ko = (ks & 3) * 2;                // 32 bytes per k-step inside a block
                         mma_ss(tacc_mma, adesc0 + (uint64_t)((ks >> 2) * 1024u + ko), bdesc0 + (uint64_t)((ks >> 2) * bblk + ko),
-                               idesc, (ks > 0 || (l == 0 && has_init)) ? 1u : 0u);
+                               idesc, 1u);
                     }
-                    mma_commit(&mma_bar[g]);
+                    mma_commit(&mma_bar[g_u]);
                 }
                 tick(8);         // MMA issue (thread 0 of the slot)
                 // while the first MMA runs: indices of this slot's next tile, and its gathered rows
@@ -240,7 +297,14 @@ __global__ void __launch_bounds__(kSlotThreads * NG, 1) mlp_fwd_kernel(const gp_
                 }
                 // while the MMA of layer 2 runs: copy the saved activation (layer-1 output, still
                 // intact in buf as this MMA's A operand) to global memory, row-major chunks
-                if (l == 2 && nc == 0 && p.save_h2) {
+                if (l == 2 && nc == 0 && p.save_h2 && t_h2) {
+                    if (wis == 0 && elect_one()) {
+                        for (int b = 0; b < (H + 63) >> 6; ++b) tma_store_2d(&maps.h2, b * 64, R0, buf_u + b * 16384);
+                        tma_store_commit();
+                        tma_store_wait_read<0>();     // buf has been read: the epilogue may overwrite it
+                    }
+                    slot_sync(g);
+                } else if (l == 2 && nc == 0 && p.save_h2) {
 #pragma unroll
                     for (int j = 0; j < CPT; ++j) {
                         const int i = t + j * kSlotThreads;
@@ -262,14 +326,13 @@ __global__ void __launch_bounds__(kSlotThreads * NG, 1) mlp_fwd_kernel(const gp_
 #pragma unroll
                     for (int c = 0; c < CH; c += 16) tmem_ld16(tacc + cb + c, *reinterpret_cast<uint32_t(*)[16]>(&v[c]));
                     tmem_ld_wait();
+                    prestore_bias(l + 1, 0, false);     // hidden layers are H wide: one chunk, and so is the next layer
 #pragma unroll
-                    for (int c = 0; c < CH; c += 8) {
-                        float f[8];
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) f[j] = fmaxf(__uint_as_float(v[c + j]) + bl[cb + c + j], 0.f);
-                        *reinterpret_cast<uint4*>(buf + sw128_off(128, row, cb + c)) = pack8(f);
-                    }
+                    for (int c = 0; c < CH; c += 8)
+                        *reinterpret_cast<uint4*>(buf + sw128_off(128, row, cb + c)) =
+                            pack8_relu(reinterpret_cast<const float*>(&v[c]));
                     fence_async_smem();
+                    tmem_st_wait();
                     tick(3);
                 } else if (p.norm_scale) {
                     // RMSNorm (layers.py:104-129): u = scale * m / (||m||/sqrt(H) + 1e-8), rounded to
@@ -281,8 +344,7 @@ __global__ void __launch_bounds__(kSlotThreads * NG, 1) mlp_fwd_kernel(const gp_
                     float ss = 0.f;
 #pragma unroll
                     for (int c = 0; c < CH; ++c) {
-                        const float m = __uint_as_float(v[c]) + bl[cb + c];
-                        v[c] = __float_as_uint(m);
+                        const float m = __uint_as_float(v[c]);
                         ss = fmaf(m, m, ss);
                     }
                     sred[half * 128 + row] = ss;
@@ -307,7 +369,7 @@ __global__ void __launch_bounds__(kSlotThreads * NG, 1) mlp_fwd_kernel(const gp_
                             tmem_ld_wait();
                             float u[16];
 #pragma unroll
-                            for (int j = 0; j < 16; ++j) u[j] = __uint_as_float(v[j]) + bl[nc + c0 + j];
+                            for (int j = 0; j < 16; ++j) u[j] = __uint_as_float(v[j]);
                             if (valid) {
                                 const int cg = nc + c0;
                                 if (p.y_bf16 && cg + 16 <= p.n_valid) {
@@ -328,6 +390,10 @@ __global__ void __launch_bounds__(kSlotThreads * NG, 1) mlp_fwd_kernel(const gp_
                             }
                         }
                     }
+                    if (nc + 128 < Nl) {      // the next column chunk of this layer reuses the accumulator
+                        prestore_bias(l, nc + 128, true);
+                        tmem_st_wait();
+                    }
                     tick(4);
                 }
                 tc_fence_before();
@@ -337,8 +403,11 @@ __global__ void __launch_bounds__(kSlotThreads * NG, 1) mlp_fwd_kernel(const gp_
         }
 
         if (p.norm_scale) {
-            // (e) output: y = resid + bf16(u), row-major chunks.  The residual chunks are requested
-            //     first and consumed after the segment walk, which hides their latency.
+            // (e) receiver-sorted segment sum of bf16(u) (fp32 accumulate, fixed order, no atomics)
+            if (p.seg_id) tile_segment_sum<H, kSlotThreads>(buf, sseg, R0, t, p.seg_out, p.seg_bnd);
+            tick(6);
+            // (f) output: y = resid + bf16(u), row-major chunks; the residual chunks (L2 hits: the tile
+            //     was this kernel's layer-0 operand) are requested together
             uint4 rq[CPT];
             if (p.resid) {
 #pragma unroll
@@ -348,25 +417,20 @@ __global__ void __launch_bounds__(kSlotThreads * NG, 1) mlp_fwd_kernel(const gp_
                     rq[j] = ldg16(p.resid + (size_t)min(R0 + r, p.rows - 1) * p.ld_out + ch * 8);
                 }
             }
-            // (f) receiver-sorted segment sum of bf16(u) (fp32 accumulate, fixed order, no atomics)
-            if (p.seg_id) tile_segment_sum<H, kSlotThreads>(buf, sseg, R0, t, p.seg_out, p.seg_bnd);
-            tick(6);
 #pragma unroll
             for (int j = 0; j < CPT; ++j) {
                 const int i = t + j * kSlotThreads;
                 const int r = i / KC, ch = i % KC;
                 if (R0 + r < p.rows) {
-                    float u[8];
-                    unpack8(*reinterpret_cast<const uint4*>(buf + sw128_off(128, r, ch * 8)), u);
-                    if (p.resid) {
-                        float e[8];
-                        unpack8(rq[j], e);
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) u[q] += e[q];
-                    }
+                    const uint4 uq = *reinterpret_cast<const uint4*>(buf + sw128_off(128, r, ch * 8));
                     if (p.y_bf16) {
-                        *reinterpret_cast<uint4*>(p.y_bf16 + (size_t)(R0 + r) * p.ld_out + ch * 8) = pack8(u);
+                        // bf16(u) + bf16 residual, exact sum rounded once to bf16
+                        *reinterpret_cast<uint4*>(p.y_bf16 + (size_t)(R0 + r) * p.ld_out + ch * 8) =
+                            p.resid ? add8_bf16(uq, rq[j]) : uq;
                     } else {
+                        float u[8];
+                        unpack8(uq, u);
+                        if (p.resid) acc8(rq[j], u);
                         float4* d = reinterpret_cast<float4*>(p.y_f32 + (size_t)(R0 + r) * p.ld_out + ch * 8);
                         d[0] = make_float4(u[0], u[1], u[2], u[3]);
                         d[1] = make_float4(u[4], u[5], u[6], u[7]);
@@ -379,6 +443,7 @@ __global__ void __launch_bounds__(kSlotThreads * NG, 1) mlp_fwd_kernel(const gp_
         if (prof) atomicAdd(p.prof + 15, 1ull);
     }
 
+    if (t_h2 && wis == 0 && elect_one()) tma_store_wait_all();
     tc_fence_before();
     __syncthreads();
     if (tid < 32) tmem_dealloc(tmem_base, kTmemCols);
@@ -420,7 +485,16 @@ int launch_fwd(const gp_mlp_fwd_args& a, cudaStream_t st) {
     int grid = (n_tiles + NG - 1) / NG;
     if (grid > gp::sm_count()) grid = gp::sm_count();
     if (grid < 1) grid = 1;
-    mlp_fwd_kernel<H, NG><<<grid, kSlotThreads * NG, smem, st>>>(a);
+    FwdMaps maps;
+    memset(&maps, 0, sizeof(maps));
+    static const bool no_tma = getenv("GP_NO_TMA") != nullptr;
+    if (!no_tma) {
+        // with gathered pre-activations the tile buffer is busy until just before layer 0, where the
+        // shorter latency of per-thread cp.async (L2-prefetched rows) beats one bulk copy
+        if (a.a_bf16 && !a.init && gp::tma_map_2d(&maps.a, a.a_bf16, a.rows, a.ka, a.lda)) maps.use |= kMapA;
+        if (a.save_h2 && gp::tma_map_2d(&maps.h2, a.save_h2, a.rows, H, H)) maps.use |= kMapH2;
+    }
+    mlp_fwd_kernel<H, NG><<<grid, kSlotThreads * NG, smem, st>>>(a, maps);
     GP_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -446,6 +520,7 @@ extern "C" int gp_mlp_fwd(const gp_mlp_fwd_args* args, int hidden, void* stream)
     if (a.norm_scale) GP_REQUIRE(a.n[a.n_layers - 1] == hidden, "gp_mlp_fwd: RMSNorm needs n_last == hidden");
     if (a.seg_id) GP_REQUIRE(a.norm_scale && a.seg_out && a.seg_bnd, "gp_mlp_fwd: segment sum needs norm + outputs");
     if (a.save_h2) GP_REQUIRE(a.n_layers >= 3, "gp_mlp_fwd: save_h2 needs at least 3 layers");
+    GP_REQUIRE(a.n_layers == 1 || a.n[a.n_layers - 1] <= hidden, "gp_mlp_fwd: a multi-layer MLP cannot widen in its last layer");
     GP_REQUIRE((a.y_bf16 != nullptr) != (a.y_f32 != nullptr), "gp_mlp_fwd: exactly one of y_bf16 / y_f32");
     if (a.norm_scale) GP_REQUIRE(a.ld_out % 8 == 0, "gp_mlp_fwd: ld_out must be a multiple of 8 with RMSNorm");
     cudaStream_t st = static_cast<cudaStream_t>(stream);

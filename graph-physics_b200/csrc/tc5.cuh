@@ -31,26 +31,72 @@ __device__ __forceinline__ void fence_mbar_init() {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+// One probe of the phase; the thread may be suspended by the hardware for up to `hint_ns`.
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity, uint32_t hint_ns = 100000u) {
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(hint_ns)
         : "memory");
     return ok != 0;
 }
-// Bounded wait: a protocol bug traps instead of hanging the GPU.
+// Bounded wait: a protocol bug traps (after ~2 s) instead of hanging the GPU.  The time-out
+// bookkeeping only starts once the first probe has failed, so the common path is probe + branch.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t spins = 0;
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
     while (!mbar_try_wait(bar, parity)) {
-        if (++spins > (1u << 26)) {
+        if (clock64() - t0 > (1ll << 32)) {
             printf("tc5: mbarrier wait timed out (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
             __trap();
         }
     }
+}
+
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+
+// ---------------------------------------------------------------- TMA (bulk tensor copies)
+// 2-D tiled tensor map over a row-major bf16 matrix, box = 64 columns x 128 rows, SWIZZLE_128B:
+// one instruction moves one 64-column block of an SW128 row tile (16 KB).  Coordinates are
+// {column, row}; rows past the end of the tensor are zero-filled on load and clipped on store.
+__device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const void* tmap, int32_t col, int32_t row, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(col), "r"(row)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const void* tmap, int32_t col, int32_t row, uint32_t smem_src) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_src), "r"(col), "r"(row)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// the shared-memory sources of all committed stores have been read (the buffers may be rewritten)
+template <int N = 0>
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");
+}
+
+// ---------------------------------------------------------------- warp-uniform helpers
+// Value of lane 0, which the compiler can treat as warp-uniform (kept in uniform registers: the
+// tcgen05.mma descriptors are then built with uniform-datapath adds instead of a per-MMA
+// vector-to-uniform broadcast loop).
+__device__ __forceinline__ int warp_uniform(int v) { return __shfl_sync(0xffffffffu, v, 0); }
+// True in exactly one lane of a converged warp.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+        "elect.sync rx|px, 0xffffffff;\n\t"
+        "selp.b32 %0, 1, 0, px;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
 }
 
 // ---------------------------------------------------------------- fences
@@ -195,5 +241,37 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 }
 __device__ __forceinline__ float bf16_lo(uint32_t p) { return __uint_as_float(p << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t p) { return __uint_as_float(p & 0xFFFF0000u); }
+
+// Mixed-precision helpers (sm_100: FHADD.BF16 / F2FP.RELU / HFMA2.BF16_V2, one instruction each).
+// c + float(low / high bf16 half of p): the bf16 -> fp32 conversion is exact, the add rounds once in fp32.
+__device__ __forceinline__ float add_bf16_lo(uint32_t p, float c) {
+    float d;
+    asm("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %1;\n\tadd.rn.f32.bf16 %0, lo, %2;\n\t}" : "=f"(d) : "r"(p), "f"(c));
+    return d;
+}
+__device__ __forceinline__ float add_bf16_hi(uint32_t p, float c) {
+    float d;
+    asm("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %1;\n\tadd.rn.f32.bf16 %0, hi, %2;\n\t}" : "=f"(d) : "r"(p), "f"(c));
+    return d;
+}
+// bf16x2( max(lo, 0), max(hi, 0) ): ReLU fused into the conversion
+__device__ __forceinline__ uint32_t pack_bf16_relu(float lo, float hi) {
+    uint32_t d;
+    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    return d;
+}
+// element-wise  h > 0 ? v : 0  on bf16 pairs (HSET2 + HMUL2): the ReLU-derivative mask without unpacking
+__device__ __forceinline__ uint32_t mask_pos_bf16x2(uint32_t v, uint32_t h) {
+    uint32_t m, d;
+    asm("set.gt.bf16x2.bf16x2 %0, %1, %2;" : "=r"(m) : "r"(h), "r"(0u));
+    asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(v), "r"(m));
+    return d;
+}
+// element-wise a + b of two bf16 pairs, exact sum rounded once to bf16
+__device__ __forceinline__ uint32_t add_bf16x2(uint32_t a, uint32_t b) {
+    uint32_t d;
+    asm("add.rn.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+    return d;
+}
 
 }  // namespace tc5

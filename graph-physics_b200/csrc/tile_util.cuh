@@ -14,6 +14,21 @@ __device__ __forceinline__ void unpack8(const uint4& q, float* f) {
     f[0] = bf16_lo(q.x); f[1] = bf16_hi(q.x); f[2] = bf16_lo(q.y); f[3] = bf16_hi(q.y);
     f[4] = bf16_lo(q.z); f[5] = bf16_hi(q.z); f[6] = bf16_lo(q.w); f[7] = bf16_hi(q.w);
 }
+// f[0..7] += the eight bf16 values of q (one FHADD each, no separate unpack)
+__device__ __forceinline__ void acc8(const uint4& q, float* f) {
+    f[0] = add_bf16_lo(q.x, f[0]); f[1] = add_bf16_hi(q.x, f[1]); f[2] = add_bf16_lo(q.y, f[2]); f[3] = add_bf16_hi(q.y, f[3]);
+    f[4] = add_bf16_lo(q.z, f[4]); f[5] = add_bf16_hi(q.z, f[5]); f[6] = add_bf16_lo(q.w, f[6]); f[7] = add_bf16_hi(q.w, f[7]);
+}
+__device__ __forceinline__ uint4 pack8_relu(const float* f) {
+    return make_uint4(pack_bf16_relu(f[0], f[1]), pack_bf16_relu(f[2], f[3]), pack_bf16_relu(f[4], f[5]),
+                      pack_bf16_relu(f[6], f[7]));
+}
+__device__ __forceinline__ uint4 mask8_pos(const uint4& v, const uint4& h) {
+    return make_uint4(mask_pos_bf16x2(v.x, h.x), mask_pos_bf16x2(v.y, h.y), mask_pos_bf16x2(v.z, h.z), mask_pos_bf16x2(v.w, h.w));
+}
+__device__ __forceinline__ uint4 add8_bf16(const uint4& a, const uint4& b) {
+    return make_uint4(add_bf16x2(a.x, b.x), add_bf16x2(a.y, b.y), add_bf16x2(a.z, b.z), add_bf16x2(a.w, b.w));
+}
 __device__ __forceinline__ uint4 pack8(const float* f) {
     return make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
 }
@@ -153,15 +168,17 @@ __device__ __forceinline__ void tile_segment_sum(const uint8_t* buf, const int* 
         const int4 sb = *reinterpret_cast<const int4*>(sseg + 8 + r8);
         const int sid[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
         const uint8_t* rowbase = colbase + r8 * 128;
+        uint32_t w[8];           // all eight rows requested before the first (store-carrying) branch
+#pragma unroll
+        for (int j = 0; j < 8; ++j) w[j] = *reinterpret_cast<const uint32_t*>(rowbase + j * 128 + ((chunk ^ j) << 4));
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             if (sid[j] != cur) {
                 flush(cur, false);
                 cur = sid[j]; s0 = 0.f; s1 = 0.f;
             }
-            const uint32_t w = *reinterpret_cast<const uint32_t*>(rowbase + j * 128 + ((chunk ^ j) << 4));
-            s0 += bf16_lo(w);
-            s1 += bf16_hi(w);
+            s0 = add_bf16_lo(w[j], s0);
+            s1 = add_bf16_hi(w[j], s1);
         }
     }
     flush(cur, true);

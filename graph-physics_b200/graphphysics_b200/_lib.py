@@ -12,7 +12,7 @@ from typing import Optional
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libgp_b200.so")
+LIB_PATH = os.environ.get("GP_B200_LIB") or os.path.join(_HERE, "lib", "libgp_b200.so")   # override: A/B builds while tuning
 
 _lib: Optional[C.CDLL] = None
 

@@ -51,8 +51,8 @@ def test_plain_mlp_norm(hidden, rows):
                 norm_scale=sd["m.7.scale"].to(dev), out=out, n_valid=hidden)
     torch.cuda.synchronize()
     # a normalised output leaves the kernel through a bf16 tile (it is rounded once, before the
-    # residual / segment sum), so fp32 storage still carries bf16 resolution: one ulp = 4e-3
-    assert rel_err(out, bf16_round(ref.float()).double()) < 4e-3
+    # residual / segment sum), so fp32 storage still carries bf16 resolution: one ulp of the largest element is up to 2^-7 = 7.8e-3 of it
+    assert rel_err(out, bf16_round(ref.float()).double()) < 8e-3
 
 
 @pytest.mark.parametrize("hidden", [128, 32])
