@@ -5,32 +5,53 @@
 // arrives in up to three `hidden`-wide pieces (receiver sums, sender sums, node-MLP delta).
 // Per 128-row tile, for each piece s:   dX += dP_s . Wp_s      (dgrad, accumulated in TMEM)
 //                                       dWp_s += dP_s^T . x    (wgrad, TMEM-resident per CTA)
+#include <stdlib.h>
+#include <string.h>
+
 #include "common.cuh"
 #include "tile_util.cuh"
 
 namespace {
 using namespace gp;
 
+// fp32 staging tile [128 rows x H] used to turn the row-per-lane TMEM read-out into row-major,
+// fully coalesced global stores: 16-byte chunk c of row r lives at chunk c ^ (r & (CPR-1)).
 template <int H>
-__global__ void __launch_bounds__(256, 1) linear_bwd_kernel(const gp_linear_bwd_args p) {
+__device__ __forceinline__ uint32_t stage_f32_off(int r, int chunk) {
+    constexpr int CPR = H / 4;                      // 16-byte chunks per row
+    constexpr int SW = CPR < 32 ? CPR : 32;
+    return (uint32_t)r * (H * 4) + (uint32_t)((chunk ^ (r & (SW - 1))) << 4);
+}
+
+struct LinMaps {
+    CUtensorMap x, src[3];
+    uint32_t use;                                   // bit 0: x, bits 1..3: bf16 sources
+};
+
+template <int H>
+__global__ void __launch_bounds__(256, 1) linear_bwd_kernel(const gp_linear_bwd_args p, const __grid_constant__ LinMaps maps) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = GP_SMEM_ALIGNED(smem_raw);
-    __shared__ uint64_t mma_bar;
+    __shared__ uint64_t mma_bar, tma_bar;
     __shared__ uint32_t tmem_slot;
 
     const int tid = threadIdx.x, row = tid & 127, half = tid >> 7;
     const int warp = warp_uniform(tid >> 5);
     const int S = p.n_src;
     const int wrows = S * H;
+    constexpr int NSTG = H >= 128 ? 2 : 1;          // tile buffers covered by the fp32 staging tile
+    const int nbuf = S > NSTG ? S : NSTG;
     uint32_t off = 0;
     uint8_t* w_t = smem + off;  off += ((H + 63) >> 6) * wrows * 128;
-    uint8_t* abuf = smem + off; off += kBufBytes;
+    uint8_t* abuf = smem + off; off += nbuf * kBufBytes;          // one gradient tile per source
     uint8_t* xbuf = smem + off;
+    float* stg = reinterpret_cast<float*>(abuf);                 // reused after the MMAs have read abuf
 
     stage_weight(w_t, p.w, wrows, H);
     cp_async_commit();
     if (tid == 0) {
         mbar_init(&mma_bar, 1);
+        mbar_init(&tma_bar, 1);
         fence_mbar_init();
     }
     if (tid < 32) tmem_alloc(&tmem_slot, 512);
@@ -44,93 +65,148 @@ __global__ void __launch_bounds__(256, 1) linear_bwd_kernel(const gp_linear_bwd_
     const uint32_t tlane = tmem_addr(tmem, (row >> 5) * 32, 0);
     const uint32_t a_s = smem_u32(abuf), x_s = smem_u32(xbuf), w_s = smem_u32(w_t);
     const uint32_t lbo_h = (H >= 128) ? 16384u : 0u;
-    uint32_t phase = 0;
+    uint32_t phase = 0, tphase = 0;
     const int n_tiles = (p.rows + 127) >> 7;
     constexpr int CH = H / 2;
+    constexpr int KC = H / 8;                        // 16-byte chunks per bf16 row
+    constexpr int CPT = 128 * KC / 256;              // bf16 chunks per thread per tile
+    constexpr int CPR = H / 4;                       // 16-byte chunks per fp32 row
+    constexpr int FPT = 128 * CPR / 256;             // fp32 chunks per thread per tile
     bool first = true;
+    uint32_t tma_blocks = (maps.use & 1u) ? (H + 63) >> 6 : 0;
+    for (int s = 0; s < S; ++s) tma_blocks += (maps.use & (2u << s)) ? (H + 63) >> 6 : 0;
 
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, first = false) {
-        const int R0 = tile << 7, grow = R0 + row;
-        const bool valid = grow < p.rows;
-        stage_rows(xbuf, p.x, nullptr, H, p.ldx, R0, p.rows, tid, 256);
+        const int R0 = tile << 7;
+        // ---- loads: x and bf16 pieces by TMA (rows past the end = 0), fp32 pieces converted on the fly
+        if (tma_blocks && warp == 0 && elect_one()) {
+            mbar_arrive_expect_tx(&tma_bar, tma_blocks * 16384u);
+            if (maps.use & 1u)
+                for (int b = 0; b < (H + 63) >> 6; ++b) tma_load_2d(x_s + b * 16384, &maps.x, b * 64, R0, &tma_bar);
+#pragma unroll
+            for (int s = 0; s < 3; ++s)          // constant indices: the descriptors must stay in parameter space
+                if (s < S && (maps.use & (2u << s)))
+                    for (int b = 0; b < (H + 63) >> 6; ++b)
+                        tma_load_2d(a_s + s * kBufBytes + b * 16384, &maps.src[s], b * 64, R0, &tma_bar);
+        }
+        if (!(maps.use & 1u)) stage_rows(xbuf, p.x, nullptr, H, p.ldx, R0, p.rows, tid, 256);
         cp_async_commit();
         for (int s = 0; s < S; ++s) {
-            // gradient piece s -> abuf (bf16), rows past the end zeroed
-            const int kc = H >> 3;
-            for (int i = tid; i < 128 * kc; i += 256) {
-                const int r = i / kc, ch = i - r * kc;
-                uint4 pk = make_uint4(0, 0, 0, 0);
-                if (R0 + r < p.rows) {
-                    if (p.src_f32[s]) {
-                        const float4* sp = reinterpret_cast<const float4*>(p.src_f32[s] + (size_t)(R0 + r) * p.ld_src[s] + ch * 8);
-                        const float4 u0 = __ldg(sp), u1 = __ldg(sp + 1);
-                        pk = make_uint4(pack_bf16(u0.x, u0.y), pack_bf16(u0.z, u0.w), pack_bf16(u1.x, u1.y), pack_bf16(u1.z, u1.w));
-                    } else {
-                        pk = ldg16(p.src_bf16[s] + (size_t)(R0 + r) * p.ld_src[s] + ch * 8);
-                    }
+            uint8_t* ab = abuf + s * kBufBytes;
+            if (p.src_f32[s]) {
+                float4 u[2 * CPT];                   // the whole piece is requested before the first conversion
+#pragma unroll
+                for (int j = 0; j < CPT; ++j) {
+                    const int i = tid + j * 256;
+                    const int r = i / KC, ch = i % KC;
+                    const float4* sp = reinterpret_cast<const float4*>(p.src_f32[s] + (size_t)min(R0 + r, p.rows - 1) * p.ld_src[s] + ch * 8);
+                    u[2 * j] = __ldg(sp);
+                    u[2 * j + 1] = __ldg(sp + 1);
                 }
-                *reinterpret_cast<uint4*>(abuf + sw128_off(128, r, ch * 8)) = pk;
+#pragma unroll
+                for (int j = 0; j < CPT; ++j) {
+                    const int i = tid + j * 256;
+                    const int r = i / KC, ch = i % KC;
+                    const bool ok = R0 + r < p.rows;      // rows past the end add nothing to the weight gradients
+                    *reinterpret_cast<uint4*>(ab + sw128_off(128, r, ch * 8)) =
+                        ok ? make_uint4(pack_bf16(u[2 * j].x, u[2 * j].y), pack_bf16(u[2 * j].z, u[2 * j].w),
+                                        pack_bf16(u[2 * j + 1].x, u[2 * j + 1].y), pack_bf16(u[2 * j + 1].z, u[2 * j + 1].w))
+                           : make_uint4(0, 0, 0, 0);
+                }
+            } else if (!(maps.use & (2u << s))) {
+#pragma unroll
+                for (int j = 0; j < CPT; ++j) {
+                    const int i = tid + j * 256;
+                    const int r = i / KC, ch = i % KC;
+                    *reinterpret_cast<uint4*>(ab + sw128_off(128, r, ch * 8)) =
+                        (R0 + r < p.rows) ? ldg16(p.src_bf16[s] + (size_t)(R0 + r) * p.ld_src[s] + ch * 8) : make_uint4(0, 0, 0, 0);
+                }
             }
-            cp_async_wait<0>();
-            fence_async_smem();
-            tc_fence_before();
-            __syncthreads();
-            if (warp == 0 && elect_one()) {
-                tc_fence_after();
-                const uint32_t id_w = idesc_bf16(H, true, true), id_d = idesc_bf16(H, false, true);
+        }
+        cp_async_wait<0>();
+        if (tma_blocks) {
+            mbar_wait(&tma_bar, tphase);
+            tphase ^= 1;
+        }
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        // ---- all MMAs of the tile in one batch:  dWp_s += dP_s^T . x   and   dX = sum_s dP_s . Wp_s
+        if (warp == 0 && elect_one()) {
+            tc_fence_after();
+            const uint32_t id_w = idesc_bf16(H, true, true), id_d = idesc_bf16(H, false, true);
+            for (int s = 0; s < S; ++s) {
+                const uint32_t as = a_s + s * kBufBytes;
                 for (int ks = 0; ks < 8; ++ks)
-                    mma_ss(tmem + 128 * (1 + s), desc_mnmajor(a_s, 128, ks, 0, lbo_h), desc_mnmajor(x_s, 128, ks), id_w,
+                    mma_ss(tmem + 128 * (1 + s), desc_mnmajor(as, 128, ks, 0, lbo_h), desc_mnmajor(x_s, 128, ks), id_w,
                            (ks > 0) ? 1u : (first ? 0u : 1u));
                 for (int ks = 0; ks < (H >> 4); ++ks)
-                    mma_ss(tmem, desc_kmajor(a_s, 128, ks), desc_mnmajor(w_s + s * H * 128, wrows, ks), id_d,
+                    mma_ss(tmem, desc_kmajor(as, 128, ks), desc_mnmajor(w_s + s * H * 128, wrows, ks), id_d,
                            (s > 0 || ks > 0) ? 1u : 0u);
-                mma_commit(&mma_bar);
             }
-            mbar_wait(&mma_bar, phase);
-            phase ^= 1;
-            tc_fence_after();
+            mma_commit(&mma_bar);
         }
-        for (int c0 = half * CH; c0 < half * CH + CH; c0 += 16) {
-            uint32_t v[16];
-            tmem_ld16(tlane + c0, v);
-            tmem_ld_wait();
-            if (valid) {
-                float f[16];
+        // while the tensor core runs: the incoming dX rows of this tile (row-major chunks)
+        float4 din[FPT];
+        if (p.dx_in) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
-                if (p.dx_in) {
-                    const float4* ip = reinterpret_cast<const float4*>(p.dx_in + (size_t)grow * H + c0);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const float4 t4 = __ldg(ip + j);
-                        f[4 * j] += t4.x; f[4 * j + 1] += t4.y; f[4 * j + 2] += t4.z; f[4 * j + 3] += t4.w;
-                    }
-                }
-                float4* d = reinterpret_cast<float4*>(p.dx_out + (size_t)grow * H + c0);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) d[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+            for (int j = 0; j < FPT; ++j) {
+                const int i = tid + j * 256;
+                const int r = i / CPR, ch = i % CPR;
+                din[j] = __ldg(reinterpret_cast<const float4*>(p.dx_in + (size_t)min(R0 + r, p.rows - 1) * H) + ch);
             }
+        }
+        mbar_wait(&mma_bar, phase);
+        phase ^= 1;
+        tc_fence_after();
+        // ---- dX: TMEM (row per lane) -> fp32 staging tile -> coalesced rows
+#pragma unroll
+        for (int c0 = 0; c0 < CH; c0 += 16) {
+            uint32_t v[16];
+            tmem_ld16(tlane + half * CH + c0, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(stg) + stage_f32_off<H>(row, (half * CH + c0) / 4 + q)) =
+                    make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
         }
         tc_fence_before();
         __syncthreads();
+#pragma unroll
+        for (int j = 0; j < FPT; ++j) {
+            const int i = tid + j * 256;
+            const int r = i / CPR, ch = i % CPR;
+            if (R0 + r < p.rows) {
+                float4 o = *reinterpret_cast<const float4*>(reinterpret_cast<const uint8_t*>(stg) + stage_f32_off<H>(r, ch));
+                if (p.dx_in) { o.x += din[j].x; o.y += din[j].y; o.z += din[j].z; o.w += din[j].w; }
+                reinterpret_cast<float4*>(p.dx_out + (size_t)(R0 + r) * H)[ch] = o;
+            }
+        }
+        fence_async_smem();      // the staging tile is refilled by TMA / per-thread copies next
+        __syncthreads();
     }
 
+    // ---- dump the weight-gradient accumulators (lane r <-> row r of dWp_s) through the staging tile
     tc_fence_after();
-    if (tid < 128) {
-        float* P = p.partials + (size_t)blockIdx.x * S * H * H;
-        for (int s = 0; s < S; ++s)
-            for (int c0 = 0; c0 < H; c0 += 16) {
-                uint32_t v[16];
-                tmem_ld16(tlane + 128 * (1 + s) + c0, v);
-                tmem_ld_wait();
-                if (row < H) {
-                    float4* d = reinterpret_cast<float4*>(P + ((size_t)s * H + row) * H + c0);
+    float* P = p.partials + (size_t)blockIdx.x * S * H * H;
+    for (int s = 0; s < S; ++s) {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        d[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
-                                           __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
-                }
-            }
+        for (int c0 = 0; c0 < CH; c0 += 16) {
+            uint32_t v[16];
+            tmem_ld16(tlane + 128 * (1 + s) + half * CH + c0, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(stg) + stage_f32_off<H>(row, (half * CH + c0) / 4 + q)) =
+                    make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        }
+        __syncthreads();
+        for (int i = tid; i < H * CPR; i += 256) {
+            const int r = i / CPR, ch = i % CPR;
+            reinterpret_cast<float4*>(P + ((size_t)s * H + r) * H)[ch] =
+                *reinterpret_cast<const float4*>(reinterpret_cast<const uint8_t*>(stg) + stage_f32_off<H>(r, ch));
+        }
+        __syncthreads();
     }
     tc_fence_before();
     __syncthreads();
@@ -139,15 +215,25 @@ __global__ void __launch_bounds__(256, 1) linear_bwd_kernel(const gp_linear_bwd_
 
 template <int H>
 int launch(const gp_linear_bwd_args& a, int32_t* grid_out, cudaStream_t st) {
-    const size_t smem = 1024 + (size_t)((H + 63) / 64) * a.n_src * H * 128 + 2 * kBufBytes;
+    const int nbuf = a.n_src > (H >= 128 ? 2 : 1) ? a.n_src : (H >= 128 ? 2 : 1);
+    const size_t smem = 1024 + (size_t)((H + 63) / 64) * a.n_src * H * 128 + (size_t)(nbuf + 1) * kBufBytes;
+    GP_REQUIRE((int)smem <= gp::max_smem_optin(), "gp_linear_bwd: needs %zu B of shared memory (> %d)", smem, gp::max_smem_optin());
     static int smem_set = 0;      // raised once per instantiation (and never inside a stream capture twice)
     if ((int)smem > smem_set) {
         GP_CHECK_CUDA(cudaFuncSetAttribute(linear_bwd_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         smem_set = (int)smem;
     }
+    LinMaps maps;
+    memset(&maps, 0, sizeof(maps));
+    static const bool no_tma = getenv("GP_NO_TMA") != nullptr;
+    if (!no_tma) {
+        if (gp::tma_map_2d(&maps.x, a.x, a.rows, H, a.ldx)) maps.use |= 1u;
+        for (int s = 0; s < a.n_src; ++s)
+            if (a.src_bf16[s] && gp::tma_map_2d(&maps.src[s], a.src_bf16[s], a.rows, H, a.ld_src[s])) maps.use |= 2u << s;
+    }
     const int n_tiles = (a.rows + 127) / 128;
     const int grid = n_tiles < gp::sm_count() ? n_tiles : gp::sm_count();
-    linear_bwd_kernel<H><<<grid, 256, smem, st>>>(a);
+    linear_bwd_kernel<H><<<grid, 256, smem, st>>>(a, maps);
     GP_CHECK_CUDA(cudaGetLastError());
     if (grid_out) *grid_out = grid;
     return 0;
