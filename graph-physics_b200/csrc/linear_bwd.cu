@@ -250,18 +250,45 @@ __global__ void segsum_gather_kernel(const gp_bf16* __restrict__ src, int ld, co
     float acc[VPT];
 #pragma unroll
     for (int i = 0; i < VPT; ++i) acc[i] = 0.f;
-    for (int j = b; j < e; ++j) {
-        const int r = perm ? __ldg(perm + j) : j;
+    auto add_row = [&](int r) {
         const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(src) + (size_t)r * ld + lane * VPT;
         if constexpr (VPT == 4) {
             const uint2 q = __ldg(reinterpret_cast<const uint2*>(rp));
-            acc[0] = add_bf16_lo(q.x, acc[0]); acc[1] = add_bf16_hi(q.x, acc[1]); acc[2] = add_bf16_lo(q.y, acc[2]); acc[3] = add_bf16_hi(q.y, acc[3]);
+            acc[0] = add_bf16_lo(q.x, acc[0]); acc[1] = add_bf16_hi(q.x, acc[1]);
+            acc[2] = add_bf16_lo(q.y, acc[2]); acc[3] = add_bf16_hi(q.y, acc[3]);
         } else if constexpr (VPT == 2) {
             const uint32_t q = __ldg(reinterpret_cast<const uint32_t*>(rp));
             acc[0] = add_bf16_lo(q, acc[0]); acc[1] = add_bf16_hi(q, acc[1]);
         } else {
             acc[0] += __bfloat162float(rp[0]);
         }
+    };
+    // the segment's row ids are fetched by the lanes in one coalesced read and broadcast, so the row
+    // loads of a segment do not wait on one another (same summation order as a serial walk)
+    for (int base = b; base < e; base += 32) {
+        const int mine = (base + lane < e) ? (perm ? __ldg(perm + base + lane) : base + lane) : 0;
+        const int n = min(32, e - base);
+        int j = 0;
+        for (; j + 4 <= n; j += 4) {
+            const int r0 = __shfl_sync(0xffffffffu, mine, j), r1 = __shfl_sync(0xffffffffu, mine, j + 1);
+            const int r2 = __shfl_sync(0xffffffffu, mine, j + 2), r3 = __shfl_sync(0xffffffffu, mine, j + 3);
+            if constexpr (VPT == 4) {
+                const __nv_bfloat16* bp = reinterpret_cast<const __nv_bfloat16*>(src) + lane * VPT;
+                const uint2 q0 = __ldg(reinterpret_cast<const uint2*>(bp + (size_t)r0 * ld));
+                const uint2 q1 = __ldg(reinterpret_cast<const uint2*>(bp + (size_t)r1 * ld));
+                const uint2 q2 = __ldg(reinterpret_cast<const uint2*>(bp + (size_t)r2 * ld));
+                const uint2 q3 = __ldg(reinterpret_cast<const uint2*>(bp + (size_t)r3 * ld));
+                const uint2 qs[4] = {q0, q1, q2, q3};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    acc[0] = add_bf16_lo(qs[k].x, acc[0]); acc[1] = add_bf16_hi(qs[k].x, acc[1]);
+                    acc[2] = add_bf16_lo(qs[k].y, acc[2]); acc[3] = add_bf16_hi(qs[k].y, acc[3]);
+                }
+            } else {
+                add_row(r0); add_row(r1); add_row(r2); add_row(r3);
+            }
+        }
+        for (; j < n; ++j) add_row(__shfl_sync(0xffffffffu, mine, j));
     }
     float* o = out + (size_t)seg * (32 * VPT) + lane * VPT;
 #pragma unroll

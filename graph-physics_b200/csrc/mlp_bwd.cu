@@ -657,32 +657,48 @@ struct ReduceSegs {
     gp_reduce_seg s[8];
     int n;
 };
-// Block = 32 elements x 8 partial-groups: thread (tx, ty) adds the partial blocks p = ty, ty+8, ...
-// in ascending order, then the 8 group sums are added in fixed order -> bit-reproducible.
+// Block = 32 lanes x 8 partial-groups: thread (tx, ty) adds the partial blocks p = ty, ty+8, ... in
+// ascending order, then the 8 group sums are added in fixed order -> bit-reproducible.  VEC = 4:
+// every lane owns four consecutive elements (16-byte loads; needs 4-element alignment of every
+// offset / stride, checked on the host), VEC = 1 is the general path.
+template <int VEC>
 __global__ void __launch_bounds__(256) reduce_multi_kernel(const float* __restrict__ partials, int n_parts, int stride,
                                                            ReduceSegs segs) {
-    __shared__ float sh[8][33];
+    __shared__ float sh[8][32 * VEC + 4];
     const gp_reduce_seg sg = segs.s[blockIdx.y];
     const int total = sg.rows * sg.cols;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    for (int base = blockIdx.x * 32; base < total; base += gridDim.x * 32) {
-        const int i = base + tx;
-        float acc = 0.f;
+    for (int base = blockIdx.x * 32 * VEC; base < total; base += gridDim.x * 32 * VEC) {
+        const int i = base + tx * VEC;
+        float acc[VEC];
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) acc[v] = 0.f;
         int r = 0, c = 0;
         if (i < total) {
             r = i / sg.cols;
             c = i - r * sg.cols;
             const float* src = partials + sg.offset + (size_t)r * sg.ld_part + c;
-            for (int pi = ty; pi < n_parts; pi += 8) acc += src[(size_t)pi * stride];
+            for (int pi = ty; pi < n_parts; pi += 8) {
+                if constexpr (VEC == 4) {
+                    const float4 q = *reinterpret_cast<const float4*>(src + (size_t)pi * stride);
+                    acc[0] += q.x; acc[1] += q.y; acc[2] += q.z; acc[3] += q.w;
+                } else {
+                    acc[0] += src[(size_t)pi * stride];
+                }
+            }
         }
-        sh[ty][tx] = acc;
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) sh[ty][tx * VEC + v] = acc[v];
         __syncthreads();
         if (ty == 0 && i < total) {
-            float t = sh[0][tx];
-#pragma unroll
-            for (int k = 1; k < 8; ++k) t += sh[k][tx];
             float* d = sg.dst + (size_t)r * sg.ld_dst + c;
-            *d = sg.accumulate ? (*d + t) : t;
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+                float t = sh[0][tx * VEC + v];
+#pragma unroll
+                for (int k = 1; k < 8; ++k) t += sh[k][tx * VEC + v];
+                d[v] = sg.accumulate ? (d[v] + t) : t;
+            }
         }
         __syncthreads();
     }
@@ -784,11 +800,21 @@ extern "C" int gp_reduce_partials_multi(const float* partials, int32_t n_parts, 
         const int t = segs_host[i].rows * segs_host[i].cols;
         if (t > max_total) max_total = t;
     }
-    int bx = (max_total + 31) / 32;
+    bool vec4 = (stride % 4 == 0) && ((reinterpret_cast<uintptr_t>(partials) & 15u) == 0);
+    for (int i = 0; i < n_segs && vec4; ++i) {
+        const gp_reduce_seg& g = segs_host[i];
+        vec4 = g.cols % 4 == 0 && g.offset % 4 == 0 && g.ld_part % 4 == 0 && g.ld_dst % 4 == 0 &&
+               (reinterpret_cast<uintptr_t>(g.dst) & 15u) == 0;
+    }
+    const int per_block = vec4 ? 128 : 32;
+    int bx = (max_total + per_block - 1) / per_block;
     if (bx > 512) bx = 512;
     if (bx < 1) bx = 1;
     dim3 grid(bx, n_segs);
-    reduce_multi_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(partials, n_parts, stride, segs);
+    if (vec4)
+        reduce_multi_kernel<4><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(partials, n_parts, stride, segs);
+    else
+        reduce_multi_kernel<1><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(partials, n_parts, stride, segs);
     GP_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

@@ -449,23 +449,39 @@ __global__ void __launch_bounds__(kSlotThreads * NG, 1) mlp_fwd_kernel(const gp_
     if (tid < 32) tmem_dealloc(tmem_base, kTmemCols);
 }
 
-__global__ void seg_fixup_kernel(const int32_t* __restrict__ rowptr, int num_segments, int H, int SUB,
-                                 const float* __restrict__ bnd, float* __restrict__ out) {
-    // one warp per segment; lanes stride the H columns
-    const int seg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+// One thread per segment classifies it (complete inside one sub-tile: nothing to do; empty: zero row;
+// spanning sub-tiles: sum of its boundary partials) from two coalesced rowptr reads; the warp then
+// walks its flagged segments together, 16 bytes of the row per lane.
+__global__ void __launch_bounds__(256) seg_fixup_kernel(const int32_t* __restrict__ rowptr, int num_segments, int H, int sub_shift,
+                                                        const float* __restrict__ bnd, float* __restrict__ out) {
+    const int seg = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
-    if (seg >= num_segments) return;
-    const int s = rowptr[seg], e = rowptr[seg + 1];
-    if (s == e) {
-        for (int c = lane; c < H; c += 32) out[(size_t)seg * H + c] = 0.f;
-        return;
+    int s = 0, e = 0;
+    bool flagged = false;
+    if (seg < num_segments) {
+        s = rowptr[seg];
+        e = rowptr[seg + 1];
+        flagged = (s == e) || ((s >> sub_shift) != ((e - 1) >> sub_shift));
     }
-    const int t0 = s / SUB, t1 = (e - 1) / SUB;
-    if (t0 == t1) return;
-    for (int c = lane; c < H; c += 32) {
-        float acc = bnd[((size_t)t0 * 2 + 1) * H + c];
-        for (int t = t0 + 1; t <= t1; ++t) acc += bnd[((size_t)t * 2) * H + c];
-        out[(size_t)seg * H + c] = acc;
+    unsigned todo = __ballot_sync(0xffffffffu, flagged);
+    const int c4 = lane * 4;
+    while (todo) {
+        const int src = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const int sg = __shfl_sync(0xffffffffu, seg, src);
+        const int ss = __shfl_sync(0xffffffffu, s, src), ee = __shfl_sync(0xffffffffu, e, src);
+        if (c4 < H) {
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ss != ee) {
+                const int t0 = ss >> sub_shift, t1 = (ee - 1) >> sub_shift;
+                acc = *reinterpret_cast<const float4*>(bnd + ((size_t)t0 * 2 + 1) * H + c4);
+                for (int t = t0 + 1; t <= t1; ++t) {
+                    const float4 b = *reinterpret_cast<const float4*>(bnd + ((size_t)t * 2) * H + c4);
+                    acc.x += b.x; acc.y += b.y; acc.z += b.z; acc.w += b.w;
+                }
+            }
+            *reinterpret_cast<float4*>(out + (size_t)sg * H + c4) = acc;
+        }
     }
 }
 
@@ -540,10 +556,13 @@ extern "C" int gp_seg_sub_rows(int32_t hidden, int32_t backward) {
 extern "C" int gp_seg_fixup(const int32_t* rowptr, int32_t num_segments, int32_t hidden, int32_t sub_rows,
                             const float* seg_bnd, float* seg_out, void* stream) {
     if (num_segments <= 0) return 0;
-    GP_REQUIRE(sub_rows > 0, "gp_seg_fixup: sub_rows must be positive");
+    GP_REQUIRE(sub_rows > 0 && (sub_rows & (sub_rows - 1)) == 0, "gp_seg_fixup: sub_rows must be a power of two");
+    GP_REQUIRE(hidden % 4 == 0 && hidden <= 128, "gp_seg_fixup: hidden must be a multiple of 4, at most 128");
+    int shift = 0;
+    while ((1 << shift) < sub_rows) ++shift;
     const int threads = 256;
-    const int blocks = (int)(((size_t)num_segments * 32 + threads - 1) / threads);
-    seg_fixup_kernel<<<blocks, threads, 0, static_cast<cudaStream_t>(stream)>>>(rowptr, num_segments, hidden, sub_rows,
+    const int blocks = (num_segments + threads - 1) / threads;
+    seg_fixup_kernel<<<blocks, threads, 0, static_cast<cudaStream_t>(stream)>>>(rowptr, num_segments, hidden, shift,
                                                                                  seg_bnd, seg_out);
     GP_CHECK_CUDA(cudaGetLastError());
     return 0;
