@@ -14,15 +14,6 @@
 namespace {
 using namespace gp;
 
-// fp32 staging tile [128 rows x H] used to turn the row-per-lane TMEM read-out into row-major,
-// fully coalesced global stores: 16-byte chunk c of row r lives at chunk c ^ (r & (CPR-1)).
-template <int H>
-__device__ __forceinline__ uint32_t stage_f32_off(int r, int chunk) {
-    constexpr int CPR = H / 4;                      // 16-byte chunks per row
-    constexpr int SW = CPR < 32 ? CPR : 32;
-    return (uint32_t)r * (H * 4) + (uint32_t)((chunk ^ (r & (SW - 1))) << 4);
-}
-
 struct LinMaps {
     CUtensorMap x, src[3];
     uint32_t use;                                   // bit 0: x, bits 1..3: bf16 sources
@@ -167,7 +158,7 @@ __global__ void __launch_bounds__(256, 1) linear_bwd_kernel(const gp_linear_bwd_
             tmem_ld_wait();
 #pragma unroll
             for (int q = 0; q < 4; ++q)
-                *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(stg) + stage_f32_off<H>(row, (half * CH + c0) / 4 + q)) =
+                *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(stg) + stage_f32_off(row, (half * CH + c0) / 4 + q, H)) =
                     make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
         }
         tc_fence_before();
@@ -177,7 +168,7 @@ __global__ void __launch_bounds__(256, 1) linear_bwd_kernel(const gp_linear_bwd_
             const int i = tid + j * 256;
             const int r = i / CPR, ch = i % CPR;
             if (R0 + r < p.rows) {
-                float4 o = *reinterpret_cast<const float4*>(reinterpret_cast<const uint8_t*>(stg) + stage_f32_off<H>(r, ch));
+                float4 o = *reinterpret_cast<const float4*>(reinterpret_cast<const uint8_t*>(stg) + stage_f32_off(r, ch, H));
                 if (p.dx_in) { o.x += din[j].x; o.y += din[j].y; o.z += din[j].z; o.w += din[j].w; }
                 reinterpret_cast<float4*>(p.dx_out + (size_t)(R0 + r) * H)[ch] = o;
             }
@@ -189,25 +180,8 @@ __global__ void __launch_bounds__(256, 1) linear_bwd_kernel(const gp_linear_bwd_
     // ---- dump the weight-gradient accumulators (lane r <-> row r of dWp_s) through the staging tile
     tc_fence_after();
     float* P = p.partials + (size_t)blockIdx.x * S * H * H;
-    for (int s = 0; s < S; ++s) {
-#pragma unroll
-        for (int c0 = 0; c0 < CH; c0 += 16) {
-            uint32_t v[16];
-            tmem_ld16(tlane + 128 * (1 + s) + half * CH + c0, v);
-            tmem_ld_wait();
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-                *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(stg) + stage_f32_off<H>(row, (half * CH + c0) / 4 + q)) =
-                    make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-        }
-        __syncthreads();
-        for (int i = tid; i < H * CPR; i += 256) {
-            const int r = i / CPR, ch = i % CPR;
-            reinterpret_cast<float4*>(P + ((size_t)s * H + r) * H)[ch] =
-                *reinterpret_cast<const float4*>(reinterpret_cast<const uint8_t*>(stg) + stage_f32_off<H>(r, ch));
-        }
-        __syncthreads();
-    }
+    for (int s = 0; s < S; ++s)
+        tmem_rows_to_global<256>(tlane, 128 * (1 + s), H, H, P + (size_t)s * H * H, H, reinterpret_cast<uint8_t*>(stg), tid);
     tc_fence_before();
     __syncthreads();
     if (tid < 32) tmem_dealloc(tmem, 512);

@@ -594,33 +594,12 @@ __global__ void __launch_bounds__(BwdCfg<H>::NT, 1) mlp_bwd_kernel(const gp_mlp_
     if ((t_da || t_out) && warp == 0 && elect_one()) tma_store_wait_all();
     // ---- dump the weight-gradient accumulators of this CTA (lane r <-> output row r)
     tc_fence_after();
+    const BwdLayout L = bwd_layout(H, ka, nb);
+    float* P = p.partials + (size_t)blockIdx.x * L.stride;
+    // the two weight-gradient matrices leave through a staging tile (ain + ha, contiguous) as coalesced rows
+    tmem_rows_to_global<NT>(tlane, kColDWB, nb, H, P + L.off_dwb, H, ain, tid);
+    tmem_rows_to_global<NT>(tlane, kColDWA, H, ka, P + L.off_dwa, ka, ain, tid);
     if (tid < 128) {
-        const BwdLayout L = bwd_layout(H, ka, nb);
-        float* P = p.partials + (size_t)blockIdx.x * L.stride;
-        for (int c0 = 0; c0 < H; c0 += 16) {
-            uint32_t v[16];
-            tmem_ld16(tlane + kColDWB + c0, v);
-            tmem_ld_wait();
-            if (row < nb) {
-                float4* d = reinterpret_cast<float4*>(P + L.off_dwb + (size_t)row * H + c0);
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    d[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
-                                       __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
-            }
-        }
-        for (int c0 = 0; c0 < ka; c0 += 16) {
-            uint32_t v[16];
-            tmem_ld16(tlane + kColDWA + c0, v);
-            tmem_ld_wait();
-            if (row < H) {
-                float4* d = reinterpret_cast<float4*>(P + L.off_dwa + (size_t)row * ka + c0);
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    d[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
-                                       __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
-            }
-        }
         uint32_t v8[8];
         tmem_ld8(tlane + kColDBB, v8);
         tmem_ld_wait();
@@ -654,7 +633,7 @@ __global__ void reduce_partials_kernel(const float* __restrict__ partials, int n
 }
 
 struct ReduceSegs {
-    gp_reduce_seg s[8];
+    gp_reduce_seg s[16];
     int n;
 };
 // Block = 32 lanes x 8 partial-groups: thread (tx, ty) adds the partial blocks p = ty, ty+8, ... in
@@ -662,10 +641,11 @@ struct ReduceSegs {
 // every lane owns four consecutive elements (16-byte loads; needs 4-element alignment of every
 // offset / stride, checked on the host), VEC = 1 is the general path.
 template <int VEC>
-__global__ void __launch_bounds__(256) reduce_multi_kernel(const float* __restrict__ partials, int n_parts, int stride,
-                                                           ReduceSegs segs) {
+__global__ void __launch_bounds__(256) reduce_multi_kernel(const __grid_constant__ ReduceSegs segs) {
     __shared__ float sh[8][32 * VEC + 4];
-    const gp_reduce_seg sg = segs.s[blockIdx.y];
+    const gp_reduce_seg& sg = segs.s[blockIdx.y];
+    const float* __restrict__ partials = sg.partials;
+    const int n_parts = sg.n_parts, stride = sg.stride;
     const int total = sg.rows * sg.cols;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     for (int base = blockIdx.x * 32 * VEC; base < total; base += gridDim.x * 32 * VEC) {
@@ -790,21 +770,25 @@ extern "C" int gp_reduce_partials(const float* partials, int32_t n_parts, int32_
 
 extern "C" int gp_reduce_partials_multi(const float* partials, int32_t n_parts, int32_t stride,
                                         const gp_reduce_seg* segs_host, int32_t n_segs, void* stream) {
-    GP_REQUIRE(n_segs >= 0 && n_segs <= 8, "gp_reduce_partials_multi: at most 8 segments");
+    GP_REQUIRE(n_segs >= 0 && n_segs <= 16, "gp_reduce_partials_multi: at most 16 segments");
     if (n_segs == 0) return 0;
     ReduceSegs segs;
     segs.n = n_segs;
     int max_total = 0;
+    bool vec4 = true;
     for (int i = 0; i < n_segs; ++i) {
-        segs.s[i] = segs_host[i];
-        const int t = segs_host[i].rows * segs_host[i].cols;
+        gp_reduce_seg& g = segs.s[i];
+        g = segs_host[i];
+        if (!g.partials) {
+            g.partials = partials;
+            g.n_parts = n_parts;
+            g.stride = stride;
+        }
+        GP_REQUIRE(g.partials != nullptr && g.n_parts > 0, "gp_reduce_partials_multi: segment %d has no partials", i);
+        const int t = g.rows * g.cols;
         if (t > max_total) max_total = t;
-    }
-    bool vec4 = (stride % 4 == 0) && ((reinterpret_cast<uintptr_t>(partials) & 15u) == 0);
-    for (int i = 0; i < n_segs && vec4; ++i) {
-        const gp_reduce_seg& g = segs_host[i];
-        vec4 = g.cols % 4 == 0 && g.offset % 4 == 0 && g.ld_part % 4 == 0 && g.ld_dst % 4 == 0 &&
-               (reinterpret_cast<uintptr_t>(g.dst) & 15u) == 0;
+        vec4 = vec4 && g.stride % 4 == 0 && (reinterpret_cast<uintptr_t>(g.partials) & 15u) == 0 && g.cols % 4 == 0 &&
+               g.offset % 4 == 0 && g.ld_part % 4 == 0 && g.ld_dst % 4 == 0 && (reinterpret_cast<uintptr_t>(g.dst) & 15u) == 0;
     }
     const int per_block = vec4 ? 128 : 32;
     int bx = (max_total + per_block - 1) / per_block;
@@ -812,9 +796,9 @@ extern "C" int gp_reduce_partials_multi(const float* partials, int32_t n_parts, 
     if (bx < 1) bx = 1;
     dim3 grid(bx, n_segs);
     if (vec4)
-        reduce_multi_kernel<4><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(partials, n_parts, stride, segs);
+        reduce_multi_kernel<4><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(segs);
     else
-        reduce_multi_kernel<1><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(partials, n_parts, stride, segs);
+        reduce_multi_kernel<1><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(segs);
     GP_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

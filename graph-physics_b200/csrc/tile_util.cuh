@@ -130,6 +130,41 @@ __device__ __forceinline__ void init_staged_to_tmem(uint32_t tacc, const uint8_t
     tmem_st_wait();
 }
 
+// fp32 staging tile [128 rows x ncols] that turns a row-per-lane TMEM read-out into row-major,
+// fully coalesced global stores: 16-byte chunk c of row r lives at chunk c ^ (r & (SW-1)),
+// SW = min(largest power of two dividing the chunks per row, 32) (conflict-free for the lane-per-row writes and the row-major reads).
+__device__ __forceinline__ uint32_t stage_f32_off(int r, int chunk, int ncols) {
+    const int cpr = ncols >> 2;
+    const int low = cpr & -cpr;                     // largest power of two dividing the chunk count
+    const int sw = low < 32 ? low : 32;
+    return (uint32_t)r * (uint32_t)(ncols * 4) + (uint32_t)((chunk ^ (r & (sw - 1))) << 4);
+}
+
+// Copy a TMEM-resident fp32 matrix (lane r = row r, columns [col0, col0 + ncols) of this warp's
+// lanes at `tlane`) to global memory, rows [0, nrows), through the staging tile `stg`
+// (>= 128 * ncols * 4 bytes).  Called by all NT threads of the CTA; part = tid >> 7.
+template <int NT>
+__device__ __forceinline__ void tmem_rows_to_global(uint32_t tlane, uint32_t col0, int nrows, int ncols, float* dst,
+                                                    int ld_dst, uint8_t* stg, int tid) {
+    const int row = tid & 127, part = tid >> 7;
+    for (int c0 = part * 16; c0 < ncols; c0 += (NT / 128) * 16) {
+        uint32_t v[16];
+        tmem_ld16(tlane + col0 + c0, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            *reinterpret_cast<uint4*>(stg + stage_f32_off(row, c0 / 4 + q, ncols)) =
+                make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    }
+    __syncthreads();
+    const int cpr = ncols >> 2;
+    for (int i = tid; i < nrows * cpr; i += NT) {
+        const int r = i / cpr, ch = i - r * cpr;
+        reinterpret_cast<float4*>(dst + (size_t)r * ld_dst)[ch] = *reinterpret_cast<const float4*>(stg + stage_f32_off(r, ch, ncols));
+    }
+    __syncthreads();
+}
+
 // Segment sum over the rows of one 128-row tile held in `buf` (bf16, SW128 layout, H columns),
 // by NT threads: thread t owns column pair (t % (H/2)) of the sub-tile of SUB = 64*H/NT rows
 // number t / (H/2).  sseg[3] = segment id of the row before the tile, sseg[4..131] = rows,

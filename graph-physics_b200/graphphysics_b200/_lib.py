@@ -168,6 +168,9 @@ class ReduceSeg(C.Structure):
         ("dst", C.c_void_p),
         ("ld_dst", C.c_int32),
         ("accumulate", C.c_int32),
+        ("partials", C.c_void_p),
+        ("n_parts", C.c_int32),
+        ("stride", C.c_int32),
     ]
 
 

@@ -56,8 +56,13 @@ class EPDEngine:
         self._build_flat()
         self._build_packed()
         H = self.H
+        # Per-CTA weight-gradient partials: kNRegions regions, one per backward launch whose reduction is
+        # still pending, so one reduction launch serves a whole processor layer (5 kernels).
         stride_max = max(ops.bwd_layout(H, 128, 128)[5], 3 * H * H)
-        self.partials = torch.empty(ops.sm_count() * stride_max, dtype=torch.float32, device=self.device)
+        self._region_elems = ops.sm_count() * stride_max
+        self.partials_all = torch.empty(self.kNRegions * self._region_elems, dtype=torch.float32, device=self.device)
+        self._pending: list = []
+        self._region = 0
         self._sq_ws = torch.empty(256, dtype=torch.float32, device=self.device)
         self.sqnorm = torch.zeros(1, dtype=torch.float32, device=self.device)
 
@@ -235,6 +240,27 @@ class EPDEngine:
         return out, e, ctx
 
     # ------------------------------------------------------------------ backward
+    kNRegions = 5
+
+    @property
+    def partials(self) -> torch.Tensor:
+        """Partial-gradient region of the next backward launch (the previous ones stay untouched until
+        `_flush_reduce`)."""
+        if self._region >= self.kNRegions:
+            self._flush_reduce()
+        return self.partials_all[self._region * self._region_elems:(self._region + 1) * self._region_elems]
+
+    def _queue_reduce(self, grid: int, stride: int, segs) -> None:
+        """Queue the reduction of the launch that just wrote the current region, and move on to the next."""
+        base = self.partials_all.data_ptr() + 4 * self._region * self._region_elems
+        self._pending += [tuple(sg) + (base, grid, stride) for sg in segs]
+        self._region += 1
+
+    def _flush_reduce(self) -> None:
+        if self._pending:
+            ops.reduce_multi(None, 0, 0, self._pending)
+        self._pending, self._region = [], 0
+
     def _reduce_stage(self, grid, ka, nb, s: _MLPSlots, ia: int, ib: int, with_scale: bool):
         """Per-CTA partial blocks of a stage over layers (ia, ib) of MLP `s` -> flat gradient buffer."""
         H = self.H
@@ -249,7 +275,7 @@ class EPDEngine:
         ]
         if with_scale:
             segs.append((o_dsc, 1, H, H, gp + 4 * s.scale_off, H, False))
-        ops.reduce_multi(self.partials, grid, stride, segs)
+        self._queue_reduce(grid, stride, segs)
 
     def _mlp_backward(self, s: _MLPSlots, rows, *, a_in, ka, h2, top, first=None, out=None, out_resid=None,
                       delta_a_out=None, seg=None, tag=None):
@@ -310,16 +336,19 @@ class EPDEngine:
             dX_new = torch.empty((N, H), dtype=torch.float32, device=dev)
             grid = ops.linear_bwd(N, H, [dPd, dPs, dQ], self.proj[l], x, dX, dX_new, self.partials)
             pe, pn = f"processor_list.{l}.edge_block.0.weight", f"processor_list.{l}.node_block.0.weight"
-            ops.reduce_multi(self.partials, grid, 3 * H * H, [
+            self._queue_reduce(grid, 3 * H * H, [
                 (0, H, H, H, gp + 4 * (self.offsets[pe] + H), 3 * H, False),
                 (H * H, H, H, H, gp + 4 * (self.offsets[pe] + 2 * H), 3 * H, False),
                 (2 * H * H, H, H, H, gp + 4 * self.offsets[pn], 2 * H, False),
             ])
+            self._flush_reduce()      # one reduction launch per processor layer
             dX, dE = dX_new, dE_new
         if self.only_processor:
+            self._flush_reduce()
             return dX, dE
         self._mlp_backward(self.enc_n, N, a_in=ctx["xin_p"], ka=ctx["xin_p"].shape[1], h2=ctx["h2n0"], top=dict(gy=dX))
         self._mlp_backward(self.enc_e, E, a_in=ctx["ea_p"], ka=ctx["ea_p"].shape[1], h2=ctx["h2e0"], top=dict(gy=dE))
+        self._flush_reduce()
         return None, None
 
     # ------------------------------------------------------------------ optimizer helpers

@@ -318,15 +318,25 @@ def segsum_gather(src: torch.Tensor, perm: Optional[torch.Tensor], rowptr: torch
     _launched()
 
 
-def reduce_multi(partials: torch.Tensor, n_parts: int, stride: int, segs) -> None:
-    """segs: list of (offset, rows, cols, ld_part, dst_ptr(int), ld_dst, accumulate)."""
-    arr = (ReduceSeg * len(segs))()
-    for i, (off, rows, cols, ldp, dst, ldd, acc) in enumerate(segs):
-        arr[i].offset, arr[i].rows, arr[i].cols, arr[i].ld_part = off, rows, cols, ldp
-        arr[i].dst, arr[i].ld_dst, arr[i].accumulate = dst, ldd, 1 if acc else 0
-    check(lib().gp_reduce_partials_multi(C.c_void_p(ptr(partials)), n_parts, stride, arr, len(segs),
-                                         C.c_void_p(stream_ptr())), "gp_reduce_partials_multi")
-    _launched()
+def reduce_multi(partials: Optional[torch.Tensor], n_parts: int, stride: int, segs) -> None:
+    """segs: list of (offset, rows, cols, ld_part, dst_ptr(int), ld_dst, accumulate) -- reduced from the
+    call-level `partials` (n_parts blocks of `stride` floats) -- optionally extended by
+    (partials_ptr(int), n_parts, stride) for a segment that lives in another partial buffer.
+    At most 16 segments per launch (longer lists are split)."""
+    for lo in range(0, len(segs), 16):
+        chunk = segs[lo:lo + 16]
+        arr = (ReduceSeg * len(chunk))()
+        for i, sg in enumerate(chunk):
+            off, rows, cols, ldp, dst, ldd, acc = sg[:7]
+            arr[i].offset, arr[i].rows, arr[i].cols, arr[i].ld_part = off, rows, cols, ldp
+            arr[i].dst, arr[i].ld_dst, arr[i].accumulate = dst, ldd, 1 if acc else 0
+            if len(sg) > 7:
+                arr[i].partials, arr[i].n_parts, arr[i].stride = sg[7], sg[8], sg[9]
+            else:
+                arr[i].partials, arr[i].n_parts, arr[i].stride = None, 0, 0
+        check(lib().gp_reduce_partials_multi(C.c_void_p(ptr(partials) if partials is not None else None), n_parts, stride,
+                                             arr, len(chunk), C.c_void_p(stream_ptr())), "gp_reduce_partials_multi")
+        _launched()
 
 
 _MSE_WS: dict = {}
