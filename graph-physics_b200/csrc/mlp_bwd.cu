@@ -43,10 +43,10 @@ __host__ __device__ inline BwdLayout bwd_layout(int H, int ka, int nb) {
 // elected thread, 16 KB per instruction, straight into / out of the SW128 layout); the flags say
 // which descriptors are valid, everything else falls back to per-thread 16-byte copies.
 struct BwdMaps {
-    CUtensorMap ain, db, gy, resid, da_out, out;
+    CUtensorMap ain, db, gy, resid, da_out, out, ha;
     uint32_t use;
 };
-enum : uint32_t { kMapAin = 1, kMapDb = 2, kMapGy = 4, kMapResid = 8, kMapDaOut = 16, kMapOut = 32 };
+enum : uint32_t { kMapAin = 1, kMapDb = 2, kMapGy = 4, kMapResid = 8, kMapDaOut = 16, kMapOut = 32, kMapHa = 64 };
 
 // Threads per CTA: 128 rows x NPART column parts (4 parts = 16 warps at H = 128, where the epilogues are
 // latency-bound and need the extra warps; 2 parts for narrower layers).
@@ -56,7 +56,13 @@ struct BwdCfg {
     static constexpr int NT = 128 * NPART;
 };
 
-template <int H>
+// MODE 0 is the general kernel.  MODE 1 / 2 are the instantiations for the two stages of the processor's
+// edge MLP at H = 128 (1: layers 3-4 with the RMSNorm backward and the gathered receiver gradient;
+// 2: layers 1-2 with the two gathered pre-activation sources, the stored delta_1 and its segment
+// sum), with every option -- including which tensors move by TMA -- fixed at compile time.  The
+// general kernel is 100 KB of code that each tile streams through the instruction cache; the
+// specialised ones keep only their own path.
+template <int H, int MODE>
 __global__ void __launch_bounds__(BwdCfg<H>::NT, 1) mlp_bwd_kernel(const gp_mlp_bwd_args p,
                                                                      const __grid_constant__ BwdMaps maps) {
     constexpr int NPART = BwdCfg<H>::NPART;
@@ -68,11 +74,17 @@ __global__ void __launch_bounds__(BwdCfg<H>::NT, 1) mlp_bwd_kernel(const gp_mlp_
 
     const int tid = threadIdx.x;
     const int row = tid & 127, part = tid >> 7;
-    const bool t_ain = maps.use & kMapAin, t_db = maps.use & kMapDb, t_gy = maps.use & kMapGy;
-    const bool t_res = maps.use & kMapResid, t_da = maps.use & kMapDaOut, t_out = maps.use & kMapOut;
+    constexpr bool F1 = MODE == 1, F2 = MODE == 2, F = F1 || F2;
+    const bool t_ain = F || (maps.use & kMapAin), t_db = F2 || (!F && (maps.use & kMapDb)), t_gy = F1 || (!F && (maps.use & kMapGy));
+    const bool t_res = F2 || (!F && (maps.use & kMapResid)), t_da = F2 || (!F && (maps.use & kMapDaOut));
+    const bool t_out = F || (maps.use & kMapOut), t_ha = !F && (maps.use & kMapHa);
+    const bool ha_given = !F && p.ha_saved != nullptr;       // h_a comes from memory: no gather, no recompute
+    const bool f_gather = F1 || (!F && p.gy_gather != nullptr);     // receiver-indexed fp32 rows are added to gy
+    const bool f_seg = F2 || (!F && p.seg_id != nullptr), f_da = F2 || (!F && p.delta_a_out != nullptr);
+    const bool f_din = F || p.need_din, f_mask = F1 || (!F && p.mask_by_ain), f_resid = F2 || (!F && p.out_resid != nullptr);
     const int warp = warp_uniform(tid >> 5);
-    const int ka = p.ka, nb = p.nb;
-    const bool norm = p.mode == 1;
+    const int ka = F ? H : p.ka, nb = F ? H : p.nb;
+    const bool norm = F1 || (!F && p.mode == 1);
 
     // ---- carve
     uint32_t off = 0;
@@ -123,7 +135,7 @@ __global__ void __launch_bounds__(BwdCfg<H>::NT, 1) mlp_bwd_kernel(const gp_mlp_
     const uint32_t lbo_h = (H >= 128) ? 16384u : 0u;      // M=128 MN-major A with < 128 valid columns: alias block
     const uint32_t lbo_nb = (nb >= 128) ? 16384u : 0u;
     uint32_t phase = 0, tphase = 0;
-    const bool has_init = p.init != nullptr;
+    const bool has_init = F2 || (!F && p.init != nullptr && !ha_given);
     const int n_tiles = (p.rows + 127) >> 7;
     constexpr int CH = H / NPART;                          // columns per thread
     const int cb = part * CH;
@@ -141,10 +153,10 @@ __global__ void __launch_bounds__(BwdCfg<H>::NT, 1) mlp_bwd_kernel(const gp_mlp_
 
     constexpr int KC = H / 8;                 // 16-byte chunks per H-wide row
     constexpr int CPT = 128 * KC / NT;       // chunks per thread in a row-major tile copy
-    const bool stage1 = p.two_inits != 0;     // which pre-activation source is gathered through shared memory
+    const bool stage1 = F2 || (!F && p.two_inits != 0);     // which pre-activation source is gathered through shared memory
     const int32_t* sidx = stage1 ? p.idx1 : p.idx0;
     const int soff = stage1 ? p.init_off1 : p.init_off0;
-    const bool du_smem = norm && p.gy_bf16 != nullptr;     // upstream gradient tile staged in qb (+ gathered rows in db)
+    const bool du_smem = F1 || (!F && norm && p.gy_bf16 != nullptr);     // upstream gradient tile staged in qb (+ gathered rows in db)
 
     const bool prof = p.prof != nullptr && tid == 0;
     long long tk = 0;
@@ -163,11 +175,11 @@ __global__ void __launch_bounds__(BwdCfg<H>::NT, 1) mlp_bwd_kernel(const gp_mlp_
         for (int j = 0; j < CPT; ++j) {
             const int gr = min(R0_ + (tid + j * NT) / KC, p.rows - 1);
             ridx[j] = (has_init && sidx) ? __ldg(sidx + gr) : gr;
-            gidx[j] = (du_smem && p.gy_gather && p.gy_idx) ? __ldg(p.gy_idx + gr) : gr;
+            gidx[j] = (du_smem && f_gather && (F1 || p.gy_idx)) ? __ldg(p.gy_idx + gr) : gr;
         }
         if (has_init && stage1) {
             const int r = min(R0_ + row, p.rows - 1);
-            i0n = p.idx0 ? __ldg(p.idx0 + r) : r;
+            i0n = (F2 || p.idx0) ? __ldg(p.idx0 + r) : r;
         }
     };
     if ((int)blockIdx.x < n_tiles) load_idx(blockIdx.x);
@@ -183,7 +195,7 @@ __global__ void __launch_bounds__(BwdCfg<H>::NT, 1) mlp_bwd_kernel(const gp_mlp_
         // ---- P0: stage inputs.  Every tile-shaped transfer uses row-major 16-byte chunks (8 lanes per
         //      cache line); tiles are transposed to the row-per-thread mapping through shared memory.
         const uint32_t tma_blocks = (t_ain ? (ka + 63) >> 6 : 0) + (t_db ? (nb + 63) >> 6 : 0) + (t_gy ? (H + 63) >> 6 : 0) +
-                                    (t_res ? (ka + 63) >> 6 : 0);
+                                    (t_res ? (ka + 63) >> 6 : 0) + (t_ha ? (H + 63) >> 6 : 0);
         if (tma_blocks && warp == 0 && elect_one()) {
             // the bulk stores of the previous tile have read their shared-memory sources (the output
             // staging buffer is only ever refilled by this thread's own loads below)
@@ -197,8 +209,21 @@ __global__ void __launch_bounds__(BwdCfg<H>::NT, 1) mlp_bwd_kernel(const gp_mlp_
                 for (int b = 0; b < (H + 63) >> 6; ++b) tma_load_2d(qb_s + b * 16384, &maps.gy, b * 64, R0, &tma_bar);
             if (t_res)
                 for (int b = 0; b < (ka + 63) >> 6; ++b) tma_load_2d(qb_s + b * 16384, &maps.resid, b * 64, R0, &tma_bar);
+            if (t_ha)
+                for (int b = 0; b < (H + 63) >> 6; ++b) tma_load_2d(ha_s + b * 16384, &maps.ha, b * 64, R0, &tma_bar);
         }
-        if (!t_ain) stage_rows(ain, p.a_bf16, p.a_f32, ka, p.lda, R0, p.rows, tid, NT);
+        if (ha_given && !t_ha) {
+#pragma unroll
+            for (int j = 0; j < CPT; ++j) {
+                const int i = tid + j * NT;
+                const int r = i / KC, ch = i % KC;
+                if (R0 + r < p.rows)
+                    cp_async16(ha_s + sw128_off(128, r, ch * 8), p.ha_saved + (size_t)(R0 + r) * H + ch * 8);
+                else
+                    *reinterpret_cast<uint4*>(ha + sw128_off(128, r, ch * 8)) = make_uint4(0, 0, 0, 0);
+            }
+        }
+        if (!t_ain) stage_rows(ain, p.a_bf16, F ? nullptr : p.a_f32, ka, p.lda, R0, p.rows, tid, NT);
         if (!norm && !t_db) {   // delta_b given: zero rows past the end so they add nothing to the weight gradients
             const int kc = nb >> 3;
             for (int i = tid; i < 128 * kc; i += NT) {
@@ -225,7 +250,7 @@ __global__ void __launch_bounds__(BwdCfg<H>::NT, 1) mlp_bwd_kernel(const gp_mlp_
                 cp_async16(ha_s + sw128_off(128, r, ch * 8), p.init + (size_t)ridx[j] * p.ld_init + soff + ch * 8);
             }
         }
-        if (du_smem && p.gy_gather) {   // receiver-indexed fp32 rows, rounded to bf16 into db; loads batched by 4 chunks
+        if (du_smem && f_gather) {   // receiver-indexed fp32 rows, rounded to bf16 into db; loads batched by 4 chunks
 #pragma unroll
             for (int j0 = 0; j0 < CPT; j0 += 4) {
                 float4 u[8];
@@ -248,7 +273,7 @@ __global__ void __launch_bounds__(BwdCfg<H>::NT, 1) mlp_bwd_kernel(const gp_mlp_
         }
         cp_async_commit();
         int sid_me = -1, sid_prev = -1, sid_next = -1;
-        if (p.seg_id && tid < 128) {
+        if (f_seg && tid < 128) {
             if (valid) sid_me = __ldg(p.seg_id + grow);
             if (row == 0) {
                 if (R0 > 0) sid_prev = __ldg(p.seg_id + R0 - 1);
@@ -269,12 +294,15 @@ __global__ void __launch_bounds__(BwdCfg<H>::NT, 1) mlp_bwd_kernel(const gp_mlp_
         }
         __syncthreads();
         tick(1);      // P0 wait
-        // accumulator pre-load: bias ba (+ the gathered pre-activation rows), so E1 adds nothing
+        // accumulator pre-load: bias ba (+ the gathered pre-activation rows), so E1 adds nothing;
+        // with h_a given the first MMA is P2 (NORM), which accumulates onto bb
 #pragma unroll
         for (int c = 0; c < CH; c += 16) {
+            if (ha_given && !norm) break;
             float f[16];
+            const float* bsrc = ha_given ? s_bb : s_ba;
 #pragma unroll
-            for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(f + j) = *reinterpret_cast<const float4*>(s_ba + cb + c + j);
+            for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(f + j) = *reinterpret_cast<const float4*>(bsrc + cb + c + j);
             if (has_init) {
                 acc8(*reinterpret_cast<const uint4*>(ha + sw128_off(128, row, cb + c)), f);
                 acc8(*reinterpret_cast<const uint4*>(ha + sw128_off(128, row, cb + c + 8)), f + 8);
@@ -289,7 +317,7 @@ __global__ void __launch_bounds__(BwdCfg<H>::NT, 1) mlp_bwd_kernel(const gp_mlp_
             tmem_st16(tlane + kColAcc + cb + c, v);
         }
         tmem_st_wait();
-        if (p.seg_id && tid < 128) {
+        if (f_seg && tid < 128) {
             sseg[4 + row] = sid_me;
             if (row == 0) {
                 sseg[3] = sid_prev;
@@ -300,7 +328,7 @@ __global__ void __launch_bounds__(BwdCfg<H>::NT, 1) mlp_bwd_kernel(const gp_mlp_
         tick(2);      // gather combine + publish
 
         // ---- P1: recompute h_a = relu(a_in . Wa^T + init + ba)
-        if (warp == 0 && elect_one()) {
+        if (!ha_given && warp == 0 && elect_one()) {
             tc_fence_after();
             const uint32_t id = idesc_bf16(H, false, false);
             for (int ks = 0; ks < (ka >> 4); ++ks)
@@ -308,9 +336,9 @@ __global__ void __launch_bounds__(BwdCfg<H>::NT, 1) mlp_bwd_kernel(const gp_mlp_
             mma_commit(&mma_bar);
         }
         if (tile + (int)gridDim.x < n_tiles) load_idx(tile + gridDim.x);
-        wait_mma();
+        if (!ha_given) wait_mma();
         tick(3);      // P1 MMA
-        {
+        if (!ha_given) {
             uint32_t v[CH];
 #pragma unroll
             for (int c = 0; c < CH; c += 16) tmem_ld16(tlane + kColAcc + cb + c, *reinterpret_cast<uint32_t(*)[16]>(&v[c]));
@@ -331,8 +359,8 @@ __global__ void __launch_bounds__(BwdCfg<H>::NT, 1) mlp_bwd_kernel(const gp_mlp_
             for (int c = 0; c < CH; c += 8)
                 *reinterpret_cast<uint4*>(ha + sw128_off(128, row, cb + c)) = pack8_relu(reinterpret_cast<const float*>(&v[c]));
             tmem_st_wait();
+            publish();
         }
-        publish();
         tick(4);      // E1
 
         // ---- P2 (NORM): m = h_a . Wb^T + bb ; delta_b = dRMSNorm(m) . du ; q = du * m/(rms+eps)
@@ -350,7 +378,7 @@ __global__ void __launch_bounds__(BwdCfg<H>::NT, 1) mlp_bwd_kernel(const gp_mlp_
             auto load_du = [&](int c0, float* du) {
                 if (du_smem) {
                     unpack8(*reinterpret_cast<const uint4*>(qb + sw128_off(128, row, c0)), du);
-                    if (p.gy_gather) acc8(*reinterpret_cast<const uint4*>(db + sw128_off(128, row, c0)), du);
+                    if (f_gather) acc8(*reinterpret_cast<const uint4*>(db + sw128_off(128, row, c0)), du);
                 } else {
                     if (p.gy_f32) {
                         const float4* gp_ = reinterpret_cast<const float4*>(p.gy_f32 + (size_t)crow * p.ld_gy + c0);
@@ -361,7 +389,7 @@ __global__ void __launch_bounds__(BwdCfg<H>::NT, 1) mlp_bwd_kernel(const gp_mlp_
 #pragma unroll
                         for (int j = 0; j < 8; ++j) du[j] = 0.f;
                     }
-                    if (p.gy_gather) {
+                    if (f_gather) {
                         const int gi = p.gy_idx ? __ldg(p.gy_idx + crow) : crow;
                         const float4* ap = reinterpret_cast<const float4*>(p.gy_gather + (size_t)gi * H + c0);
                         const float4 t0 = __ldg(ap), t1 = __ldg(ap + 1);
@@ -464,7 +492,7 @@ __global__ void __launch_bounds__(BwdCfg<H>::NT, 1) mlp_bwd_kernel(const gp_mlp_
             for (int ks = 0; ks < 8; ++ks)
                 mma_ss(tmem + kColDBA, desc_mnmajor(ha_s, 128, ks, 0, lbo_h), desc_mnmajor(ones_s, 128, ks), id_1,
                        (ks > 0) ? 1u : acc_flag);
-            if (p.need_din) {
+            if (f_din) {
                 const uint32_t id_d = idesc_bf16(ka, false, true);
                 for (int ks = 0; ks < (H >> 4); ++ks)
                     mma_ss(tmem + kColAcc, desc_kmajor(ha_s, 128, ks), desc_mnmajor(wa_s, H, ks), id_d, ks > 0 ? 1u : 0u);
@@ -472,12 +500,12 @@ __global__ void __launch_bounds__(BwdCfg<H>::NT, 1) mlp_bwd_kernel(const gp_mlp_
             mma_commit(&mma_bar);
         }
         // while the tensor core runs: delta_a tile -> global (row-major chunks), and its segment sum
-        if (p.delta_a_out && t_da) {
+        if (f_da && t_da) {
             if (warp == 0 && elect_one()) {
                 for (int b = 0; b < (H + 63) >> 6; ++b) tma_store_2d(&maps.da_out, b * 64, R0, ha_s + b * 16384);
                 tma_store_commit();
             }
-        } else if (p.delta_a_out) {
+        } else if (f_da) {
 #pragma unroll
             for (int j = 0; j < CPT; ++j) {
                 const int i = tid + j * NT;
@@ -487,12 +515,12 @@ __global__ void __launch_bounds__(BwdCfg<H>::NT, 1) mlp_bwd_kernel(const gp_mlp_
                         *reinterpret_cast<const uint4*>(ha + sw128_off(128, r, ch * 8));
             }
         }
-        if (p.seg_id) tile_segment_sum<H, NT>(ha, sseg, R0, tid, p.seg_out, p.seg_bnd);
+        if (f_seg) tile_segment_sum<H, NT>(ha, sseg, R0, tid, p.seg_out, p.seg_bnd);
         tick(9);      // P4 issue + copy-out + segment walk
         wait_mma();
         tick(10);     // P4 MMA wait
-        if (p.need_din) {
-            const bool via_smem = p.out_bf16 != nullptr && ka == H;     // bf16 tile output: transpose through shared memory
+        if (f_din) {
+            const bool via_smem = F || (p.out_bf16 != nullptr && ka == H);     // bf16 tile output: transpose through shared memory
             uint8_t* ob = (t_out && norm) ? qb : db;                    // staging tile (free since P3)
             const int nsplit = (ka >= 16 * NPART) ? NPART : (ka >= 32 ? 2 : 1);   // column parts that take part
             const int kh = ka / nsplit;
@@ -506,7 +534,7 @@ __global__ void __launch_bounds__(BwdCfg<H>::NT, 1) mlp_bwd_kernel(const gp_mlp_
                     for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
                     if (via_smem) {
                         uint4 q0 = pack8(f), q1 = pack8(f + 8);
-                        if (p.mask_by_ain) {
+                        if (f_mask) {
                             q0 = mask8_pos(q0, *reinterpret_cast<const uint4*>(ain + sw128_off(128, row, c0)));
                             q1 = mask8_pos(q1, *reinterpret_cast<const uint4*>(ain + sw128_off(128, row, c0 + 8)));
                         }
@@ -518,7 +546,7 @@ __global__ void __launch_bounds__(BwdCfg<H>::NT, 1) mlp_bwd_kernel(const gp_mlp_
                         *reinterpret_cast<uint4*>(ob + sw128_off(128, row, c0 + 8)) = q1;
                         continue;
                     }
-                    if (p.mask_by_ain) {
+                    if (f_mask) {
                         float av[16];
                         unpack8(*reinterpret_cast<const uint4*>(ain + sw128_off(128, row, c0)), av);
                         unpack8(*reinterpret_cast<const uint4*>(ain + sw128_off(128, row, c0 + 8)), av + 8);
@@ -526,7 +554,7 @@ __global__ void __launch_bounds__(BwdCfg<H>::NT, 1) mlp_bwd_kernel(const gp_mlp_
                         for (int j = 0; j < 16; ++j) f[j] = av[j] > 0.f ? f[j] : 0.f;
                     }
                     if (valid) {
-                        if (p.out_resid) {
+                        if (f_resid) {
                             float rv[16];
                             const gp_bf16* rp = p.out_resid + (size_t)grow * p.ld_out + c0;
                             unpack8(ldg16(rp), rv);
@@ -556,7 +584,7 @@ __global__ void __launch_bounds__(BwdCfg<H>::NT, 1) mlp_bwd_kernel(const gp_mlp_
                 }
             } else if (via_smem) {
                 uint4 rq[CPT];
-                if (p.out_resid) {       // residual chunks requested together, before the barrier
+                if (f_resid) {       // residual chunks requested together, before the barrier
 #pragma unroll
                     for (int j = 0; j < CPT; ++j) {
                         const int i = tid + j * NT;
@@ -570,7 +598,7 @@ __global__ void __launch_bounds__(BwdCfg<H>::NT, 1) mlp_bwd_kernel(const gp_mlp_
                     const int r = i / KC, ch = i % KC;
                     if (R0 + r < p.rows) {
                         uint4 q = *reinterpret_cast<const uint4*>(db + sw128_off(128, r, ch * 8));
-                        if (p.out_resid) {
+                        if (f_resid) {
                             q = add8_bf16(q, rq[j]);
                         }
                         *reinterpret_cast<uint4*>(p.out_bf16 + (size_t)(R0 + r) * p.ld_out + ch * 8) = q;
@@ -697,6 +725,7 @@ int launch_bwd(const gp_mlp_bwd_args& a, int32_t* grid_out, cudaStream_t st) {
         if (a.mode == 0 && gp::tma_map_2d(&maps.db, a.delta_b, a.rows, a.nb, a.ld_db)) use |= kMapDb;
         if (a.mode == 1 && a.gy_bf16 && gp::tma_map_2d(&maps.gy, a.gy_bf16, a.rows, H, a.ld_gy)) use |= kMapGy;
         if (a.delta_a_out && gp::tma_map_2d(&maps.da_out, a.delta_a_out, a.rows, H, H)) use |= kMapDaOut;
+        if (a.ha_saved && gp::tma_map_2d(&maps.ha, a.ha_saved, a.rows, H, H)) use |= kMapHa;
         if (a.need_din && a.out_bf16 && a.ka == H && gp::tma_map_2d(&maps.out, a.out_bf16, a.rows, a.ka, a.ld_out)) {
             // the residual rides through the spare tile buffer; GIVEN mode only (NORM keeps du / q there)
             if (!a.out_resid)
@@ -709,14 +738,32 @@ int launch_bwd(const gp_mlp_bwd_args& a, int32_t* grid_out, cudaStream_t st) {
     smem += (size_t)((a.mode == 1 || (maps.use & kMapResid)) ? 4 : 3) * kBufBytes + 128 * 128 + 3 * 128 * 4 + 2 * BwdCfg<H>::NPART * 128 * 4 + 144 * 4;
     GP_REQUIRE((int)smem <= gp::max_smem_optin(), "gp_mlp_bwd_stage: needs %zu B of shared memory (> %d)", smem,
                gp::max_smem_optin());
-    static int smem_set = 0;      // raised once per instantiation (and never inside a stream capture twice)
-    if ((int)smem > smem_set) {
-        GP_CHECK_CUDA(cudaFuncSetAttribute(mlp_bwd_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        smem_set = (int)smem;
+    // the two stages of the processor's edge MLP get their own instantiations (H = 128 only)
+    int fast = 0;
+    if (H == 128 && a.a_bf16 && a.ka == H && a.nb == H && !a.ha_saved && a.need_din && a.out_bf16) {
+        if (a.mode == 1 && a.gy_bf16 && a.gy_gather && a.gy_idx && !a.init && a.mask_by_ain && !a.out_resid && !a.delta_a_out &&
+            !a.seg_id && maps.use == (kMapAin | kMapGy | kMapOut))
+            fast = 1;
+        if (a.mode == 0 && a.init && a.two_inits && a.idx0 && a.idx1 && !a.mask_by_ain && a.out_resid && a.delta_a_out && a.seg_id &&
+            maps.use == (kMapAin | kMapDb | kMapResid | kMapDaOut | kMapOut))
+            fast = 2;
+    }
+    static int smem_set[3] = {0, 0, 0};      // raised once per instantiation (and never inside a stream capture twice)
+    if ((int)smem > smem_set[fast]) {
+        cudaError_t e = fast == 1   ? cudaFuncSetAttribute(mlp_bwd_kernel<H, (H == 128 ? 1 : 0)>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                        : fast == 2 ? cudaFuncSetAttribute(mlp_bwd_kernel<H, (H == 128 ? 2 : 0)>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                                    : cudaFuncSetAttribute(mlp_bwd_kernel<H, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        GP_CHECK_CUDA(e);
+        smem_set[fast] = (int)smem;
     }
     const int n_tiles = (a.rows + 127) / 128;
     int grid = n_tiles < gp::sm_count() ? n_tiles : gp::sm_count();
-    mlp_bwd_kernel<H><<<grid, BwdCfg<H>::NT, smem, st>>>(a, maps);
+    if (fast == 1)
+        mlp_bwd_kernel<H, (H == 128 ? 1 : 0)><<<grid, BwdCfg<H>::NT, smem, st>>>(a, maps);
+    else if (fast == 2)
+        mlp_bwd_kernel<H, (H == 128 ? 2 : 0)><<<grid, BwdCfg<H>::NT, smem, st>>>(a, maps);
+    else
+        mlp_bwd_kernel<H, 0><<<grid, BwdCfg<H>::NT, smem, st>>>(a, maps);
     GP_CHECK_CUDA(cudaGetLastError());
     if (grid_out) *grid_out = grid;
     return 0;

@@ -31,20 +31,24 @@ constexpr int kSlotThreads = 256;
 // TMA descriptors of the tile-shaped global tensors (valid ones flagged in `use`): the layer-0
 // operand is bulk-loaded and the saved activation bulk-stored by one elected thread per slot.
 struct FwdMaps {
-    CUtensorMap a, h2;
+    CUtensorMap a, h[3];     // h[i]: saved output of layer i (save_h1, save_h2, save_h3)
     uint32_t use;
 };
-enum : uint32_t { kMapA = 1, kMapH2 = 2 };
+enum : uint32_t { kMapA = 1, kMapH = 2 /* << layer */ };
 
 __device__ __forceinline__ void slot_sync(int g) { asm volatile("bar.sync %0, 256;" ::"r"(g + 1) : "memory"); }
 
-template <int H, int NG>
+// kEdge = true is the instantiation for the processor's edge MLP (4 H-wide layers, two gathered
+// pre-activation sources, RMSNorm, bf16 residual output, segment sum): every optional path is
+// resolved at compile time, which cuts the code the two out-of-phase slots stream through the
+// instruction cache (a 10% larger kernel measured 13% slower).
+template <int H, int NG, bool kEdge>
 __global__ void __launch_bounds__(kSlotThreads * NG, 1) mlp_fwd_kernel(const gp_mlp_fwd_args p,
                                                                        const __grid_constant__ FwdMaps maps) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = GP_SMEM_ALIGNED(smem_raw);
     __shared__ uint64_t mma_bar[NG], tma_bar[NG];
-    const bool t_a = maps.use & kMapA, t_h2 = maps.use & kMapH2;
+    const bool t_a = !kEdge && (maps.use & kMapA);
     __shared__ uint32_t tmem_slot;
 
     const int tid = threadIdx.x;
@@ -58,7 +62,11 @@ __global__ void __launch_bounds__(kSlotThreads * NG, 1) mlp_fwd_kernel(const gp_
     const int wis = warp_u - g_u * (kSlotThreads / 32);    // warp in slot
     const int row = t & 127;                 // row in tile == TMEM lane
     const int half = t >> 7;                 // column half
-    const int L = p.n_layers;
+    constexpr bool E = kEdge;
+    const int L = E ? 4 : p.n_layers;
+    const bool f_norm = E || p.norm_scale != nullptr, f_seg = E || p.seg_id != nullptr, f_resid = E || p.resid != nullptr;
+    const bool f_ybf = E || p.y_bf16 != nullptr, f_abf = E || p.a_bf16 != nullptr, f_idx0 = E || p.idx0 != nullptr;
+    const int ka = E ? H : p.ka;
     constexpr int CH = H / 2;                // columns per thread in H-wide layers
     constexpr int KC = H / 8;                // 16-byte chunks per H-wide row
     constexpr int CPT = 128 * KC / kSlotThreads;   // chunks per thread in a row-major tile copy
@@ -90,7 +98,7 @@ __global__ void __launch_bounds__(kSlotThreads * NG, 1) mlp_fwd_kernel(const gp_
             sbias[l * kBiasStride + i] = (p.bias[l] && i < p.n[l]) ? p.bias[l][i] : 0.f;
     }
     cp_async_commit();
-    if (p.norm_scale)
+    if (f_norm)
         for (int i = tid; i < H; i += blockDim.x) sscale[i] = p.norm_scale[i];
     if (tid == 0) {
         for (int i = 0; i < NG; ++i) {
@@ -112,7 +120,7 @@ __global__ void __launch_bounds__(kSlotThreads * NG, 1) mlp_fwd_kernel(const gp_
     const uint32_t tacc = tmem_addr(tmem_base, (row >> 5) * 32, g * 128);         // this warp's lanes
     const uint32_t buf_s = smem_u32(buf);
     uint32_t phase = 0, tphase = 0;
-    const bool has_init = p.init != nullptr;
+    const bool has_init = E || p.init != nullptr;
     const int n_tiles = (p.rows + 127) >> 7;
     const int tile_stride = gridDim.x * NG;
 
@@ -130,13 +138,13 @@ __global__ void __launch_bounds__(kSlotThreads * NG, 1) mlp_fwd_kernel(const gp_
 
     // gather indices of a tile (prefetched one tile ahead): i0n = this thread's row in the directly
     // loaded source; ridx[] = rows of the chunks this thread copies for the staged source
-    const bool stage1 = p.two_inits != 0;           // which source goes through buf
+    const bool stage1 = E || p.two_inits != 0;           // which source goes through buf
     const int32_t* sidx = stage1 ? p.idx1 : p.idx0;
     const int soff = stage1 ? p.init_off1 : p.init_off0;
     int i0n = 0, ridx[CPT];
     auto load_idx = [&](int tile_) {
         const int r = min((tile_ << 7) + row, p.rows - 1);
-        i0n = p.idx0 ? __ldg(p.idx0 + r) : r;
+        i0n = f_idx0 ? __ldg(p.idx0 + r) : r;
 #pragma unroll
         for (int j = 0; j < CPT; ++j) {
             const int gr = min((tile_ << 7) + (t + j * kSlotThreads) / KC, p.rows - 1);
@@ -176,7 +184,7 @@ __global__ void __launch_bounds__(kSlotThreads * NG, 1) mlp_fwd_kernel(const gp_
         // (a) segment ids of the tile (+ one row of context on each side): requested now, stored
         //     to shared memory later so their latency is not exposed
         int sid_me = -1, sid_prev = -1, sid_next = -1;
-        if (p.seg_id && t < 128) {
+        if (f_seg && t < 128) {
             if (valid) sid_me = __ldg(p.seg_id + grow);
             if (row == 0) {
                 if (R0 > 0) sid_prev = __ldg(p.seg_id + R0 - 1);
@@ -204,9 +212,9 @@ __global__ void __launch_bounds__(kSlotThreads * NG, 1) mlp_fwd_kernel(const gp_
                 for (int i = 0; i < CH / 8; ++i) dq[i] = ldg16(dp + i * 8);
             }
             // L2 prefetch of the layer-0 operand tile, which is staged right after
-            if (p.a_bf16 && t < 128) {
+            if (f_abf && t < 128) {
                 const gp_bf16* rp = p.a_bf16 + (size_t)min(grow, p.rows - 1) * p.lda;
-                for (int c = 0; c < p.ka; c += 64) asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + c));
+                for (int c = 0; c < ka; c += 64) asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + c));
             }
             cp_async_wait<0>();
             slot_sync(g);
@@ -233,7 +241,7 @@ __global__ void __launch_bounds__(kSlotThreads * NG, 1) mlp_fwd_kernel(const gp_
         } else {
             prestore_bias(0, 0, true);
         }
-        if (p.seg_id && t < 128) {
+        if (f_seg && t < 128) {
             sseg[4 + row] = sid_me;
             if (row == 0) {
                 sseg[3] = sid_prev;
@@ -244,12 +252,12 @@ __global__ void __launch_bounds__(kSlotThreads * NG, 1) mlp_fwd_kernel(const gp_
         //     results are never stored); bulk-loaded when a descriptor exists (rows past the end = 0)
         if (t_a) {
             if (wis == 0 && elect_one()) {
-                const int nblk = (p.ka + 63) >> 6;
+                const int nblk = (ka + 63) >> 6;
                 mbar_arrive_expect_tx(&tma_bar[g_u], nblk * 16384u);
                 for (int b = 0; b < nblk; ++b) tma_load_2d(buf_u + b * 16384, &maps.a, b * 64, R0, &tma_bar[g_u]);
             }
         } else {
-            stage_rows(buf, p.a_bf16, p.a_f32, p.ka, p.lda, R0, p.rows, t, kSlotThreads);
+            stage_rows(buf, p.a_bf16, E ? nullptr : p.a_f32, ka, p.lda, R0, p.rows, t, kSlotThreads);
             cp_async_commit();
         }
         tick(0);                 // issue of loads + gathers + TMEM pre-load (this thread)
@@ -266,11 +274,11 @@ __global__ void __launch_bounds__(kSlotThreads * NG, 1) mlp_fwd_kernel(const gp_
 
         // (d) layers
         for (int l = 0; l < L; ++l) {
-            const int K = p.k[l];
-            const int Nl = p.n[l];
+            const int K = E ? H : p.k[l];
+            const int Nl = E ? H : p.n[l];
             const bool last = (l == L - 1);
             for (int nc = 0; nc < Nl; nc += 128) {
-                const int ncols = min(128, Nl - nc);
+                const int ncols = E ? H : min(128, Nl - nc);
                 if (wis == 0 && elect_one()) {
                     tc_fence_after();
                     const uint32_t idesc = idesc_bf16(ncols, false, false);
@@ -295,25 +303,30 @@ __global__ void __launch_bounds__(kSlotThreads * NG, 1) mlp_fwd_kernel(const gp_
                             asm volatile("prefetch.global.L2 [%0];" ::"l"(p.init + (size_t)ridx[j] * p.ld_init + soff +
                                                                          ((t + j * kSlotThreads) % KC) * 8));
                 }
-                // while the MMA of layer 2 runs: copy the saved activation (layer-1 output, still
-                // intact in buf as this MMA's A operand) to global memory, row-major chunks
-                if (l == 2 && nc == 0 && p.save_h2 && t_h2) {
-                    if (wis == 0 && elect_one()) {
-                        for (int b = 0; b < (H + 63) >> 6; ++b) tma_store_2d(&maps.h2, b * 64, R0, buf_u + b * 16384);
-                        tma_store_commit();
-                        tma_store_wait_read<0>();     // buf has been read: the epilogue may overwrite it
-                    }
-                    slot_sync(g);
-                } else if (l == 2 && nc == 0 && p.save_h2) {
+                // while the MMA of layer l runs: copy the saved activation (output of layer l-1, still
+                // intact in buf as this MMA's A operand) to global memory -- one bulk store, or
+                // row-major 16-byte chunks
+                gp_bf16* const sv = (nc != 0 || l == 0) ? nullptr : (l == 1 ? p.save_h1 : (l == 2 ? p.save_h2 : p.save_h3));
+                if (sv) {
+                    if (maps.use & (kMapH << (l - 1))) {
+                        if (wis == 0 && elect_one()) {
+                            // (constant indices keep the descriptors in parameter space)
+                            const void* mp = l == 1 ? &maps.h[0] : (l == 2 ? &maps.h[1] : &maps.h[2]);
+                            for (int b = 0; b < (H + 63) >> 6; ++b) tma_store_2d(mp, b * 64, R0, buf_u + b * 16384);
+                            tma_store_commit();
+                            tma_store_wait_read<0>();     // buf has been read: the epilogue may overwrite it
+                        }
+                    } else {
 #pragma unroll
-                    for (int j = 0; j < CPT; ++j) {
-                        const int i = t + j * kSlotThreads;
-                        const int r = i / KC, ch = i % KC;
-                        if (R0 + r < p.rows)
-                            *reinterpret_cast<uint4*>(p.save_h2 + (size_t)(R0 + r) * H + ch * 8) =
-                                *reinterpret_cast<const uint4*>(buf + sw128_off(128, r, ch * 8));
+                        for (int j = 0; j < CPT; ++j) {
+                            const int i = t + j * kSlotThreads;
+                            const int r = i / KC, ch = i % KC;
+                            if (R0 + r < p.rows)
+                                *reinterpret_cast<uint4*>(sv + (size_t)(R0 + r) * H + ch * 8) =
+                                    *reinterpret_cast<const uint4*>(buf + sw128_off(128, r, ch * 8));
+                        }
                     }
-                    slot_sync(g);    // every chunk is out before any thread overwrites buf in the epilogue
+                    slot_sync(g);    // the tile is out (or read) before any thread overwrites buf in the epilogue
                 }
                 mbar_wait(&mma_bar[g], phase);
                 phase ^= 1;
@@ -334,7 +347,7 @@ __global__ void __launch_bounds__(kSlotThreads * NG, 1) mlp_fwd_kernel(const gp_
                     fence_async_smem();
                     tmem_st_wait();
                     tick(3);
-                } else if (p.norm_scale) {
+                } else if (f_norm) {
                     // RMSNorm (layers.py:104-129): u = scale * m / (||m||/sqrt(H) + 1e-8), rounded to
                     // bf16 once; that value feeds the segment sum and the residual alike.
                     uint32_t v[CH];
@@ -402,14 +415,14 @@ __global__ void __launch_bounds__(kSlotThreads * NG, 1) mlp_fwd_kernel(const gp_
             }
         }
 
-        if (p.norm_scale) {
+        if (f_norm) {
             // (e) receiver-sorted segment sum of bf16(u) (fp32 accumulate, fixed order, no atomics)
-            if (p.seg_id) tile_segment_sum<H, kSlotThreads>(buf, sseg, R0, t, p.seg_out, p.seg_bnd);
+            if (f_seg) tile_segment_sum<H, kSlotThreads>(buf, sseg, R0, t, p.seg_out, p.seg_bnd);
             tick(6);
             // (f) output: y = resid + bf16(u), row-major chunks; the residual chunks (L2 hits: the tile
             //     was this kernel's layer-0 operand) are requested together
             uint4 rq[CPT];
-            if (p.resid) {
+            if (f_resid) {
 #pragma unroll
                 for (int j = 0; j < CPT; ++j) {
                     const int i = t + j * kSlotThreads;
@@ -423,14 +436,14 @@ __global__ void __launch_bounds__(kSlotThreads * NG, 1) mlp_fwd_kernel(const gp_
                 const int r = i / KC, ch = i % KC;
                 if (R0 + r < p.rows) {
                     const uint4 uq = *reinterpret_cast<const uint4*>(buf + sw128_off(128, r, ch * 8));
-                    if (p.y_bf16) {
+                    if (f_ybf) {
                         // bf16(u) + bf16 residual, exact sum rounded once to bf16
                         *reinterpret_cast<uint4*>(p.y_bf16 + (size_t)(R0 + r) * p.ld_out + ch * 8) =
-                            p.resid ? add8_bf16(uq, rq[j]) : uq;
+                            f_resid ? add8_bf16(uq, rq[j]) : uq;
                     } else {
                         float u[8];
                         unpack8(uq, u);
-                        if (p.resid) acc8(rq[j], u);
+                        if (f_resid) acc8(rq[j], u);
                         float4* d = reinterpret_cast<float4*>(p.y_f32 + (size_t)(R0 + r) * p.ld_out + ch * 8);
                         d[0] = make_float4(u[0], u[1], u[2], u[3]);
                         d[1] = make_float4(u[4], u[5], u[6], u[7]);
@@ -443,7 +456,7 @@ __global__ void __launch_bounds__(kSlotThreads * NG, 1) mlp_fwd_kernel(const gp_
         if (prof) atomicAdd(p.prof + 15, 1ull);
     }
 
-    if (t_h2 && wis == 0 && elect_one()) tma_store_wait_all();
+    if ((maps.use & (7u * kMapH)) && wis == 0 && elect_one()) tma_store_wait_all();
     tc_fence_before();
     __syncthreads();
     if (tid < 32) tmem_dealloc(tmem_base, kTmemCols);
@@ -485,7 +498,7 @@ __global__ void __launch_bounds__(256) seg_fixup_kernel(const int32_t* __restric
     }
 }
 
-template <int H, int NG>
+template <int H, int NG, bool kEdge>
 int launch_fwd(const gp_mlp_fwd_args& a, cudaStream_t st) {
     size_t smem = 1024;
     for (int l = 0; l < a.n_layers; ++l) smem += (size_t)((a.k[l] + 63) / 64) * a.n[l] * 128;
@@ -494,7 +507,7 @@ int launch_fwd(const gp_mlp_fwd_args& a, cudaStream_t st) {
                gp::max_smem_optin());
     static int smem_set = 0;      // raised once per instantiation (and never inside a stream capture twice)
     if ((int)smem > smem_set) {
-        GP_CHECK_CUDA(cudaFuncSetAttribute(mlp_fwd_kernel<H, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        GP_CHECK_CUDA(cudaFuncSetAttribute(mlp_fwd_kernel<H, NG, kEdge>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         smem_set = (int)smem;
     }
     const int n_tiles = (a.rows + 127) / 128;
@@ -508,9 +521,11 @@ int launch_fwd(const gp_mlp_fwd_args& a, cudaStream_t st) {
         // with gathered pre-activations the tile buffer is busy until just before layer 0, where the
         // shorter latency of per-thread cp.async (L2-prefetched rows) beats one bulk copy
         if (a.a_bf16 && !a.init && gp::tma_map_2d(&maps.a, a.a_bf16, a.rows, a.ka, a.lda)) maps.use |= kMapA;
-        if (a.save_h2 && gp::tma_map_2d(&maps.h2, a.save_h2, a.rows, H, H)) maps.use |= kMapH2;
+        gp_bf16* const sv[3] = {a.save_h1, a.save_h2, a.save_h3};
+        for (int i = 0; i < 3; ++i)
+            if (sv[i] && gp::tma_map_2d(&maps.h[i], sv[i], a.rows, H, H)) maps.use |= kMapH << i;
     }
-    mlp_fwd_kernel<H, NG><<<grid, kSlotThreads * NG, smem, st>>>(a, maps);
+    mlp_fwd_kernel<H, NG, kEdge><<<grid, kSlotThreads * NG, smem, st>>>(a, maps);
     GP_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -535,15 +550,21 @@ extern "C" int gp_mlp_fwd(const gp_mlp_fwd_args* args, int hidden, void* stream)
                            "gp_mlp_fwd: init rows need n[0]==hidden and 16-byte aligned offsets");
     if (a.norm_scale) GP_REQUIRE(a.n[a.n_layers - 1] == hidden, "gp_mlp_fwd: RMSNorm needs n_last == hidden");
     if (a.seg_id) GP_REQUIRE(a.norm_scale && a.seg_out && a.seg_bnd, "gp_mlp_fwd: segment sum needs norm + outputs");
+    if (a.save_h1) GP_REQUIRE(a.n_layers >= 2, "gp_mlp_fwd: save_h1 needs at least 2 layers");
     if (a.save_h2) GP_REQUIRE(a.n_layers >= 3, "gp_mlp_fwd: save_h2 needs at least 3 layers");
+    if (a.save_h3) GP_REQUIRE(a.n_layers >= 4, "gp_mlp_fwd: save_h3 needs 4 layers");
     GP_REQUIRE(a.n_layers == 1 || a.n[a.n_layers - 1] <= hidden, "gp_mlp_fwd: a multi-layer MLP cannot widen in its last layer");
     GP_REQUIRE((a.y_bf16 != nullptr) != (a.y_f32 != nullptr), "gp_mlp_fwd: exactly one of y_bf16 / y_f32");
     if (a.norm_scale) GP_REQUIRE(a.ld_out % 8 == 0, "gp_mlp_fwd: ld_out must be a multiple of 8 with RMSNorm");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    // the processor's edge MLP gets the instantiation with every option fixed at compile time
+    bool edge = a.init && a.two_inits && a.idx0 && a.idx1 && a.a_bf16 && a.n_layers == 4 && a.ka == hidden && a.norm_scale &&
+                a.resid && a.seg_id && a.y_bf16;
+    for (int l = 0; l < a.n_layers && edge; ++l) edge = a.k[l] == hidden && a.n[l] == hidden;
     switch (hidden) {
-        case 128: return launch_fwd<128, 2>(a, st);
-        case 64: return launch_fwd<64, 2>(a, st);
-        case 32: return launch_fwd<32, 2>(a, st);
+        case 128: return edge ? launch_fwd<128, 2, true>(a, st) : launch_fwd<128, 2, false>(a, st);
+        case 64: return launch_fwd<64, 2, false>(a, st);
+        case 32: return launch_fwd<32, 2, false>(a, st);
         default: gp::set_error("gp_mlp_fwd: unsupported hidden size %d (32, 64, 128)", hidden); return -1;
     }
 }

@@ -78,6 +78,8 @@ class MlpFwdArgs(C.Structure):
         ("ld_out", C.c_int32),
         ("n_valid", C.c_int32),
         ("save_h2", C.c_void_p),
+        ("save_h1", C.c_void_p),
+        ("save_h3", C.c_void_p),
         ("seg_id", C.c_void_p),
         ("seg_out", C.c_void_p),
         ("seg_bnd", C.c_void_p),
@@ -99,6 +101,7 @@ class MlpBwdArgs(C.Structure):
         ("idx0", C.c_void_p),
         ("idx1", C.c_void_p),
         ("two_inits", C.c_int32),
+        ("ha_saved", C.c_void_p),
         ("wa", C.c_void_p),
         ("ba", C.c_void_p),
         ("wb", C.c_void_p),

@@ -14,6 +14,8 @@ and the one activation per MLP the forward saved (the output of its second layer
 """
 from __future__ import annotations
 
+import os
+
 from typing import Dict, List, Optional, Tuple
 
 import torch
@@ -53,6 +55,10 @@ class EPDEngine:
         self.device = next(model.parameters()).device
         if self.device.type != "cuda":
             raise RuntimeError("graphphysics_b200 runs on CUDA devices only (there is no CPU fallback)")
+        # Saving h1 / h3 as well costs the forward more (two extra tile stores per MLP, each holding the
+        # tile buffer until the copy engine has read it) than the backward gains from skipping the
+        # recompute: 15.4 vs 14.3 ms/step on the benchmark.  Kept as an option.
+        self.save_all = os.environ.get("GP_B200_SAVE_ALL", "0") == "1"
         self._build_flat()
         self._build_packed()
         H = self.H
@@ -177,6 +183,19 @@ class EPDEngine:
         out[:, : t.shape[1]] = t
         return out
 
+    def _saved(self, rows: int, save: bool):
+        """Buffers for the hidden activations the backward reads back: (h1, h2, h3) bf16 [rows, H].
+        h2 is needed (it is the input of backward stage B); with save_all, h1 / h3 replace the recompute
+        of layers 0 / 2 -- and with it the gathers of stage A -- at the price of 4H more bytes per row."""
+        if not save:
+            return None
+        mk = lambda: torch.empty((rows, self.H), dtype=torch.bfloat16, device=self.device)
+        return (mk(), mk(), mk()) if self.save_all else (None, mk(), None)
+
+    @staticmethod
+    def _save_kw(sv):
+        return {} if sv is None else dict(save_h1=sv[0], save_h2=sv[1], save_h3=sv[2])
+
     def _mlp(self, s: _MLPSlots, rows, a, ka, out, n_valid, **kw):
         return ops.mlp_fwd(rows, self.H, s.packed, s.bias, a=a, ka=ka, norm_scale=s.scale, out=out, n_valid=n_valid, **kw)
 
@@ -188,13 +207,13 @@ class EPDEngine:
         ops.mlp_fwd(N, H, [self.proj[l]], [None], a=x, ka=H, out=P, n_valid=3 * H)
         e2 = torch.empty((E, H), dtype=bf, device=dev)
         agg = torch.empty((N, H), dtype=torch.float32, device=dev)
-        h2e = torch.empty((E, H), dtype=bf, device=dev) if save else None
-        self._mlp(self.edge[l], E, e, H, e2, H, save_h2=h2e, resid=e, init=P, init_off0=0, init_off1=H,
+        h2e = self._saved(E, save)
+        self._mlp(self.edge[l], E, e, H, e2, H, **self._save_kw(h2e), resid=e, init=P, init_off0=0, init_off1=H,
                   idx0=g.dst, idx1=g.src, two_inits=True, seg_id=g.dst, seg_out=agg, seg_bnd=bnd, tag="edge_fwd")
         ops.seg_fixup(g.rowptr_dst, H, bnd, agg)
         x2 = torch.empty((N, H), dtype=bf, device=dev)
-        h2n = torch.empty((N, H), dtype=bf, device=dev) if save else None
-        self._mlp(self.node[l], N, agg, H, x2, H, save_h2=h2n, resid=x, init=P, init_off0=2 * H)
+        h2n = self._saved(N, save)
+        self._mlp(self.node[l], N, agg, H, x2, H, **self._save_kw(h2n), resid=x, init=P, init_off0=2 * H)
         return x2, e2, ((x, e, P, agg, h2e, h2n) if save else None)
 
     def forward(self, x_in: torch.Tensor, edge_attr: torch.Tensor, g: GraphCSR, save: bool, after_block=None):
@@ -215,10 +234,9 @@ class EPDEngine:
             ea_p = self._pad_cols(edge_attr[g.perm_dst64], self.enc_e.packed[0].shape[1])
             x = torch.empty((N, H), dtype=bf, device=dev)
             e = torch.empty((E, H), dtype=bf, device=dev)
-            h2n0 = torch.empty((N, H), dtype=bf, device=dev) if save else None
-            h2e0 = torch.empty((E, H), dtype=bf, device=dev) if save else None
-            self._mlp(self.enc_n, N, xin_p, xin_p.shape[1], x, H, save_h2=h2n0)
-            self._mlp(self.enc_e, E, ea_p, ea_p.shape[1], e, H, save_h2=h2e0)
+            h2n0, h2e0 = self._saved(N, save), self._saved(E, save)
+            self._mlp(self.enc_n, N, xin_p, xin_p.shape[1], x, H, **self._save_kw(h2n0))
+            self._mlp(self.enc_e, E, ea_p, ea_p.shape[1], e, H, **self._save_kw(h2e0))
             if save:
                 ctx.update(xin_p=xin_p, ea_p=ea_p, h2n0=h2n0, h2e0=h2e0)
         bnd = torch.empty(ops.seg_bnd_size(E, H), dtype=torch.float32, device=dev)
@@ -233,8 +251,8 @@ class EPDEngine:
             return x, e, ctx
         out_size = self.dec.shape[3][0]
         out = torch.empty((N, out_size), dtype=torch.float32, device=dev)
-        h2d = torch.empty((N, H), dtype=bf, device=dev) if save else None
-        ops.mlp_fwd(N, H, self.dec.packed, self.dec.bias, a=x, ka=H, out=out, n_valid=out_size, save_h2=h2d)
+        h2d = self._saved(N, save)
+        ops.mlp_fwd(N, H, self.dec.packed, self.dec.bias, a=x, ka=H, out=out, n_valid=out_size, **self._save_kw(h2d))
         if save:
             ctx.update(x_last=x, h2d=h2d)
         return out, e, ctx
@@ -282,12 +300,13 @@ class EPDEngine:
         """Backward through the 4-layer MLP `s`: stage B over layers (2,3), stage A over (0,1).
         top = dict(gy=..., gy_gather=..., gy_idx=...) for a normalised MLP, or dict(delta_b=...)."""
         H, dev = self.H, self.device
+        h1, h2, h3 = h2 if isinstance(h2, tuple) else (None, h2, None)
         delta2 = torch.empty((rows, H), dtype=torch.bfloat16, device=dev)
         gridB = ops.mlp_bwd_stage(rows, H, a=h2, ka=H, wa=s.packed[2], ba=s.bias[2], wb=s.packed[3], bb=s.bias[3],
                                   partials=self.partials, norm_scale=s.scale, out=delta2, mask_by_ain=True,
-                                  tag=(tag + "_B") if tag else None, **top)
+                                  ha_saved=h3, tag=(tag + "_B") if tag else None, **top)
         self._reduce_stage(gridB, H, s.packed[3].shape[0], s, 2, 3, s.scale is not None)
-        kw = dict(first or {})
+        kw = dict(first or {}) if h1 is None else dict(ha_saved=h1)     # saved h1: no gathers, no recompute
         if seg is not None:
             kw.update(seg_id=seg[0], seg_out=seg[1], seg_bnd=seg[2])
         gridA = ops.mlp_bwd_stage(rows, H, a=a_in, ka=ka, wa=s.packed[0], ba=s.bias[0], wb=s.packed[1], bb=s.bias[1],

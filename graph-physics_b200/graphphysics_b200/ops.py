@@ -103,6 +103,8 @@ def mlp_fwd(
     out: torch.Tensor,
     n_valid: int,
     save_h2: Optional[torch.Tensor] = None,
+    save_h1: Optional[torch.Tensor] = None,
+    save_h3: Optional[torch.Tensor] = None,
     seg_id: Optional[torch.Tensor] = None,
     seg_out: Optional[torch.Tensor] = None,
     seg_bnd: Optional[torch.Tensor] = None,
@@ -141,7 +143,9 @@ def mlp_fwd(
         args.y_f32 = ptr(out)
     args.ld_out = out.stride(0)
     args.n_valid = n_valid
-    args.save_h2 = ptr(save_h2)
+    args.save_h2, args.save_h1, args.save_h3 = ptr(save_h2), ptr(save_h1), ptr(save_h3)
+    for sv in (save_h1, save_h2, save_h3):
+        assert sv is None or (sv.dtype == torch.bfloat16 and sv.is_contiguous() and sv.shape == (rows, hidden))
     args.seg_id, args.seg_out, args.seg_bnd = ptr(seg_id), ptr(seg_out), ptr(seg_bnd)
     args.prof = ptr(prof)
     ev = PROFILE.begin(tag)
@@ -201,6 +205,7 @@ def mlp_bwd_stage(
     idx0: Optional[torch.Tensor] = None,
     idx1: Optional[torch.Tensor] = None,
     two_inits: bool = False,
+    ha_saved: Optional[torch.Tensor] = None,
     delta_b: Optional[torch.Tensor] = None,
     norm_scale: Optional[torch.Tensor] = None,
     gy: Optional[torch.Tensor] = None,
@@ -231,6 +236,9 @@ def mlp_bwd_stage(
         args.init_off0, args.init_off1 = init_off0, init_off1
         args.idx0, args.idx1 = ptr(idx0), ptr(idx1)
         args.two_inits = 1 if two_inits else 0
+    if ha_saved is not None:
+        assert ha_saved.dtype == torch.bfloat16 and ha_saved.is_contiguous() and ha_saved.shape == (rows, hidden)
+        args.ha_saved = ptr(ha_saved)
     args.wa, args.ba, args.wb, args.bb = ptr(wa), ptr(ba), ptr(wb), ptr(bb)
     args.nb = wb.shape[0]
     assert wa.shape == (hidden, ka) and wb.shape[1] == hidden

@@ -70,6 +70,8 @@ typedef struct gp_mlp_fwd_args {
     int32_t ld_out;
     int32_t n_valid;       /* columns of the last layer actually written */
     gp_bf16* save_h2;      /* optional [rows][hidden]: output of layer index 1 (after relu) */
+    gp_bf16* save_h1;      /* optional [rows][hidden]: output of layer index 0; lets gp_mlp_bwd_stage skip its recompute */
+    gp_bf16* save_h3;      /* optional [rows][hidden]: output of layer index 2 (4-layer MLPs) */
     const int32_t* seg_id; /* optional [rows], non-decreasing */
     float* seg_out;        /* [num_segments][hidden] */
     float* seg_bnd;        /* [ceil(rows/sub)][2][hidden], sub = gp_seg_sub_rows(hidden, 0) */
@@ -94,7 +96,8 @@ int gp_seg_fixup(const int32_t* rowptr, int32_t num_segments, int32_t hidden, in
  * (graphphysics/models/layers.py:104-129, 163-210, 1016-1060) for
  * LightningModule.training_step (graphphysics/training/lightning_module.py:270-342).
  *
- *   h_a   = relu(a_in . Wa^T + init rows + ba)                       (recomputed)
+ *   h_a   = relu(a_in . Wa^T + init rows + ba)     (recomputed -- or read back from ha_saved, the copy the
+ *                                                   forward wrote (save_h1 / save_h3); then init / idx are unused)
  *   mode 1 (NORM):  m = h_a . Wb^T + bb;  du = gy (+ gy_gather[gy_idx]);  delta_b = d RMSNorm(m)/dm . du
  *   mode 0 (GIVEN): delta_b read from memory
  *   dWb += delta_b^T h_a ;  dbb += sum delta_b ;  dscale += sum du * m/(rms+eps)
@@ -115,6 +118,7 @@ typedef struct gp_mlp_bwd_args {
     const int32_t* idx0;
     const int32_t* idx1;
     int32_t two_inits;
+    const gp_bf16* ha_saved; /* optional [rows][hidden] bf16: h_a as stored by the forward */
     const gp_bf16* wa; /* packed [hidden][ka] */
     const float* ba;
     const gp_bf16* wb; /* packed [nb][hidden] */

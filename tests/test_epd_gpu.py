@@ -124,3 +124,33 @@ def test_graphnet_block_standalone_api():
     ok &= check_close(ed.grad, e64.grad, "de", 5e-3, 5e-2, rep)
     print("\n".join(rep))
     assert ok, "\n".join(rep)
+
+
+def test_saved_activations_equal_recompute(monkeypatch):
+    """The backward recomputes h1 / h3 from the layer inputs and the gathered pre-activations (default)
+    or reads them back from the forward (GP_B200_SAVE_ALL=1): the recomputed tiles repeat the
+    forward's instruction sequence, so both modes must give the same gradients (to fp32 rounding of
+    the differently ordered partial sums: 1e-5)."""
+    from graphphysics_b200.graph import Data
+    from graphphysics_b200.models.processors import EncodeProcessDecode
+    dev = torch.device("cuda:0")
+    torch.manual_seed(7)
+    pos, ei, ea = _mesh_graph(30, 17)
+    N = pos.shape[0]
+    x, G = torch.randn(N, 11), torch.randn(N, 2)
+    grads = []
+    sd = None
+    for save_all in ("1", "0"):
+        monkeypatch.setenv("GP_B200_SAVE_ALL", save_all)
+        model = EncodeProcessDecode(3, 11, 3, 2, hidden_size=128)
+        if sd is None:
+            sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+        model.load_state_dict(sd)
+        model = model.to(dev)
+        assert model.engine.save_all == (save_all == "1")
+        out = model(Data(x=x.to(dev), edge_index=ei.to(dev), edge_attr=ea.to(dev)))
+        (out * G.to(dev)).sum().backward()
+        torch.cuda.synchronize()
+        grads.append({k: v.detach().float().cpu() for k, v in model.engine.grads_by_name().items()})
+    for k in grads[0]:
+        assert l2_rel(grads[0][k], grads[1][k]) < 1e-5, k
