@@ -162,7 +162,7 @@ def main():
     N, E = host.x.shape[0], host.edge_index.shape[1]
     L, H = CONFIG["model"]["message_passing_num"], CONFIG["model"]["hidden_size"]
     tr = Trainer(CONFIG, learning_rate=1e-4, num_steps=100000, warmup=1000, device=dev, process_group=pg, seed=0)
-    graphed = (world == 1) and not args.no_graph
+    graphed = not args.no_graph
     tr.enable_cuda_graph(graphed)
     resident = host.to(dev)
 
@@ -252,9 +252,14 @@ def main():
         if world == 1 and not args.no_cpu_baseline:
             cb = run_reference(args)
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
-        torch.distributed.destroy_process_group()
+        # The captured steps hold NCCL work; tearing the communicator down under them can block, and
+        # nothing is left to do: synchronise, then leave without the teardown.
+        barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
     return 0
 
 

@@ -30,13 +30,14 @@ def _accumulate_global(norm, data: torch.Tensor, group) -> None:
     if norm._host_calls >= norm._max_accumulations:
         return
     d = data.detach()
-    stats = torch.cat([d.sum(0), (d ** 2).sum(0), d.new_tensor([float(d.shape[0])])])
+    stats = torch.cat([d.sum(0), (d ** 2).sum(0), torch.full((1,), float(d.shape[0]), dtype=d.dtype, device=d.device)])   # (no H2D copy: capturable)
     dist.all_reduce(stats, op=dist.ReduceOp.SUM, group=group)
     k = d.shape[1]
-    norm._acc_sum += stats[:k][None]
-    norm._acc_sum_squared += stats[k:2 * k][None]
-    norm._acc_count += stats[2 * k]
-    norm._num_accumulations += 1
+    gate = (norm._num_accumulations < norm._max_accumulations).to(torch.float32)     # device-side freeze (graph replay)
+    norm._acc_sum += gate * stats[:k][None]
+    norm._acc_sum_squared += gate * stats[k:2 * k][None]
+    norm._acc_count += gate * stats[2 * k]
+    norm._num_accumulations += gate
     norm._host_calls += 1
 
 

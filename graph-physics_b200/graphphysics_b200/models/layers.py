@@ -122,10 +122,13 @@ class Normalizer(nn.Module):
         return normalized_batch_data * self._std_with_epsilon() + self._mean()
 
     def _accumulate(self, batched_data: torch.Tensor):
-        self._acc_sum += batched_data.sum(dim=0, keepdim=True)
-        self._acc_sum_squared += (batched_data ** 2).sum(dim=0, keepdim=True)
-        self._acc_count += batched_data.shape[0]
-        self._num_accumulations += 1
+        # `gate` repeats the freeze test of layers.py:347 on the device, so a captured CUDA graph of the
+        # step (which cannot re-evaluate the host-side `if`) stops accumulating at the same call
+        gate = (self._num_accumulations < self._max_accumulations).to(torch.float32)
+        self._acc_sum += gate * batched_data.sum(dim=0, keepdim=True)
+        self._acc_sum_squared += gate * (batched_data ** 2).sum(dim=0, keepdim=True)
+        self._acc_count += gate * batched_data.shape[0]
+        self._num_accumulations += gate
         self._host_calls += 1
 
     def _mean(self) -> torch.Tensor:

@@ -73,10 +73,9 @@ class Trainer:
     def enable_cuda_graph(self, enabled: bool = True) -> None:
         """Capture the whole step (CSR build, forward, loss, backward, clip, AdamW, schedule) once per
         input shape and replay it afterwards.  Valid while the batch SHAPES repeat (fixed-size meshes,
-        the synthetic benchmark); contents -- including the topology -- may change freely.  Not combined
-        with data parallelism in this round."""
-        if enabled and self.pg is not None:
-            raise NotImplementedError("CUDA-graph replay of the step is single-GPU in this round")
+        the synthetic benchmark); contents -- including the topology -- may change freely.  With data
+        parallelism the NCCL all-reduces (normaliser statistics, flat gradient) are captured with the
+        rest; every rank must then see the same sequence of batch shapes."""
         self.use_cuda_graph = bool(enabled)
 
     def training_step(self, batch) -> torch.Tensor:
@@ -94,7 +93,10 @@ class Trainer:
                 getattr(static, k).copy_(getattr(batch, k), non_blocking=True)
             self._training_step_eager(static)          # first step of this shape runs eagerly (allocations, smem attributes)
             graph = torch.cuda.CUDAGraph()
-            with no_csr_cache(), torch.cuda.graph(graph):
+            # with a process group, NCCL's watchdog thread polls CUDA events while we capture: only
+            # this thread's calls belong to the capture
+            mode = "thread_local" if self.pg is not None else "global"
+            with no_csr_cache(), torch.cuda.graph(graph, capture_error_mode=mode):
                 self._training_step_eager(static)
             self.step_index -= 1                        # the capture pass enqueued nothing; undo its host-side count
             self._graphs[key] = (graph, static, fields)

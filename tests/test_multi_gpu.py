@@ -29,6 +29,11 @@ def _run(rank, world, port, fn, ret):
     try:
         ret[rank] = fn(rank, world)
     finally:
+        if getattr(fn, "hard_exit", False):
+            # captured CUDA graphs hold NCCL work; skip the communicator teardown (as bench.py does)
+            dist.barrier()
+            torch.cuda.synchronize()
+            os._exit(0)
         dist.destroy_process_group()
 
 
@@ -53,6 +58,36 @@ def _ddp_worker(rank, world):
     ref = flat.clone()
     dist.broadcast(ref, src=0)
     return losses, bool(torch.equal(ref, flat)), tr.model.state_dict()["_node_normalizer._acc_count"].item()
+
+
+def _ddp_graph_worker(rank, world):
+    """Same, with the whole step (NCCL all-reduces included) captured into a CUDA graph and replayed."""
+    from graphphysics_b200.synthetic import cylinder_flow_batch
+    from graphphysics_b200.training.loop import Trainer
+    dev = torch.device("cuda", rank)
+    out = []
+    for graphed in (False, True):
+        tr = Trainer(CFG, learning_rate=1e-3, num_steps=100, warmup=2, device=dev, process_group=dist.group.WORLD, seed=rank)
+        tr.enable_cuda_graph(graphed)
+        losses = []
+        for step in range(5):      # graphed: 1 eager + capture (no step) + 3 replays = 4 optimizer steps
+            batch = cylinder_flow_batch(2, nx=24, ny=12, seed=10 * rank + (step % 2)).to(dev)
+            losses.append(float(tr.training_step(batch)))
+        out.append((losses, tr.engine.flat.data.clone(), tr.step_index))
+    (l_e, p_e, n_e), (l_g, p_g, n_g) = out
+    ref = p_g.clone()
+    dist.broadcast(ref, src=0)
+    return bool(torch.equal(ref, p_g)), n_e, n_g, float((p_e - p_g).abs().max()), l_e, l_g
+
+
+_ddp_graph_worker.hard_exit = True
+
+
+def test_ddp_cuda_graph_replay_two_gpus():
+    _need_two()
+    (same0, ne, ng, d0, le, lg), (same1, _, _, d1, _, _) = _spawn(_ddp_graph_worker)
+    assert same0 and same1, "parameters diverged between ranks under graph replay"
+    assert np.isfinite(le + lg).all() and d0 < 1.0 and d1 < 1.0
 
 
 def test_ddp_two_gpus_keeps_ranks_in_lockstep():
