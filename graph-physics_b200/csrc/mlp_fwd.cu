@@ -38,17 +38,18 @@ enum : uint32_t { kMapA = 1, kMapH = 2 /* << layer */ };
 
 __device__ __forceinline__ void slot_sync(int g) { asm volatile("bar.sync %0, 256;" ::"r"(g + 1) : "memory"); }
 
-// kEdge = true is the instantiation for the processor's edge MLP (4 H-wide layers, two gathered
-// pre-activation sources, RMSNorm, bf16 residual output, segment sum): every optional path is
-// resolved at compile time, which cuts the code the two out-of-phase slots stream through the
-// instruction cache (a 10% larger kernel measured 13% slower).
-template <int H, int NG, bool kEdge>
+// kMode 1 / 2 are the instantiations for the processor's edge MLP (4 H-wide layers, two gathered
+// pre-activation sources, RMSNorm, bf16 residual output, segment sum) and node MLP (fp32 aggregate
+// as layer-0 operand, the node's own pre-activation row, RMSNorm, bf16 residual output): every
+// optional path is resolved at compile time, which cuts the code the two out-of-phase slots stream
+// through the instruction cache (a 10% larger kernel measured 13% slower).  kMode 0 is general.
+template <int H, int NG, int kMode>
 __global__ void __launch_bounds__(kSlotThreads * NG, 1) mlp_fwd_kernel(const gp_mlp_fwd_args p,
                                                                        const __grid_constant__ FwdMaps maps) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = GP_SMEM_ALIGNED(smem_raw);
     __shared__ uint64_t mma_bar[NG], tma_bar[NG];
-    const bool t_a = !kEdge && (maps.use & kMapA);
+    const bool t_a = kMode == 0 && (maps.use & kMapA);
     __shared__ uint32_t tmem_slot;
 
     const int tid = threadIdx.x;
@@ -62,10 +63,11 @@ __global__ void __launch_bounds__(kSlotThreads * NG, 1) mlp_fwd_kernel(const gp_
     const int wis = warp_u - g_u * (kSlotThreads / 32);    // warp in slot
     const int row = t & 127;                 // row in tile == TMEM lane
     const int half = t >> 7;                 // column half
-    constexpr bool E = kEdge;
+    constexpr bool kEdge = kMode == 1, kNode = kMode == 2, E = kEdge || kNode;     // E: a 4-layer H-wide processor MLP
     const int L = E ? 4 : p.n_layers;
-    const bool f_norm = E || p.norm_scale != nullptr, f_seg = E || p.seg_id != nullptr, f_resid = E || p.resid != nullptr;
-    const bool f_ybf = E || p.y_bf16 != nullptr, f_abf = E || p.a_bf16 != nullptr, f_idx0 = E || p.idx0 != nullptr;
+    const bool f_norm = E || p.norm_scale != nullptr, f_resid = E || p.resid != nullptr, f_ybf = E || p.y_bf16 != nullptr;
+    const bool f_seg = kEdge || (!E && p.seg_id != nullptr), f_abf = kEdge || (!E && p.a_bf16 != nullptr);
+    const bool f_idx0 = kEdge || (!E && p.idx0 != nullptr);
     const int ka = E ? H : p.ka;
     constexpr int CH = H / 2;                // columns per thread in H-wide layers
     constexpr int KC = H / 8;                // 16-byte chunks per H-wide row
@@ -138,7 +140,7 @@ __global__ void __launch_bounds__(kSlotThreads * NG, 1) mlp_fwd_kernel(const gp_
 
     // gather indices of a tile (prefetched one tile ahead): i0n = this thread's row in the directly
     // loaded source; ridx[] = rows of the chunks this thread copies for the staged source
-    const bool stage1 = E || p.two_inits != 0;           // which source goes through buf
+    const bool stage1 = kEdge || (!E && p.two_inits != 0);           // which source goes through buf
     const int32_t* sidx = stage1 ? p.idx1 : p.idx0;
     const int soff = stage1 ? p.init_off1 : p.init_off0;
     int i0n = 0, ridx[CPT];
@@ -257,7 +259,7 @@ __global__ void __launch_bounds__(kSlotThreads * NG, 1) mlp_fwd_kernel(const gp_
                 for (int b = 0; b < nblk; ++b) tma_load_2d(buf_u + b * 16384, &maps.a, b * 64, R0, &tma_bar[g_u]);
             }
         } else {
-            stage_rows(buf, p.a_bf16, E ? nullptr : p.a_f32, ka, p.lda, R0, p.rows, t, kSlotThreads);
+            stage_rows(buf, kNode ? nullptr : p.a_bf16, kEdge ? nullptr : p.a_f32, ka, p.lda, R0, p.rows, t, kSlotThreads);
             cp_async_commit();
         }
         tick(0);                 // issue of loads + gathers + TMEM pre-load (this thread)
@@ -498,7 +500,7 @@ __global__ void __launch_bounds__(256) seg_fixup_kernel(const int32_t* __restric
     }
 }
 
-template <int H, int NG, bool kEdge>
+template <int H, int NG, int kMode>
 int launch_fwd(const gp_mlp_fwd_args& a, cudaStream_t st) {
     size_t smem = 1024;
     for (int l = 0; l < a.n_layers; ++l) smem += (size_t)((a.k[l] + 63) / 64) * a.n[l] * 128;
@@ -507,7 +509,7 @@ int launch_fwd(const gp_mlp_fwd_args& a, cudaStream_t st) {
                gp::max_smem_optin());
     static int smem_set = 0;      // raised once per instantiation (and never inside a stream capture twice)
     if ((int)smem > smem_set) {
-        GP_CHECK_CUDA(cudaFuncSetAttribute(mlp_fwd_kernel<H, NG, kEdge>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        GP_CHECK_CUDA(cudaFuncSetAttribute(mlp_fwd_kernel<H, NG, kMode>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         smem_set = (int)smem;
     }
     const int n_tiles = (a.rows + 127) / 128;
@@ -525,7 +527,7 @@ int launch_fwd(const gp_mlp_fwd_args& a, cudaStream_t st) {
         for (int i = 0; i < 3; ++i)
             if (sv[i] && gp::tma_map_2d(&maps.h[i], sv[i], a.rows, H, H)) maps.use |= kMapH << i;
     }
-    mlp_fwd_kernel<H, NG, kEdge><<<grid, kSlotThreads * NG, smem, st>>>(a, maps);
+    mlp_fwd_kernel<H, NG, kMode><<<grid, kSlotThreads * NG, smem, st>>>(a, maps);
     GP_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -557,14 +559,16 @@ extern "C" int gp_mlp_fwd(const gp_mlp_fwd_args* args, int hidden, void* stream)
     GP_REQUIRE((a.y_bf16 != nullptr) != (a.y_f32 != nullptr), "gp_mlp_fwd: exactly one of y_bf16 / y_f32");
     if (a.norm_scale) GP_REQUIRE(a.ld_out % 8 == 0, "gp_mlp_fwd: ld_out must be a multiple of 8 with RMSNorm");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    // the processor's edge MLP gets the instantiation with every option fixed at compile time
-    bool edge = a.init && a.two_inits && a.idx0 && a.idx1 && a.a_bf16 && a.n_layers == 4 && a.ka == hidden && a.norm_scale &&
-                a.resid && a.seg_id && a.y_bf16;
-    for (int l = 0; l < a.n_layers && edge; ++l) edge = a.k[l] == hidden && a.n[l] == hidden;
+    // the processor's edge and node MLPs get instantiations with every option fixed at compile time
+    bool proc = a.init && a.n_layers == 4 && a.ka == hidden && a.norm_scale && a.resid && a.y_bf16;
+    for (int l = 0; l < a.n_layers && proc; ++l) proc = a.k[l] == hidden && a.n[l] == hidden;
+    const bool edge = proc && a.two_inits && a.idx0 && a.idx1 && a.a_bf16 && a.seg_id;
+    const bool node = proc && !a.two_inits && !a.idx0 && a.a_f32 && !a.seg_id;
     switch (hidden) {
-        case 128: return edge ? launch_fwd<128, 2, true>(a, st) : launch_fwd<128, 2, false>(a, st);
-        case 64: return launch_fwd<64, 2, false>(a, st);
-        case 32: return launch_fwd<32, 2, false>(a, st);
+        case 128:
+            return edge ? launch_fwd<128, 2, 1>(a, st) : node ? launch_fwd<128, 2, 2>(a, st) : launch_fwd<128, 2, 0>(a, st);
+        case 64: return launch_fwd<64, 2, 0>(a, st);
+        case 32: return launch_fwd<32, 2, 0>(a, st);
         default: gp::set_error("gp_mlp_fwd: unsupported hidden size %d (32, 64, 128)", hidden); return -1;
     }
 }

@@ -57,13 +57,29 @@ __device__ __forceinline__ void stage_rows(uint8_t* buf, const gp_bf16* a_bf16, 
             cp_async16(buf_s + sw128_off(128, r, ch * 8), a_bf16 + (size_t)gr * lda + ch * 8);
         }
     } else if (a_f32) {
-        for (int i = t; i < 128 * kc; i += nthreads) {
-            const int r = i >> sh, ch = i & (kc - 1);
-            const int gr = min(R0 + r, rows - 1);
-            const float4* s = reinterpret_cast<const float4*>(a_f32 + (size_t)gr * lda + ch * 8);
-            const float4 u0 = __ldg(s), u1 = __ldg(s + 1);
-            *reinterpret_cast<uint4*>(buf + sw128_off(128, r, ch * 8)) =
-                make_uint4(pack_bf16(u0.x, u0.y), pack_bf16(u0.z, u0.w), pack_bf16(u1.x, u1.y), pack_bf16(u1.z, u1.w));
+        // four chunks per round: their eight 16-byte loads are in flight together
+        for (int i0 = t; i0 < 128 * kc; i0 += 4 * nthreads) {
+            float4 u[8];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int i = i0 + j * nthreads;
+                if (i < 128 * kc) {
+                    const int r = i >> sh, ch = i & (kc - 1);
+                    const float4* s = reinterpret_cast<const float4*>(a_f32 + (size_t)min(R0 + r, rows - 1) * lda + ch * 8);
+                    u[2 * j] = __ldg(s);
+                    u[2 * j + 1] = __ldg(s + 1);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int i = i0 + j * nthreads;
+                if (i < 128 * kc) {
+                    const int r = i >> sh, ch = i & (kc - 1);
+                    *reinterpret_cast<uint4*>(buf + sw128_off(128, r, ch * 8)) =
+                        make_uint4(pack_bf16(u[2 * j].x, u[2 * j].y), pack_bf16(u[2 * j].z, u[2 * j].w),
+                                   pack_bf16(u[2 * j + 1].x, u[2 * j + 1].y), pack_bf16(u[2 * j + 1].z, u[2 * j + 1].w));
+                }
+            }
         }
     }
 }
