@@ -335,7 +335,35 @@ __global__ void __launch_bounds__(BwdCfg<H>::NT, 1) mlp_bwd_kernel(const gp_mlp_
                 mma_ss(tmem + kColAcc, desc_kmajor(ain_s, 128, ks), desc_kmajor(wa_s, H, ks), id, 1u);
             mma_commit(&mma_bar);
         }
-        if (tile + (int)gridDim.x < n_tiles) load_idx(tile + gridDim.x);
+        if (tile + (int)gridDim.x < n_tiles) {
+            // next tile: its row ids now, and everything P0 will ask for into L2 (bulk tiles by the
+            // copy engine, gathered rows one prefetch per 128-byte line), so that P0 waits on L2 only
+            const int Rn = (tile + (int)gridDim.x) << 7;
+            load_idx(tile + gridDim.x);
+            if (warp == 0 && elect_one()) {
+                if (t_ain) for (int b = 0; b < (ka + 63) >> 6; ++b) tma_prefetch_2d(&maps.ain, b * 64, Rn);
+                if (t_db) for (int b = 0; b < (nb + 63) >> 6; ++b) tma_prefetch_2d(&maps.db, b * 64, Rn);
+                if (t_gy) for (int b = 0; b < (H + 63) >> 6; ++b) tma_prefetch_2d(&maps.gy, b * 64, Rn);
+                if (t_res) for (int b = 0; b < (ka + 63) >> 6; ++b) tma_prefetch_2d(&maps.resid, b * 64, Rn);
+                if (t_ha) for (int b = 0; b < (H + 63) >> 6; ++b) tma_prefetch_2d(&maps.ha, b * 64, Rn);
+            }
+#pragma unroll
+            for (int j = 0; j < CPT; ++j) {
+                const int i = tid + j * NT;
+                if ((i & 7) == 0) {         // chunk 0 of a 128-byte line
+                    if (has_init)
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(p.init + (size_t)ridx[j] * p.ld_init + soff + (i % KC) * 8));
+                    if (du_smem && f_gather) {       // fp32 rows: two lines per 8-chunk group
+                        const float* gp_ = p.gy_gather + (size_t)gidx[j] * H + (i % KC) * 8;
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(gp_));
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(gp_ + 32));
+                    }
+                }
+            }
+            if (has_init && stage1 && tid < 128)
+                for (int c = 0; c < H; c += 64)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(p.init + (size_t)i0n * p.ld_init + p.init_off0 + c));
+        }
         if (!ha_given) wait_mma();
         tick(3);      // P1 MMA
         if (!ha_given) {

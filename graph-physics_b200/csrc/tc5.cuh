@@ -74,6 +74,12 @@ __device__ __forceinline__ void tma_store_2d(const void* tmap, int32_t col, int3
                  ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_src), "r"(col), "r"(row)
                  : "memory");
 }
+// bring one box into L2 only (no shared-memory destination, no completion tracking)
+__device__ __forceinline__ void tma_prefetch_2d(const void* tmap, int32_t col, int32_t row) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];"
+                 ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(col), "r"(row)
+                 : "memory");
+}
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // the shared-memory sources of all committed stores have been read (the buffers may be rewritten)
 template <int N = 0>
