@@ -59,7 +59,9 @@ struct BwdCfg {
 // MODE 0 is the general kernel.  MODE 1 / 2 are the instantiations for the two stages of the processor's
 // edge MLP at H = 128 (1: layers 3-4 with the RMSNorm backward and the gathered receiver gradient;
 // 2: layers 1-2 with the two gathered pre-activation sources, the stored delta_1 and its segment
-// sum), with every option -- including which tensors move by TMA -- fixed at compile time.  The
+// sum), MODE 3 / 4 those of the node MLP (3: fp32 upstream gradient read per row; 4: fp32 aggregate
+// as operand, fp32 d_agg output), with every option -- including which tensors move by TMA -- fixed
+// at compile time.  The
 // general kernel is 100 KB of code that each tile streams through the instruction cache; the
 // specialised ones keep only their own path.
 template <int H, int MODE>
@@ -74,17 +76,34 @@ __global__ void __launch_bounds__(BwdCfg<H>::NT, 1) mlp_bwd_kernel(const gp_mlp_
 
     const int tid = threadIdx.x;
     const int row = tid & 127, part = tid >> 7;
-    constexpr bool F1 = MODE == 1, F2 = MODE == 2, F = F1 || F2;
-    const bool t_ain = F || (maps.use & kMapAin), t_db = F2 || (!F && (maps.use & kMapDb)), t_gy = F1 || (!F && (maps.use & kMapGy));
-    const bool t_res = F2 || (!F && (maps.use & kMapResid)), t_da = F2 || (!F && (maps.use & kMapDaOut));
-    const bool t_out = F || (maps.use & kMapOut), t_ha = !F && (maps.use & kMapHa);
+    // option tables of the specialised instantiations:    general, edge B, edge A, node B, node A
+    constexpr bool F = MODE != 0, F1 = MODE == 1;
+    constexpr bool kNorm[5]   = {false, true,  false, true,  false};
+    constexpr bool kTAin[5]   = {false, true,  true,  true,  false};   // a_in tile by TMA (else: fp32 rows, converted)
+    constexpr bool kTDb[5]    = {false, false, true,  false, true};
+    constexpr bool kTGy[5]    = {false, true,  false, false, false};
+    constexpr bool kTRes[5]   = {false, false, true,  false, false};
+    constexpr bool kTDa[5]    = {false, false, true,  false, true};
+    constexpr bool kTOut[5]   = {false, true,  true,  true,  false};   // bf16 output tile through shared memory + TMA
+    constexpr bool kGather[5] = {false, true,  false, false, false};
+    constexpr bool kSeg[5]    = {false, false, true,  false, false};
+    constexpr bool kMask[5]   = {false, true,  false, true,  false};
+    constexpr bool kInit[5]   = {false, false, true,  false, true};
+    constexpr bool kTwo[5]    = {false, false, true,  false, false};
+    const bool t_ain = F ? kTAin[MODE] : bool(maps.use & kMapAin), t_db = F ? kTDb[MODE] : bool(maps.use & kMapDb);
+    const bool t_gy = F ? kTGy[MODE] : bool(maps.use & kMapGy), t_res = F ? kTRes[MODE] : bool(maps.use & kMapResid);
+    const bool t_da = F ? kTDa[MODE] : bool(maps.use & kMapDaOut), t_out = F ? kTOut[MODE] : bool(maps.use & kMapOut);
+    const bool t_ha = !F && (maps.use & kMapHa);
     const bool ha_given = !F && p.ha_saved != nullptr;       // h_a comes from memory: no gather, no recompute
-    const bool f_gather = F1 || (!F && p.gy_gather != nullptr);     // receiver-indexed fp32 rows are added to gy
-    const bool f_seg = F2 || (!F && p.seg_id != nullptr), f_da = F2 || (!F && p.delta_a_out != nullptr);
-    const bool f_din = F || p.need_din, f_mask = F1 || (!F && p.mask_by_ain), f_resid = F2 || (!F && p.out_resid != nullptr);
+    const bool f_gather = F ? kGather[MODE] : p.gy_gather != nullptr;     // receiver-indexed fp32 rows are added to gy
+    const bool f_seg = F ? kSeg[MODE] : p.seg_id != nullptr, f_da = F ? kTDa[MODE] : p.delta_a_out != nullptr;
+    const bool f_din = F || p.need_din, f_mask = F ? kMask[MODE] : bool(p.mask_by_ain);
+    const bool f_resid = F ? kTRes[MODE] : p.out_resid != nullptr;
+    const bool f_obf = F ? kTOut[MODE] : p.out_bf16 != nullptr;          // bf16 (else fp32) d_in output
+    const bool f_gyf32 = F ? MODE == 3 : p.gy_f32 != nullptr;
     const int warp = warp_uniform(tid >> 5);
     const int ka = F ? H : p.ka, nb = F ? H : p.nb;
-    const bool norm = F1 || (!F && p.mode == 1);
+    const bool norm = F ? kNorm[MODE] : p.mode == 1;
 
     // ---- carve
     uint32_t off = 0;
@@ -135,7 +154,7 @@ __global__ void __launch_bounds__(BwdCfg<H>::NT, 1) mlp_bwd_kernel(const gp_mlp_
     const uint32_t lbo_h = (H >= 128) ? 16384u : 0u;      // M=128 MN-major A with < 128 valid columns: alias block
     const uint32_t lbo_nb = (nb >= 128) ? 16384u : 0u;
     uint32_t phase = 0, tphase = 0;
-    const bool has_init = F2 || (!F && p.init != nullptr && !ha_given);
+    const bool has_init = F ? kInit[MODE] : (p.init != nullptr && !ha_given);
     const int n_tiles = (p.rows + 127) >> 7;
     constexpr int CH = H / NPART;                          // columns per thread
     const int cb = part * CH;
@@ -153,10 +172,10 @@ __global__ void __launch_bounds__(BwdCfg<H>::NT, 1) mlp_bwd_kernel(const gp_mlp_
 
     constexpr int KC = H / 8;                 // 16-byte chunks per H-wide row
     constexpr int CPT = 128 * KC / NT;       // chunks per thread in a row-major tile copy
-    const bool stage1 = F2 || (!F && p.two_inits != 0);     // which pre-activation source is gathered through shared memory
+    const bool stage1 = F ? kTwo[MODE] : p.two_inits != 0;     // which pre-activation source is gathered through shared memory
     const int32_t* sidx = stage1 ? p.idx1 : p.idx0;
     const int soff = stage1 ? p.init_off1 : p.init_off0;
-    const bool du_smem = F1 || (!F && norm && p.gy_bf16 != nullptr);     // upstream gradient tile staged in qb (+ gathered rows in db)
+    const bool du_smem = F ? kTGy[MODE] : (norm && p.gy_bf16 != nullptr);     // upstream gradient tile staged in qb (+ gathered rows in db)
 
     const bool prof = p.prof != nullptr && tid == 0;
     long long tk = 0;
@@ -179,7 +198,7 @@ __global__ void __launch_bounds__(BwdCfg<H>::NT, 1) mlp_bwd_kernel(const gp_mlp_
         }
         if (has_init && stage1) {
             const int r = min(R0_ + row, p.rows - 1);
-            i0n = (F2 || p.idx0) ? __ldg(p.idx0 + r) : r;
+            i0n = (MODE == 2 || p.idx0) ? __ldg(p.idx0 + r) : r;
         }
     };
     if ((int)blockIdx.x < n_tiles) load_idx(blockIdx.x);
@@ -223,7 +242,7 @@ __global__ void __launch_bounds__(BwdCfg<H>::NT, 1) mlp_bwd_kernel(const gp_mlp_
                     *reinterpret_cast<uint4*>(ha + sw128_off(128, r, ch * 8)) = make_uint4(0, 0, 0, 0);
             }
         }
-        if (!t_ain) stage_rows(ain, p.a_bf16, F ? nullptr : p.a_f32, ka, p.lda, R0, p.rows, tid, NT);
+        if (!t_ain) stage_rows(ain, MODE == 4 ? nullptr : p.a_bf16, (F && MODE != 4) ? nullptr : p.a_f32, ka, p.lda, R0, p.rows, tid, NT);
         if (!norm && !t_db) {   // delta_b given: zero rows past the end so they add nothing to the weight gradients
             const int kc = nb >> 3;
             for (int i = tid; i < 128 * kc; i += NT) {
@@ -408,7 +427,7 @@ __global__ void __launch_bounds__(BwdCfg<H>::NT, 1) mlp_bwd_kernel(const gp_mlp_
                     unpack8(*reinterpret_cast<const uint4*>(qb + sw128_off(128, row, c0)), du);
                     if (f_gather) acc8(*reinterpret_cast<const uint4*>(db + sw128_off(128, row, c0)), du);
                 } else {
-                    if (p.gy_f32) {
+                    if (f_gyf32) {
                         const float4* gp_ = reinterpret_cast<const float4*>(p.gy_f32 + (size_t)crow * p.ld_gy + c0);
                         const float4 t0 = __ldg(gp_), t1 = __ldg(gp_ + 1);
                         du[0] = t0.x; du[1] = t0.y; du[2] = t0.z; du[3] = t0.w;
@@ -430,17 +449,17 @@ __global__ void __launch_bounds__(BwdCfg<H>::NT, 1) mlp_bwd_kernel(const gp_mlp_
 #pragma unroll
             for (int c = 0; c < CH; c += 16) tmem_ld16(tlane + kColAcc + cb + c, *reinterpret_cast<uint32_t(*)[16]>(&v[c]));
             tmem_ld_wait();
+            // du is read once and kept in registers for both passes (the direct fp32 path issues all
+            // of its row loads here, back to back)
+            float duv[CH];
+#pragma unroll
+            for (int c = 0; c < CH; c += 8) load_du(cb + c, duv + c);
             float ss = 0.f, dot = 0.f;
 #pragma unroll
-            for (int c = 0; c < CH; c += 8) {
-                float du[8];
-                load_du(cb + c, du);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float m = __uint_as_float(v[c + j]);
-                    ss = fmaf(m, m, ss);
-                    dot = fmaf(du[j] * s_g[cb + c + j], m, dot);
-                }
+            for (int c = 0; c < CH; ++c) {
+                const float m = __uint_as_float(v[c]);
+                ss = fmaf(m, m, ss);
+                dot = fmaf(duv[c] * s_g[cb + c], m, dot);
             }
             s_red[(0 * NPART + part) * 128 + row] = ss;
             s_red[(1 * NPART + part) * 128 + row] = dot;
@@ -459,13 +478,12 @@ __global__ void __launch_bounds__(BwdCfg<H>::NT, 1) mlp_bwd_kernel(const gp_mlp_
             const float coef = (valid && rms > 0.f) ? dot * s1 * s1 / (rms * H) : 0.f;
 #pragma unroll
             for (int c = 0; c < CH; c += 8) {
-                float du[8], dm[8], q[8];
-                load_du(cb + c, du);
+                float dm[8], q[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const float m = __uint_as_float(v[c + j]);
-                    dm[j] = fmaf(s_g[cb + c + j] * du[j], s, -(coef * m));
-                    q[j] = (du[j] * m) * s;
+                    dm[j] = fmaf(s_g[cb + c + j] * duv[c + j], s, -(coef * m));
+                    q[j] = (duv[c + j] * m) * s;
                 }
                 *reinterpret_cast<uint4*>(db + sw128_off(128, row, cb + c)) = pack8(dm);
                 *reinterpret_cast<uint4*>(qb + sw128_off(128, row, cb + c)) = pack8(q);
@@ -548,7 +566,7 @@ __global__ void __launch_bounds__(BwdCfg<H>::NT, 1) mlp_bwd_kernel(const gp_mlp_
         wait_mma();
         tick(10);     // P4 MMA wait
         if (f_din) {
-            const bool via_smem = F || (p.out_bf16 != nullptr && ka == H);     // bf16 tile output: transpose through shared memory
+            const bool via_smem = F ? kTOut[MODE] : (p.out_bf16 != nullptr && ka == H);     // bf16 tile output: transpose through shared memory
             uint8_t* ob = (t_out && norm) ? qb : db;                    // staging tile (free since P3)
             const int nsplit = (ka >= 16 * NPART) ? NPART : (ka >= 32 ? 2 : 1);   // column parts that take part
             const int kh = ka / nsplit;
@@ -590,7 +608,7 @@ __global__ void __launch_bounds__(BwdCfg<H>::NT, 1) mlp_bwd_kernel(const gp_mlp_
 #pragma unroll
                             for (int j = 0; j < 16; ++j) f[j] += rv[j];
                         }
-                        if (p.out_bf16) {
+                        if (f_obf) {
                             uint4* d = reinterpret_cast<uint4*>(p.out_bf16 + (size_t)grow * p.ld_out + c0);
                             d[0] = pack8(f);
                             d[1] = pack8(f + 8);
@@ -766,22 +784,34 @@ int launch_bwd(const gp_mlp_bwd_args& a, int32_t* grid_out, cudaStream_t st) {
     smem += (size_t)((a.mode == 1 || (maps.use & kMapResid)) ? 4 : 3) * kBufBytes + 128 * 128 + 3 * 128 * 4 + 2 * BwdCfg<H>::NPART * 128 * 4 + 144 * 4;
     GP_REQUIRE((int)smem <= gp::max_smem_optin(), "gp_mlp_bwd_stage: needs %zu B of shared memory (> %d)", smem,
                gp::max_smem_optin());
-    // the two stages of the processor's edge MLP get their own instantiations (H = 128 only)
+    // the stages of the processor's edge and node MLPs get their own instantiations (H = 128 only)
     int fast = 0;
-    if (H == 128 && a.a_bf16 && a.ka == H && a.nb == H && !a.ha_saved && a.need_din && a.out_bf16) {
-        if (a.mode == 1 && a.gy_bf16 && a.gy_gather && a.gy_idx && !a.init && a.mask_by_ain && !a.out_resid && !a.delta_a_out &&
-            !a.seg_id && maps.use == (kMapAin | kMapGy | kMapOut))
-            fast = 1;
-        if (a.mode == 0 && a.init && a.two_inits && a.idx0 && a.idx1 && !a.mask_by_ain && a.out_resid && a.delta_a_out && a.seg_id &&
-            maps.use == (kMapAin | kMapDb | kMapResid | kMapDaOut | kMapOut))
-            fast = 2;
+    if (H == 128 && a.ka == H && a.nb == H && !a.ha_saved && a.need_din) {
+        const bool plain = !a.out_resid && !a.delta_a_out && !a.seg_id;
+        if (a.mode == 1 && a.a_bf16 && a.out_bf16 && !a.init && a.mask_by_ain && plain) {
+            if (a.gy_bf16 && a.gy_gather && a.gy_idx && maps.use == (kMapAin | kMapGy | kMapOut)) fast = 1;          // edge B
+            if (a.gy_f32 && !a.gy_gather && maps.use == (kMapAin | kMapOut)) fast = 3;                                // node B
+        }
+        if (a.mode == 0 && a.init && !a.mask_by_ain && a.delta_a_out) {
+            if (a.a_bf16 && a.out_bf16 && a.two_inits && a.idx0 && a.idx1 && a.out_resid && a.seg_id &&
+                maps.use == (kMapAin | kMapDb | kMapResid | kMapDaOut | kMapOut))
+                fast = 2;                                                                                             // edge A
+            if (a.a_f32 && a.out_f32 && !a.two_inits && !a.idx0 && !a.out_resid && !a.seg_id && maps.use == (kMapDb | kMapDaOut))
+                fast = 4;                                                                                             // node A
+        }
     }
-    static int smem_set[3] = {0, 0, 0};      // raised once per instantiation (and never inside a stream capture twice)
+    auto set_smem = [&](int bytes) -> cudaError_t {
+        switch (fast) {
+            case 1: return cudaFuncSetAttribute(mlp_bwd_kernel<H, (H == 128 ? 1 : 0)>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+            case 2: return cudaFuncSetAttribute(mlp_bwd_kernel<H, (H == 128 ? 2 : 0)>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+            case 3: return cudaFuncSetAttribute(mlp_bwd_kernel<H, (H == 128 ? 3 : 0)>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+            case 4: return cudaFuncSetAttribute(mlp_bwd_kernel<H, (H == 128 ? 4 : 0)>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+            default: return cudaFuncSetAttribute(mlp_bwd_kernel<H, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+        }
+    };
+    static int smem_set[5] = {0, 0, 0, 0, 0};      // raised once per instantiation (and never inside a stream capture twice)
     if ((int)smem > smem_set[fast]) {
-        cudaError_t e = fast == 1   ? cudaFuncSetAttribute(mlp_bwd_kernel<H, (H == 128 ? 1 : 0)>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                        : fast == 2 ? cudaFuncSetAttribute(mlp_bwd_kernel<H, (H == 128 ? 2 : 0)>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                                    : cudaFuncSetAttribute(mlp_bwd_kernel<H, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        GP_CHECK_CUDA(e);
+        GP_CHECK_CUDA(set_smem((int)smem));
         smem_set[fast] = (int)smem;
     }
     const int n_tiles = (a.rows + 127) / 128;
@@ -790,6 +820,10 @@ int launch_bwd(const gp_mlp_bwd_args& a, int32_t* grid_out, cudaStream_t st) {
         mlp_bwd_kernel<H, (H == 128 ? 1 : 0)><<<grid, BwdCfg<H>::NT, smem, st>>>(a, maps);
     else if (fast == 2)
         mlp_bwd_kernel<H, (H == 128 ? 2 : 0)><<<grid, BwdCfg<H>::NT, smem, st>>>(a, maps);
+    else if (fast == 3)
+        mlp_bwd_kernel<H, (H == 128 ? 3 : 0)><<<grid, BwdCfg<H>::NT, smem, st>>>(a, maps);
+    else if (fast == 4)
+        mlp_bwd_kernel<H, (H == 128 ? 4 : 0)><<<grid, BwdCfg<H>::NT, smem, st>>>(a, maps);
     else
         mlp_bwd_kernel<H, 0><<<grid, BwdCfg<H>::NT, smem, st>>>(a, maps);
     GP_CHECK_CUDA(cudaGetLastError());

@@ -330,7 +330,9 @@ class EPDEngine:
             Gp[:, :out_size] = d_out
             dX = torch.empty((N, H), dtype=torch.float32, device=dev)
             self._mlp_backward(self.dec, N, a_in=ctx["x_last"], ka=H, h2=ctx["h2d"], top=dict(delta_b=Gp), out=dX)
-        dE = dE_sorted
+        # nobody consumes the last edge latent: its gradient is zero.  An explicit zero tile keeps the top
+        # layer on the same specialised kernel as the others (a memset is cheaper than the general path).
+        dE = dE_sorted if dE_sorted is not None else torch.zeros((E, H), dtype=bf, device=dev)
         bnd = torch.empty(ops.seg_bnd_size(E, H, backward=True), dtype=torch.float32, device=dev)
         gp = self.gflat.data_ptr()
         for l in reversed(range(self.L)):
