@@ -22,6 +22,11 @@
 #include "common.cuh"
 #include "tile_util.cuh"
 
+struct gp_mlp_fwd_args;
+namespace gp {
+int try_linear_fwd(const gp_mlp_fwd_args& a, int hidden, cudaStream_t st);
+}
+
 namespace {
 using namespace gp;
 
@@ -559,6 +564,10 @@ extern "C" int gp_mlp_fwd(const gp_mlp_fwd_args* args, int hidden, void* stream)
     GP_REQUIRE((a.y_bf16 != nullptr) != (a.y_f32 != nullptr), "gp_mlp_fwd: exactly one of y_bf16 / y_f32");
     if (a.norm_scale) GP_REQUIRE(a.ld_out % 8 == 0, "gp_mlp_fwd: ld_out must be a multiple of 8 with RMSNorm");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    {   // wide single-layer projections have their own kernel (linear_fwd.cu)
+        const int taken = gp::try_linear_fwd(a, hidden, st);
+        if (taken != 0) return taken < 0 ? taken : 0;
+    }
     // the processor's edge and node MLPs get instantiations with every option fixed at compile time
     bool proc = a.init && a.n_layers == 4 && a.ka == hidden && a.norm_scale && a.resid && a.y_bf16;
     for (int l = 0; l < a.n_layers && proc; ++l) proc = a.k[l] == hidden && a.n[l] == hidden;
