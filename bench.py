@@ -224,13 +224,18 @@ def main():
     alg_bytes = {"edge_fwd": E * (8 * H + 8) + 4 * N * H, "edge_bwd_B": E * (6 * H) + 4 * N * H,
                  "edge_bwd_A": E * (10 * H + 8) + 4 * N * H}
     alg_flops = {"edge_fwd": E * 8 * H * H, "edge_bwd_B": E * 12 * H * H, "edge_bwd_A": E * 10 * H * H}
+    # dram__bytes_read.sum + dram__bytes_write.sum per launch of the same kernels on this workload, from the
+    # `ncu --set full` captures summarised in profiles/r01_final_summary.md (below the algorithmic bytes: the
+    # gathered rows and the residual tile hit L2)
+    ncu_dram_bytes = {"edge_fwd": 227.6e6, "edge_bwd_B": 302.0e6, "edge_bwd_A": 527.1e6} if (E, N, H) == (372752, 64424, 128) else {}
     roof = None
     if prof:
         top = max(prof, key=lambda k: prof[k]["total_ms"])
         avg_ms = prof[top]["total_ms"] / max(prof[top]["calls"], 1)
         ach = alg_bytes[top] / (avg_ms * 1e-3) / 1e9
         roof = {"bound": "hbm", "kernel": top, "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-                "traffic": None, "peak_source": peak_src, "avg_launch_ms": avg_ms,
+                "traffic": ncu_dram_bytes.get(top), "traffic_source": "profiles/r01_final_summary.md (ncu --set full, per launch, bytes)",
+                "algorithmic_bytes": alg_bytes[top], "peak_source": peak_src, "avg_launch_ms": avg_ms,
                 "share_of_step": (prof[top]["total_ms"] / n_prof) / (ms_res / args.steps),
                 "tensor": {"achieved_tflops": alg_flops[top] / (avg_ms * 1e-3) / 1e12, "peak_tflops": tf_peak,
                            "frac": alg_flops[top] / (avg_ms * 1e-3) / 1e12 / tf_peak},
