@@ -36,3 +36,15 @@ class HaloPlan:
         else:
             dist.all_to_all_single(inp, out, self.recv_counts, self.send_counts, group=group)
         x.index_copy_(0, self.recv_idx, inp)
+
+    def exchange_grad_(self, dx: torch.Tensor, group=None) -> None:
+        """Transpose of `exchange_`: the gradient rows of the ghost copies travel back to their owners
+        and are added to the owners' rows; the ghost rows are then zeroed (what a rank computed for a
+        ghost before the exchange overwrote it has no consumer).  fp32, in place."""
+        h = dx.shape[1]
+        out = dx.index_select(0, self.recv_idx).contiguous()
+        inp = torch.empty((int(sum(self.send_counts)), h), dtype=dx.dtype, device=dx.device)
+        dist.all_to_all_single(inp, out, self.send_counts, self.recv_counts, group=group)
+        dx.index_add_(0, self.send_idx, inp)           # a row sent to several peers collects all of them
+        dx.index_fill_(0, self.recv_idx, 0.0)
+

@@ -314,10 +314,12 @@ class EPDEngine:
                                   delta_a_out=delta_a_out, tag=(tag + "_A") if tag else None, **kw)
         self._reduce_stage(gridA, ka, H, s, 0, 1, False)
 
-    def backward(self, ctx, d_out: torch.Tensor, dE_sorted: Optional[torch.Tensor] = None):
+    def backward(self, ctx, d_out: torch.Tensor, dE_sorted: Optional[torch.Tensor] = None, before_block=None):
         """Fills self.gflat with d loss / d parameters.  d_out is d loss / d output ([N,out] fp32, or
         [N,H] with only_processor); dE_sorted (bf16, receiver-sorted) is the gradient of the last
-        edge latent when somebody consumes it.  Returns (dX_in, dE_in_sorted) for only_processor."""
+        edge latent when somebody consumes it.  Returns (dX_in, dE_in_sorted) for only_processor.
+        `before_block(dX)` (optional) runs on the fp32 gradient of a block's node output before that
+        block's backward -- the transpose of forward's `after_block` (reverse halo exchange)."""
         H, dev = self.H, self.device
         g: GraphCSR = ctx["g"]
         N, E = g.num_nodes, g.num_edges
@@ -337,6 +339,8 @@ class EPDEngine:
         gp = self.gflat.data_ptr()
         for l in reversed(range(self.L)):
             x, e, P, agg, h2e, h2n = ctx["layers"][l]
+            if before_block is not None:
+                before_block(dX)
             # node MLP:  x' = x + norm(MLP([x, agg]))
             dagg = torch.empty((N, H), dtype=torch.float32, device=dev)
             dQ = torch.empty((N, H), dtype=bf, device=dev)

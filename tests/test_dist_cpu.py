@@ -82,6 +82,35 @@ def test_halo_exchange_two_ranks():
     assert _spawn(_halo_worker) == [True, True]
 
 
+def _halo_grad_worker(rank, world):
+    """exchange_grad_ is the transpose of exchange_:  sum_ranks <exchange(x), g>  ==  sum_ranks <x_owned-part, exchange_grad(g)>
+    for integer-valued (exactly representable) x and g, with the ghost rows of x treated as dead inputs."""
+    import torch.distributed as dist
+    from graphphysics_b200.dist.halo import HaloPlan
+    from graphphysics_b200.dist.partition import build_local_graphs, partition_nodes
+    pos, ei = _mesh()
+    lg = build_local_graphs(ei, partition_nodes(pos, world), world)[rank]
+    plan = HaloPlan(lg, world, "cpu")
+    gen = torch.Generator().manual_seed(100 + rank)
+    x = torch.randint(-8, 9, (lg.num_local, 3), generator=gen).float()
+    g = torch.randint(-8, 9, (lg.num_local, 3), generator=gen).float()
+    y = x.clone()
+    plan.exchange_(y)                                   # y = A x  (ghost rows of x do not reach y)
+    lhs = (y * g).sum()
+    gt = g.clone()
+    plan.exchange_grad_(gt)                             # gt = A^T g
+    rhs = (x * gt).sum()
+    both = torch.stack([lhs, rhs])
+    dist.all_reduce(both)
+    ghosts_zero = bool((gt[lg.num_owned:] == 0).all())
+    return float(both[0]), float(both[1]), ghosts_zero
+
+
+def test_halo_gradient_exchange_is_the_transpose():
+    for lhs, rhs, ghosts_zero in _spawn(_halo_grad_worker):
+        assert lhs == rhs and ghosts_zero
+
+
 def _ddp_worker(rank, world):
     from graphphysics_b200.dist.ddp import accumulate_normalizers_globally, allreduce_mean_, broadcast_
     from graphphysics_b200.graph import Data
