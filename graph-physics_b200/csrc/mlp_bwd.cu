@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(BwdCfg<H>::NT, 1) mlp_bwd_kernel(const gp_mlp_
     constexpr bool kTGy[5]    = {false, true,  false, false, false};
     constexpr bool kTRes[5]   = {false, false, true,  false, false};
     constexpr bool kTDa[5]    = {false, false, true,  false, true};
-    constexpr bool kTOut[5]   = {false, true,  true,  true,  false};   // bf16 output tile through shared memory + TMA
+    constexpr bool kTOut[5]   = {false, true,  true,  true,  true};    // bf16 output tile through shared memory + TMA
     constexpr bool kGather[5] = {false, true,  false, false, false};
     constexpr bool kSeg[5]    = {false, false, true,  false, false};
     constexpr bool kMask[5]   = {false, true,  false, true,  false};
@@ -95,7 +95,8 @@ __global__ void __launch_bounds__(BwdCfg<H>::NT, 1) mlp_bwd_kernel(const gp_mlp_
     const bool t_da = F ? kTDa[MODE] : bool(maps.use & kMapDaOut), t_out = F ? kTOut[MODE] : bool(maps.use & kMapOut);
     const bool t_ha = !F && (maps.use & kMapHa);
     const bool ha_given = !F && p.ha_saved != nullptr;       // h_a comes from memory: no gather, no recompute
-    const bool f_gather = F ? kGather[MODE] : p.gy_gather != nullptr;     // receiver-indexed fp32 rows are added to gy
+    const bool f_gather = F ? kGather[MODE] : (p.gy_gather != nullptr || p.gy_gather_bf16 != nullptr);   // receiver-indexed rows are added to gy
+    const bool f_gbf = F ? kGather[MODE] : p.gy_gather_bf16 != nullptr;       // ... stored as bf16 (the specialised edge stage B: always)
     const bool f_seg = F ? kSeg[MODE] : p.seg_id != nullptr, f_da = F ? kTDa[MODE] : p.delta_a_out != nullptr;
     const bool f_din = F || p.need_din, f_mask = F ? kMask[MODE] : bool(p.mask_by_ain);
     const bool f_resid = F ? kTRes[MODE] : p.out_resid != nullptr;
@@ -269,7 +270,14 @@ __global__ void __launch_bounds__(BwdCfg<H>::NT, 1) mlp_bwd_kernel(const gp_mlp_
                 cp_async16(ha_s + sw128_off(128, r, ch * 8), p.init + (size_t)ridx[j] * p.ld_init + soff + ch * 8);
             }
         }
-        if (du_smem && f_gather) {   // receiver-indexed fp32 rows, rounded to bf16 into db; loads batched by 4 chunks
+        if (du_smem && f_gather && f_gbf) {   // receiver-indexed bf16 rows -> db
+#pragma unroll
+            for (int j = 0; j < CPT; ++j) {
+                const int i = tid + j * NT;
+                const int r = i / KC, ch = i % KC;
+                cp_async16(db_s + sw128_off(128, r, ch * 8), p.gy_gather_bf16 + (size_t)gidx[j] * H + ch * 8);
+            }
+        } else if (du_smem && f_gather) {   // receiver-indexed fp32 rows, rounded to bf16 into db; loads batched by 4 chunks
 #pragma unroll
             for (int j0 = 0; j0 < CPT; j0 += 4) {
                 float4 u[8];
@@ -372,7 +380,9 @@ __global__ void __launch_bounds__(BwdCfg<H>::NT, 1) mlp_bwd_kernel(const gp_mlp_
                 if ((i & 7) == 0) {         // chunk 0 of a 128-byte line
                     if (has_init)
                         asm volatile("prefetch.global.L2 [%0];" ::"l"(p.init + (size_t)ridx[j] * p.ld_init + soff + (i % KC) * 8));
-                    if (du_smem && f_gather) {       // fp32 rows: two lines per 8-chunk group
+                    if (du_smem && f_gather && f_gbf) {
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(p.gy_gather_bf16 + (size_t)gidx[j] * H + (i % KC) * 8));
+                    } else if (du_smem && f_gather) {       // fp32 rows: two lines per 8-chunk group
                         const float* gp_ = p.gy_gather + (size_t)gidx[j] * H + (i % KC) * 8;
                         asm volatile("prefetch.global.L2 [%0];" ::"l"(gp_));
                         asm volatile("prefetch.global.L2 [%0];" ::"l"(gp_ + 32));
@@ -789,14 +799,15 @@ int launch_bwd(const gp_mlp_bwd_args& a, int32_t* grid_out, cudaStream_t st) {
     if (H == 128 && a.ka == H && a.nb == H && !a.ha_saved && a.need_din) {
         const bool plain = !a.out_resid && !a.delta_a_out && !a.seg_id;
         if (a.mode == 1 && a.a_bf16 && a.out_bf16 && !a.init && a.mask_by_ain && plain) {
-            if (a.gy_bf16 && a.gy_gather && a.gy_idx && maps.use == (kMapAin | kMapGy | kMapOut)) fast = 1;          // edge B
-            if (a.gy_f32 && !a.gy_gather && maps.use == (kMapAin | kMapOut)) fast = 3;                                // node B
+            if (a.gy_bf16 && a.gy_gather_bf16 && a.gy_idx && maps.use == (kMapAin | kMapGy | kMapOut)) fast = 1;     // edge B
+            if (a.gy_f32 && !a.gy_gather && !a.gy_gather_bf16 && maps.use == (kMapAin | kMapOut)) fast = 3;          // node B
         }
         if (a.mode == 0 && a.init && !a.mask_by_ain && a.delta_a_out) {
             if (a.a_bf16 && a.out_bf16 && a.two_inits && a.idx0 && a.idx1 && a.out_resid && a.seg_id &&
                 maps.use == (kMapAin | kMapDb | kMapResid | kMapDaOut | kMapOut))
                 fast = 2;                                                                                             // edge A
-            if (a.a_f32 && a.out_f32 && !a.two_inits && !a.idx0 && !a.out_resid && !a.seg_id && maps.use == (kMapDb | kMapDaOut))
+            if (a.a_f32 && a.out_bf16 && !a.two_inits && !a.idx0 && !a.out_resid && !a.seg_id &&
+                maps.use == (kMapDb | kMapDaOut | kMapOut))
                 fast = 4;                                                                                             // node A
         }
     }
@@ -852,6 +863,8 @@ extern "C" int gp_mlp_bwd_stage(const gp_mlp_bwd_args* args, int hidden, int32_t
         GP_REQUIRE(a.nb == hidden, "gp_mlp_bwd_stage: NORM mode needs nb == hidden");
         GP_REQUIRE(!(a.gy_bf16 && a.gy_f32) && (a.gy_bf16 || a.gy_f32 || a.gy_gather),
                    "gp_mlp_bwd_stage: NORM mode needs gy_bf16 or gy_f32 (not both), or at least gy_gather");
+        GP_REQUIRE(!a.gy_gather_bf16 || (a.gy_bf16 && !a.gy_gather && a.gy_idx),
+                   "gp_mlp_bwd_stage: gy_gather_bf16 needs gy_bf16 and gy_idx, and excludes gy_gather");
     } else {
         GP_REQUIRE(a.mode == 0 && a.delta_b != nullptr && a.ld_db % 8 == 0, "gp_mlp_bwd_stage: GIVEN mode needs delta_b");
     }

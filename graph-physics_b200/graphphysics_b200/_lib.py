@@ -115,6 +115,7 @@ class MlpBwdArgs(C.Structure):
         ("gy_f32", C.c_void_p),
         ("ld_gy", C.c_int32),
         ("gy_gather", C.c_void_p),
+        ("gy_gather_bf16", C.c_void_p),
         ("gy_idx", C.c_void_p),
         ("need_din", C.c_int32),
         ("mask_by_ain", C.c_int32),

@@ -342,7 +342,7 @@ class EPDEngine:
             if before_block is not None:
                 before_block(dX)
             # node MLP:  x' = x + norm(MLP([x, agg]))
-            dagg = torch.empty((N, H), dtype=torch.float32, device=dev)
+            dagg = torch.empty((N, H), dtype=bf, device=dev)       # rounded where it is produced (its consumer stages it as bf16 anyway)
             dQ = torch.empty((N, H), dtype=bf, device=dev)
             self._mlp_backward(self.node[l], N, a_in=agg, ka=H, h2=h2n, top=dict(gy=dX), out=dagg, delta_a_out=dQ,
                                first=dict(init=P, init_off0=2 * H))

@@ -252,7 +252,12 @@ def mlp_bwd_stage(
                 assert gy.dtype == torch.float32
                 args.gy_f32 = ptr(gy)
             args.ld_gy = gy.stride(0)
-        args.gy_gather, args.gy_idx = ptr(gy_gather), ptr(gy_idx)
+        if gy_gather is not None and gy_gather.dtype == torch.bfloat16:
+            assert gy_gather.is_contiguous() and gy_gather.shape[1] == hidden
+            args.gy_gather_bf16 = ptr(gy_gather)
+        else:
+            args.gy_gather = ptr(gy_gather)
+        args.gy_idx = ptr(gy_idx)
     else:
         args.mode = 0
         assert delta_b is not None and delta_b.dtype == torch.bfloat16

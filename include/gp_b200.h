@@ -132,6 +132,7 @@ typedef struct gp_mlp_bwd_args {
     const float* gy_f32;
     int32_t ld_gy;
     const float* gy_gather; /* optional fp32 [.][hidden] rows added to gy */
+    const gp_bf16* gy_gather_bf16; /* the same rows stored as bf16 (needs gy_bf16; at most one of the two) */
     const int32_t* gy_idx;
     int32_t need_din;
     int32_t mask_by_ain;
