@@ -221,8 +221,8 @@ def main():
 
     # roofline of the dominant kernel (SURVEY §8d algorithmic bytes, bf16 storage)
     hbm_peak, tf_peak, peak_src = peaks()
-    alg_bytes = {"edge_fwd": E * (8 * H + 8) + 4 * N * H, "edge_bwd_B": E * (6 * H) + 2 * N * H,
-                 "edge_bwd_A": E * (10 * H + 8) + 4 * N * H}
+    alg_bytes = {"edge_fwd": E * (8 * H + 8) + 2 * N * H, "edge_bwd_B": E * (6 * H) + 2 * N * H,
+                 "edge_bwd_A": E * (10 * H + 8) + 2 * N * H}
     alg_flops = {"edge_fwd": E * 8 * H * H, "edge_bwd_B": E * 12 * H * H, "edge_bwd_A": E * 10 * H * H}
     # dram__bytes_read.sum + dram__bytes_write.sum per launch of the same kernels on this workload, from the
     # `ncu --set full` captures summarised in profiles/r01_final_summary.md (below the algorithmic bytes: the

@@ -214,9 +214,9 @@ int launch(const gp_linear_bwd_args& a, int32_t* grid_out, cudaStream_t st) {
 }
 
 // out[n][:] = sum over j in [rowptr[n], rowptr[n+1]) of src[perm[j]][:]   (bf16 rows, fp32 sum, fixed order)
-template <int VPT>
+template <int VPT, typename OutT>
 __global__ void segsum_gather_kernel(const gp_bf16* __restrict__ src, int ld, const int32_t* __restrict__ perm,
-                                     const int32_t* __restrict__ rowptr, int num_segments, float* __restrict__ out) {
+                                     const int32_t* __restrict__ rowptr, int num_segments, OutT* __restrict__ out) {
     const int seg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (seg >= num_segments) return;
@@ -264,9 +264,17 @@ __global__ void segsum_gather_kernel(const gp_bf16* __restrict__ src, int ld, co
         }
         for (; j < n; ++j) add_row(__shfl_sync(0xffffffffu, mine, j));
     }
-    float* o = out + (size_t)seg * (32 * VPT) + lane * VPT;
+    OutT* o = out + (size_t)seg * (32 * VPT) + lane * VPT;
+    if constexpr (sizeof(OutT) == 4) {
 #pragma unroll
-    for (int i = 0; i < VPT; ++i) o[i] = acc[i];
+        for (int i = 0; i < VPT; ++i) o[i] = acc[i];
+    } else if constexpr (VPT == 4) {
+        *reinterpret_cast<uint2*>(o) = make_uint2(pack_bf16(acc[0], acc[1]), pack_bf16(acc[2], acc[3]));
+    } else if constexpr (VPT == 2) {
+        *reinterpret_cast<uint32_t*>(o) = pack_bf16(acc[0], acc[1]);
+    } else {
+        *reinterpret_cast<__nv_bfloat16*>(o) = __float2bfloat16(acc[0]);
+    }
 }
 }  // namespace
 
@@ -287,18 +295,29 @@ extern "C" int gp_linear_bwd(const gp_linear_bwd_args* args, int hidden, int32_t
     }
 }
 
-extern "C" int gp_segsum_gather(const gp_bf16* src, int32_t ld, const int32_t* perm, const int32_t* rowptr,
-                                int32_t num_segments, int32_t hidden, float* out, void* stream) {
+template <typename OutT>
+static int segsum_gather_launch(const gp_bf16* src, int32_t ld, const int32_t* perm, const int32_t* rowptr, int32_t num_segments,
+                                int32_t hidden, OutT* out, void* stream) {
     if (num_segments <= 0) return 0;
     const int threads = 256;
     const int blocks = (int)(((size_t)num_segments * 32 + threads - 1) / threads);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     switch (hidden) {
-        case 128: segsum_gather_kernel<4><<<blocks, threads, 0, st>>>(src, ld, perm, rowptr, num_segments, out); break;
-        case 64: segsum_gather_kernel<2><<<blocks, threads, 0, st>>>(src, ld, perm, rowptr, num_segments, out); break;
-        case 32: segsum_gather_kernel<1><<<blocks, threads, 0, st>>>(src, ld, perm, rowptr, num_segments, out); break;
+        case 128: segsum_gather_kernel<4, OutT><<<blocks, threads, 0, st>>>(src, ld, perm, rowptr, num_segments, out); break;
+        case 64: segsum_gather_kernel<2, OutT><<<blocks, threads, 0, st>>>(src, ld, perm, rowptr, num_segments, out); break;
+        case 32: segsum_gather_kernel<1, OutT><<<blocks, threads, 0, st>>>(src, ld, perm, rowptr, num_segments, out); break;
         default: gp::set_error("gp_segsum_gather: unsupported hidden size %d", hidden); return -1;
     }
     GP_CHECK_CUDA(cudaGetLastError());
     return 0;
+}
+
+extern "C" int gp_segsum_gather(const gp_bf16* src, int32_t ld, const int32_t* perm, const int32_t* rowptr,
+                                int32_t num_segments, int32_t hidden, float* out, void* stream) {
+    return segsum_gather_launch<float>(src, ld, perm, rowptr, num_segments, hidden, out, stream);
+}
+
+extern "C" int gp_segsum_gather_bf16(const gp_bf16* src, int32_t ld, const int32_t* perm, const int32_t* rowptr,
+                                     int32_t num_segments, int32_t hidden, gp_bf16* out, void* stream) {
+    return segsum_gather_launch<gp_bf16>(src, ld, perm, rowptr, num_segments, hidden, out, stream);
 }

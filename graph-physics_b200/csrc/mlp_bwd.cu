@@ -59,8 +59,8 @@ struct BwdCfg {
 // MODE 0 is the general kernel.  MODE 1 / 2 are the instantiations for the two stages of the processor's
 // edge MLP at H = 128 (1: layers 3-4 with the RMSNorm backward and the gathered receiver gradient;
 // 2: layers 1-2 with the two gathered pre-activation sources, the stored delta_1 and its segment
-// sum), MODE 3 / 4 those of the node MLP (3: fp32 upstream gradient read per row; 4: fp32 aggregate
-// as operand, fp32 d_agg output), with every option -- including which tensors move by TMA -- fixed
+// sum), MODE 3 / 4 those of the node MLP (3: fp32 upstream gradient read per row; 4: bf16 aggregate as
+// operand, bf16 d_agg output), with every option -- including which tensors move by TMA -- fixed
 // at compile time.  The
 // general kernel is 100 KB of code that each tile streams through the instruction cache; the
 // specialised ones keep only their own path.
@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(BwdCfg<H>::NT, 1) mlp_bwd_kernel(const gp_mlp_
     // option tables of the specialised instantiations:    general, edge B, edge A, node B, node A
     constexpr bool F = MODE != 0, F1 = MODE == 1;
     constexpr bool kNorm[5]   = {false, true,  false, true,  false};
-    constexpr bool kTAin[5]   = {false, true,  true,  true,  false};   // a_in tile by TMA (else: fp32 rows, converted)
+    constexpr bool kTAin[5]   = {false, true,  true,  true,  true};    // a_in tile by TMA
     constexpr bool kTDb[5]    = {false, false, true,  false, true};
     constexpr bool kTGy[5]    = {false, true,  false, false, false};
     constexpr bool kTRes[5]   = {false, false, true,  false, false};
@@ -243,7 +243,7 @@ __global__ void __launch_bounds__(BwdCfg<H>::NT, 1) mlp_bwd_kernel(const gp_mlp_
                     *reinterpret_cast<uint4*>(ha + sw128_off(128, r, ch * 8)) = make_uint4(0, 0, 0, 0);
             }
         }
-        if (!t_ain) stage_rows(ain, MODE == 4 ? nullptr : p.a_bf16, (F && MODE != 4) ? nullptr : p.a_f32, ka, p.lda, R0, p.rows, tid, NT);
+        if (!t_ain) stage_rows(ain, p.a_bf16, F ? nullptr : p.a_f32, ka, p.lda, R0, p.rows, tid, NT);
         if (!norm && !t_db) {   // delta_b given: zero rows past the end so they add nothing to the weight gradients
             const int kc = nb >> 3;
             for (int i = tid; i < 128 * kc; i += NT) {
@@ -571,7 +571,7 @@ __global__ void __launch_bounds__(BwdCfg<H>::NT, 1) mlp_bwd_kernel(const gp_mlp_
                         *reinterpret_cast<const uint4*>(ha + sw128_off(128, r, ch * 8));
             }
         }
-        if (f_seg) tile_segment_sum<H, NT>(ha, sseg, R0, tid, p.seg_out, p.seg_bnd);
+        if (f_seg) tile_segment_sum<H, NT>(ha, sseg, R0, tid, MODE == 2 ? nullptr : p.seg_out, p.seg_bnd, p.seg_out_bf16);
         tick(9);      // P4 issue + copy-out + segment walk
         wait_mma();
         tick(10);     // P4 MMA wait
@@ -803,11 +803,11 @@ int launch_bwd(const gp_mlp_bwd_args& a, int32_t* grid_out, cudaStream_t st) {
             if (a.gy_f32 && !a.gy_gather && !a.gy_gather_bf16 && maps.use == (kMapAin | kMapOut)) fast = 3;          // node B
         }
         if (a.mode == 0 && a.init && !a.mask_by_ain && a.delta_a_out) {
-            if (a.a_bf16 && a.out_bf16 && a.two_inits && a.idx0 && a.idx1 && a.out_resid && a.seg_id &&
+            if (a.a_bf16 && a.out_bf16 && a.two_inits && a.idx0 && a.idx1 && a.out_resid && a.seg_id && a.seg_out_bf16 &&
                 maps.use == (kMapAin | kMapDb | kMapResid | kMapDaOut | kMapOut))
                 fast = 2;                                                                                             // edge A
-            if (a.a_f32 && a.out_bf16 && !a.two_inits && !a.idx0 && !a.out_resid && !a.seg_id &&
-                maps.use == (kMapDb | kMapDaOut | kMapOut))
+            if (a.a_bf16 && a.out_bf16 && !a.two_inits && !a.idx0 && !a.out_resid && !a.seg_id &&
+                maps.use == (kMapAin | kMapDb | kMapDaOut | kMapOut))
                 fast = 4;                                                                                             // node A
         }
     }
@@ -869,7 +869,8 @@ extern "C" int gp_mlp_bwd_stage(const gp_mlp_bwd_args* args, int hidden, int32_t
         GP_REQUIRE(a.mode == 0 && a.delta_b != nullptr && a.ld_db % 8 == 0, "gp_mlp_bwd_stage: GIVEN mode needs delta_b");
     }
     if (a.need_din) GP_REQUIRE((a.out_bf16 != nullptr) != (a.out_f32 != nullptr), "gp_mlp_bwd_stage: need one output");
-    if (a.seg_id) GP_REQUIRE(a.seg_out && a.seg_bnd, "gp_mlp_bwd_stage: segment sum needs outputs");
+    if (a.seg_id) GP_REQUIRE(((a.seg_out != nullptr) != (a.seg_out_bf16 != nullptr)) && a.seg_bnd,
+                             "gp_mlp_bwd_stage: segment sum needs seg_bnd and exactly one of seg_out / seg_out_bf16");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     switch (hidden) {
         case 128: return launch_bwd<128>(a, grid_out, st);

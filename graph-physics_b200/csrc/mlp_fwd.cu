@@ -44,7 +44,7 @@ enum : uint32_t { kMapA = 1, kMapH = 2 /* << layer */ };
 __device__ __forceinline__ void slot_sync(int g) { asm volatile("bar.sync %0, 256;" ::"r"(g + 1) : "memory"); }
 
 // kMode 1 / 2 are the instantiations for the processor's edge MLP (4 H-wide layers, two gathered
-// pre-activation sources, RMSNorm, bf16 residual output, segment sum) and node MLP (fp32 aggregate
+// pre-activation sources, RMSNorm, bf16 residual output, segment sum) and node MLP (bf16 aggregate
 // as layer-0 operand, the node's own pre-activation row, RMSNorm, bf16 residual output): every
 // optional path is resolved at compile time, which cuts the code the two out-of-phase slots stream
 // through the instruction cache (a 10% larger kernel measured 13% slower).  kMode 0 is general.
@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(kSlotThreads * NG, 1) mlp_fwd_kernel(const gp_
     constexpr bool kEdge = kMode == 1, kNode = kMode == 2, E = kEdge || kNode;     // E: a 4-layer H-wide processor MLP
     const int L = E ? 4 : p.n_layers;
     const bool f_norm = E || p.norm_scale != nullptr, f_resid = E || p.resid != nullptr, f_ybf = E || p.y_bf16 != nullptr;
-    const bool f_seg = kEdge || (!E && p.seg_id != nullptr), f_abf = kEdge || (!E && p.a_bf16 != nullptr);
+    const bool f_seg = kEdge || (!E && p.seg_id != nullptr), f_abf = E || p.a_bf16 != nullptr;
     const bool f_idx0 = kEdge || (!E && p.idx0 != nullptr);
     const int ka = E ? H : p.ka;
     constexpr int CH = H / 2;                // columns per thread in H-wide layers
@@ -264,7 +264,7 @@ __global__ void __launch_bounds__(kSlotThreads * NG, 1) mlp_fwd_kernel(const gp_
                 for (int b = 0; b < nblk; ++b) tma_load_2d(buf_u + b * 16384, &maps.a, b * 64, R0, &tma_bar[g_u]);
             }
         } else {
-            stage_rows(buf, kNode ? nullptr : p.a_bf16, kEdge ? nullptr : p.a_f32, ka, p.lda, R0, p.rows, t, kSlotThreads);
+            stage_rows(buf, p.a_bf16, E ? nullptr : p.a_f32, ka, p.lda, R0, p.rows, t, kSlotThreads);
             cp_async_commit();
         }
         tick(0);                 // issue of loads + gathers + TMEM pre-load (this thread)
@@ -424,7 +424,7 @@ __global__ void __launch_bounds__(kSlotThreads * NG, 1) mlp_fwd_kernel(const gp_
 
         if (f_norm) {
             // (e) receiver-sorted segment sum of bf16(u) (fp32 accumulate, fixed order, no atomics)
-            if (f_seg) tile_segment_sum<H, kSlotThreads>(buf, sseg, R0, t, p.seg_out, p.seg_bnd);
+            if (f_seg) tile_segment_sum<H, kSlotThreads>(buf, sseg, R0, t, kEdge ? nullptr : p.seg_out, p.seg_bnd, p.seg_out_bf16);
             tick(6);
             // (f) output: y = resid + bf16(u), row-major chunks; the residual chunks (L2 hits: the tile
             //     was this kernel's layer-0 operand) are requested together
@@ -472,8 +472,9 @@ __global__ void __launch_bounds__(kSlotThreads * NG, 1) mlp_fwd_kernel(const gp_
 // One thread per segment classifies it (complete inside one sub-tile: nothing to do; empty: zero row;
 // spanning sub-tiles: sum of its boundary partials) from two coalesced rowptr reads; the warp then
 // walks its flagged segments together, 16 bytes of the row per lane.
+template <typename OutT>
 __global__ void __launch_bounds__(256) seg_fixup_kernel(const int32_t* __restrict__ rowptr, int num_segments, int H, int sub_shift,
-                                                        const float* __restrict__ bnd, float* __restrict__ out) {
+                                                        const float* __restrict__ bnd, OutT* __restrict__ out) {
     const int seg = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
     int s = 0, e = 0;
@@ -500,7 +501,10 @@ __global__ void __launch_bounds__(256) seg_fixup_kernel(const int32_t* __restric
                     acc.x += b.x; acc.y += b.y; acc.z += b.z; acc.w += b.w;
                 }
             }
-            *reinterpret_cast<float4*>(out + (size_t)sg * H + c4) = acc;
+            if constexpr (sizeof(OutT) == 4)
+                *reinterpret_cast<float4*>(out + (size_t)sg * H + c4) = acc;
+            else
+                *reinterpret_cast<uint2*>(out + (size_t)sg * H + c4) = make_uint2(pack_bf16(acc.x, acc.y), pack_bf16(acc.z, acc.w));
         }
     }
 }
@@ -556,7 +560,8 @@ extern "C" int gp_mlp_fwd(const gp_mlp_fwd_args* args, int hidden, void* stream)
     if (a.init) GP_REQUIRE(a.n[0] == hidden && a.ld_init % 8 == 0 && a.init_off0 % 8 == 0 && a.init_off1 % 8 == 0,
                            "gp_mlp_fwd: init rows need n[0]==hidden and 16-byte aligned offsets");
     if (a.norm_scale) GP_REQUIRE(a.n[a.n_layers - 1] == hidden, "gp_mlp_fwd: RMSNorm needs n_last == hidden");
-    if (a.seg_id) GP_REQUIRE(a.norm_scale && a.seg_out && a.seg_bnd, "gp_mlp_fwd: segment sum needs norm + outputs");
+    if (a.seg_id) GP_REQUIRE(a.norm_scale && ((a.seg_out != nullptr) != (a.seg_out_bf16 != nullptr)) && a.seg_bnd,
+                             "gp_mlp_fwd: segment sum needs norm, seg_bnd and exactly one of seg_out / seg_out_bf16");
     if (a.save_h1) GP_REQUIRE(a.n_layers >= 2, "gp_mlp_fwd: save_h1 needs at least 2 layers");
     if (a.save_h2) GP_REQUIRE(a.n_layers >= 3, "gp_mlp_fwd: save_h2 needs at least 3 layers");
     if (a.save_h3) GP_REQUIRE(a.n_layers >= 4, "gp_mlp_fwd: save_h3 needs 4 layers");
@@ -571,8 +576,8 @@ extern "C" int gp_mlp_fwd(const gp_mlp_fwd_args* args, int hidden, void* stream)
     // the processor's edge and node MLPs get instantiations with every option fixed at compile time
     bool proc = a.init && a.n_layers == 4 && a.ka == hidden && a.norm_scale && a.resid && a.y_bf16;
     for (int l = 0; l < a.n_layers && proc; ++l) proc = a.k[l] == hidden && a.n[l] == hidden;
-    const bool edge = proc && a.two_inits && a.idx0 && a.idx1 && a.a_bf16 && a.seg_id;
-    const bool node = proc && !a.two_inits && !a.idx0 && a.a_f32 && !a.seg_id;
+    const bool edge = proc && a.two_inits && a.idx0 && a.idx1 && a.a_bf16 && a.seg_id && a.seg_out_bf16;
+    const bool node = proc && !a.two_inits && !a.idx0 && a.a_bf16 && !a.seg_id;
     switch (hidden) {
         case 128:
             return edge ? launch_fwd<128, 2, 1>(a, st) : node ? launch_fwd<128, 2, 2>(a, st) : launch_fwd<128, 2, 0>(a, st);
@@ -587,8 +592,9 @@ extern "C" int gp_seg_sub_rows(int32_t hidden, int32_t backward) {
     return (backward && hidden >= 128) ? hidden / 8 : hidden / 4;
 }
 
-extern "C" int gp_seg_fixup(const int32_t* rowptr, int32_t num_segments, int32_t hidden, int32_t sub_rows,
-                            const float* seg_bnd, float* seg_out, void* stream) {
+template <typename OutT>
+static int seg_fixup_launch(const int32_t* rowptr, int32_t num_segments, int32_t hidden, int32_t sub_rows, const float* seg_bnd,
+                            OutT* seg_out, void* stream) {
     if (num_segments <= 0) return 0;
     GP_REQUIRE(sub_rows > 0 && (sub_rows & (sub_rows - 1)) == 0, "gp_seg_fixup: sub_rows must be a power of two");
     GP_REQUIRE(hidden % 4 == 0 && hidden <= 128, "gp_seg_fixup: hidden must be a multiple of 4, at most 128");
@@ -596,8 +602,18 @@ extern "C" int gp_seg_fixup(const int32_t* rowptr, int32_t num_segments, int32_t
     while ((1 << shift) < sub_rows) ++shift;
     const int threads = 256;
     const int blocks = (num_segments + threads - 1) / threads;
-    seg_fixup_kernel<<<blocks, threads, 0, static_cast<cudaStream_t>(stream)>>>(rowptr, num_segments, hidden, shift,
-                                                                                 seg_bnd, seg_out);
+    seg_fixup_kernel<OutT><<<blocks, threads, 0, static_cast<cudaStream_t>(stream)>>>(rowptr, num_segments, hidden, shift,
+                                                                                       seg_bnd, seg_out);
     GP_CHECK_CUDA(cudaGetLastError());
     return 0;
+}
+
+extern "C" int gp_seg_fixup(const int32_t* rowptr, int32_t num_segments, int32_t hidden, int32_t sub_rows,
+                            const float* seg_bnd, float* seg_out, void* stream) {
+    return seg_fixup_launch<float>(rowptr, num_segments, hidden, sub_rows, seg_bnd, seg_out, stream);
+}
+
+extern "C" int gp_seg_fixup_bf16(const int32_t* rowptr, int32_t num_segments, int32_t hidden, int32_t sub_rows,
+                                 const float* seg_bnd, gp_bf16* seg_out_bf16, void* stream) {
+    return seg_fixup_launch<gp_bf16>(rowptr, num_segments, hidden, sub_rows, seg_bnd, seg_out_bf16, stream);
 }

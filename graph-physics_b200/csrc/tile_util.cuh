@@ -185,11 +185,11 @@ __device__ __forceinline__ void tmem_rows_to_global(uint32_t tlane, uint32_t col
 // by NT threads: thread t owns column pair (t % (H/2)) of the sub-tile of SUB = 64*H/NT rows
 // number t / (H/2).  sseg[3] = segment id of the row before the tile, sseg[4..131] = rows,
 // sseg[132] = row after; -1 marks "no row".  A piece that neither continues from the previous
-// sub-tile nor into the next one is a complete segment and goes to seg_out; other pieces go to
+// sub-tile nor into the next one is a complete segment and goes to seg_out (fp32) or seg_out_bf16; other pieces go to
 // seg_bnd[sub-tile][0 = continues from before | 1 = continues after] for gp_seg_fixup.
 template <int H, int NT>
 __device__ __forceinline__ void tile_segment_sum(const uint8_t* buf, const int* sseg, int R0, int t, float* seg_out,
-                                                 float* seg_bnd) {
+                                                 float* seg_bnd, gp_bf16* seg_out_bf16 = nullptr) {
     constexpr int NP = H / 2;            // column pairs
     constexpr int SUB = 128 * NP / NT;   // rows per sub-tile
     static_assert(SUB % 8 == 0, "sub-tile must be a multiple of 8 rows");
@@ -207,9 +207,13 @@ __device__ __forceinline__ void tile_segment_sum(const uint8_t* buf, const int* 
         if (seg >= 0) {
             const bool before = first_piece && (seg_prev == seg);
             const bool after = last_piece && (seg_next == seg);
-            float* d = (!before && !after) ? seg_out + (size_t)seg * H + c
-                                           : seg_bnd + (sub_index * 2 + (before ? 0 : 1)) * H + c;
-            *reinterpret_cast<float2*>(d) = make_float2(s0, s1);
+            if (!before && !after && seg_out_bf16) {       // complete segment, bf16 output: rounded once, here
+                *reinterpret_cast<uint32_t*>(seg_out_bf16 + (size_t)seg * H + c) = pack_bf16(s0, s1);
+            } else {
+                float* d = (!before && !after) ? seg_out + (size_t)seg * H + c
+                                               : seg_bnd + (sub_index * 2 + (before ? 0 : 1)) * H + c;
+                *reinterpret_cast<float2*>(d) = make_float2(s0, s1);
+            }
         }
         first_piece = false;
     };

@@ -82,6 +82,7 @@ class MlpFwdArgs(C.Structure):
         ("save_h3", C.c_void_p),
         ("seg_id", C.c_void_p),
         ("seg_out", C.c_void_p),
+        ("seg_out_bf16", C.c_void_p),
         ("seg_bnd", C.c_void_p),
         ("prof", C.c_void_p),
     ]
@@ -126,6 +127,7 @@ class MlpBwdArgs(C.Structure):
         ("delta_a_out", C.c_void_p),
         ("seg_id", C.c_void_p),
         ("seg_out", C.c_void_p),
+        ("seg_out_bf16", C.c_void_p),
         ("seg_bnd", C.c_void_p),
         ("partials", C.c_void_p),
         ("prof", C.c_void_p),

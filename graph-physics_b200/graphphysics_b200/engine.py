@@ -206,7 +206,7 @@ class EPDEngine:
         P = torch.empty((N, 3 * H), dtype=bf, device=dev)
         ops.mlp_fwd(N, H, [self.proj[l]], [None], a=x, ka=H, out=P, n_valid=3 * H)
         e2 = torch.empty((E, H), dtype=bf, device=dev)
-        agg = torch.empty((N, H), dtype=torch.float32, device=dev)
+        agg = torch.empty((N, H), dtype=bf, device=dev)        # segment sums, rounded once where they are produced
         h2e = self._saved(E, save)
         self._mlp(self.edge[l], E, e, H, e2, H, **self._save_kw(h2e), resid=e, init=P, init_off0=0, init_off1=H,
                   idx0=g.dst, idx1=g.src, two_inits=True, seg_id=g.dst, seg_out=agg, seg_bnd=bnd, tag="edge_fwd")
@@ -349,13 +349,13 @@ class EPDEngine:
             # edge MLP:  e' = e + u,  agg = segment-sum(u)   =>   du = dE' + dagg[dst]
             dE_new = torch.empty((E, H), dtype=bf, device=dev)
             d1 = torch.empty((E, H), dtype=bf, device=dev)
-            dPd = torch.empty((N, H), dtype=torch.float32, device=dev)
+            dPd = torch.empty((N, H), dtype=bf, device=dev)
             self._mlp_backward(self.edge[l], E, a_in=e, ka=H, h2=h2e, top=dict(gy=dE, gy_gather=dagg, gy_idx=g.dst),
                                out=dE_new, out_resid=dE, delta_a_out=d1, seg=(g.dst, dPd, bnd),
                                first=dict(init=P, init_off0=0, init_off1=H, idx0=g.dst, idx1=g.src, two_inits=True),
                                tag="edge_bwd")
             ops.seg_fixup(g.rowptr_dst, H, bnd, dPd, backward=True)
-            dPs = torch.empty((N, H), dtype=torch.float32, device=dev)
+            dPs = torch.empty((N, H), dtype=bf, device=dev)
             ops.segsum_gather(d1, g.perm_src, g.rowptr_src, H, dPs)
             # projection P = x . Wp^T, plus the residual path of x
             dX_new = torch.empty((N, H), dtype=torch.float32, device=dev)

@@ -146,7 +146,11 @@ def mlp_fwd(
     args.save_h2, args.save_h1, args.save_h3 = ptr(save_h2), ptr(save_h1), ptr(save_h3)
     for sv in (save_h1, save_h2, save_h3):
         assert sv is None or (sv.dtype == torch.bfloat16 and sv.is_contiguous() and sv.shape == (rows, hidden))
-    args.seg_id, args.seg_out, args.seg_bnd = ptr(seg_id), ptr(seg_out), ptr(seg_bnd)
+    args.seg_id, args.seg_bnd = ptr(seg_id), ptr(seg_bnd)
+    if seg_out is not None and seg_out.dtype == torch.bfloat16:
+        args.seg_out_bf16 = ptr(seg_out)
+    else:
+        args.seg_out = ptr(seg_out)
     args.prof = ptr(prof)
     ev = PROFILE.begin(tag)
     check(lib().gp_mlp_fwd(C.byref(args), C.c_int(hidden), C.c_void_p(stream_ptr())), "gp_mlp_fwd")
@@ -158,8 +162,9 @@ def mlp_fwd(
 def seg_fixup(rowptr: torch.Tensor, hidden: int, seg_bnd: torch.Tensor, seg_out: torch.Tensor,
               backward: bool = False) -> None:
     assert rowptr.dtype == torch.int32
+    fn = lib().gp_seg_fixup_bf16 if seg_out.dtype == torch.bfloat16 else lib().gp_seg_fixup
     check(
-        lib().gp_seg_fixup(C.c_void_p(ptr(rowptr)), C.c_int32(rowptr.numel() - 1), C.c_int32(hidden),
+        fn(C.c_void_p(ptr(rowptr)), C.c_int32(rowptr.numel() - 1), C.c_int32(hidden),
                            C.c_int32(seg_sub_rows(hidden, backward)), C.c_void_p(ptr(seg_bnd)), C.c_void_p(ptr(seg_out)),
                            C.c_void_p(stream_ptr())),
         "gp_seg_fixup",
@@ -273,7 +278,11 @@ def mlp_bwd_stage(
         args.mask_by_ain = 1 if mask_by_ain else 0
         args.out_resid = ptr(out_resid)
     args.delta_a_out = ptr(delta_a_out)
-    args.seg_id, args.seg_out, args.seg_bnd = ptr(seg_id), ptr(seg_out), ptr(seg_bnd)
+    args.seg_id, args.seg_bnd = ptr(seg_id), ptr(seg_bnd)
+    if seg_out is not None and seg_out.dtype == torch.bfloat16:
+        args.seg_out_bf16 = ptr(seg_out)
+    else:
+        args.seg_out = ptr(seg_out)
     stride = bwd_layout(hidden, ka, args.nb)[5]
     assert partials.dtype == torch.float32 and partials.numel() >= stride * min(sm_count(), (rows + 127) // 128)
     args.partials = ptr(partials)
@@ -322,8 +331,9 @@ def linear_bwd(rows: int, hidden: int, srcs: Sequence[torch.Tensor], w: torch.Te
 
 def segsum_gather(src: torch.Tensor, perm: Optional[torch.Tensor], rowptr: torch.Tensor, hidden: int,
                   out: torch.Tensor) -> None:
+    fn = lib().gp_segsum_gather_bf16 if out.dtype == torch.bfloat16 else lib().gp_segsum_gather
     check(
-        lib().gp_segsum_gather(C.c_void_p(ptr(src)), C.c_int32(src.stride(0)), C.c_void_p(ptr(perm)),
+        fn(C.c_void_p(ptr(src)), C.c_int32(src.stride(0)), C.c_void_p(ptr(perm)),
                                C.c_void_p(ptr(rowptr)), C.c_int32(rowptr.numel() - 1), C.c_int32(hidden),
                                C.c_void_p(ptr(out)), C.c_void_p(stream_ptr())),
         "gp_segsum_gather",

@@ -74,6 +74,7 @@ typedef struct gp_mlp_fwd_args {
     gp_bf16* save_h3;      /* optional [rows][hidden]: output of layer index 2 (4-layer MLPs) */
     const int32_t* seg_id; /* optional [rows], non-decreasing */
     float* seg_out;        /* [num_segments][hidden] */
+    gp_bf16* seg_out_bf16; /* ... or the same sums rounded once to bf16 (exactly one of the two with seg_id) */
     float* seg_bnd;        /* [ceil(rows/sub)][2][hidden], sub = gp_seg_sub_rows(hidden, 0) */
     unsigned long long* prof; /* optional [16] device counters: SM cycles per phase, summed over tiles (tuning aid) */
 } gp_mlp_fwd_args;
@@ -87,6 +88,9 @@ int gp_mlp_fwd(const gp_mlp_fwd_args* args, int hidden, void* stream);
 int gp_seg_sub_rows(int32_t hidden, int32_t backward);
 int gp_seg_fixup(const int32_t* rowptr, int32_t num_segments, int32_t hidden, int32_t sub_rows, const float* seg_bnd,
                  float* seg_out, void* stream);
+/* Same for a kernel that wrote seg_out_bf16 (the pieces are combined in fp32 and rounded once). */
+int gp_seg_fixup_bf16(const int32_t* rowptr, int32_t num_segments, int32_t hidden, int32_t sub_rows, const float* seg_bnd,
+                      gp_bf16* seg_out_bf16, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Two-layer backward stage of the same MLP (tcgen05): recomputes layer `a` from its streamed
@@ -143,6 +147,7 @@ typedef struct gp_mlp_bwd_args {
     gp_bf16* delta_a_out; /* optional [rows][hidden] */
     const int32_t* seg_id;
     float* seg_out;
+    gp_bf16* seg_out_bf16; /* alternative to seg_out: sums rounded once to bf16 */
     float* seg_bnd;
     float* partials; /* [grid][stride] floats, grid <= SM count */
     unsigned long long* prof; /* optional [16] device counters: SM cycles per phase (tuning aid) */
@@ -186,6 +191,9 @@ int gp_linear_bwd(const gp_linear_bwd_args* args, int hidden, int32_t* grid_out,
  * perm may be NULL (identity). */
 int gp_segsum_gather(const gp_bf16* src, int32_t ld, const int32_t* perm, const int32_t* rowptr, int32_t num_segments,
                      int32_t hidden, float* out, void* stream);
+/* Same sums (fp32 accumulate), rounded once to bf16. */
+int gp_segsum_gather_bf16(const gp_bf16* src, int32_t ld, const int32_t* perm, const int32_t* rowptr, int32_t num_segments,
+                          int32_t hidden, gp_bf16* out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Training-step glue (graphphysics/training/lightning_module.py:270-342, 494-511;

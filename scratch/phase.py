@@ -11,7 +11,7 @@ m = EncodeProcessDecode(1, 11, 3, 2, hidden_size=H).to(dev); eng = m.engine
 g = get_csr(b.edge_index, N)
 x = torch.randn(N, H, device=dev).to(torch.bfloat16); e = torch.randn(E, H, device=dev).to(torch.bfloat16)
 P = torch.randn(N, 3*H, device=dev).to(torch.bfloat16)
-bnd = torch.empty(ops.seg_bnd_size(E, H), device=dev); agg = torch.empty((N, H), device=dev); e2 = torch.empty_like(e)
+bnd = torch.empty(ops.seg_bnd_size(E, H), device=dev); agg = torch.empty((N, H), device=dev, dtype=torch.bfloat16); e2 = torch.empty_like(e)
 names = ["issue loads+gather+tmem_st", "wait loads/sync", "mma wait (x4)", "hidden epilogue (x3)", "norm epilogue", "slot sync after epi", "resid ld + segment walk", "output pass + sync", "mma issue (x4)"]
 for it in range(3):
     prof = torch.zeros(16, dtype=torch.int64, device=dev)

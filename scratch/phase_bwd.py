@@ -13,7 +13,7 @@ bf = torch.bfloat16
 e = torch.randn(E, H, device=dev).to(bf); h2 = torch.randn(E, H, device=dev).abs().to(bf); P = torch.randn(N, 3*H, device=dev).to(bf)
 dE = torch.randn(E, H, device=dev).to(bf); dagg = torch.randn(N, H, device=dev).to(bf)
 delta2 = torch.empty((E, H), dtype=bf, device=dev); dEn = torch.empty_like(delta2); d1 = torch.empty_like(delta2)
-dPd = torch.empty((N, H), device=dev); bnd = torch.empty(ops.seg_bnd_size(E, H, backward=True), device=dev)
+dPd = torch.empty((N, H), device=dev, dtype=bf); bnd = torch.empty(ops.seg_bnd_size(E, H, backward=True), device=dev)
 names = ["P0 issue", "P0 wait+sync", "gather combine+publish", "P1 MMA", "E1", "P2 MMA", "E2 norm bwd", "P3 MMAs", "E3", "P4 issue+copyout+walk", "P4 MMA wait", "E4+output"]
 for it in range(2):
   for stage in ("B", "A"):

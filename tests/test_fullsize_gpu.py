@@ -58,6 +58,17 @@ def test_segment_sum_exact_at_full_size():
     y_res, agg_res = outs[True]
     assert torch.equal(y_res, (e.float() + u.float()).to(bf))
     assert torch.equal(agg_res, agg)
+    # bf16 segment sums (what the engine uses; this call runs the compile-time specialised edge kernel, the
+    # fp32 calls above the general one): the same fp32 sums rounded once, and the same outputs, bit for bit
+    y16 = torch.empty((E, H), dtype=bf, device=dev)
+    agg16 = torch.full((N, H), float("nan"), dtype=bf, device=dev)
+    bnd = torch.full((ops.seg_bnd_size(E, H),), float("nan"), device=dev)
+    eng._mlp(eng.edge[0], E, e, H, y16, H, resid=e, init=P, init_off0=0, init_off1=H, idx0=g.dst, idx1=g.src,
+             two_inits=True, seg_id=g.dst, seg_out=agg16, seg_bnd=bnd)
+    ops.seg_fixup(g.rowptr_dst, H, bnd, agg16)
+    torch.cuda.synchronize()
+    assert torch.equal(y16, y_res)
+    assert torch.equal(agg16, agg.to(bf))
 
 
 def test_forward_backward_is_deterministic_at_full_size():
