@@ -95,8 +95,10 @@ __global__ void __launch_bounds__(BwdCfg<H>::NT, 1) mlp_bwd_kernel(const gp_mlp_
     const bool t_da = F ? kTDa[MODE] : bool(maps.use & kMapDaOut), t_out = F ? kTOut[MODE] : bool(maps.use & kMapOut);
     const bool t_ha = !F && (maps.use & kMapHa);
     const bool ha_given = !F && p.ha_saved != nullptr;       // h_a comes from memory: no gather, no recompute
-    const bool f_gather = F ? kGather[MODE] : (p.gy_gather != nullptr || p.gy_gather_bf16 != nullptr);   // receiver-indexed rows are added to gy
-    const bool f_gbf = F ? kGather[MODE] : p.gy_gather_bf16 != nullptr;       // ... stored as bf16 (the specialised edge stage B: always)
+    // receiver-indexed rows are added to gy: bf16 rows or none in the specialised stage B (the edge encoder's
+    // stage B is the same kernel without them), any form in the general kernel
+    const bool f_gather = F ? (kGather[MODE] && p.gy_gather_bf16 != nullptr) : (p.gy_gather != nullptr || p.gy_gather_bf16 != nullptr);
+    const bool f_gbf = F ? kGather[MODE] : p.gy_gather_bf16 != nullptr;
     const bool f_seg = F ? kSeg[MODE] : p.seg_id != nullptr, f_da = F ? kTDa[MODE] : p.delta_a_out != nullptr;
     const bool f_din = F || p.need_din, f_mask = F ? kMask[MODE] : bool(p.mask_by_ain);
     const bool f_resid = F ? kTRes[MODE] : p.out_resid != nullptr;
@@ -799,7 +801,8 @@ int launch_bwd(const gp_mlp_bwd_args& a, int32_t* grid_out, cudaStream_t st) {
     if (H == 128 && a.ka == H && a.nb == H && !a.ha_saved && a.need_din) {
         const bool plain = !a.out_resid && !a.delta_a_out && !a.seg_id;
         if (a.mode == 1 && a.a_bf16 && a.out_bf16 && !a.init && a.mask_by_ain && plain) {
-            if (a.gy_bf16 && a.gy_gather_bf16 && a.gy_idx && maps.use == (kMapAin | kMapGy | kMapOut)) fast = 1;     // edge B
+            if (a.gy_bf16 && !a.gy_gather && (!a.gy_gather_bf16 || a.gy_idx) && maps.use == (kMapAin | kMapGy | kMapOut))
+                fast = 1;                                                                                             // edge B (+ edge encoder B)
             if (a.gy_f32 && !a.gy_gather && !a.gy_gather_bf16 && maps.use == (kMapAin | kMapOut)) fast = 3;          // node B
         }
         if (a.mode == 0 && a.init && !a.mask_by_ain && a.delta_a_out) {
