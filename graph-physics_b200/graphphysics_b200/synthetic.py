@@ -112,3 +112,22 @@ def cylinder_flow_batch(batch_size: int = 32, nx: int = 64, ny: int = 32, seed: 
     if pin and torch.cuda.is_available():
         t = {k: v.pin_memory() for k, v in t.items()}
     return Data(**t)
+
+
+def kuhn_box_graph(nx: int, ny: int, nz: int):
+    """pos (N,3) float32 and the directed edge list (2,E) int64 of the 6-tetrahedra-per-cell (Kuhn)
+    triangulation of a structured box, built from its 7 edge directions instead of from the
+    tetrahedra (same graph as mesh_edges(faces_of_cells(box_tet_mesh(...))), without the 100M-key
+    sort): 14 neighbours per interior node.  Sorted by (row, col) like PyG's coalesce."""
+    xs, ys, zs = np.meshgrid(np.linspace(0, 1, nx), np.linspace(0, 1, ny), np.linspace(0, 1, nz), indexing="ij")
+    pos = np.stack([xs.ravel(), ys.ravel(), zs.ravel()], -1).astype(np.float32)
+    idx = np.arange(nx * ny * nz, dtype=np.int64).reshape(nx, ny, nz)
+    rows, cols = [], []
+    for dx, dy, dz in ((1, 0, 0), (0, 1, 0), (0, 0, 1), (1, 1, 0), (0, 1, 1), (1, 0, 1), (1, 1, 1)):
+        a = idx[: nx - dx, : ny - dy, : nz - dz].ravel()
+        b = idx[dx:, dy:, dz:].ravel()
+        rows += [a, b]
+        cols += [b, a]
+    row, col = np.concatenate(rows), np.concatenate(cols)
+    order = np.argsort(row * np.int64(nx * ny * nz) + col, kind="stable")
+    return pos, np.stack([row[order], col[order]])
