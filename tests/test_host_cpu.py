@@ -171,3 +171,15 @@ def test_shipped_training_configs_parse_verbatim():
     bad["model"]["use_silu_activation"] = True
     with pytest.raises(NotImplementedError):
         get_model(bad)
+
+
+def test_kuhn_box_graph_equals_tetra_mesh_edges():
+    """The direct generator of the structured tetrahedral mesh graph (used for the 1M-node runs) gives
+    exactly the edge list of FaceToEdge on the 6-tets-per-cell mesh (torch_graph.py:194-210 semantics)."""
+    import numpy as np
+    from graphphysics_b200.synthetic import box_tet_mesh, faces_of_cells, kuhn_box_graph, mesh_edges
+    for shape in ((6, 5, 4), (3, 3, 3), (2, 7, 3)):
+        pos, ei = kuhn_box_graph(*shape)
+        p2, tets = box_tet_mesh(*shape)
+        assert np.array_equal(pos, p2)
+        assert np.array_equal(ei, mesh_edges(faces_of_cells(tets), len(p2)))
