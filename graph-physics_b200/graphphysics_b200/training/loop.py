@@ -56,6 +56,7 @@ class Trainer:
         self._loss = torch.zeros(1, dtype=torch.float32, device=device)
         self._opt_state = torch.zeros(1, dtype=torch.int32, device=device)     # optimizer steps done (device copy)
         self._graphs = {}            # input shapes -> (CUDAGraph, static batch)
+        self._copy_stream, self._staged, self._staged_ready = None, None, None
         self.use_cuda_graph = False
         if self.pg is not None:
             from ..dist.ddp import broadcast_
@@ -78,9 +79,29 @@ class Trainer:
         rest; every rank must then see the same sequence of batch shapes."""
         self.use_cuda_graph = bool(enabled)
 
-    def training_step(self, batch) -> torch.Tensor:
+    def stage(self, batch) -> None:
+        """Start the host-to-device copy of the NEXT step's batch (pinned host memory) on a side stream, so
+        that it overlaps the kernels of the step in flight -- what a DataLoader with pin_memory and
+        non_blocking copies does in the reference's Lightning loop.  `training_step(None)` consumes it."""
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+        with torch.cuda.stream(self._copy_stream):
+            self._staged = batch.to(self.device, non_blocking=True)
+            self._staged_ready = torch.cuda.Event()
+            self._staged_ready.record(self._copy_stream)
+
+    def training_step(self, batch=None) -> torch.Tensor:
         """lightning_module.py:270-342 + the optimizer step Lightning does afterwards.
-        Returns the loss as a device scalar (no host sync here)."""
+        Returns the loss as a device scalar (no host sync here).  batch=None takes the batch handed to
+        `stage()`."""
+        if batch is None:
+            if self._staged is None:
+                raise ValueError("training_step(None) needs a batch staged with stage()")
+            torch.cuda.current_stream(self.device).wait_event(self._staged_ready)
+            batch, self._staged = self._staged, None
+            for v in batch.__dict__.values():           # the side stream allocated these tensors
+                if torch.is_tensor(v):
+                    v.record_stream(torch.cuda.current_stream(self.device))
         if not self.use_cuda_graph:
             return self._training_step_eager(batch)
         from ..graph import Data, no_csr_cache

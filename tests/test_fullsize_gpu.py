@@ -107,3 +107,30 @@ def test_graph_replay_equals_eager_step_at_full_size():
     assert n_e == n_g == 4
     assert l_e == l_g, (l_e, l_g)
     assert torch.equal(p_e, p_g)
+
+
+def test_staged_host_batches_equal_resident_batches():
+    """Trainer.stage() (pinned host batch copied on a side stream while the previous step runs) feeds the
+    same values as handing a device batch to training_step: identical losses and parameters."""
+    from graphphysics_b200.synthetic import cylinder_flow_batch
+    from graphphysics_b200.training.loop import Trainer
+    dev = torch.device("cuda:0")
+    host = [cylinder_flow_batch(4, seed=s, pin=True) for s in (0, 1)]
+    res = []
+    for staged in (False, True):
+        tr = Trainer(CFG, learning_rate=1e-3, num_steps=1000, warmup=10, device=dev, seed=0)
+        tr.enable_cuda_graph(True)
+        losses = []
+        if staged:
+            tr.stage(host[0])
+            for i in range(4):
+                loss = tr.training_step(None)
+                tr.stage(host[(i + 1) % 2])
+                losses.append(float(loss))
+        else:
+            for i in range(4):
+                losses.append(float(tr.training_step(host[i % 2].to(dev))))
+        torch.cuda.synchronize()
+        res.append((losses, tr.engine.flat.data.clone()))
+    assert res[0][0] == res[1][0]
+    assert torch.equal(res[0][1], res[1][1])
