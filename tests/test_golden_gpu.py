@@ -109,3 +109,32 @@ def test_cuda_graph_replay_matches_eager_steps():
     assert s0 == s1 == 6 and d0 == d1 == 6
     assert l0 == l1, (l0, l1)
     assert torch.equal(p0, p1)
+
+
+def test_rollout_rmse_matches_reference_within_one_percent():
+    """Trainer.rollout on the CUDA kernels vs the reference's roll-out over its own mock cylinder trajectory
+    (tests/golden/rollout.npz): both RMSE metrics within 1 % (the north-star bar), every predicted frame
+    within the bf16 drift bound."""
+    from graphphysics_b200.graph import Data
+    from graphphysics_b200.training.loop import Trainer
+    dev = torch.device("cuda:0")
+    z = np.load(os.path.join(G, "rollout.npz"))
+    cfg = {"model": {"type": "epd", "message_passing_num": 3, "hidden_size": 64, "node_input_size": 2, "output_size": 2,
+                     "edge_input_size": 3},
+           "index": {"feature_index_start": 0, "feature_index_end": 2, "output_index_start": 0, "output_index_end": 2,
+                     "node_type_index": 2}}
+    tr = Trainer(cfg, learning_rate=1e-3, num_steps=10, warmup=2, device=dev)
+    sd = {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd/")}
+    missing, unexpected = tr.model.load_state_dict(sd, strict=False)
+    assert not unexpected and all("_std_epsilon" in m or m == "" for m in missing), (missing, unexpected)
+    ei, ea, pos = (torch.from_numpy(z[k]).to(dev) for k in ("edge_index", "edge_attr", "pos"))
+    frames = [Data(x=torch.from_numpy(x).to(dev), y=torch.from_numpy(y).to(dev), pos=pos, edge_index=ei, edge_attr=ea)
+              for x, y in zip(z["frames"], z["ys"])]
+    res = tr.rollout(frames)
+    r1, rall = float(z["val_1step_rmse"]), float(z["val_all_rollout_rmse"])
+    print(f"val_1step_rmse {res['val_1step_rmse']:.6f} (reference {r1:.6f}); "
+          f"val_all_rollout_rmse {res['val_all_rollout_rmse']:.6f} (reference {rall:.6f})")
+    assert abs(res["val_1step_rmse"] - r1) < 1e-2 * r1
+    assert abs(res["val_all_rollout_rmse"] - rall) < 1e-2 * rall
+    got = torch.stack(res["predictions"]).cpu()
+    assert l2_rel(got, torch.from_numpy(z["predictions"])) < 2e-2

@@ -109,3 +109,27 @@ def test_l2_loss_masking():
     nt = torch.tensor([0.0, 6.0, 5.0])
     assert float(O.l2_loss(tgt, out, nt)) == pytest.approx((1 + 4 + 25 + 36) / 4)
     assert bool(O.boundary_mask(nt).tolist() == [False, True, False])
+
+
+def test_rollout_matches_reference():
+    """Autoregressive roll-out over the reference's mock cylinder trajectory (tests/golden/rollout.npz, made by
+    oracle/make_golden_rollout.py with the reference's Simulator): the oracle's simulator_forward + rollout
+    reproduce every predicted frame and both RMSE metrics (lightning_module.py:375-409, 446-486)."""
+    z = np.load(os.path.join(G, "rollout.npz"))
+    sd = {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd/")}
+    msd = {k[len("model."):]: v for k, v in sd.items() if k.startswith("model.")}
+    norms = {}
+    for name, key, size in (("node", "_node_normalizer", 11), ("edge", "_edge_normalizer", 3), ("output", "_output_normalizer", 2)):
+        norms[name] = O.Normalizer(size)
+        norms[name].load(sd, key)
+    index = dict(feature_index_start=0, feature_index_end=2, output_index_start=0, output_index_end=2, node_type_index=2)
+    ei, ea = torch.from_numpy(z["edge_index"]), torch.from_numpy(z["edge_attr"])
+    frames, ys = torch.from_numpy(z["frames"]), torch.from_numpy(z["ys"])
+
+    def step(x_raw, y):
+        model_fn = lambda nf, ef: O.epd_forward(msd, nf, ef, ei, 3, mode=None)
+        return O.simulator_forward(model_fn, norms, x_raw, y, ea, index, training=False)[2]
+
+    preds, r1, rall = O.rollout(step, list(frames), list(ys), 0, 2, 2)
+    np.testing.assert_allclose(torch.stack(preds).numpy(), z["predictions"], rtol=1e-3, atol=1e-5)
+    assert abs(r1 - float(z["val_1step_rmse"])) < 1e-5 and abs(rall - float(z["val_all_rollout_rmse"])) < 1e-5
