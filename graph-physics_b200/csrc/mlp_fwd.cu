@@ -299,7 +299,7 @@ __global__ void __launch_bounds__(kSlotThreads * NG, 1) mlp_fwd_kernel(const gp_
                     }
                     mma_commit(&mma_bar[g_u]);
                 }
-                tick(8);         // MMA issue (thread 0 of the slot)
+                tick(9 + l);     // MMA issue (elected thread of the slot), per layer
                 // while the first MMA runs: indices of this slot's next tile, and its gathered rows
                 // into L2, so the next tile's pre-load does not start with two dependent misses
                 if (l == 0 && nc == 0 && has_init && tile + tile_stride < n_tiles) load_idx(tile + tile_stride);
