@@ -23,7 +23,12 @@
 namespace {
 using namespace gp;
 
-constexpr uint32_t kColAcc = 0, kColDWB = 128, kColDWA = 256, kColDBB = 384, kColDBA = 400, kColDSC = 416;
+// TMEM columns.  General kernel: ACC 0, dWb 128, dWa 256, dbb 384, dba 400, dscale 416.  Specialised
+// instantiations (H = ka = nb = 128) compute every bias gradient as 16 extra columns of its weight
+// gradient (the B operand is [activation tile | ones tile], N = 144), one MMA chain instead of two:
+// ACC 0, [dWb | dbb] 128..271, [dWa | dba] 272..415, dscale 416.
+constexpr uint32_t kColAcc = 0, kColDWB = 128, kColDBA = 400, kColDSC = 416;
+template <bool F> struct BwdCols { static constexpr uint32_t DWA = F ? 272 : 256, DBB = F ? 256 : 384; };
 
 struct BwdLayout {
     int off_dwb, off_dwa, off_dbb, off_dba, off_dsc, stride;
@@ -112,11 +117,20 @@ __global__ void __launch_bounds__(BwdCfg<H>::NT, 1) mlp_bwd_kernel(const gp_mlp_
     uint32_t off = 0;
     uint8_t* wa_t = smem + off;  off += ((ka + 63) >> 6) * H * 128;          // [H rows][ka]
     uint8_t* wb_t = smem + off;  off += ((H + 63) >> 6) * nb * 128;          // [nb rows][H]
-    uint8_t* ain = smem + off;   off += kBufBytes;
-    uint8_t* ha = smem + off;    off += kBufBytes;
-    uint8_t* db = smem + off;    off += kBufBytes;
-    uint8_t* qb = smem + off;    off += (norm || t_res) ? kBufBytes : 0;      // NORM: du / q tile; else residual tile
-    uint8_t* ones = smem + off;  off += 128 * 128;
+    // Tile buffers.  General kernel: ain, ha, db, qb, ones back to back.  Specialised instantiations: the two
+    // 64-column blocks of ha are 48 KB apart and the ones tile sits where "block 2" of both ha and ain
+    // falls (ha0 | db | ha1 | ain | ones | qb), so [ha | ones] and [ain | ones] are valid 144-column MN-major
+    // operands with block strides of 48 KB and 16 KB.
+    constexpr uint32_t kHaStride = F ? 49152u : 16384u;     // bytes between the 64-column blocks of ha
+    constexpr uint32_t HR = kHaStride / 128u;               // the same as a "rows" argument of the tile helpers
+    uint8_t* const tiles = smem + off;
+    uint8_t* ain = tiles + (F ? 65536 : 0);
+    uint8_t* ha = tiles + (F ? 0 : kBufBytes);
+    uint8_t* db = tiles + (F ? 16384 : 2 * kBufBytes);
+    uint8_t* ones = tiles + (F ? 98304 : 3 * kBufBytes + ((norm || t_res) ? kBufBytes : 0));
+    uint8_t* qb = tiles + (F ? 114688 : 3 * kBufBytes);     // NORM: du / q tile; else residual tile (absent in node stage A)
+    off += 3 * kBufBytes + ((norm || t_res) ? kBufBytes : 0) + 128 * 128;
+    constexpr uint32_t kColDWA = BwdCols<F>::DWA, kColDBB = BwdCols<F>::DBB;
     float* s_ba = reinterpret_cast<float*>(smem + off);  off += 128 * 4;
     float* s_bb = reinterpret_cast<float*>(smem + off);  off += 128 * 4;
     float* s_g = reinterpret_cast<float*>(smem + off);   off += 128 * 4;
@@ -155,6 +169,7 @@ __global__ void __launch_bounds__(BwdCfg<H>::NT, 1) mlp_bwd_kernel(const gp_mlp_
     const uint32_t ain_s = smem_u32(ain), ha_s = smem_u32(ha), db_s = smem_u32(db), qb_s = smem_u32(qb);
     const uint32_t wa_s = smem_u32(wa_t), wb_s = smem_u32(wb_t), ones_s = smem_u32(ones);
     const uint32_t lbo_h = (H >= 128) ? 16384u : 0u;      // M=128 MN-major A with < 128 valid columns: alias block
+    const uint32_t lbo_ha = F ? kHaStride : lbo_h;         // the same for an A operand that lives in ha
     const uint32_t lbo_nb = (nb >= 128) ? 16384u : 0u;
     uint32_t phase = 0, tphase = 0;
     const bool has_init = F ? kInit[MODE] : (p.init != nullptr && !ha_given);
@@ -232,7 +247,7 @@ __global__ void __launch_bounds__(BwdCfg<H>::NT, 1) mlp_bwd_kernel(const gp_mlp_
             if (t_res)
                 for (int b = 0; b < (ka + 63) >> 6; ++b) tma_load_2d(qb_s + b * 16384, &maps.resid, b * 64, R0, &tma_bar);
             if (t_ha)
-                for (int b = 0; b < (H + 63) >> 6; ++b) tma_load_2d(ha_s + b * 16384, &maps.ha, b * 64, R0, &tma_bar);
+                for (int b = 0; b < (H + 63) >> 6; ++b) tma_load_2d(ha_s + b * kHaStride, &maps.ha, b * 64, R0, &tma_bar);
         }
         if (ha_given && !t_ha) {
 #pragma unroll
@@ -240,9 +255,9 @@ __global__ void __launch_bounds__(BwdCfg<H>::NT, 1) mlp_bwd_kernel(const gp_mlp_
                 const int i = tid + j * NT;
                 const int r = i / KC, ch = i % KC;
                 if (R0 + r < p.rows)
-                    cp_async16(ha_s + sw128_off(128, r, ch * 8), p.ha_saved + (size_t)(R0 + r) * H + ch * 8);
+                    cp_async16(ha_s + sw128_off(HR, r, ch * 8), p.ha_saved + (size_t)(R0 + r) * H + ch * 8);
                 else
-                    *reinterpret_cast<uint4*>(ha + sw128_off(128, r, ch * 8)) = make_uint4(0, 0, 0, 0);
+                    *reinterpret_cast<uint4*>(ha + sw128_off(HR, r, ch * 8)) = make_uint4(0, 0, 0, 0);
             }
         }
         if (!t_ain) stage_rows(ain, p.a_bf16, F ? nullptr : p.a_f32, ka, p.lda, R0, p.rows, tid, NT);
@@ -269,7 +284,7 @@ __global__ void __launch_bounds__(BwdCfg<H>::NT, 1) mlp_bwd_kernel(const gp_mlp_
             for (int j = 0; j < CPT; ++j) {
                 const int i = tid + j * NT;
                 const int r = i / KC, ch = i % KC;
-                cp_async16(ha_s + sw128_off(128, r, ch * 8), p.init + (size_t)ridx[j] * p.ld_init + soff + ch * 8);
+                cp_async16(ha_s + sw128_off(HR, r, ch * 8), p.init + (size_t)ridx[j] * p.ld_init + soff + ch * 8);
             }
         }
         if (du_smem && f_gather && f_gbf) {   // receiver-indexed bf16 rows -> db
@@ -333,8 +348,8 @@ __global__ void __launch_bounds__(BwdCfg<H>::NT, 1) mlp_bwd_kernel(const gp_mlp_
 #pragma unroll
             for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(f + j) = *reinterpret_cast<const float4*>(bsrc + cb + c + j);
             if (has_init) {
-                acc8(*reinterpret_cast<const uint4*>(ha + sw128_off(128, row, cb + c)), f);
-                acc8(*reinterpret_cast<const uint4*>(ha + sw128_off(128, row, cb + c + 8)), f + 8);
+                acc8(*reinterpret_cast<const uint4*>(ha + sw128_off(HR, row, cb + c)), f);
+                acc8(*reinterpret_cast<const uint4*>(ha + sw128_off(HR, row, cb + c + 8)), f + 8);
                 if (stage1) {
                     acc8(dq[c / 8], f);
                     acc8(dq[c / 8 + 1], f + 8);
@@ -416,7 +431,7 @@ __global__ void __launch_bounds__(BwdCfg<H>::NT, 1) mlp_bwd_kernel(const gp_mlp_
             }
 #pragma unroll
             for (int c = 0; c < CH; c += 8)
-                *reinterpret_cast<uint4*>(ha + sw128_off(128, row, cb + c)) = pack8_relu(reinterpret_cast<const float*>(&v[c]));
+                *reinterpret_cast<uint4*>(ha + sw128_off(HR, row, cb + c)) = pack8_relu(reinterpret_cast<const float*>(&v[c]));
             tmem_st_wait();
             publish();
         }
@@ -428,7 +443,7 @@ __global__ void __launch_bounds__(BwdCfg<H>::NT, 1) mlp_bwd_kernel(const gp_mlp_
                 tc_fence_after();
                 const uint32_t id = idesc_bf16(H, false, false);
                 for (int ks = 0; ks < (H >> 4); ++ks)
-                    mma_ss(tmem + kColAcc, desc_kmajor(ha_s, 128, ks), desc_kmajor(wb_s, nb, ks), id, 1u);
+                    mma_ss(tmem + kColAcc, desc_kmajor(ha_s, HR, ks), desc_kmajor(wb_s, nb, ks), id, 1u);
                 mma_commit(&mma_bar);
             }
             wait_mma();
@@ -507,13 +522,15 @@ __global__ void __launch_bounds__(BwdCfg<H>::NT, 1) mlp_bwd_kernel(const gp_mlp_
         // ---- P3: dWb += delta_b^T h_a ; dbb += delta_b^T 1 ; dscale += q^T 1 ; acc = delta_b . Wb
         if (warp == 0 && elect_one()) {
             tc_fence_after();
-            const uint32_t id_w = idesc_bf16(H, true, true), id_1 = idesc_bf16(16, true, true);
+            // [dWb | dbb] in one chain when the ones tile is "block 2" of ha (specialised instantiations)
+            const uint32_t id_w = idesc_bf16(F ? H + 16 : H, true, true), id_1 = idesc_bf16(16, true, true);
             for (int ks = 0; ks < 8; ++ks)
-                mma_ss(tmem + kColDWB, desc_mnmajor(db_s, 128, ks, 0, lbo_nb), desc_mnmajor(ha_s, 128, ks), id_w,
+                mma_ss(tmem + kColDWB, desc_mnmajor(db_s, 128, ks, 0, lbo_nb), desc_mnmajor(ha_s, HR, ks), id_w,
                        (ks > 0) ? 1u : acc_flag);
-            for (int ks = 0; ks < 8; ++ks)
-                mma_ss(tmem + kColDBB, desc_mnmajor(db_s, 128, ks, 0, lbo_nb), desc_mnmajor(ones_s, 128, ks), id_1,
-                       (ks > 0) ? 1u : acc_flag);
+            if (!F)
+                for (int ks = 0; ks < 8; ++ks)
+                    mma_ss(tmem + kColDBB, desc_mnmajor(db_s, 128, ks, 0, lbo_nb), desc_mnmajor(ones_s, 128, ks), id_1,
+                           (ks > 0) ? 1u : acc_flag);
             if (norm)
                 for (int ks = 0; ks < 8; ++ks)
                     mma_ss(tmem + kColDSC, desc_mnmajor(qb_s, 128, ks, 0, lbo_h), desc_mnmajor(ones_s, 128, ks), id_1,
@@ -533,7 +550,7 @@ __global__ void __launch_bounds__(BwdCfg<H>::NT, 1) mlp_bwd_kernel(const gp_mlp_
             tmem_ld_wait();
 #pragma unroll
             for (int c = 0; c < CH; c += 8) {
-                uint4* hp = reinterpret_cast<uint4*>(ha + sw128_off(128, row, cb + c));
+                uint4* hp = reinterpret_cast<uint4*>(ha + sw128_off(HR, row, cb + c));
                 *hp = mask8_pos(pack8(reinterpret_cast<const float*>(&v[c])), *hp);
             }
         }
@@ -543,24 +560,26 @@ __global__ void __launch_bounds__(BwdCfg<H>::NT, 1) mlp_bwd_kernel(const gp_mlp_
         // ---- P4: dWa += delta_a^T a_in ; dba += delta_a^T 1 ; d_in = delta_a . Wa
         if (warp == 0 && elect_one()) {
             tc_fence_after();
-            const uint32_t id_w = idesc_bf16(ka, true, true), id_1 = idesc_bf16(16, true, true);
+            // [dWa | dba] likewise: the ones tile follows ain
+            const uint32_t id_w = idesc_bf16(F ? ka + 16 : ka, true, true), id_1 = idesc_bf16(16, true, true);
             for (int ks = 0; ks < 8; ++ks)
-                mma_ss(tmem + kColDWA, desc_mnmajor(ha_s, 128, ks, 0, lbo_h), desc_mnmajor(ain_s, 128, ks), id_w,
+                mma_ss(tmem + kColDWA, desc_mnmajor(ha_s, HR, ks, 0, lbo_ha), desc_mnmajor(ain_s, 128, ks), id_w,
                        (ks > 0) ? 1u : acc_flag);
-            for (int ks = 0; ks < 8; ++ks)
-                mma_ss(tmem + kColDBA, desc_mnmajor(ha_s, 128, ks, 0, lbo_h), desc_mnmajor(ones_s, 128, ks), id_1,
-                       (ks > 0) ? 1u : acc_flag);
+            if (!F)
+                for (int ks = 0; ks < 8; ++ks)
+                    mma_ss(tmem + kColDBA, desc_mnmajor(ha_s, HR, ks, 0, lbo_ha), desc_mnmajor(ones_s, 128, ks), id_1,
+                           (ks > 0) ? 1u : acc_flag);
             if (f_din) {
                 const uint32_t id_d = idesc_bf16(ka, false, true);
                 for (int ks = 0; ks < (H >> 4); ++ks)
-                    mma_ss(tmem + kColAcc, desc_kmajor(ha_s, 128, ks), desc_mnmajor(wa_s, H, ks), id_d, ks > 0 ? 1u : 0u);
+                    mma_ss(tmem + kColAcc, desc_kmajor(ha_s, HR, ks), desc_mnmajor(wa_s, H, ks), id_d, ks > 0 ? 1u : 0u);
             }
             mma_commit(&mma_bar);
         }
         // while the tensor core runs: delta_a tile -> global (row-major chunks), and its segment sum
         if (f_da && t_da) {
             if (warp == 0 && elect_one()) {
-                for (int b = 0; b < (H + 63) >> 6; ++b) tma_store_2d(&maps.da_out, b * 64, R0, ha_s + b * 16384);
+                for (int b = 0; b < (H + 63) >> 6; ++b) tma_store_2d(&maps.da_out, b * 64, R0, ha_s + b * kHaStride);
                 tma_store_commit();
             }
         } else if (f_da) {
@@ -570,10 +589,10 @@ __global__ void __launch_bounds__(BwdCfg<H>::NT, 1) mlp_bwd_kernel(const gp_mlp_
                 const int r = i / KC, ch = i % KC;
                 if (R0 + r < p.rows)
                     *reinterpret_cast<uint4*>(p.delta_a_out + (size_t)(R0 + r) * H + ch * 8) =
-                        *reinterpret_cast<const uint4*>(ha + sw128_off(128, r, ch * 8));
+                        *reinterpret_cast<const uint4*>(ha + sw128_off(HR, r, ch * 8));
             }
         }
-        if (f_seg) tile_segment_sum<H, NT>(ha, sseg, R0, tid, MODE == 2 ? nullptr : p.seg_out, p.seg_bnd, p.seg_out_bf16);
+        if (f_seg) tile_segment_sum<H, NT>(ha, sseg, R0, tid, MODE == 2 ? nullptr : p.seg_out, p.seg_bnd, p.seg_out_bf16, kHaStride);
         tick(9);      // P4 issue + copy-out + segment walk
         wait_mma();
         tick(10);     // P4 MMA wait
@@ -678,13 +697,16 @@ __global__ void __launch_bounds__(BwdCfg<H>::NT, 1) mlp_bwd_kernel(const gp_mlp_
     }
 
     if ((t_da || t_out) && warp == 0 && elect_one()) tma_store_wait_all();
+    __syncthreads();      // the staging tile below reuses buffers the last bulk stores were reading
     // ---- dump the weight-gradient accumulators of this CTA (lane r <-> output row r)
     tc_fence_after();
     const BwdLayout L = bwd_layout(H, ka, nb);
     float* P = p.partials + (size_t)blockIdx.x * L.stride;
-    // the two weight-gradient matrices leave through a staging tile (ain + ha, contiguous) as coalesced rows
-    tmem_rows_to_global<NT>(tlane, kColDWB, nb, H, P + L.off_dwb, H, ain, tid);
-    tmem_rows_to_global<NT>(tlane, kColDWA, H, ka, P + L.off_dwa, ka, ain, tid);
+    // the two weight-gradient matrices leave through a 64 KB staging tile (two adjacent dead tile buffers) as
+    // coalesced rows
+    uint8_t* const stg = tiles + (F ? 16384 : 0);
+    tmem_rows_to_global<NT>(tlane, kColDWB, nb, H, P + L.off_dwb, H, stg, tid);
+    tmem_rows_to_global<NT>(tlane, kColDWA, H, ka, P + L.off_dwa, ka, stg, tid);
     if (tid < 128) {
         uint32_t v8[8];
         tmem_ld8(tlane + kColDBB, v8);
@@ -814,6 +836,8 @@ int launch_bwd(const gp_mlp_bwd_args& a, int32_t* grid_out, cudaStream_t st) {
                 fast = 4;                                                                                             // node A
         }
     }
+    static const bool force_general = getenv("GP_BWD_GENERAL") != nullptr;      // A/B testing of the instantiations
+    if (force_general) fast = 0;
     auto set_smem = [&](int bytes) -> cudaError_t {
         switch (fast) {
             case 1: return cudaFuncSetAttribute(mlp_bwd_kernel<H, (H == 128 ? 1 : 0)>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);

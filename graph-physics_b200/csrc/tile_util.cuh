@@ -189,7 +189,8 @@ __device__ __forceinline__ void tmem_rows_to_global(uint32_t tlane, uint32_t col
 // seg_bnd[sub-tile][0 = continues from before | 1 = continues after] for gp_seg_fixup.
 template <int H, int NT>
 __device__ __forceinline__ void tile_segment_sum(const uint8_t* buf, const int* sseg, int R0, int t, float* seg_out,
-                                                 float* seg_bnd, gp_bf16* seg_out_bf16 = nullptr) {
+                                                 float* seg_bnd, gp_bf16* seg_out_bf16 = nullptr,
+                                                 uint32_t block_stride = 128 * 128) {
     constexpr int NP = H / 2;            // column pairs
     constexpr int SUB = 128 * NP / NT;   // rows per sub-tile
     static_assert(SUB % 8 == 0, "sub-tile must be a multiple of 8 rows");
@@ -198,7 +199,7 @@ __device__ __forceinline__ void tile_segment_sum(const uint8_t* buf, const int* 
     const int c = cp * 2;
     const size_t sub_index = (size_t)(R0 + rb) / SUB;
     const uint32_t chunk = (c & 63) >> 3;
-    const uint8_t* colbase = buf + (c >> 6) * (128 * 128) + (c & 7) * 2;
+    const uint8_t* colbase = buf + (c >> 6) * block_stride + (c & 7) * 2;     // block_stride: bytes between 64-column blocks
     const int seg_prev = sseg[3 + rb], seg_next = sseg[4 + rb + SUB];
     int cur = sseg[4 + rb];
     bool first_piece = true;

@@ -206,3 +206,24 @@ def test_encoder_and_decoder_backward(hidden):
                       ("m.6.bias", db3[:2]), ("m.4.bias", db2), ("m.2.bias", db1), ("m.0.bias", db0)):
         ok &= check_close(got, sd64[name].grad, "decoder " + name, 1e-3, 2e-3, rep)
     assert ok, "\n".join(rep)
+
+
+def test_specialised_backward_instantiations_equal_general(tmp_path):
+    """The compile-time specialised stage kernels (edge stage B / A: TMA everywhere, bias gradients folded into
+    the weight-gradient MMAs, interleaved tile layout) must give the same bits as the general kernel on the
+    same inputs: every output tensor and every weight / bias / scale gradient partial sum."""
+    import os
+    import subprocess
+    import sys
+    helper = os.path.join(os.path.dirname(os.path.abspath(__file__)), "cmp_bwd_modes.py")
+    for general in (True, False):
+        env = dict(os.environ)
+        env.pop("GP_BWD_GENERAL", None)
+        if general:
+            env["GP_BWD_GENERAL"] = "1"
+        subprocess.run([sys.executable, helper, str(tmp_path)], check=True, env=env, capture_output=True, timeout=300)
+    a, b = torch.load(tmp_path / "cmp_general.pt"), torch.load(tmp_path / "cmp_fast.pt")
+    assert set(a) == set(b) and len(a) == 6
+    for k in a:
+        assert torch.isfinite(b[k]).all(), k
+        assert torch.equal(a[k], b[k]), k
