@@ -1,19 +1,16 @@
 // mlp_bwd.cu -- two-layer backward stage of the fused MLP on tcgen05 (gp_mlp_bwd_stage).
 //
-// One persistent CTA of 256 threads per SM.  Resident in shared memory: the two packed weights
-// (each used K-major for the recompute and MN-major for dgrad), a tile of ones (bias gradients
-// as delta^T . 1 on the tensor core) and the activation buffers Ain / Ha / Db / Q of one
-// 128-row tile.  TMEM holds the working accumulator plus the weight-gradient accumulators,
-// which persist across all tiles of the CTA:
-//     cols   0..127  ACC   working accumulator (recompute, dgrad)
-//     cols 128..255  DWB   dWb  [nb x H]
-//     cols 256..383  DWA   dWa  [H x ka]
-//     cols 384..399  DBB   sum delta_b   (16 identical columns)
-//     cols 400..415  DBA   sum delta_a
-//     cols 416..431  DSC   sum du * m/(rms+eps)   (RMSNorm scale gradient)
+// One persistent CTA per SM, 512 threads at H = 128 (256 below): one 128-row tile at a time.
+// Resident in shared memory: the two packed weights (each used K-major for the recompute and
+// MN-major for dgrad), a tile of ones (bias / scale gradients as delta^T . 1 on the tensor core)
+// and the activation buffers Ain / Ha / Db / Q of the tile.  Contiguous tiles arrive and leave by
+// TMA (one elected thread, mbarrier), gathered rows by 16-byte cp.async; the next tile's row ids are
+// loaded and its data prefetched into L2 while this tile computes.  TMEM holds the working
+// accumulator plus the weight-gradient accumulators, which persist across all tiles of the CTA
+// (column map below); each CTA dumps them once, as coalesced rows, into its partial block.
 // Thread (row = tid & 127, part = tid >> 7) owns row `row` of the tile and one part (1/2 or 1/4) of its
 // columns, so ReLU masks, the RMSNorm backward and residuals are thread-local apart from one
-// two-float exchange between the halves.
+// two-float exchange between the parts.
 #include <stdlib.h>
 #include <string.h>
 

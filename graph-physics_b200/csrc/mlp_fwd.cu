@@ -9,11 +9,13 @@
 //
 // Thread (row = t & 127, half = t >> 7) of a slot owns row `row` of the tile (== TMEM lane) and
 // one half of its columns: bias, ReLU and RMSNorm are thread-local apart from one float
-// exchanged between the halves.  Everything that goes to or comes from global memory as a tile
-// (layer-0 operand, saved activation, output + residual) moves in row-major 16-byte chunks, one
-// chunk per lane, so a warp touches 4 cache lines per instruction instead of 32; the tile is
-// transposed between the two mappings through the swizzled shared-memory buffer.  The copy-out
-// of the saved activation runs while the next layer's MMA is in flight.
+// exchanged between the halves.  The bias is stored into the accumulator before the MMAs, so the
+// epilogues only convert (ReLU fused into the bf16 conversion).  Everything that goes to or comes
+// from global memory as a tile (layer-0 operand, gathered rows, saved activation, output + residual)
+// moves by TMA or in row-major 16-byte chunks, one chunk per lane, so a warp touches 4 cache lines
+// per instruction instead of 32; the tile is transposed between the two mappings through the
+// swizzled shared-memory buffer.  The saved activation leaves by one TMA store while the next
+// layer's MMA is in flight; the next tile's row ids and gathered rows are prefetched meanwhile.
 // The receiver-sorted segment sum re-partitions through shared memory (column pairs x sub-tiles
 // of H/4 rows) and uses no atomics.
 #include <stdlib.h>
