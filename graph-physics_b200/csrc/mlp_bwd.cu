@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(BwdCfg<H>::NT, 1) mlp_bwd_kernel(const gp_mlp_
     constexpr int NT = BwdCfg<H>::NT;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = GP_SMEM_ALIGNED(smem_raw);
-    __shared__ uint64_t mma_bar, tma_bar;
+    __shared__ uint64_t mma_bar, tma_bar, wg_bar;     // wg_bar: completion of the weight-gradient MMA chains
     __shared__ uint32_t tmem_slot;
 
     const int tid = threadIdx.x;
@@ -151,6 +151,7 @@ __global__ void __launch_bounds__(BwdCfg<H>::NT, 1) mlp_bwd_kernel(const gp_mlp_
     }
     if (tid == 0) {
         mbar_init(&mma_bar, 1);
+        mbar_init(&wg_bar, 1);
         mbar_init(&tma_bar, 1);
         fence_mbar_init();
     }
@@ -174,6 +175,12 @@ __global__ void __launch_bounds__(BwdCfg<H>::NT, 1) mlp_bwd_kernel(const gp_mlp_
     constexpr int CH = H / NPART;                          // columns per thread
     const int cb = part * CH;
 
+    uint32_t wphase = 0;
+    auto wait_wg = [&]() {
+        mbar_wait(&wg_bar, wphase);
+        wphase ^= 1;
+        tc_fence_after();
+    };
     auto wait_mma = [&]() {
         mbar_wait(&mma_bar, phase);
         phase ^= 1;
@@ -519,6 +526,12 @@ __global__ void __launch_bounds__(BwdCfg<H>::NT, 1) mlp_bwd_kernel(const gp_mlp_
         // ---- P3: dWb += delta_b^T h_a ; dbb += delta_b^T 1 ; dscale += q^T 1 ; acc = delta_b . Wb
         if (warp == 0 && elect_one()) {
             tc_fence_after();
+            // the dgrad chain first, on its own barrier: the epilogue that needs it starts while the
+            // weight-gradient chains (which nobody waits for until their operands are rewritten) still run
+            const uint32_t id_d = idesc_bf16(H, false, true);
+            for (int ks = 0; ks < (nb >> 4); ++ks)
+                mma_ss(tmem + kColAcc, desc_kmajor(db_s, 128, ks), desc_mnmajor(wb_s, nb, ks), id_d, ks > 0 ? 1u : 0u);
+            mma_commit(&mma_bar);
             // [dWb | dbb] in one chain when the ones tile is "block 2" of ha (specialised instantiations)
             const uint32_t id_w = idesc_bf16(F ? H + 16 : H, true, true), id_1 = idesc_bf16(16, true, true);
             for (int ks = 0; ks < 8; ++ks)
@@ -532,24 +545,24 @@ __global__ void __launch_bounds__(BwdCfg<H>::NT, 1) mlp_bwd_kernel(const gp_mlp_
                 for (int ks = 0; ks < 8; ++ks)
                     mma_ss(tmem + kColDSC, desc_mnmajor(qb_s, 128, ks, 0, lbo_h), desc_mnmajor(ones_s, 128, ks), id_1,
                            (ks > 0) ? 1u : acc_flag);
-            const uint32_t id_d = idesc_bf16(H, false, true);
-            for (int ks = 0; ks < (nb >> 4); ++ks)
-                mma_ss(tmem + kColAcc, desc_kmajor(db_s, 128, ks), desc_mnmajor(wb_s, nb, ks), id_d, ks > 0 ? 1u : 0u);
-            mma_commit(&mma_bar);
+            mma_commit(&wg_bar);
         }
         wait_mma();
-        tick(7);      // P3 MMAs
-        // delta_a = acc * (h_a > 0), written in place over h_a (its readers have completed)
+        tick(7);      // P3 dgrad MMAs
+        // delta_a = acc * (h_a > 0), written in place over h_a once its reader (the dWb chain) has completed
         {
             uint32_t v[CH];
 #pragma unroll
             for (int c = 0; c < CH; c += 16) tmem_ld16(tlane + kColAcc + cb + c, *reinterpret_cast<uint32_t(*)[16]>(&v[c]));
             tmem_ld_wait();
+            uint4 o[CH / 8];
 #pragma unroll
-            for (int c = 0; c < CH; c += 8) {
-                uint4* hp = reinterpret_cast<uint4*>(ha + sw128_off(HR, row, cb + c));
-                *hp = mask8_pos(pack8(reinterpret_cast<const float*>(&v[c])), *hp);
-            }
+            for (int c = 0; c < CH; c += 8)
+                o[c / 8] = mask8_pos(pack8(reinterpret_cast<const float*>(&v[c])),
+                                     *reinterpret_cast<const uint4*>(ha + sw128_off(HR, row, cb + c)));
+            wait_wg();
+#pragma unroll
+            for (int c = 0; c < CH; c += 8) *reinterpret_cast<uint4*>(ha + sw128_off(HR, row, cb + c)) = o[c / 8];
         }
         publish();
         tick(8);      // E3
@@ -557,7 +570,14 @@ __global__ void __launch_bounds__(BwdCfg<H>::NT, 1) mlp_bwd_kernel(const gp_mlp_
         // ---- P4: dWa += delta_a^T a_in ; dba += delta_a^T 1 ; d_in = delta_a . Wa
         if (warp == 0 && elect_one()) {
             tc_fence_after();
-            // [dWa | dba] likewise: the ones tile follows ain
+            // d_in first (its epilogue overlaps the weight-gradient chain); [dWa | dba] likewise in one chain:
+            // the ones tile follows ain
+            if (f_din) {
+                const uint32_t id_d = idesc_bf16(ka, false, true);
+                for (int ks = 0; ks < (H >> 4); ++ks)
+                    mma_ss(tmem + kColAcc, desc_kmajor(ha_s, HR, ks), desc_mnmajor(wa_s, H, ks), id_d, ks > 0 ? 1u : 0u);
+                mma_commit(&mma_bar);
+            }
             const uint32_t id_w = idesc_bf16(F ? ka + 16 : ka, true, true), id_1 = idesc_bf16(16, true, true);
             for (int ks = 0; ks < 8; ++ks)
                 mma_ss(tmem + kColDWA, desc_mnmajor(ha_s, HR, ks, 0, lbo_ha), desc_mnmajor(ain_s, 128, ks), id_w,
@@ -566,12 +586,7 @@ __global__ void __launch_bounds__(BwdCfg<H>::NT, 1) mlp_bwd_kernel(const gp_mlp_
                 for (int ks = 0; ks < 8; ++ks)
                     mma_ss(tmem + kColDBA, desc_mnmajor(ha_s, HR, ks, 0, lbo_ha), desc_mnmajor(ones_s, 128, ks), id_1,
                            (ks > 0) ? 1u : acc_flag);
-            if (f_din) {
-                const uint32_t id_d = idesc_bf16(ka, false, true);
-                for (int ks = 0; ks < (H >> 4); ++ks)
-                    mma_ss(tmem + kColAcc, desc_kmajor(ha_s, HR, ks), desc_mnmajor(wa_s, H, ks), id_d, ks > 0 ? 1u : 0u);
-            }
-            mma_commit(&mma_bar);
+            mma_commit(&wg_bar);
         }
         // while the tensor core runs: delta_a tile -> global (row-major chunks), and its segment sum
         if (f_da && t_da) {
@@ -591,8 +606,8 @@ __global__ void __launch_bounds__(BwdCfg<H>::NT, 1) mlp_bwd_kernel(const gp_mlp_
         }
         if (f_seg) tile_segment_sum<H, NT>(ha, sseg, R0, tid, MODE == 2 ? nullptr : p.seg_out, p.seg_bnd, p.seg_out_bf16, kHaStride);
         tick(9);      // P4 issue + copy-out + segment walk
-        wait_mma();
-        tick(10);     // P4 MMA wait
+        if (f_din) wait_mma();
+        tick(10);     // P4 d_in MMA wait
         if (f_din) {
             const bool via_smem = F ? kTOut[MODE] : (p.out_bf16 != nullptr && ka == H);     // bf16 tile output: transpose through shared memory
             uint8_t* ob = (t_out && norm) ? qb : db;                    // staging tile (free since P3)
@@ -687,6 +702,7 @@ __global__ void __launch_bounds__(BwdCfg<H>::NT, 1) mlp_bwd_kernel(const gp_mlp_
             const bool ob_refilled_by_tma = norm ? t_gy : t_db;
             if (t_out && ob_refilled_by_tma) tma_store_wait_read<1>(); else tma_store_wait_read<0>();
         }
+        wait_wg();         // the weight-gradient chain of P4 has read ha / ain
         fence_async_smem();
         tc_fence_before();
         __syncthreads();   // buffers and ACC are free for the next tile
