@@ -57,6 +57,7 @@ class Trainer:
         self._opt_state = torch.zeros(1, dtype=torch.int32, device=device)     # optimizer steps done (device copy)
         self._graphs = {}            # input shapes -> (CUDAGraph, static batch)
         self._copy_stream, self._staged, self._staged_ready = None, None, None
+        self._part = None            # PartitionedEPD when the mesh is split over the process group
         self.use_cuda_graph = False
         if self.pg is not None:
             from ..dist.ddp import broadcast_
@@ -78,6 +79,53 @@ class Trainer:
         parallelism the NCCL all-reduces (normaliser statistics, flat gradient) are captured with the
         rest; every rank must then see the same sequence of batch shapes."""
         self.use_cuda_graph = bool(enabled)
+
+    def enable_node_partition(self, pos, edge_index) -> None:
+        """Split ONE large mesh over the ranks of the process group (BASELINE config 5): every rank owns a
+        coordinate-bisection part of the nodes plus ghost copies of the senders it needs, runs the fused
+        kernels on its part, exchanges ghost rows per message-passing step (forward) and their gradients
+        (backward), and the weight gradients are summed over ranks.  `pos` (N,3|2) and `edge_index` (2,E) are
+        the mesh every later batch must have.  Replaces the data-parallel mode of this Trainer: the ranks now
+        see the SAME batch."""
+        import numpy as np
+        import torch.distributed as dist
+        from ..dist.partition import build_local_graphs, partition_nodes
+        from ..dist.partitioned import PartitionedEPD
+        if self.pg is None or not self.fused:
+            raise ValueError("enable_node_partition needs a process group and the fused EPD model")
+        world, rank = dist.get_world_size(self.pg), dist.get_rank(self.pg)
+        pos_np = pos.detach().cpu().numpy() if torch.is_tensor(pos) else np.asarray(pos)
+        ei_np = edge_index.detach().cpu().numpy() if torch.is_tensor(edge_index) else np.asarray(edge_index)
+        lg = build_local_graphs(ei_np, partition_nodes(pos_np, world), world)[rank]
+        self._part = PartitionedEPD(self.processor, lg, world, self.pg)
+        self._owned = torch.from_numpy(lg.owned).to(self.device)
+
+    def _partitioned_step(self, batch) -> torch.Tensor:
+        """One training step on the node-partitioned mesh: identical normalisation on every rank (all see
+        the whole batch), local forward/backward with halo exchanges, loss = mean over the masked nodes of
+        ALL ranks."""
+        import torch.distributed as dist
+        sim, eng, part = self.model, self.engine, self._part
+        sim.train()
+        if not batch.x.is_cuda:
+            batch = batch.to(self.device, non_blocking=True)
+        node_type = batch.x[:, sim.node_type_index]
+        graph, target = sim._build_input_graph(batch, True)
+        mask = prepare_mask(node_type, self.loss_masks)[self._owned].contiguous()
+        out, ctx = part.forward(graph.x, graph.edge_attr, save=True)
+        counts = torch.stack([mask.sum().float(), mask.sum().float()])
+        dist.all_reduce(counts[1:], group=self.pg)
+        n_loc, n_all = (float(v) for v in counts.tolist())                 # one host read per step in this mode
+        d_out = torch.zeros_like(out)
+        if n_loc > 0:
+            ops.masked_mse(out, target[self._owned].contiguous(), mask, self._loss, d_out, grad_scale=n_loc / n_all)
+            self._loss.mul_(n_loc / n_all)
+        else:
+            self._loss.zero_()                                             # this part holds no node of the loss
+        dist.all_reduce(self._loss, group=self.pg)
+        part.backward(ctx, d_out)                                          # weight gradients summed over ranks
+        self.optimizer_step()
+        return self._loss[0]
 
     def stage(self, batch) -> None:
         """Start the host-to-device copy of the NEXT step's batch (pinned host memory) on a side stream, so
@@ -102,6 +150,8 @@ class Trainer:
             for v in batch.__dict__.values():           # the side stream allocated these tensors
                 if torch.is_tensor(v):
                     v.record_stream(torch.cuda.current_stream(self.device))
+        if self._part is not None:
+            return self._partitioned_step(batch)
         if not self.use_cuda_graph:
             return self._training_step_eager(batch)
         from ..graph import Data, no_csr_cache

@@ -167,3 +167,34 @@ def test_node_partitioned_training_gradients_equal_unpartitioned():
         # values tip by one ulp (see tests/test_epd_gpu.py on how that propagates): 3e-2 in l2
         assert norm > 0 and err < 3e-2, err
 
+
+def _partition_trainer_worker(rank, world):
+    """Trainer.enable_node_partition: three optimizer steps on one mesh split over the ranks vs the same
+    Trainer on one GPU with the whole mesh."""
+    from graphphysics_b200.synthetic import cylinder_flow_batch
+    from graphphysics_b200.training.loop import Trainer
+    dev = torch.device("cuda", rank)
+    cfg = {"model": {"type": "epd", "message_passing_num": 3, "hidden_size": 128, "node_input_size": 2, "output_size": 2,
+                     "edge_input_size": 3},
+           "index": {"feature_index_start": 0, "feature_index_end": 2, "output_index_start": 0, "output_index_end": 2,
+                     "node_type_index": 2}}
+    batch = cylinder_flow_batch(1, nx=60, ny=30, seed=3).to(dev)
+    ref = Trainer(cfg, learning_rate=1e-3, num_steps=100, warmup=2, device=dev, seed=5)
+    l_ref = [float(ref.training_step(batch)) for _ in range(3)]
+    tr = Trainer(cfg, learning_rate=1e-3, num_steps=100, warmup=2, device=dev, process_group=dist.group.WORLD, seed=5)
+    tr.enable_node_partition(batch.pos, batch.edge_index)
+    l_part = [float(tr.training_step(batch)) for _ in range(3)]
+    drift = float((tr.engine.flat.data - ref.engine.flat.data).norm() / ref.engine.flat.data.norm())
+    flat = tr.engine.flat.data
+    other = flat.clone()
+    dist.broadcast(other, src=0)
+    return l_ref, l_part, drift, bool(torch.equal(other, flat))
+
+
+def test_trainer_node_partition_matches_single_gpu_training():
+    _need_two()
+    for l_ref, l_part, drift, same in _spawn(_partition_trainer_worker):
+        assert same, "ranks diverged"
+        assert np.allclose(l_part, l_ref, rtol=1e-2), (l_part, l_ref)
+        assert drift < 1e-2, drift
+
