@@ -138,3 +138,28 @@ def test_rollout_rmse_matches_reference_within_one_percent():
     assert abs(res["val_all_rollout_rmse"] - rall) < 1e-2 * rall
     got = torch.stack(res["predictions"]).cpu()
     assert l2_rel(got, torch.from_numpy(z["predictions"])) < 2e-2
+
+
+def test_graphed_rollout_equals_eager_rollout():
+    """Trainer.rollout under enable_cuda_graph(): the captured per-frame step gives the same predictions as
+    the eager loop, bit for bit, on the reference's mock trajectory."""
+    from graphphysics_b200.graph import Data
+    from graphphysics_b200.training.loop import Trainer
+    dev = torch.device("cuda:0")
+    z = np.load(os.path.join(G, "rollout.npz"))
+    cfg = {"model": {"type": "epd", "message_passing_num": 3, "hidden_size": 64, "node_input_size": 2, "output_size": 2,
+                     "edge_input_size": 3},
+           "index": {"feature_index_start": 0, "feature_index_end": 2, "output_index_start": 0, "output_index_end": 2,
+                     "node_type_index": 2}}
+    tr = Trainer(cfg, learning_rate=1e-3, num_steps=10, warmup=2, device=dev)
+    tr.model.load_state_dict({k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd/")}, strict=False)
+    ei, ea, pos = (torch.from_numpy(z[k]).to(dev) for k in ("edge_index", "edge_attr", "pos"))
+    frames = [Data(x=torch.from_numpy(x).to(dev), y=torch.from_numpy(y).to(dev), pos=pos, edge_index=ei, edge_attr=ea)
+              for x, y in zip(z["frames"], z["ys"])]
+    eager = tr.rollout(frames)
+    tr.enable_cuda_graph(True)
+    graphed = tr.rollout(frames)
+    again = tr.rollout(frames)                      # second call replays the cached graph
+    for a, b, c in zip(eager["predictions"], graphed["predictions"], again["predictions"]):
+        assert torch.equal(a, b) and torch.equal(a, c)
+    assert eager["val_all_rollout_rmse"] == graphed["val_all_rollout_rmse"] == again["val_all_rollout_rmse"]
