@@ -16,6 +16,8 @@ void set_error(const char* fmt, ...) {
 }
 
 static int g_sm_count = 0, g_smem_optin = 0, g_cc = 0;
+static bool g_launch_overlap = false;
+bool launch_overlap() { return g_launch_overlap; }
 static void probe_device() {
     if (g_sm_count) return;
     int dev = 0;
@@ -70,6 +72,11 @@ bool tma_map_2d(CUtensorMap* map, const void* base, long long rows, int cols, lo
 }  // namespace gp
 
 extern "C" int gp_version(void) { return 100; }
+extern "C" int gp_set_launch_overlap(int enabled) {
+    const int old = gp::g_launch_overlap ? 1 : 0;
+    gp::g_launch_overlap = enabled != 0;
+    return old;
+}
 extern "C" const char* gp_last_error(void) { return gp::g_err; }
 extern "C" int gp_device_info(int* out3) {
     GP_REQUIRE(out3 != nullptr, "gp_device_info: null output");

@@ -18,6 +18,26 @@ int max_smem_optin();
 // their per-thread copy path.
 bool tma_map_2d(CUtensorMap* map, const void* base, long long rows, int cols, long long ld);
 
+// Launch-overlap switch (gp_set_launch_overlap): when on, the persistent MLP kernels are launched with
+// programmatic stream serialization, so their prologue (weight staging, TMEM allocation) overlaps the tail
+// of the previous kernel in the stream.
+bool launch_overlap();
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = launch_overlap() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+
 #define GP_CHECK_CUDA(expr)                                                                    \
     do {                                                                                       \
         cudaError_t e__ = (expr);                                                              \

@@ -51,6 +51,10 @@ __global__ void __launch_bounds__(256, 1) linear_bwd_kernel(const gp_linear_bwd_
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    // everything above is independent of the previous kernel in the stream (parameters only); from here on
+    // its outputs are read, and the next kernel may start its own prologue
+    pdl_wait();
+    pdl_launch_dependents();
 
     const uint32_t tmem = tmem_slot;
     const uint32_t tlane = tmem_addr(tmem, (row >> 5) * 32, 0);
@@ -207,8 +211,7 @@ int launch(const gp_linear_bwd_args& a, int32_t* grid_out, cudaStream_t st) {
     }
     const int n_tiles = (a.rows + 127) / 128;
     const int grid = n_tiles < gp::sm_count() ? n_tiles : gp::sm_count();
-    linear_bwd_kernel<H><<<grid, 256, smem, st>>>(a, maps);
-    GP_CHECK_CUDA(cudaGetLastError());
+    GP_CHECK_CUDA(gp::launch_kernel(linear_bwd_kernel<H>, dim3(grid), dim3(256), smem, st, a, maps));
     if (grid_out) *grid_out = grid;
     return 0;
 }

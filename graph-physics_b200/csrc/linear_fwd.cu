@@ -53,6 +53,10 @@ __global__ void __launch_bounds__(256, 1) linear_fwd_kernel(const gp_mlp_fwd_arg
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    // everything above is independent of the previous kernel in the stream (parameters only); from here on
+    // its outputs are read, and the next kernel may start its own prologue
+    pdl_wait();
+    pdl_launch_dependents();
 
     const uint32_t tmem = tmem_slot;
     const uint32_t tlane = tmem_addr(tmem, (row >> 5) * 32, 0);
@@ -145,8 +149,7 @@ int try_linear_fwd(const gp_mlp_fwd_args& a, int hidden, cudaStream_t st) {
     }
     const int n_tiles = (a.rows + 127) / 128;
     const int grid = n_tiles < sm_count() ? n_tiles : sm_count();
-    linear_fwd_kernel<128><<<grid, 256, smem, st>>>(a, maps);
-    GP_CHECK_CUDA(cudaGetLastError());
+    GP_CHECK_CUDA(gp::launch_kernel(linear_fwd_kernel<128>, dim3(grid), dim3(256), smem, st, a, maps));
     return 1;
 }
 }  // namespace gp

@@ -161,6 +161,10 @@ __global__ void __launch_bounds__(BwdCfg<H>::NT, 1) mlp_bwd_kernel(const gp_mlp_
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    // everything above is independent of the previous kernel in the stream (parameters only); from here on
+    // its outputs are read, and the next kernel may start its own prologue
+    pdl_wait();
+    pdl_launch_dependents();
 
     const uint32_t tmem = tmem_slot;
     const uint32_t tlane = tmem_addr(tmem, (row >> 5) * 32, 0);
@@ -867,17 +871,19 @@ int launch_bwd(const gp_mlp_bwd_args& a, int32_t* grid_out, cudaStream_t st) {
     }
     const int n_tiles = (a.rows + 127) / 128;
     int grid = n_tiles < gp::sm_count() ? n_tiles : gp::sm_count();
+    const dim3 g3(grid), b3(BwdCfg<H>::NT);
+    cudaError_t le;
     if (fast == 1)
-        mlp_bwd_kernel<H, (H == 128 ? 1 : 0)><<<grid, BwdCfg<H>::NT, smem, st>>>(a, maps);
+        le = gp::launch_kernel(mlp_bwd_kernel<H, (H == 128 ? 1 : 0)>, g3, b3, smem, st, a, maps);
     else if (fast == 2)
-        mlp_bwd_kernel<H, (H == 128 ? 2 : 0)><<<grid, BwdCfg<H>::NT, smem, st>>>(a, maps);
+        le = gp::launch_kernel(mlp_bwd_kernel<H, (H == 128 ? 2 : 0)>, g3, b3, smem, st, a, maps);
     else if (fast == 3)
-        mlp_bwd_kernel<H, (H == 128 ? 3 : 0)><<<grid, BwdCfg<H>::NT, smem, st>>>(a, maps);
+        le = gp::launch_kernel(mlp_bwd_kernel<H, (H == 128 ? 3 : 0)>, g3, b3, smem, st, a, maps);
     else if (fast == 4)
-        mlp_bwd_kernel<H, (H == 128 ? 4 : 0)><<<grid, BwdCfg<H>::NT, smem, st>>>(a, maps);
+        le = gp::launch_kernel(mlp_bwd_kernel<H, (H == 128 ? 4 : 0)>, g3, b3, smem, st, a, maps);
     else
-        mlp_bwd_kernel<H, 0><<<grid, BwdCfg<H>::NT, smem, st>>>(a, maps);
-    GP_CHECK_CUDA(cudaGetLastError());
+        le = gp::launch_kernel(mlp_bwd_kernel<H, 0>, g3, b3, smem, st, a, maps);
+    GP_CHECK_CUDA(le);
     if (grid_out) *grid_out = grid;
     return 0;
 }

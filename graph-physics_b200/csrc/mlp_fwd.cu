@@ -123,6 +123,10 @@ __global__ void __launch_bounds__(kSlotThreads * NG, 1) mlp_fwd_kernel(const gp_
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    // everything above is independent of the previous kernel in the stream (parameters only); from here on
+    // its outputs are read, and the next kernel may start its own prologue
+    pdl_wait();
+    pdl_launch_dependents();
 
     const uint32_t tmem_base = tmem_slot;
     const uint32_t tacc_mma = tmem_base + g_u * 128;                             // D operand (lane 0)
@@ -538,8 +542,7 @@ int launch_fwd(const gp_mlp_fwd_args& a, cudaStream_t st) {
         for (int i = 0; i < 3; ++i)
             if (sv[i] && gp::tma_map_2d(&maps.h[i], sv[i], a.rows, H, H)) maps.use |= kMapH << i;
     }
-    mlp_fwd_kernel<H, NG, kMode><<<grid, kSlotThreads * NG, smem, st>>>(a, maps);
-    GP_CHECK_CUDA(cudaGetLastError());
+    GP_CHECK_CUDA(gp::launch_kernel(mlp_fwd_kernel<H, NG, kMode>, dim3(grid), dim3(kSlotThreads * NG), smem, st, a, maps));
     return 0;
 }
 }  // namespace

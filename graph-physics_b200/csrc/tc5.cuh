@@ -89,6 +89,13 @@ __device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// A kernel launched with the programmatic-stream-serialization attribute may start while the previous
+// kernel of the stream is still draining; everything it does before pdl_wait() must be independent of
+// that kernel (it is used for the weight staging / TMEM allocation prologue).  No-ops otherwise.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---------------------------------------------------------------- warp-uniform helpers
 // Value of lane 0, which the compiler can treat as warp-uniform (kept in uniform registers: the
 // tcgen05.mma descriptors are then built with uniform-datapath adds instead of a per-MMA

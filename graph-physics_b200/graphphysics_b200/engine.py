@@ -59,6 +59,9 @@ class EPDEngine:
         # tile buffer until the copy engine has read it) than the backward gains from skipping the
         # recompute: 15.4 vs 14.3 ms/step on the benchmark.  Kept as an option.
         self.save_all = os.environ.get("GP_B200_SAVE_ALL", "0") == "1"
+        # the engine packs the operand copies of the weights once per step, several launches before any MLP
+        # kernel reads them, so the kernels may overlap their prologue with the previous kernel's tail
+        self._overlap = os.environ.get("GP_B200_NO_PDL") is None
         self._build_flat()
         self._build_packed()
         H = self.H
@@ -216,7 +219,24 @@ class EPDEngine:
         self._mlp(self.node[l], N, agg, H, x2, H, **self._save_kw(h2n), resid=x, init=P, init_off0=2 * H)
         return x2, e2, ((x, e, P, agg, h2e, h2n) if save else None)
 
-    def forward(self, x_in: torch.Tensor, edge_attr: torch.Tensor, g: GraphCSR, save: bool, after_block=None):
+    def forward(self, *args, **kwargs):
+        """See _forward.  Launch overlap (programmatic dependent launch) is on only inside the engine's own
+        launch sequences, where no parameter tensor is written right before an MLP kernel."""
+        prev = ops.set_launch_overlap(self._overlap)
+        try:
+            return self._forward(*args, **kwargs)
+        finally:
+            ops.set_launch_overlap(prev)
+
+    def backward(self, *args, **kwargs):
+        """See _backward (launch overlap as in forward)."""
+        prev = ops.set_launch_overlap(self._overlap)
+        try:
+            return self._backward(*args, **kwargs)
+        finally:
+            ops.set_launch_overlap(prev)
+
+    def _forward(self, x_in: torch.Tensor, edge_attr: torch.Tensor, g: GraphCSR, save: bool, after_block=None):
         """x_in [N, node_in] / edge_attr [E, edge_in] fp32 in the caller's edge order (latent
         [N,H] / [E,H] when only_processor).  Returns (out, e_last_sorted, ctx).
         `after_block(x)` (optional) runs on the node latent after the encoder and after every block
@@ -314,7 +334,7 @@ class EPDEngine:
                                   delta_a_out=delta_a_out, tag=(tag + "_A") if tag else None, **kw)
         self._reduce_stage(gridA, ka, H, s, 0, 1, False)
 
-    def backward(self, ctx, d_out: torch.Tensor, dE_sorted: Optional[torch.Tensor] = None, before_block=None):
+    def _backward(self, ctx, d_out: torch.Tensor, dE_sorted: Optional[torch.Tensor] = None, before_block=None):
         """Fills self.gflat with d loss / d parameters.  d_out is d loss / d output ([N,out] fp32, or
         [N,H] with only_processor); dE_sorted (bf16, receiver-sorted) is the gradient of the last
         edge latent when somebody consumes it.  Returns (dX_in, dE_in_sorted) for only_processor.

@@ -159,6 +159,13 @@ def mlp_fwd(
     return out
 
 
+def set_launch_overlap(enabled: bool) -> bool:
+    """gp_set_launch_overlap: programmatic dependent launch for the persistent MLP kernels (their weight-staging
+    prologue overlaps the tail of the previous kernel).  Safe when the packed weights / biases are not written
+    by the launch immediately before an MLP kernel, which holds for the engine.  Returns the previous setting."""
+    return bool(lib().gp_set_launch_overlap(1 if enabled else 0))
+
+
 def seg_fixup(rowptr: torch.Tensor, hidden: int, seg_bnd: torch.Tensor, seg_out: torch.Tensor,
               backward: bool = False) -> None:
     assert rowptr.dtype == torch.int32

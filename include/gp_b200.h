@@ -27,6 +27,12 @@ int gp_version(void);
 const char* gp_last_error(void);
 /* out[0]=SM count, out[1]=max dynamic smem per block, out[2]=compute capability major*10+minor */
 int gp_device_info(int* out3);
+/* Launch overlap (programmatic dependent launch): when enabled (returns the previous setting; default off),
+ * gp_mlp_fwd / gp_mlp_bwd_stage / gp_linear_bwd start while the previous kernel of the stream is still
+ * draining and stage their packed weights, biases and scales before waiting for it.  Enable only when those
+ * parameter tensors are never written by the kernel launched immediately before one of these calls (the
+ * engine packs the weights once per step, several launches earlier). */
+int gp_set_launch_overlap(int enabled);
 
 /* ---------------------------------------------------------------------------------------------
  * Fused row-tile MLP forward (tcgen05).  Replaces the nn.Sequential built by build_mlp
