@@ -233,7 +233,7 @@ def main():
     # dram__bytes_read.sum + dram__bytes_write.sum per launch of the same kernels on this workload, from the
     # `ncu --set full` captures summarised in profiles/r01_final_summary.md (below the algorithmic bytes: the
     # gathered rows and the residual tile hit L2)
-    ncu_dram_bytes = {"edge_fwd": 216.5e6, "edge_bwd_B": 286.6e6, "edge_bwd_A": 518.1e6} if (E, N, H) == (372752, 64424, 128) else {}
+    ncu_dram_bytes = {"edge_fwd": 220.5e6, "edge_bwd_B": 284.2e6, "edge_bwd_A": 517.7e6} if (E, N, H) == (372752, 64424, 128) else {}
     roof = None
     if prof:
         top = max(prof, key=lambda k: prof[k]["total_ms"])
