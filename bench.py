@@ -261,6 +261,20 @@ def main():
                         "pipeline": "next batch copied (pinned host -> device, side stream) during the current step; loss .item() every step",
                         "ms_per_step": ms_e2e / args.steps, "train_steps_per_s": args.steps / (ms_e2e * 1e-3)},
                 "gpu_launches": launches, "clocks": clocks, "roofline": roof, "loss_last": loss_host[-1]}
+        if world == 1:
+            # secondary figure (outside every timed region above): autoregressive roll-out on ONE mesh of the same
+            # shape, per-frame step replayed from a CUDA graph -- the reference's validation loop (R1)
+            try:
+                one = cylinder_flow_batch(1, seed=0).to(dev)
+                tr.rollout([one] * 5)
+                torch.cuda.synchronize()
+                t0 = time.time()
+                tr.rollout([one] * 100)
+                torch.cuda.synchronize()
+                line["rollout"] = {"frames_per_s": 100 / (time.time() - t0), "nodes": int(one.x.shape[0]),
+                                   "directed_edges": int(one.edge_index.shape[1]), "launch": "cuda-graph replay" if graphed else "eager"}
+            except Exception as exc:       # never let the side figure break the contract line
+                line["rollout"] = {"error": str(exc)[:200]}
         if world == 1 and not args.no_cpu_baseline:
             cb = run_reference(args)
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
