@@ -71,7 +71,16 @@ bool tma_map_2d(CUtensorMap* map, const void* base, long long rows, int cols, lo
 }
 }  // namespace gp
 
-extern "C" int gp_version(void) { return 100; }
+extern "C" int gp_version(void) { return 200; }
+// sizeof of the argument structs as this library was compiled: a binding checks its own layout against it
+extern "C" int gp_sizeof_struct(const char* name) {
+    if (!name) return -1;
+#define GP_SZ(T) if (!strcmp(name, #T)) return (int)sizeof(T);
+    GP_SZ(gp_mlp_fwd_args) GP_SZ(gp_mlp_bwd_args) GP_SZ(gp_linear_bwd_args) GP_SZ(gp_pack_entry) GP_SZ(gp_reduce_seg)
+    GP_SZ(gp_attention_args)
+#undef GP_SZ
+    return -1;
+}
 extern "C" int gp_set_launch_overlap(int enabled) {
     const int old = gp::g_launch_overlap ? 1 : 0;
     gp::g_launch_overlap = enabled != 0;

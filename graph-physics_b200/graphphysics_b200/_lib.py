@@ -147,7 +147,6 @@ class LinearBwdArgs(C.Structure):
         ("dx_in", C.c_void_p),
         ("dx_out", C.c_void_p),
         ("partials", C.c_void_p),
-        ("prof", C.c_void_p),
     ]
 
 

@@ -92,13 +92,28 @@ class EPDEngine:
         self.offsets: Dict[str, int] = offs
         self.shapes = {name: tuple(p.shape) for name, p in named}
         self.numels = {name: p.numel() for name, p in named}
+        self.bind_param_grads()
+
+    def bind_param_grads(self) -> None:
+        """Every nn.Parameter's `.grad` is a view of the flat gradient buffer the backward kernels write,
+        so torch optimizers, `clip_grad_norm_(model.parameters())` and Lightning's `configure_optimizers`
+        see the gradients (the parameters themselves are views of `flat`, so in-place updates land there).
+        Each backward OVERWRITES the buffer (zero_grad-then-backward semantics, what the reference's
+        training_step does); re-bound after every backward because `zero_grad(set_to_none=True)` drops it."""
+        for name, p in self.model.named_parameters():
+            o = self.offsets[name]
+            g = p.grad
+            if g is None or g.data_ptr() != self.gflat.data_ptr() + 4 * o:
+                p.grad = self.gflat[o:o + p.numel()].view(p.shape)
 
     def is_bound(self) -> bool:
-        """False once somebody replaced the parameter storage (e.g. model.to(...)): rebuild then."""
+        """False once somebody replaced the storage of ANY parameter (model.to(...), load_state_dict(assign=True),
+        a standalone engine built on one of the blocks): the owner rebuilds the engine then."""
         base = self.flat.data_ptr()
-        for name, p in self.model.named_parameters():
-            return p.data_ptr() == base + 4 * self.offsets[name]
-        return True
+        named = list(self.model.named_parameters())
+        if len(named) != len(self.offsets):
+            return False
+        return all(name in self.offsets and p.data_ptr() == base + 4 * self.offsets[name] for name, p in named)
 
     def views_of(self, buf: torch.Tensor) -> Dict[str, torch.Tensor]:
         return {n: buf[o:o + self.numels[n]].view(self.shapes[n]) for n, o in self.offsets.items()}
@@ -450,6 +465,7 @@ class EPDFunction(torch.autograd.Function):
         eng = ctx.engine
         eng.backward(ctx.saved, d_out.contiguous())
         ctx.saved = None
+        eng.bind_param_grads()
         gflat = eng.gflat
         if eng.flat.grad is not None and eng.flat.grad.data_ptr() == gflat.data_ptr():
             gflat = gflat.clone()        # autograd would otherwise add the buffer to itself
@@ -473,6 +489,7 @@ class BlockFunction(torch.autograd.Function):
         de_sorted = de[g.perm_dst64].to(torch.bfloat16).contiguous()
         dX, dE = eng.backward(ctx.saved, dx.contiguous(), de_sorted)
         ctx.saved = None
+        eng.bind_param_grads()
         ge = torch.empty((g.num_edges, eng.H), dtype=torch.float32, device=dx.device)
         ge[g.perm_dst64] = dE.float()
         gflat = eng.gflat

@@ -70,8 +70,38 @@ class Trainer:
         return self.processor.engine if self.fused else self._flat
 
     def current_lr(self) -> float:
-        """LR used by the next optimizer step (CosineWarmupScheduler, scheduler.py:51-67)."""
-        return self.learning_rate * lr_factor(self.step_index - 1, self.warmup, self.num_steps)
+        """LR the LAST completed optimizer step used (what Lightning's LR monitor logs after a step;
+        CosineWarmupScheduler, scheduler.py:51-67).  Before the first step: the LR of step 0."""
+        return self.learning_rate * lr_factor(max(self.step_index - 1, 0), self.warmup, self.num_steps)
+
+    def next_lr(self) -> float:
+        """LR the next optimizer step will use."""
+        return self.learning_rate * lr_factor(self.step_index, self.warmup, self.num_steps)
+
+    # ------------------------------------------------------------------ checkpoint / resume
+    def state_dict(self) -> Dict[str, Any]:
+        """Everything a resumed run needs to continue bit-identically (the reference resumes from a Lightning
+        checkpoint holding model, optimizer and scheduler state, train.py:228-262): Simulator weights and
+        normaliser statistics (reference keys), AdamW moments over the flat parameter buffer, the device-side
+        optimizer step counter and the host step index."""
+        return {"model": {k: v.detach().clone() for k, v in self.model.state_dict().items()},
+                "exp_avg": self.exp_avg.clone(), "exp_avg_sq": self.exp_avg_sq.clone(),
+                "opt_state": self._opt_state.clone(), "step_index": int(self.step_index),
+                "hparams": {"learning_rate": self.learning_rate, "num_steps": self.num_steps, "warmup": self.warmup}}
+
+    def load_state_dict(self, state: Dict[str, Any]) -> None:
+        """In-place restore: every buffer keeps its address, so captured CUDA graphs stay valid."""
+        self.model.load_state_dict(state["model"])              # copies into the flat buffer's views in place
+        eng = self.engine
+        if hasattr(eng, "is_bound") and not eng.is_bound():
+            raise RuntimeError("load_state_dict re-allocated parameter storage (assign=True is not supported here)")
+        self.exp_avg.copy_(state["exp_avg"])
+        self.exp_avg_sq.copy_(state["exp_avg_sq"])
+        self._opt_state.copy_(state["opt_state"])
+        self.step_index = int(state["step_index"])
+        for norm in (self.model._output_normalizer, self.model._node_normalizer, self.model._edge_normalizer):
+            if norm is not None:
+                norm._host_calls = None                          # re-read the device counter once
 
     def enable_cuda_graph(self, enabled: bool = True) -> None:
         """Capture the whole step (CSR build, forward, loss, backward, clip, AdamW, schedule) once per

@@ -27,6 +27,9 @@ int gp_version(void);
 const char* gp_last_error(void);
 /* out[0]=SM count, out[1]=max dynamic smem per block, out[2]=compute capability major*10+minor */
 int gp_device_info(int* out3);
+/* sizeof(struct `name`) as compiled into the library ("gp_mlp_fwd_args", ...; -1 = unknown name): lets a
+ * binding (ctypes / cffi stub) verify its own struct layout before the first call. */
+int gp_sizeof_struct(const char* name);
 /* Launch overlap (programmatic dependent launch): when enabled (returns the previous setting; default off),
  * gp_mlp_fwd / gp_mlp_bwd_stage / gp_linear_bwd start while the previous kernel of the stream is still
  * draining and stage their packed weights, biases and scales before waiting for it.  Enable only when those

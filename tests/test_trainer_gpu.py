@@ -1,0 +1,84 @@
+"""GPU: host-side contracts of the engine / Trainer that the reference's users rely on --
+torch optimizers see gradients, checkpoints resume bit-identically."""
+import copy
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+CFG = {"model": {"type": "epd", "message_passing_num": 2, "hidden_size": 32, "node_input_size": 2, "output_size": 2,
+                 "edge_input_size": 3},
+       "index": {"feature_index_start": 0, "feature_index_end": 2, "output_index_start": 0, "output_index_end": 2,
+                 "node_type_index": 2}}
+
+
+def _batch(seed=0):
+    from graphphysics_b200.synthetic import cylinder_flow_batch
+    return cylinder_flow_batch(2, nx=20, ny=10, seed=seed)
+
+
+def test_torch_optimizer_and_clip_see_the_gradients():
+    """nn.Parameter.grad must be populated (views of the flat gradient buffer), so a stock
+    torch optimizer / clip_grad_norm_ built on model.parameters() works as in the reference's
+    configure_optimizers (lightning_module.py:494-511)."""
+    from graphphysics_b200.graph import Data
+    from graphphysics_b200.models.processors import EncodeProcessDecode
+    dev = torch.device("cuda:0")
+    torch.manual_seed(0)
+    b = _batch().to(dev)
+    model = EncodeProcessDecode(2, 11, 3, 2, hidden_size=32).to(dev)
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-2)
+    x = torch.randn(b.x.shape[0], 11, device=dev)
+    before = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    for it in range(2):                         # second round: zero_grad(set_to_none=True) dropped the views
+        opt.zero_grad()
+        out = model(Data(x=x, edge_index=b.edge_index, edge_attr=b.edge_attr))
+        out.square().mean().backward()
+        grads = model.engine.grads_by_name()
+        for name, p in model.named_parameters():
+            assert p.grad is not None, name
+            assert torch.equal(p.grad, grads[name]), name
+        total = torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
+        assert torch.isfinite(total) and float(total) > 0
+        opt.step()
+    after = model.state_dict()
+    changed = sum(int(not torch.equal(before[k], after[k])) for k in before)
+    assert changed == len(before), f"only {changed} of {len(before)} tensors were updated"
+    assert model.engine.is_bound()
+    # a parameter whose storage was replaced un-binds the engine (every parameter is checked, not the first)
+    last = list(model.parameters())[-1]
+    last.data = last.data.clone()
+    assert not model.engine.is_bound()
+
+
+@pytest.mark.parametrize("graphed", [False, True])
+def test_trainer_resume_is_bit_identical(graphed):
+    """Trainer.state_dict / load_state_dict carry AdamW moments, the device step counter, the
+    schedule position and the normalisers; 3 + 3 steps with a save/load in between equal 6 straight steps."""
+    from graphphysics_b200.training.loop import Trainer
+    dev = torch.device("cuda:0")
+    batches = [_batch(s).to(dev) for s in range(6)]
+
+    def make():
+        tr = Trainer(copy.deepcopy(CFG), learning_rate=1e-3, num_steps=50, warmup=4, device=dev, seed=0)
+        tr.enable_cuda_graph(graphed)
+        return tr
+
+    a = make()
+    la = [float(a.training_step(b)) for b in batches]
+    b1 = make()
+    lb = [float(b1.training_step(b)) for b in batches[:3]]
+    state = copy.deepcopy(b1.state_dict())
+    b2 = make()
+    b2.training_step(batches[5])                   # dirty every buffer first
+    b2.load_state_dict(state)
+    assert b2.step_index == 3 and b2.next_lr() == a.learning_rate * __import__(
+        "graphphysics_b200.utils.scheduler", fromlist=["lr_factor"]).lr_factor(3, 4, 50)
+    lb += [float(b2.training_step(b)) for b in batches[3:]]
+    assert la == lb, (la, lb)
+    sa, sb = a.model.state_dict(), b2.model.state_dict()
+    for k in sa:
+        assert torch.equal(sa[k], sb[k]), k
+    assert torch.equal(a.exp_avg, b2.exp_avg) and torch.equal(a.exp_avg_sq, b2.exp_avg_sq)
