@@ -1,0 +1,133 @@
+"""Generate the reference goldens for the BENCHMARKED configuration and for cylinder.json verbatim
+(build container only; TEST INFRASTRUCTURE).
+
+    python oracle/make_golden_bench.py
+
+Uses the UNMODIFIED reference modules through oracle/ref_shim.py.
+
+  tests/golden/epd_l15_h128.npz   EncodeProcessDecode(15, 2+9, 3, 2, hidden 128) -- BASELINE configs[1] -- on ONE
+      graph of the benchmark batch (graphphysics_b200.synthetic.cylinder_flow_batch(1, seed=0)): output, scalar,
+      every gradient's norm and the full gradients of a spread of tensors.  The 2.87 M weights are NOT stored:
+      they are oracle.cpu_train.default_state_dict(seed=0) (reference default init under a fixed seed), and the
+      fixture holds per-tensor checksums so that a drift of torch's RNG / init is detected instead of mis-read
+      as a parity failure.
+  tests/golden/cylinder_json_step.npz   training_config/cylinder.json verbatim (epd, 5 layers, hidden 32) on the
+      reference's own mock cylinder trajectory (tests/mock_vtu, real velocities): three training steps
+      (Simulator + L2Loss + clip + AdamW + CosineWarmupScheduler) and one eval-mode one-step prediction."""
+from __future__ import annotations
+
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "graph-physics_b200"))
+from oracle import gp_oracle as O  # noqa: E402
+from oracle import ref_shim  # noqa: E402
+from oracle.cpu_train import default_state_dict  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+FULL_GRADS = ["decode_module.6.weight", "decode_module.6.bias", "decode_module.0.weight", "nodes_encoder.0.weight",
+              "nodes_encoder.7.scale", "edges_encoder.0.weight", "edges_encoder.6.bias",
+              "processor_list.0.edge_block.0.bias", "processor_list.0.edge_block.7.scale", "processor_list.0.node_block.6.weight",
+              "processor_list.7.edge_block.2.bias", "processor_list.7.node_block.7.scale", "processor_list.7.edge_block.6.bias",
+              "processor_list.14.edge_block.0.bias", "processor_list.14.node_block.0.bias", "processor_list.14.node_block.7.scale"]
+
+
+def bench_graph():
+    from graphphysics_b200.synthetic import cylinder_flow_batch
+    b = cylinder_flow_batch(1, seed=0)
+    return b
+
+
+def main():
+    ref = ref_shim.import_reference()
+    processors, simulator = ref["processors"], ref["simulator"]
+    NT = ref["nodetype"].NodeType
+    from torch_geometric.data import Data
+    torch.set_num_threads(8)
+
+    # ---------------------------------------------------------------- 1) benchmark configuration
+    L, H = 15, 128
+    b = bench_graph()
+    N, E = b.x.shape[0], b.edge_index.shape[1]
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(N, 11, generator=g)
+    ea = torch.randn(E, 3, generator=g)
+    G = torch.randn(N, 2, generator=g)
+    sd = default_state_dict(L, 11, 3, 2, H, seed=0)
+    model = processors.EncodeProcessDecode(L, 11, 3, 2, hidden_size=H)
+    model.load_state_dict(sd)
+    out = model(Data(x=x, edge_index=b.edge_index, edge_attr=ea))
+    s = (out * G).sum()
+    s.backward()
+    grads = {k: p.grad for k, p in model.named_parameters()}
+    np.savez_compressed(
+        f"{OUT}/epd_l15_h128.npz", x=x.numpy(), edge_attr=ea.numpy(), edge_index=b.edge_index.numpy(), G=G.numpy(),
+        out=out.detach().numpy(), scalar=np.float64(s.item()), L=L, H=H,
+        **{"gnorm/" + k: np.float64(v.double().norm().item()) for k, v in grads.items()},
+        **{"grad/" + k: grads[k].numpy() for k in FULL_GRADS},
+        **{"sdsum/" + k: np.array([v.double().sum().item(), v.double().abs().sum().item()]) for k, v in sd.items()})
+    print(f"epd_l15_h128: N={N} E={E} params={sum(v.numel() for v in sd.values())} |out|={out.norm().item():.4f} scalar={s.item():.6f}")
+
+    # ---------------------------------------------------------------- 2) cylinder.json verbatim
+    cfg = json.load(open(f"{ref_shim.REFERENCE_ROOT}/training_config/cylinder.json"))
+    m, index = cfg["model"], cfg["index"]
+    z = np.load(f"{OUT}/cylinder_mesh.npz")
+    pos = z["points"][:, :2].astype(np.float32)
+    ei = O.face_to_edge(z["triangles"].astype(np.int64), len(pos))
+    ea = O.edge_features(pos, ei)
+    vel = z["velocity"]
+    N = len(pos)
+    nt = np.zeros(N, np.int64)
+    nt[pos[:, 0] < pos[:, 0].min() + 1e-6] = int(NT.INFLOW)
+    nt[pos[:, 0] > pos[:, 0].max() - 1e-6] = int(NT.OUTFLOW)
+    nt[(pos[:, 1] < pos[:, 1].min() + 1e-6) | (pos[:, 1] > pos[:, 1].max() - 1e-6)] = int(NT.WALL_BOUNDARY)
+    T = vel.shape[0] - 1
+    frames = [torch.cat([torch.from_numpy(vel[t]), torch.from_numpy(nt)[:, None].float(), torch.full((N, 1), float(t))], 1)
+              for t in range(T)]
+    ys = [torch.from_numpy(vel[t + 1]) for t in range(T)]
+    ei_t, ea_t, pos_t = torch.from_numpy(ei), torch.from_numpy(ea), torch.from_numpy(pos)
+    torch.manual_seed(21)
+    # parse_parameters.py:96, 177: the model's node input is the JSON value + the 9-wide one-hot node type
+    model = processors.EncodeProcessDecode(m["message_passing_num"], m["node_input_size"] + 9, m["edge_input_size"],
+                                           m["output_size"], hidden_size=m["hidden_size"])
+    sd0 = {k: v.clone() for k, v in model.state_dict().items()}
+    sim = simulator.Simulator(node_input_size=m["node_input_size"] + 9, edge_input_size=m["edge_input_size"],
+                              output_size=m["output_size"], model=model, device=torch.device("cpu"), **index)
+    opt = torch.optim.AdamW(sim.parameters(), lr=1e-3, weight_decay=1e-4, betas=(0.9, 0.95))
+    sch = ref["scheduler"].CosineWarmupScheduler(opt, warmup=2, max_iters=10)
+    lossf = ref["loss"].L2Loss()
+    losses, lrs, gn = [], [], []
+    sim.train()
+    for st in range(3):
+        bb = Data(x=frames[st].clone(), y=ys[st], pos=pos_t, edge_index=ei_t, edge_attr=ea_t)
+        net, tgt, _ = sim(bb)
+        loss = lossf(tgt, net, bb.x[:, index["node_type_index"]], masks=[NT.NORMAL, NT.OUTFLOW])
+        opt.zero_grad()
+        loss.backward()
+        gn.append(float(torch.nn.utils.clip_grad_norm_(sim.parameters(), 1.0)))
+        lrs.append(opt.param_groups[0]["lr"])
+        opt.step()
+        sch.step()
+        losses.append(loss.item())
+    sim.eval()
+    with torch.no_grad():
+        bb = Data(x=frames[3].clone(), y=ys[3], pos=pos_t, edge_index=ei_t, edge_attr=ea_t)
+        net, tgt, outp = sim(bb)
+    np.savez_compressed(f"{OUT}/cylinder_json_step.npz", pos=pos, edge_index=ei, edge_attr=ea, frames=torch.stack(frames).numpy(),
+                        ys=torch.stack(ys).numpy(), losses=np.array(losses), lrs=np.array(lrs), grad_norms=np.array(gn),
+                        eval_net=net.numpy(), eval_target=tgt.numpy(), eval_outputs=outp.numpy(),
+                        **{"sd0/" + k: v.numpy() for k, v in sd0.items()},
+                        **{"sd3/" + k: v.detach().numpy() for k, v in sim.state_dict().items()})
+    print("cylinder_json_step: losses", losses, "lrs", lrs, "grad norms", gn)
+    for f in ("epd_l15_h128.npz", "cylinder_json_step.npz"):
+        print(f"  {f:28s} {os.path.getsize(os.path.join(OUT, f)) / 1024:8.1f} KiB")
+
+
+if __name__ == "__main__":
+    main()

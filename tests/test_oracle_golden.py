@@ -133,3 +133,56 @@ def test_rollout_matches_reference():
     preds, r1, rall = O.rollout(step, list(frames), list(ys), 0, 2, 2)
     np.testing.assert_allclose(torch.stack(preds).numpy(), z["predictions"], rtol=1e-3, atol=1e-5)
     assert abs(r1 - float(z["val_1step_rmse"])) < 1e-5 and abs(rall - float(z["val_all_rollout_rmse"])) < 1e-5
+
+
+def _bench_golden():
+    """tests/golden/epd_l15_h128.npz (oracle/make_golden_bench.py): the weights are default_state_dict(seed=0),
+    verified against the fixture's checksums before anything is compared."""
+    from oracle.cpu_train import default_state_dict
+    z = np.load(os.path.join(G, "epd_l15_h128.npz"))
+    sd = default_state_dict(int(z["L"]), 11, 3, 2, int(z["H"]), seed=0)
+    for k, v in sd.items():
+        got = np.array([v.double().sum().item(), v.double().abs().sum().item()])
+        assert np.allclose(got, z["sdsum/" + k], rtol=1e-9, atol=1e-12), \
+            f"default init of {k} is not the one the golden was made with (torch RNG / init changed): regenerate"
+    return z, sd
+
+
+def test_benchmark_config_l15_h128_matches_reference():
+    """The oracle at the BENCHMARKED depth and width (BASELINE configs[1]: 15 layers, hidden 128) on one graph of the
+    benchmark batch, against the reference's own modules: output, scalar, every gradient's norm, 16 full gradients."""
+    torch.set_num_threads(8)
+    z, sd = _bench_golden()
+    sd = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    out = O.epd_forward(sd, torch.from_numpy(z["x"]), torch.from_numpy(z["edge_attr"]), torch.from_numpy(z["edge_index"]), 15)
+    np.testing.assert_allclose(out.detach().numpy(), z["out"], rtol=2e-4, atol=2e-5)
+    s = (out * torch.from_numpy(z["G"])).sum()
+    assert abs(s.item() - float(z["scalar"])) < 1e-4
+    s.backward()
+    for k, p in sd.items():
+        gn = float(z["gnorm/" + k])
+        assert abs(p.grad.double().norm().item() - gn) <= 1e-3 * gn + 1e-7, k
+        if "grad/" + k in z.files:
+            ref = z["grad/" + k]
+            assert np.linalg.norm(p.grad.numpy() - ref) <= 1e-3 * np.linalg.norm(ref) + 1e-7, k
+
+
+def test_cylinder_json_verbatim_matches_reference():
+    """training_config/cylinder.json verbatim on the reference's mock cylinder trajectory: three training steps and
+    an eval step of the reference (tests/golden/cylinder_json_step.npz) reproduced by the oracle's CPU trainer."""
+    import json
+    cfg = json.load(open(os.path.join(G, "training_configs.json")))["cylinder"]
+    m, index = cfg["model"], cfg["index"]
+    z = np.load(os.path.join(G, "cylinder_json_step.npz"))
+    sd0 = {k[4:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd0/")}
+    tr = CpuTrainer(sd0, m["message_passing_num"], index, m["output_size"], m["node_input_size"] + 9, m["edge_input_size"],
+                    lr=1e-3, num_steps=10, warmup=2)
+    ei, ea = torch.from_numpy(z["edge_index"]), torch.from_numpy(z["edge_attr"])
+    frames, ys = torch.from_numpy(z["frames"]), torch.from_numpy(z["ys"])
+    for s in range(3):
+        loss = tr.training_step(frames[s], ys[s], ea, ei)
+        assert abs(loss - z["losses"][s]) <= 2e-5 * max(1.0, abs(z["losses"][s])), (s, loss, z["losses"][s])
+    with torch.no_grad():
+        net, tgt, outp = tr.forward(frames[3], ys[3], ea, ei, training=False)
+    np.testing.assert_allclose(net.numpy(), z["eval_net"], rtol=5e-3, atol=5e-5)
+    np.testing.assert_allclose(outp.numpy(), z["eval_outputs"], rtol=5e-3, atol=5e-5)
