@@ -23,11 +23,19 @@ import types
 import torch
 import torch.nn as nn
 
-REFERENCE_ROOT = "/root/reference"
+import os
+
+# The reference tree in the build container; on the GPU box (no /root/reference) the copy staged by
+# oracle/build_ref.py into the git-ignored oracle/_ref/.
+_STAGED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+REFERENCE_ROOT = "/root/reference" if os.path.isdir("/root/reference/graphphysics") else _STAGED
 
 
-def install():
+def install(root: str = None):
+    root = root or REFERENCE_ROOT
     if "torch_geometric" in sys.modules and getattr(sys.modules["torch_geometric"], "_gp_shim", False):
+        if root not in sys.path:
+            sys.path.insert(0, root)
         return
     tg = types.ModuleType("torch_geometric")
     tg._gp_shim = True
@@ -108,13 +116,13 @@ def install():
 
     sys.modules.update({"torch_geometric": tg, "torch_geometric.nn": tg_nn, "torch_geometric.data": tg_data,
                         "dgl": dgl, "dgl.sparse": dglsp})
-    if REFERENCE_ROOT not in sys.path:
-        sys.path.insert(0, REFERENCE_ROOT)
+    if root not in sys.path:
+        sys.path.insert(0, root)
 
 
-def import_reference():
+def import_reference(root: str = None):
     """Returns the reference modules (layers, processors, simulator, loss, scheduler, nodetype)."""
-    install()
+    install(root)
     import importlib
     names = ["graphphysics.models.layers", "graphphysics.models.processors", "graphphysics.models.simulator",
              "graphphysics.utils.loss", "graphphysics.utils.scheduler", "graphphysics.utils.nodetype"]

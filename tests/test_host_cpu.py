@@ -193,11 +193,16 @@ def test_bench_reference_arm_prints_the_contract_line():
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+    from oracle import build_ref
+    build_ref.main()                   # stages the reference modules when /root/reference is present (build container)
+    staged = os.path.exists(os.path.join(root, "oracle", "_ref", "MANIFEST.json"))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
+                          "--ref-graphs", "2"],
                          capture_output=True, text=True, timeout=600, check=True).stdout.strip().splitlines()[-1]
     line = json.loads(out)
     for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
               "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
         assert k in line, k
-    assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port"
+    assert line["impl"] == "reference" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == ("reference" if staged else "port")      # the reference's own modules when staged
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
