@@ -46,11 +46,14 @@ def test_torch_optimizer_and_clip_see_the_gradients():
     after = model.state_dict()
     changed = sum(int(not torch.equal(before[k], after[k])) for k in before)
     assert changed == len(before), f"only {changed} of {len(before)} tensors were updated"
-    assert model.engine.is_bound()
-    # a parameter whose storage was replaced un-binds the engine (every parameter is checked, not the first)
+    eng = model.engine
+    assert eng.is_bound()
+    # a parameter whose storage was replaced un-binds the engine (every parameter is checked, not the first);
+    # the `engine` property then builds a fresh one over the current values
     last = list(model.parameters())[-1]
     last.data = last.data.clone()
-    assert not model.engine.is_bound()
+    assert not eng.is_bound()
+    assert model.engine is not eng and model.engine.is_bound()
 
 
 @pytest.mark.parametrize("graphed", [False, True])
