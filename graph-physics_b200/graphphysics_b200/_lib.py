@@ -189,3 +189,20 @@ class AttentionArgs(C.Structure):
         ("dq", C.c_void_p), ("dk", C.c_void_p), ("dv", C.c_void_p),
         ("edge_a", C.c_void_p), ("edge_ds", C.c_void_p),
     ]
+
+
+class Gemm3Args(C.Structure):
+    _fields_ = [
+        ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32),
+        ("a", C.c_void_p), ("a_sm", C.c_int64), ("a_sk", C.c_int64),
+        ("b", C.c_void_p), ("b_sn", C.c_int64), ("b_sk", C.c_int64),
+        ("c", C.c_void_p), ("c_sm", C.c_int64), ("c_sn", C.c_int64),
+        ("bias", C.c_void_p),
+        ("relu", C.c_int32), ("accumulate", C.c_int32),
+        ("split_k", C.c_int32),
+        ("partials", C.c_void_p),
+    ]
+
+
+# header struct name -> ctypes class, beyond the core six (tests/test_boundary_cpu.py checks every one)
+EXTRA_STRUCTS = {"gp_gemm3_args": Gemm3Args}

@@ -4,6 +4,8 @@ sm_100a kernels.  `graph` is any object with `.x`, `.edge_index`, `.edge_attr` (
 graphphysics_b200.graph.Data)."""
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.nn as nn
 
@@ -15,10 +17,15 @@ class EncodeProcessDecode(nn.Module):
     def __init__(self, message_passing_num: int, node_input_size: int, edge_input_size: int, output_size: int,
                  hidden_size: int = 128, only_processor: bool = False, use_rope_embeddings: bool = False,
                  use_gated_attention: bool = False, use_gated_mlp: bool = False, rope_pos_dimension: int = 3,
-                 rope_base: float = 10000.0, use_temporal_block: bool = False):
+                 rope_base: float = 10000.0, use_temporal_block: bool = False, precision: str = None):
         super().__init__()
         if use_temporal_block:
             raise NotImplementedError("use_temporal_block is not implemented on the sm_100a path (SURVEY §8f N3)")
+        # "bf16": the fused kernels (bf16 MMA operands and storage, fp32 accumulate) -- the timed path;
+        # "tight": split-precision GEMMs (bf16 hi+lo, three MMAs per product, fp32 storage), graphphysics_b200/tight.py
+        self.precision = precision or os.environ.get("GP_B200_PRECISION", "bf16")
+        if self.precision not in ("bf16", "tight"):
+            raise ValueError(f"precision must be 'bf16' or 'tight', got {self.precision!r}")
         self.only_processor = only_processor
         self.hidden_size = hidden_size
         self.d = output_size
@@ -45,6 +52,9 @@ class EncodeProcessDecode(nn.Module):
         return self._engine
 
     def forward(self, graph) -> torch.Tensor:
+        if self.precision == "tight":
+            from ..tight import epd_forward
+            return epd_forward(self, graph)
         from ..engine import BlockFunction, EPDFunction
         eng = self.engine
         x, edge_attr = graph.x, graph.edge_attr

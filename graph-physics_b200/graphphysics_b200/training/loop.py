@@ -45,7 +45,9 @@ class Trainer:
         self.clip, self.wd, self.betas, self.eps = gradient_clip_val, weight_decay, betas, eps
         self.pg = process_group
         self.step_index = 0
-        self.fused = hasattr(self.processor, "engine")      # EPD: engine-driven forward/backward, no autograd tape
+        # EPD on the fused kernels: engine-driven forward/backward, no autograd tape (precision="tight" and the
+        # Transformer run under autograd over flat parameter / gradient buffers)
+        self.fused = hasattr(type(self.processor), "engine") and getattr(self.processor, "precision", "bf16") == "bf16"
         self._flat = None if self.fused else None
         if not self.fused:
             from ..engine import FlatParams

@@ -29,7 +29,7 @@ def get_model(param: Dict[str, Any], only_processor: bool = False):
         return EncodeProcessDecode(message_passing_num=m["message_passing_num"], node_input_size=node_input_size,
                                    edge_input_size=m["edge_input_size"], output_size=m["output_size"],
                                    hidden_size=m["hidden_size"], only_processor=only_processor,
-                                   use_gated_mlp=m.get("use_gated_mlp", False), **common)
+                                   use_gated_mlp=m.get("use_gated_mlp", False), precision=m.get("precision"), **common)
     if model_type == "transformer":
         from ..models.processors import EncodeTransformDecode
         return EncodeTransformDecode(message_passing_num=m["message_passing_num"], node_input_size=node_input_size,

@@ -281,6 +281,31 @@ typedef struct gp_attention_args {
 int gp_csr_attention_fwd(const gp_attention_args* args, void* stream);
 int gp_csr_attention_bwd(const gp_attention_args* args, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Split-precision GEMM (tcgen05): the "tight" arithmetic mode (SURVEY §7 iii).  Every fp32 operand is split into
+ * three bf16 terms hi + mid + lo on the fly (24 mantissa bits) and one product is six MMAs (fp32 accumulate in
+ * TMEM, smallest terms first), i.e. fp32-grade products on the bf16 tensor path.  Replaces torch.nn.functional.linear inside build_mlp
+ * (graphphysics/models/layers.py:163-210) -- forward, dgrad and wgrad alike, by choice of strides -- when the
+ * model is built with precision="tight"; brings the whole model within 1e-3 of the fp32 reference.
+ *   C(m, n) = [C(m, n) +] bias[n] + sum_k A(m, k) * B(n, k),  then max(., 0) if relu
+ *   A(m, k) = a[m*a_sm + k*a_sk],  B(n, k) = b[n*b_sn + k*b_sk],  C(m, n) = c[m*c_sm + n*c_sn]  (fp32, element strides)
+ * split_k > 1 cuts K over CTAs (partials: split_k*M*N floats of scratch, reduced in fixed order).
+ * --------------------------------------------------------------------------------------------- */
+typedef struct gp_gemm3_args {
+    int32_t M, N, K;
+    const float* a;
+    int64_t a_sm, a_sk;
+    const float* b;
+    int64_t b_sn, b_sk;
+    float* c;
+    int64_t c_sm, c_sn;
+    const float* bias;
+    int32_t relu, accumulate;
+    int32_t split_k;
+    float* partials;
+} gp_gemm3_args;
+int gp_gemm3(const gp_gemm3_args* args, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
