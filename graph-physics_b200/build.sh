@@ -3,7 +3,7 @@
 set -e
 cd "$(dirname "$0")"
 mkdir -p graphphysics_b200/lib build
-FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC"
+FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC ${GP_EXTRA_FLAGS:-}"
 pids=()
 for f in csrc/*.cu; do
   o=build/$(basename "$f" .cu).o

@@ -27,6 +27,7 @@
 struct gp_mlp_fwd_args;
 namespace gp {
 int try_linear_fwd(const gp_mlp_fwd_args& a, int hidden, cudaStream_t st);
+int try_edge_fwd2(const gp_mlp_fwd_args& a, cudaStream_t st);
 }
 
 namespace {
@@ -583,6 +584,10 @@ extern "C" int gp_mlp_fwd(const gp_mlp_fwd_args* args, int hidden, void* stream)
     for (int l = 0; l < a.n_layers && proc; ++l) proc = a.k[l] == hidden && a.n[l] == hidden;
     const bool edge = proc && a.two_inits && a.idx0 && a.idx1 && a.a_bf16 && a.seg_id && a.seg_out_bf16;
     const bool node = proc && !a.two_inits && !a.idx0 && a.a_bf16 && !a.seg_id;
+    if (edge && hidden == 128) {      // the CTA-pair, warp-specialised edge kernel (edge_fwd2.cu)
+        const int taken = gp::try_edge_fwd2(a, st);
+        if (taken != 0) return taken < 0 ? taken : 0;
+    }
     switch (hidden) {
         case 128:
             return edge ? launch_fwd<128, 2, 1>(a, st) : node ? launch_fwd<128, 2, 2>(a, st) : launch_fwd<128, 2, 0>(a, st);
