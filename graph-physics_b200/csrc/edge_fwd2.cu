@@ -47,14 +47,13 @@ constexpr uint32_t kOffAct = 4 * kWHalf;                 // 65536
 constexpr uint32_t kOffU = kOffAct + 2 * kTile;
 constexpr uint32_t kOffG = kOffU + 2 * kTile;
 // With ~226 KB of shared memory per CTA the L1 is a few KB, so per-tile parameter reads must not go to global memory
-// (and nothing may spill): b2..b4 live in shared memory, b1 and the RMSNorm scale in the TMEM columns the two
-// accumulators leave free (every lane holds the whole vector).
-constexpr uint32_t kOffBias = kOffG + kTile;             // float bias[3][128] (layers 1..3)
-constexpr uint32_t kOffSeg = kOffBias + 3 * H * 4;       // int sseg[2][136]: ids at [4..131], [3] = row before, [132] = row after
-constexpr uint32_t kOffBar = kOffSeg + 2 * 136 * 4;
+// (and nothing may spill): the four biases and the RMSNorm scale live in shared memory.  All 512 TMEM columns are
+// accumulators: two per slot, so the pre-load of a slot's NEXT tile (bias + gathered rows) is written while the
+// current tile's MMAs run.
+constexpr uint32_t kOffBias = kOffG + kTile;             // float bias[4][128], scale[128]
+constexpr uint32_t kOffBar = kOffBias + 5 * H * 4;
 constexpr uint32_t kSmemBytes = kOffBar + 14 * 8 + 8;
 static_assert(kSmemBytes <= 232448, "shared memory budget of one CTA");
-constexpr uint32_t kColScale = 256, kColB1 = kColScale + H;        // TMEM columns [256, 384): scale, [384, 512): b1
 
 struct Fwd2Maps {
     CUtensorMap e, h2;
@@ -147,8 +146,32 @@ __device__ __forceinline__ void st_global_f2_if(void* ptr, float a, float b, boo
 // once, pieces cut by the sub-tile -> seg_bnd for gp_seg_fixup_bf16), but straight-line: the row loop is unrolled
 // with predicated stores instead of a branch per segment change.  The drain warps share the SM's instruction cache
 // with four other roles, and every taken branch of the branchy walk cost an instruction-fetch stall
-// (stall_no_inst at each reconvergence point in the ncu source view).
-__device__ __forceinline__ void segment_walk_unit(const uint8_t* buf, const int* sseg, int R0, int unit, float* seg_bnd,
+// (stall_no_inst at each reconvergence point in the ncu source view).  The segment ids come straight from global
+// memory (coalesced, 34 per unit; rows past the end read as -1).
+struct WalkIds {
+    int4 v[8];
+    int prev, next;
+};
+__device__ __forceinline__ WalkIds walk_load_ids(const int32_t* __restrict__ seg_id, int rows, int R0, int unit) {
+    const int rb = R0 + (unit / (H / 2)) * 32;
+    WalkIds w;
+    if (rb + 32 <= rows) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) w.v[i] = __ldg(reinterpret_cast<const int4*>(seg_id + rb) + i);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int r = rb + 4 * i;
+            w.v[i] = make_int4(r < rows ? __ldg(seg_id + r) : -1, r + 1 < rows ? __ldg(seg_id + r + 1) : -1,
+                               r + 2 < rows ? __ldg(seg_id + r + 2) : -1, r + 3 < rows ? __ldg(seg_id + r + 3) : -1);
+        }
+    }
+    // context rows of the TILE only (a sub-tile inside the tile sees its neighbours through the same array)
+    w.prev = (rb > 0 && rb - 1 < rows) ? __ldg(seg_id + rb - 1) : -1;
+    w.next = (rb + 32 < rows) ? __ldg(seg_id + rb + 32) : -1;
+    return w;
+}
+__device__ __forceinline__ void segment_walk_unit(const uint8_t* buf, const WalkIds& ids, int R0, int unit, float* seg_bnd,
                                                   gp_bf16* seg_out_bf16) {
     constexpr int NP = H / 2, SUB = 32;
     const int part = unit / NP, cp = unit - part * NP;
@@ -156,15 +179,14 @@ __device__ __forceinline__ void segment_walk_unit(const uint8_t* buf, const int*
     const size_t sub_index = (size_t)(R0 + rb) / SUB;
     const uint32_t chunk = (c & 63) >> 3;
     const uint8_t* colbase = buf + (c >> 6) * 16384 + (c & 7) * 2;
-    const int seg_prev = sseg[3 + rb], seg_next = sseg[4 + rb + SUB];
+    const int seg_prev = ids.prev, seg_next = ids.next;
     float* const bnd0 = seg_bnd + (sub_index * 2) * H + c;           // piece continuing from the previous sub-tile
-    int cur = sseg[4 + rb];
+    int cur = ids.v[0].x;
     bool first = true;
     float s0 = 0.f, s1 = 0.f;
 #pragma unroll
     for (int r8 = 0; r8 < SUB; r8 += 8) {
-        const int4 sa = *reinterpret_cast<const int4*>(sseg + 4 + rb + r8);
-        const int4 sb = *reinterpret_cast<const int4*>(sseg + 8 + rb + r8);
+        const int4 sa = ids.v[r8 / 4], sb = ids.v[r8 / 4 + 1];
         const int sid[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
         const uint8_t* rowbase = colbase + (rb + r8) * 128;
         uint32_t w[8];
@@ -225,8 +247,7 @@ edge_fwd2_kernel(const gp_mlp_fwd_args p, const __grid_constant__ Fwd2Maps maps)
     for (int l = 0; l < 4; ++l) stage_weight(smem + kOffW + l * kWHalf, p.w[l] + (size_t)rank * 64 * H, 64, H);
     cp_async_commit();
     float* sbias = reinterpret_cast<float*>(smem + kOffBias);
-    for (int i = tid; i < 3 * H; i += kNT) sbias[i] = p.bias[1 + (i >> 7)][i & 127];
-    if (tid < 2 * H) reinterpret_cast<float*>(smem + kOffAct)[tid] = tid < H ? p.norm_scale[tid] : p.bias[0][tid - H];   // scratch
+    for (int i = tid; i < 5 * H; i += kNT) sbias[i] = i < 4 * H ? p.bias[i >> 7][i & 127] : p.norm_scale[i - 4 * H];
     if (tid == 0) {
         for (int s = 0; s < 2; ++s) {
             mbar_init(&B.a_ready[s], 8);      // 4 epilogue warps x 2 CTAs
@@ -249,24 +270,6 @@ edge_fwd2_kernel(const gp_mlp_fwd_args p, const __grid_constant__ Fwd2Maps maps)
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = B.tmem_slot;
-    if (warp < 4) {          // RMSNorm scale and b1 -> TMEM columns of every lane (read back per chunk by the epilogues)
-        const uint32_t tl = tmem_addr(tmem_base, warp * 32, 0);
-        const float* sv = reinterpret_cast<const float*>(smem + kOffAct);     // [scale | b1], staged before the barrier above
-#pragma unroll 1
-        for (int c = 0; c < 2 * H; c += 16) {
-            uint32_t v[16];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const uint4 q4 = *reinterpret_cast<const uint4*>(sv + c + 4 * i);
-                v[4 * i] = q4.x; v[4 * i + 1] = q4.y; v[4 * i + 2] = q4.z; v[4 * i + 3] = q4.w;
-            }
-            tmem_st16(tl + kColScale + c, v);          // kColB1 == kColScale + H
-        }
-        tmem_st_wait();
-    }
-    fence_async_smem();               // the scratch in ACT is rewritten by bulk copies (async proxy) from here on
-    tc_fence_before();
-    __syncthreads();
     cluster_sync_all();               // both CTAs' weights, barriers and TMEM exist before any cross-CTA traffic
     tc_fence_after();
     pdl_wait();
@@ -288,82 +291,93 @@ edge_fwd2_kernel(const gp_mlp_fwd_args p, const __grid_constant__ Fwd2Maps maps)
         uint8_t* act = smem + kOffAct + s * kTile;
         uint8_t* ubuf = smem + kOffU + s * kTile;
         const uint8_t* gbuf = smem + kOffG;
-        int* sseg = reinterpret_cast<int*>(smem + kOffSeg) + s * 136;
         const uint32_t act_u = smem_u32(smem + kOffAct) + (uint32_t)(warp >> 2) * kTile;
-        const uint32_t tlane = tmem_addr(tmem_base, (row >> 5) * 32, 0);
-        const uint32_t tacc = tlane + s * 128;
+        const uint32_t tslot = tmem_addr(tmem_base, (row >> 5) * 32, s * 256);     // this slot's two accumulators
         const uint32_t a_ready_leader = mapa_u32(smem_u32(&B.a_ready[s]), 0);
         uint32_t ph_mma = 0;
         const bool issuer = ((warp & 3) == 0) && lane == 0;      // the thread that issues this slot's bulk copies
+        const int q0 = cid * 2 + s;
 
-        PROF_DECL(tid == 0);
-        int q = cid * 2 + s;
-        if (q < n_pairs && issuer) {
-            const int R0 = (2 * q + (int)rank) << 7;
-            mbar_arrive_expect_tx(&B.tma_e[s], kTile);
-            tma_load_2d(act_u, &maps.e, 0, R0, &B.tma_e[s]);
-            tma_load_2d(act_u + 16384, &maps.e, 64, R0, &B.tma_e[s]);
-        }
-        int i_dst_next = q < n_pairs ? __ldg(p.idx0 + min(((2 * q + (int)rank) << 7) + row, p.rows - 1)) : 0;
-        for (int k = 0; q < n_pairs; ++k, q += q_stride) {
-            const int R0 = (2 * q + (int)rank) << 7;
-            const int grow = R0 + row;
-            const int i_dst = i_dst_next;        // loaded a tile ago
-            int sid_prev = -1, sid_next = -1;
-            if (row == 0) {
-                if (R0 > 0 && R0 - 1 < p.rows) sid_prev = __ldg(p.seg_id + R0 - 1);
-                if (R0 + 128 < p.rows) sid_next = __ldg(p.seg_id + R0 + 128);
-            }
-            const int sid_me = grow < p.rows ? i_dst : -1;       // the segment id is the receiver (seg_id == idx0 here)
-            // ---- accumulator pre-load: b1 + P[dst][0:H] + P[src][H:2H] (fp32); the receiver rows are sorted and read
-            //      directly (requested before the wait), the sender rows come from the staging buffer
+        // Accumulator pre-load of the tile `qq` of this slot, in two passes that each fit one MMA wait window of the
+        // tile before it: (1) bias b1 + staged sender rows P[src][H:2H] -> accumulator `tn`, after which the staging
+        // buffer goes back to the producers; (2) + receiver rows P[dst][0:H], read directly (sorted, L2-prefetched
+        // during pass 1).  kk = index of that tile in the slot's sequence (barrier phases).
+        auto preload_pass1 = [&](int kk, uint32_t tn, int i_dst) {
             const gp_bf16* pd = p.init + (size_t)i_dst * p.ld_init + p.init_off0;
-            uint4 dq[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) dq[i] = ldg16(pd + i * 8);
-            PROF_COUNT(15);
-            PROF_TICK(0);        // tile bookkeeping + index loads
-            mbar_wait(&B.g_full[s], k & 1);
-            PROF_TICK(1);        // waiting for the staged sender rows
-            // pass 1: b1 + sender rows; the staging buffer goes back to the producers right after it
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(pd));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(pd + 64));
+            mbar_wait(&B.g_full[s], kk & 1);
 #pragma unroll 1
             for (int c2 = 0; c2 < H; c2 += 32) {
-                uint32_t f[32];
-                tmem_ld16(tlane + kColB1 + c2, *reinterpret_cast<uint32_t(*)[16]>(&f[0]));
-                tmem_ld16(tlane + kColB1 + c2 + 16, *reinterpret_cast<uint32_t(*)[16]>(&f[16]));
-                tmem_ld_wait();
+                float f[32];
 #pragma unroll
-                for (int i = 0; i < 4; ++i)
-                    acc8(*reinterpret_cast<const uint4*>(gbuf + sw128_off(128, row, c2 + i * 8)), reinterpret_cast<float*>(f) + 8 * i);
-                tmem_st16(tacc + c2, *reinterpret_cast<const uint32_t(*)[16]>(&f[0]));
-                tmem_st16(tacc + c2 + 16, *reinterpret_cast<const uint32_t(*)[16]>(&f[16]));
+                for (int i = 0; i < 8; ++i) *reinterpret_cast<float4*>(f + 4 * i) = *reinterpret_cast<const float4*>(sbias + c2 + 4 * i);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) acc8(*reinterpret_cast<const uint4*>(gbuf + sw128_off(128, row, c2 + i * 8)), f + 8 * i);
+                tmem_st16(tn + c2, *reinterpret_cast<const uint32_t(*)[16]>(f));
+                tmem_st16(tn + c2 + 16, *reinterpret_cast<const uint32_t(*)[16]>(f + 16));
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&B.g_empty[s]);
             tmem_st_wait();
-            // pass 2: + receiver rows (requested at the top of the tile)
+        };
+        auto preload_pass2 = [&](uint32_t tn, int i_dst) {
+            const gp_bf16* pd = p.init + (size_t)i_dst * p.ld_init + p.init_off0;
+            uint4 dq[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) dq[i] = ldg16(pd + i * 8);
 #pragma unroll
             for (int c2 = 0; c2 < H; c2 += 32) {
                 uint32_t f[32];
-                tmem_ld16(tacc + c2, *reinterpret_cast<uint32_t(*)[16]>(&f[0]));
-                tmem_ld16(tacc + c2 + 16, *reinterpret_cast<uint32_t(*)[16]>(&f[16]));
+                tmem_ld16(tn + c2, *reinterpret_cast<uint32_t(*)[16]>(&f[0]));
+                tmem_ld16(tn + c2 + 16, *reinterpret_cast<uint32_t(*)[16]>(&f[16]));
                 tmem_ld_wait();
 #pragma unroll
                 for (int i = 0; i < 4; ++i) acc8(dq[c2 / 8 + i], reinterpret_cast<float*>(f) + 8 * i);
-                tmem_st16(tacc + c2, *reinterpret_cast<const uint32_t(*)[16]>(&f[0]));
-                tmem_st16(tacc + c2 + 16, *reinterpret_cast<const uint32_t(*)[16]>(&f[16]));
+                tmem_st16(tn + c2, *reinterpret_cast<const uint32_t(*)[16]>(&f[0]));
+                tmem_st16(tn + c2 + 16, *reinterpret_cast<const uint32_t(*)[16]>(&f[16]));
             }
-            if (q + q_stride < n_pairs) i_dst_next = __ldg(p.idx0 + min(((2 * (q + q_stride) + (int)rank) << 7) + row, p.rows - 1));
             tmem_st_wait();
-            tc_fence_before();
-            PROF_TICK(2);        // accumulator pre-load
-            mbar_wait(&B.tma_e[s], k & 1);       // this tile's e is in ACT (bulk copy issued a tile ago)
-            if (lane == 0) mbar_arrive_cluster(a_ready_leader);
-            PROF_TICK(3);        // waiting for the e tile
+        };
+        auto dst_of = [&](int qq) { return __ldg(p.idx0 + min(((2 * qq + (int)rank) << 7) + row, p.rows - 1)); };
 
+        PROF_DECL(tid == 0);
+        int i_dst_next = 0;
+        if (q0 < n_pairs) {
+            // first tile of the slot: its e tile, and its pre-load up front (nothing to hide it behind)
+            if (issuer) {
+                const int R0 = (2 * q0 + (int)rank) << 7;
+                mbar_arrive_expect_tx(&B.tma_e[s], kTile);
+                tma_load_2d(act_u, &maps.e, 0, R0, &B.tma_e[s]);
+                tma_load_2d(act_u + 16384, &maps.e, 64, R0, &B.tma_e[s]);
+            }
+            const int i0 = dst_of(q0);
+            preload_pass1(0, tslot, i0);
+            preload_pass2(tslot, i0);
+            if (q0 + q_stride < n_pairs) i_dst_next = dst_of(q0 + q_stride);
+            tc_fence_before();
+            mbar_wait(&B.tma_e[s], 0);
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(a_ready_leader);
+        }
+        int q = q0;
+        for (int k = 0; q < n_pairs; ++k, q += q_stride) {
+            const int R0 = (2 * q + (int)rank) << 7;
+            const bool has_next = q + q_stride < n_pairs;
+            const uint32_t tacc = tslot + (k & 1) * 128;          // this tile's accumulator
+            const uint32_t tnext = tslot + ((k + 1) & 1) * 128;   // the next tile's
+            PROF_COUNT(15);
+            PROF_TICK(0);
             // ---- layers
 #pragma unroll 1
             for (int l = 0; l < 4; ++l) {
+                // the MMA wait windows of layers 0 and 1 carry the next tile's accumulator pre-load
+                if (has_next && l == 0) preload_pass1(k + 1, tnext, i_dst_next);
+                if (has_next && l == 1) {
+                    preload_pass2(tnext, i_dst_next);
+                    if (q + 2 * q_stride < n_pairs) i_dst_next = dst_of(q + 2 * q_stride);
+                }
+                PROF_TICK(1 + (l < 2 ? l : 2));     // 1: pre-load pass 1, 2: pass 2, 3: (nothing)
                 mbar_wait(&B.mma_done[s], ph_mma);
                 ph_mma ^= 1;
                 tc_fence_after();
@@ -375,7 +389,7 @@ edge_fwd2_kernel(const gp_mlp_fwd_args p, const __grid_constant__ Fwd2Maps maps)
                         named_sync(1 + s, kEpi);
                         PROF_TICK(16);   // (l = 2) bulk store of h2 has read ACT
                     }
-                    const float* bn = sbias + l * H;      // bias of layer l + 1: the next layer accumulates onto it
+                    const float* bn = sbias + (l + 1) * H;      // bias of layer l + 1: the next layer accumulates onto it
 #pragma unroll 1
                     for (int c2 = 0; c2 < H; c2 += 64) {
                         uint32_t v[64];
@@ -416,7 +430,7 @@ edge_fwd2_kernel(const gp_mlp_fwd_args p, const __grid_constant__ Fwd2Maps maps)
                 } else {
                     // ---- RMSNorm (layers.py:104-129): u = scale * m / (||m||/sqrt(H) + 1e-8), rounded to bf16 once.
                     // ACT is free (the last MMA has read it): the next tile's e starts arriving now.
-                    if (q + q_stride < n_pairs && issuer) {
+                    if (has_next && issuer) {
                         const int Rn = (2 * (q + q_stride) + (int)rank) << 7;
                         mbar_arrive_expect_tx(&B.tma_e[s], kTile);
                         tma_load_2d(act_u, &maps.e, 0, Rn, &B.tma_e[s]);
@@ -442,31 +456,35 @@ edge_fwd2_kernel(const gp_mlp_fwd_args p, const __grid_constant__ Fwd2Maps maps)
                     PROF_TICK(6);    // norm: sum of squares
                     if (k > 0) mbar_wait(&B.u_empty[s], (k - 1) & 1);     // the drain warps are done with the previous u
                     PROF_TICK(7);    // waiting for the drain warps
+                    const float* sc = sbias + 4 * H;
 #pragma unroll 1
                     for (int c2 = 0; c2 < H; c2 += 32) {
-                        uint32_t v[32], g[32];
+                        uint32_t v[32];
                         tmem_ld16(tacc + c2, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
                         tmem_ld16(tacc + c2 + 16, *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
-                        tmem_ld16(tlane + kColScale + c2, *reinterpret_cast<uint32_t(*)[16]>(&g[0]));
-                        tmem_ld16(tlane + kColScale + c2 + 16, *reinterpret_cast<uint32_t(*)[16]>(&g[16]));
                         tmem_ld_wait();
 #pragma unroll
                         for (int c = 0; c < 32; c += 8) {
+                            const float4 g0 = *reinterpret_cast<const float4*>(sc + c2 + c), g1 = *reinterpret_cast<const float4*>(sc + c2 + c + 4);
                             float u[8];
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) u[i] = __uint_as_float(g[c + i]) * (__uint_as_float(v[c + i]) * rinv);
+                            u[0] = g0.x * (__uint_as_float(v[c]) * rinv);     u[1] = g0.y * (__uint_as_float(v[c + 1]) * rinv);
+                            u[2] = g0.z * (__uint_as_float(v[c + 2]) * rinv); u[3] = g0.w * (__uint_as_float(v[c + 3]) * rinv);
+                            u[4] = g1.x * (__uint_as_float(v[c + 4]) * rinv); u[5] = g1.y * (__uint_as_float(v[c + 5]) * rinv);
+                            u[6] = g1.z * (__uint_as_float(v[c + 6]) * rinv); u[7] = g1.w * (__uint_as_float(v[c + 7]) * rinv);
                             *reinterpret_cast<uint4*>(ubuf + sw128_off(128, row, c2 + c)) = pack8(u);
                         }
                     }
-                    sseg[4 + row] = sid_me;
-                    if (row == 0) {
-                        sseg[3] = sid_prev;
-                        sseg[132] = sid_next;
-                    }
-                    tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&B.u_full[s]);
                     PROF_TICK(8);    // norm: scale + write u
+                    if (has_next) {
+                        // the next tile's layer 0: its accumulator was pre-loaded during this tile, its e tile is landing
+                        tc_fence_before();
+                        mbar_wait(&B.tma_e[s], (k + 1) & 1);
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_cluster(a_ready_leader);
+                        PROF_TICK(3);    // waiting for the next e tile
+                    }
                 }
             }
         }
@@ -476,7 +494,6 @@ edge_fwd2_kernel(const gp_mlp_fwd_args p, const __grid_constant__ Fwd2Maps maps)
         const int s = (warp - 8) >> 2;
         const int d = (tid - 2 * kEpi) & (kDrain - 1);
         const uint8_t* ubuf = smem + kOffU + s * kTile;
-        const int* sseg = reinterpret_cast<const int*>(smem + kOffSeg) + s * 136;
         constexpr int KC = H / 8;
         PROF_DECL(tid == 2 * kEpi);
         int q = cid * 2 + s;
@@ -518,7 +535,10 @@ edge_fwd2_kernel(const gp_mlp_fwd_args p, const __grid_constant__ Fwd2Maps maps)
             // receiver-sorted segment sum of bf16(u): same partition as the single-CTA kernel (sub-tiles of 32 rows x
             // column pairs), two units per thread
 #pragma unroll 1
-            for (int un = 0; un < 2; ++un) segment_walk_unit(ubuf, sseg, R0, d + un * kDrain, p.seg_bnd, p.seg_out_bf16);
+            for (int un = 0; un < 2; ++un) {
+                const WalkIds ids = walk_load_ids(p.seg_id, p.rows, R0, d + un * kDrain);
+                segment_walk_unit(ubuf, ids, R0, d + un * kDrain, p.seg_bnd, p.seg_out_bf16);
+            }
             __syncwarp();
             if (lane == 0) mbar_arrive(&B.u_empty[s]);
             PROF_TICK(12);       // drain: segment walk
@@ -529,10 +549,11 @@ edge_fwd2_kernel(const gp_mlp_fwd_args p, const __grid_constant__ Fwd2Maps maps)
             const int s = warp - 16;
             const uint32_t act_u = smem_u32(smem + kOffAct) + (uint32_t)s * kTile;
             const uint32_t w_u = smem_u32(smem + kOffW);
-            const uint32_t tacc = tmem_base + s * 128;
             const uint32_t idesc = idesc_bf16(H, false, false, 256);
             uint32_t ph = 0;
-            for (int q = cid * 2 + s; q < n_pairs; q += q_stride) {
+            int k = 0;
+            for (int q = cid * 2 + s; q < n_pairs; q += q_stride, ++k) {
+                const uint32_t tacc = tmem_base + s * 256 + (k & 1) * 128;      // the slot's accumulators alternate per tile
 #pragma unroll 1
                 for (int l = 0; l < 4; ++l) {
                     mbar_wait_cluster(&B.a_ready[s], ph);
