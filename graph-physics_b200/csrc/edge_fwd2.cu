@@ -47,12 +47,14 @@ constexpr uint32_t kOffAct = 4 * kWHalf;                 // 65536
 constexpr uint32_t kOffU = kOffAct + 2 * kTile;
 constexpr uint32_t kOffG = kOffU + 2 * kTile;
 // With ~226 KB of shared memory per CTA the L1 is a few KB, so per-tile parameter reads must not go to global memory
-// (and nothing may spill): the four biases and the RMSNorm scale live in shared memory.  All 512 TMEM columns are
-// accumulators: two per slot, so the pre-load of a slot's NEXT tile (bias + gathered rows) is written while the
-// current tile's MMAs run.
+// (and nothing may spill): the four biases and the RMSNorm scale live in shared memory.
+// TMEM per slot: a 128-column fp32 accumulator and 64 columns holding the bf16 activation of the hidden layers as the
+// A operand of the next MMA (tcgen05.mma with A in tensor memory), so h1 / h3 never touch shared memory: the L1/shared
+// data pipe is the busiest unit of this kernel (operand fetch + epilogue stores + staging, ~75 % in the ncu capture).
 constexpr uint32_t kOffBias = kOffG + kTile;             // float bias[4][128], scale[128]
 constexpr uint32_t kOffBar = kOffBias + 5 * H * 4;
 constexpr uint32_t kSmemBytes = kOffBar + 14 * 8 + 8;
+constexpr uint32_t kSlotCols = 192, kColAct = 128;      // TMEM columns of a slot: [0, 128) accumulator, [128, 192) activation
 static_assert(kSmemBytes <= 232448, "shared memory budget of one CTA");
 
 struct Fwd2Maps {
@@ -115,6 +117,16 @@ __device__ __forceinline__ void mma2_ss(uint32_t tmem_d, uint64_t adesc, uint64_
         "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         :
         : "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// the same with the A operand in tensor memory (each CTA reads its own 128 lanes at `tmem_a`)
+__device__ __forceinline__ void mma2_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        :
+        : "r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
 // all pair MMAs issued so far arrive on `bar` (same offset) in BOTH CTAs when complete
@@ -255,8 +267,8 @@ edge_fwd2_kernel(const gp_mlp_fwd_args p, const __grid_constant__ Fwd2Maps maps)
             mbar_init(&B.tma_e[s], 1);
             mbar_init(&B.u_full[s], 4);
             mbar_init(&B.u_empty[s], 4);
-            mbar_init(&B.g_full[s], 64);      // (two producer warps) one barrier pair per consuming slot: each sees its own phases in order
-            mbar_init(&B.g_empty[s], 4);
+            mbar_init(&B.g_full[s], 64);      // two producer warps x 32 lanes (cp.async completions); one barrier pair per
+            mbar_init(&B.g_empty[s], 4);      // consuming slot: each slot sees its own phases in order
         }
         fence_mbar_init();
     }
@@ -275,7 +287,8 @@ edge_fwd2_kernel(const gp_mlp_fwd_args p, const __grid_constant__ Fwd2Maps maps)
     pdl_wait();
     pdl_launch_dependents();
 
-    // register budget per role (the launch gives every warp 96): the epilogue warps take what the others hand back
+    // Register budget per role: the launch gives every warp 96 registers per thread and setmaxnreg only moves
+    // registers inside the CTA's own allocation (640 x 96): 8 x 128 + 8 x 80 + 4 x 64 = 20 x 96 exactly.
     if (warp < 8) {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 128;");
     } else if (warp < 16) {
@@ -292,104 +305,72 @@ edge_fwd2_kernel(const gp_mlp_fwd_args p, const __grid_constant__ Fwd2Maps maps)
         uint8_t* ubuf = smem + kOffU + s * kTile;
         const uint8_t* gbuf = smem + kOffG;
         const uint32_t act_u = smem_u32(smem + kOffAct) + (uint32_t)(warp >> 2) * kTile;
-        const uint32_t tslot = tmem_addr(tmem_base, (row >> 5) * 32, s * 256);     // this slot's two accumulators
+        const uint32_t tacc = tmem_addr(tmem_base, (row >> 5) * 32, s * kSlotCols);
+        const uint32_t tact = tacc + kColAct;
         const uint32_t a_ready_leader = mapa_u32(smem_u32(&B.a_ready[s]), 0);
         uint32_t ph_mma = 0;
         const bool issuer = ((warp & 3) == 0) && lane == 0;      // the thread that issues this slot's bulk copies
-        const int q0 = cid * 2 + s;
+        auto dst_of = [&](int qq) { return __ldg(p.idx0 + min(((2 * qq + (int)rank) << 7) + row, p.rows - 1)); };
 
-        // Accumulator pre-load of the tile `qq` of this slot, in two passes that each fit one MMA wait window of the
-        // tile before it: (1) bias b1 + staged sender rows P[src][H:2H] -> accumulator `tn`, after which the staging
-        // buffer goes back to the producers; (2) + receiver rows P[dst][0:H], read directly (sorted, L2-prefetched
-        // during pass 1).  kk = index of that tile in the slot's sequence (barrier phases).
-        auto preload_pass1 = [&](int kk, uint32_t tn, int i_dst) {
-            const gp_bf16* pd = p.init + (size_t)i_dst * p.ld_init + p.init_off0;
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(pd));
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(pd + 64));
-            mbar_wait(&B.g_full[s], kk & 1);
-#pragma unroll 1
+        PROF_DECL(tid == 0);
+        int q = cid * 2 + s;
+        if (q < n_pairs && issuer) {
+            const int R0 = (2 * q + (int)rank) << 7;
+            mbar_arrive_expect_tx(&B.tma_e[s], kTile);
+            tma_load_2d(act_u, &maps.e, 0, R0, &B.tma_e[s]);
+            tma_load_2d(act_u + 16384, &maps.e, 64, R0, &B.tma_e[s]);
+        }
+        int i_dst_next = q < n_pairs ? dst_of(q) : 0;
+        for (int k = 0; q < n_pairs; ++k, q += q_stride) {
+            const int R0 = (2 * q + (int)rank) << 7;
+            const bool has_next = q + q_stride < n_pairs;
+            // ---- accumulator pre-load: b1 + P[src][H:2H] (staged rows; the buffer goes back to the producers right
+            //      after this pass) + P[dst][0:H] (sorted: read directly, requested before the wait)
+            const gp_bf16* pd = p.init + (size_t)i_dst_next * p.ld_init + p.init_off0;
+            uint4 dq[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) dq[i] = ldg16(pd + i * 8);
+            PROF_COUNT(15);
+            PROF_TICK(0);        // tile bookkeeping + requests
+            mbar_wait(&B.g_full[s], k & 1);
+            PROF_TICK(1);        // waiting for the staged sender rows
+#pragma unroll
             for (int c2 = 0; c2 < H; c2 += 32) {
                 float f[32];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) *reinterpret_cast<float4*>(f + 4 * i) = *reinterpret_cast<const float4*>(sbias + c2 + 4 * i);
 #pragma unroll
-                for (int i = 0; i < 4; ++i) acc8(*reinterpret_cast<const uint4*>(gbuf + sw128_off(128, row, c2 + i * 8)), f + 8 * i);
-                tmem_st16(tn + c2, *reinterpret_cast<const uint32_t(*)[16]>(f));
-                tmem_st16(tn + c2 + 16, *reinterpret_cast<const uint32_t(*)[16]>(f + 16));
+                for (int i = 0; i < 4; ++i) {
+                    acc8(*reinterpret_cast<const uint4*>(gbuf + sw128_off(128, row, c2 + i * 8)), f + 8 * i);
+                    acc8(dq[c2 / 8 + i], f + 8 * i);
+                }
+                tmem_st16(tacc + c2, *reinterpret_cast<const uint32_t(*)[16]>(f));
+                tmem_st16(tacc + c2 + 16, *reinterpret_cast<const uint32_t(*)[16]>(f + 16));
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&B.g_empty[s]);
+            if (has_next) i_dst_next = dst_of(q + q_stride);
             tmem_st_wait();
-        };
-        auto preload_pass2 = [&](uint32_t tn, int i_dst) {
-            const gp_bf16* pd = p.init + (size_t)i_dst * p.ld_init + p.init_off0;
-            uint4 dq[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) dq[i] = ldg16(pd + i * 8);
-#pragma unroll
-            for (int c2 = 0; c2 < H; c2 += 32) {
-                uint32_t f[32];
-                tmem_ld16(tn + c2, *reinterpret_cast<uint32_t(*)[16]>(&f[0]));
-                tmem_ld16(tn + c2 + 16, *reinterpret_cast<uint32_t(*)[16]>(&f[16]));
-                tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 4; ++i) acc8(dq[c2 / 8 + i], reinterpret_cast<float*>(f) + 8 * i);
-                tmem_st16(tn + c2, *reinterpret_cast<const uint32_t(*)[16]>(&f[0]));
-                tmem_st16(tn + c2 + 16, *reinterpret_cast<const uint32_t(*)[16]>(&f[16]));
-            }
-            tmem_st_wait();
-        };
-        auto dst_of = [&](int qq) { return __ldg(p.idx0 + min(((2 * qq + (int)rank) << 7) + row, p.rows - 1)); };
-
-        PROF_DECL(tid == 0);
-        int i_dst_next = 0;
-        if (q0 < n_pairs) {
-            // first tile of the slot: its e tile, and its pre-load up front (nothing to hide it behind)
-            if (issuer) {
-                const int R0 = (2 * q0 + (int)rank) << 7;
-                mbar_arrive_expect_tx(&B.tma_e[s], kTile);
-                tma_load_2d(act_u, &maps.e, 0, R0, &B.tma_e[s]);
-                tma_load_2d(act_u + 16384, &maps.e, 64, R0, &B.tma_e[s]);
-            }
-            const int i0 = dst_of(q0);
-            preload_pass1(0, tslot, i0);
-            preload_pass2(tslot, i0);
-            if (q0 + q_stride < n_pairs) i_dst_next = dst_of(q0 + q_stride);
             tc_fence_before();
-            mbar_wait(&B.tma_e[s], 0);
+            PROF_TICK(2);        // accumulator pre-load
+            mbar_wait(&B.tma_e[s], k & 1);       // this tile's e is in ACT (bulk copy issued a tile ago)
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(a_ready_leader);
-        }
-        int q = q0;
-        for (int k = 0; q < n_pairs; ++k, q += q_stride) {
-            const int R0 = (2 * q + (int)rank) << 7;
-            const bool has_next = q + q_stride < n_pairs;
-            const uint32_t tacc = tslot + (k & 1) * 128;          // this tile's accumulator
-            const uint32_t tnext = tslot + ((k + 1) & 1) * 128;   // the next tile's
-            PROF_COUNT(15);
-            PROF_TICK(0);
+            PROF_TICK(3);        // waiting for the e tile
+
             // ---- layers
 #pragma unroll 1
             for (int l = 0; l < 4; ++l) {
-                // the MMA wait windows of layers 0 and 1 carry the next tile's accumulator pre-load
-                if (has_next && l == 0) preload_pass1(k + 1, tnext, i_dst_next);
-                if (has_next && l == 1) {
-                    preload_pass2(tnext, i_dst_next);
-                    if (q + 2 * q_stride < n_pairs) i_dst_next = dst_of(q + 2 * q_stride);
-                }
-                PROF_TICK(1 + (l < 2 ? l : 2));     // 1: pre-load pass 1, 2: pass 2, 3: (nothing)
                 mbar_wait(&B.mma_done[s], ph_mma);
                 ph_mma ^= 1;
                 tc_fence_after();
                 PROF_TICK(4);    // waiting for the pair MMA (both CTAs' operands + issue + tensor time), x4
                 if (l < 3) {
-                    if (l == 2 && maps.save_h2) {
-                        // the bulk store of h2 must have read ACT before h3 overwrites it
-                        if (issuer) tma_store_wait_read<0>();
-                        named_sync(1 + s, kEpi);
-                        PROF_TICK(16);   // (l = 2) bulk store of h2 has read ACT
-                    }
-                    const float* bn = sbias + (l + 1) * H;      // bias of layer l + 1: the next layer accumulates onto it
+                    // hidden layer: relu(acc) -> bf16 -> TMEM (A operand of the next MMA); the accumulator restarts from
+                    // the next layer's bias.  h2 (l == 1) additionally goes to ACT -- free since layer 0 -- and from
+                    // there to global memory by one bulk store (it is the input of backward stage B).
+                    const float* bn = sbias + (l + 1) * H;
+                    const bool to_smem = (l == 1) && maps.save_h2;
 #pragma unroll 1
                     for (int c2 = 0; c2 < H; c2 += 64) {
                         uint32_t v[64];
@@ -406,31 +387,41 @@ edge_fwd2_kernel(const gp_mlp_fwd_args p, const __grid_constant__ Fwd2Maps maps)
                             }
                             tmem_st16(tacc + c2 + c, b16);
                         }
+                        uint32_t hp[32];          // 64 bf16 values: column j of the operand holds elements (2j, 2j+1)
 #pragma unroll
-                        for (int c = 0; c < 64; c += 8)
-                            *reinterpret_cast<uint4*>(act + sw128_off(128, row, c2 + c)) = pack8_relu(reinterpret_cast<const float*>(&v[c]));
+                        for (int c = 0; c < 64; c += 2) hp[c >> 1] = pack_bf16_relu(__uint_as_float(v[c]), __uint_as_float(v[c + 1]));
+                        tmem_st16(tact + (c2 >> 1), *reinterpret_cast<const uint32_t(*)[16]>(&hp[0]));
+                        tmem_st16(tact + (c2 >> 1) + 16, *reinterpret_cast<const uint32_t(*)[16]>(&hp[16]));
+                        if (to_smem) {
+#pragma unroll
+                            for (int c = 0; c < 64; c += 8)
+                                *reinterpret_cast<uint4*>(act + sw128_off(128, row, c2 + c)) =
+                                    make_uint4(hp[c >> 1], hp[(c >> 1) + 1], hp[(c >> 1) + 2], hp[(c >> 1) + 3]);
+                        }
                     }
-                    PROF_TICK(17);   // TMEM -> ReLU -> ACT, bias pre-store
-                    fence_async_smem();
+                    PROF_TICK(17);   // TMEM -> ReLU -> TMEM, bias pre-store
                     tmem_st_wait();
                     tc_fence_before();
-                    PROF_TICK(18);   // proxy fence + TMEM store wait
-                    if (l == 1 && maps.save_h2) {
+                    PROF_TICK(18);   // TMEM store wait
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cluster(a_ready_leader);
+                    PROF_TICK(5);    // arrive
+                    if (to_smem) {
+                        fence_async_smem();
                         named_sync(1 + s, kEpi);             // the whole h2 tile is in ACT
                         if (issuer) {                        // bulk-copy groups are per thread: always the same thread
                             tma_store_2d(&maps.h2, 0, R0, act_u);
                             tma_store_2d(&maps.h2, 64, R0, act_u + 16384);
                             tma_store_commit();
                         }
-                        PROF_TICK(19);   // (l = 1) slot barrier + bulk store issue
+                        PROF_TICK(19);   // (l = 1) slot barrier + bulk store issue (off the MMA's critical path)
                     }
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive_cluster(a_ready_leader);
-                    PROF_TICK(5);    // arrive
                 } else {
                     // ---- RMSNorm (layers.py:104-129): u = scale * m / (||m||/sqrt(H) + 1e-8), rounded to bf16 once.
-                    // ACT is free (the last MMA has read it): the next tile's e starts arriving now.
+                    // ACT is free (layer 0 read e long ago; the bulk store of h2, if any, must have read it too): the next
+                    // tile's e starts arriving now.
                     if (has_next && issuer) {
+                        if (maps.save_h2) tma_store_wait_read<0>();
                         const int Rn = (2 * (q + q_stride) + (int)rank) << 7;
                         mbar_arrive_expect_tx(&B.tma_e[s], kTile);
                         tma_load_2d(act_u, &maps.e, 0, Rn, &B.tma_e[s]);
@@ -457,7 +448,7 @@ edge_fwd2_kernel(const gp_mlp_fwd_args p, const __grid_constant__ Fwd2Maps maps)
                     if (k > 0) mbar_wait(&B.u_empty[s], (k - 1) & 1);     // the drain warps are done with the previous u
                     PROF_TICK(7);    // waiting for the drain warps
                     const float* sc = sbias + 4 * H;
-#pragma unroll 1
+#pragma unroll 2
                     for (int c2 = 0; c2 < H; c2 += 32) {
                         uint32_t v[32];
                         tmem_ld16(tacc + c2, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
@@ -477,14 +468,6 @@ edge_fwd2_kernel(const gp_mlp_fwd_args p, const __grid_constant__ Fwd2Maps maps)
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&B.u_full[s]);
                     PROF_TICK(8);    // norm: scale + write u
-                    if (has_next) {
-                        // the next tile's layer 0: its accumulator was pre-loaded during this tile, its e tile is landing
-                        tc_fence_before();
-                        mbar_wait(&B.tma_e[s], (k + 1) & 1);
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive_cluster(a_ready_leader);
-                        PROF_TICK(3);    // waiting for the next e tile
-                    }
                 }
             }
         }
@@ -550,23 +533,30 @@ edge_fwd2_kernel(const gp_mlp_fwd_args p, const __grid_constant__ Fwd2Maps maps)
             const uint32_t act_u = smem_u32(smem + kOffAct) + (uint32_t)s * kTile;
             const uint32_t w_u = smem_u32(smem + kOffW);
             const uint32_t idesc = idesc_bf16(H, false, false, 256);
+            const uint32_t tacc = tmem_base + s * kSlotCols, tact = tacc + kColAct;
             uint32_t ph = 0;
-            int k = 0;
-            for (int q = cid * 2 + s; q < n_pairs; q += q_stride, ++k) {
-                const uint32_t tacc = tmem_base + s * 256 + (k & 1) * 128;      // the slot's accumulators alternate per tile
+            for (int q = cid * 2 + s; q < n_pairs; q += q_stride) {
 #pragma unroll 1
                 for (int l = 0; l < 4; ++l) {
                     mbar_wait_cluster(&B.a_ready[s], ph);
                     ph ^= 1;
                     tc_fence_after();
                     if (elect_one()) {
-                        const uint64_t ad = desc_kmajor(act_u, 128, 0);
                         const uint64_t bd = desc_kmajor(w_u + l * kWHalf, 64, 0);
+                        // the accumulator already holds the bias (and, for layer 0, the gathered rows)
+                        if (l == 0) {        // A = the e tile in shared memory
+                            const uint64_t ad = desc_kmajor(act_u, 128, 0);
 #pragma unroll
-                        for (int ks = 0; ks < H / 16; ++ks) {
-                            const uint32_t ko = (ks & 3) * 2;
-                            // the accumulator already holds the bias (and, for layer 0, the gathered rows)
-                            mma2_ss(tacc, ad + (uint64_t)((ks >> 2) * 1024u + ko), bd + (uint64_t)((ks >> 2) * 512u + ko), idesc, 1u);
+                            for (int ks = 0; ks < H / 16; ++ks) {
+                                const uint32_t ko = (ks & 3) * 2;
+                                mma2_ss(tacc, ad + (uint64_t)((ks >> 2) * 1024u + ko), bd + (uint64_t)((ks >> 2) * 512u + ko), idesc, 1u);
+                            }
+                        } else {             // A = the previous layer's bf16 activation in tensor memory (8 columns per k-step)
+#pragma unroll
+                            for (int ks = 0; ks < H / 16; ++ks) {
+                                const uint32_t ko = (ks & 3) * 2;
+                                mma2_ts(tacc, tact + ks * 8, bd + (uint64_t)((ks >> 2) * 512u + ko), idesc, 1u);
+                            }
                         }
                         mma2_commit_both(&B.mma_done[s]);
                     }
@@ -574,7 +564,7 @@ edge_fwd2_kernel(const gp_mlp_fwd_args p, const __grid_constant__ Fwd2Maps maps)
                 }
             }
         }
-    } else {
+    } else if (warp < 20) {
         // =========================================================================== gather producers: P[src] rows -> G
         // two warps, 64 rows each; the rows are pulled into L2 before the staging buffer is free, so the copies that
         // follow the hand-over are L2 hits

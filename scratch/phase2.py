@@ -14,7 +14,7 @@ g = get_csr(b.edge_index, N)
 x = torch.randn(N, H, device=dev).to(torch.bfloat16); e = torch.randn(E, H, device=dev).to(torch.bfloat16)
 P = torch.randn(N, 3*H, device=dev).to(torch.bfloat16)
 bnd = torch.empty(ops.seg_bnd_size(E, H), device=dev); agg = torch.empty((N, H), device=dev, dtype=torch.bfloat16); e2 = torch.empty_like(e)
-names = ["epi: bookkeeping + idx", "epi: wait staged rows", "epi: acc pre-load", "epi: wait e tile", "epi: wait MMA (x4)", "epi: hidden epilogue (x3)",
+names = ["epi: bookkeeping + requests", "epi: wait staged rows", "epi: acc pre-load", "epi: wait e tile", "epi: wait MMA (x4)", "epi: hidden epilogue (x3)",
          "epi: norm sumsq+exchange", "epi: wait drain", "epi: norm scale+write u", "drain: resid requests", "drain: wait u", "drain: e'=e+u", "drain: segment walk",
          "prod: issue+idx", "prod: wait staging"]
 h2 = torch.empty((E, H), device=dev, dtype=torch.bfloat16) if os.environ.get('SAVE_H2') else None
@@ -29,6 +29,7 @@ for it in range(3):
     print(f"iter {it}: {st.elapsed_time(en)*1e3:.0f} us, tiles of CTA0/slot0 {tiles}, cycles/tile per phase:")
     for i, n in enumerate(names):
         print(f"    {n:32s} {p[i]/tiles:9.0f}")
-    for i, n in ((16, "epi: l=2 wait h2 store read"), (17, "epi: hidden convert (x3)"), (18, "epi: fences (x3)"), (19, "epi: l=1 sync + store issue")):
+    for i, n in ((16, "epi: l=2 wait h2 store read"), (17, "epi: hidden convert (x3)"), (18, "epi: fences (x3)"), (19, "epi: l=1 sync + store issue"),
+                 (20, "pre: requests + wait accumulator"), (21, "pre: wait staged rows"), (22, "pre: sums + TMEM stores")):
         print(f"    {n:32s} {p[i]/tiles:9.0f}")
     print(f"    {'epilogue total':32s} {(sum(p[:9])+sum(p[16:20]))/tiles:9.0f}   drain total {sum(p[9:13])/tiles:9.0f}   producer total {sum(p[13:15])/tiles:9.0f}")
