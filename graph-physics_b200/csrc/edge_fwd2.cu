@@ -144,15 +144,6 @@ __device__ __forceinline__ void tmem_ld2(uint32_t taddr, uint32_t& a, uint32_t& 
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0,%1}, [%2];" : "=r"(a), "=r"(b) : "r"(taddr) : "memory");
 }
 
-__device__ __forceinline__ void st_global_u32_if(void* ptr, uint32_t v, bool pred) {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t@p st.global.b32 [%0], %1;\n\t}" ::"l"(ptr), "r"(v), "r"((uint32_t)pred) : "memory");
-}
-__device__ __forceinline__ void st_global_f2_if(void* ptr, float a, float b, bool pred) {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %3, 0;\n\t@p st.global.v2.f32 [%0], {%1, %2};\n\t}" ::"l"(ptr), "f"(a), "f"(b),
-                 "r"((uint32_t)pred)
-                 : "memory");
-}
-
 // Segment sum of one (32-row sub-tile, column pair) unit of the bf16 tile `buf` -- the partition, the summation order
 // and the output convention of tile_segment_sum<128, 256> (tile_util.cuh; complete segments -> seg_out_bf16 rounded
 // once, pieces cut by the sub-tile -> seg_bnd for gp_seg_fixup_bf16), but straight-line: the row loop is unrolled

@@ -608,7 +608,10 @@ __global__ void __launch_bounds__(BwdCfg<H>::NT, 1) mlp_bwd_kernel(const gp_mlp_
                         *reinterpret_cast<const uint4*>(ha + sw128_off(HR, r, ch * 8));
             }
         }
-        if (f_seg) tile_segment_sum<H, NT>(ha, sseg, R0, tid, MODE == 2 ? nullptr : p.seg_out, p.seg_bnd, p.seg_out_bf16, kHaStride);
+        if (f_seg) {
+            if (MODE == 2) tile_segment_sum_bf16_flat<H, NT>(ha, sseg, R0, tid, p.seg_bnd, p.seg_out_bf16, kHaStride);     // straight-line walk
+            else tile_segment_sum<H, NT>(ha, sseg, R0, tid, p.seg_out, p.seg_bnd, p.seg_out_bf16, kHaStride);
+        }
         tick(9);      // P4 issue + copy-out + segment walk
         if (f_din) wait_mma();
         tick(10);     // P4 d_in MMA wait

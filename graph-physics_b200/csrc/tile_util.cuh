@@ -240,4 +240,63 @@ __device__ __forceinline__ void tile_segment_sum(const uint8_t* buf, const int* 
     flush(cur, true);
 }
 
+
+// Predicated global stores (no branch): a taken branch costs an instruction-fetch bubble in these large kernels.
+__device__ __forceinline__ void st_global_u32_if(void* ptr, uint32_t v, bool pred) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t@p st.global.b32 [%0], %1;\n\t}" ::"l"(ptr), "r"(v), "r"((uint32_t)pred) : "memory");
+}
+__device__ __forceinline__ void st_global_f2_if(void* ptr, float a, float b, bool pred) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %3, 0;\n\t@p st.global.v2.f32 [%0], {%1, %2};\n\t}" ::"l"(ptr), "f"(a), "f"(b),
+                 "r"((uint32_t)pred)
+                 : "memory");
+}
+
+// tile_segment_sum for bf16 segment outputs, straight-line: same partition (thread = column pair x sub-tile of
+// SUB = 64*H/NT rows), same summation order and the same outputs bit for bit, but the row loop is fully unrolled with
+// predicated stores instead of one branch per segment change (the branchy walk stalls on instruction fetch at every
+// reconvergence point: ncu source view of the round-2 edge kernels).
+template <int H, int NT>
+__device__ __forceinline__ void tile_segment_sum_bf16_flat(const uint8_t* buf, const int* sseg, int R0, int t, float* seg_bnd,
+                                                           gp_bf16* seg_out_bf16, uint32_t block_stride = 128 * 128) {
+    constexpr int NP = H / 2;
+    constexpr int SUB = 128 * NP / NT;
+    static_assert(SUB % 8 == 0, "sub-tile must be a multiple of 8 rows");
+    const int part = t / NP, cp = t - part * NP;
+    const int rb = part * SUB, c = cp * 2;
+    const size_t sub_index = (size_t)(R0 + rb) / SUB;
+    const uint32_t chunk = (c & 63) >> 3;
+    const uint8_t* colbase = buf + (c >> 6) * block_stride + (c & 7) * 2;
+    const int seg_prev = sseg[3 + rb], seg_next = sseg[4 + rb + SUB];
+    float* const bnd0 = seg_bnd + (sub_index * 2) * H + c;           // piece continuing from the previous sub-tile
+    int cur = sseg[4 + rb];
+    bool first = true;
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int r8 = 0; r8 < SUB; r8 += 8) {
+        const int4 sa = *reinterpret_cast<const int4*>(sseg + 4 + rb + r8);
+        const int4 sb = *reinterpret_cast<const int4*>(sseg + 8 + rb + r8);
+        const int sid[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
+        const uint8_t* rowbase = colbase + (rb + r8) * 128;
+        uint32_t w[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) w[j] = *reinterpret_cast<const uint32_t*>(rowbase + j * 128 + ((chunk ^ j) << 4));
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const bool brk = sid[j] != cur;
+            const bool before = first && (seg_prev == cur);
+            st_global_u32_if(seg_out_bf16 + (size_t)cur * H + c, pack_bf16(s0, s1), brk && !before && cur >= 0);
+            st_global_f2_if(bnd0, s0, s1, brk && before && cur >= 0);
+            first = first && !brk;
+            s0 = brk ? 0.f : s0;
+            s1 = brk ? 0.f : s1;
+            cur = sid[j];
+            s0 = add_bf16_lo(w[j], s0);
+            s1 = add_bf16_hi(w[j], s1);
+        }
+    }
+    const bool before = first && (seg_prev == cur), after = (seg_next == cur);
+    st_global_u32_if(seg_out_bf16 + (size_t)cur * H + c, pack_bf16(s0, s1), !before && !after && cur >= 0);
+    st_global_f2_if(before ? bnd0 : bnd0 + H, s0, s1, (before || after) && cur >= 0);
+}
+
 }  // namespace gp

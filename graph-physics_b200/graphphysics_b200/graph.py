@@ -50,12 +50,18 @@ class GraphCSR:
     rowptr_src    : [N+1] sender segments of perm_src
     """
 
-    def __init__(self, edge_index: torch.Tensor, num_nodes: int):
+    def __init__(self, edge_index: torch.Tensor, num_nodes: int, _persistent: bool = False):
         assert edge_index.dim() == 2 and edge_index.shape[0] == 2
-        # node ids fit 32 bits: the radix sorts run half as many passes on int32 keys as on int64
-        src, dst = edge_index[0].int(), edge_index[1].int()
         self.num_nodes = int(num_nodes)
-        self.num_edges = int(src.numel())
+        self.num_edges = int(edge_index.shape[1])
+        self._inv_perm: Optional[torch.Tensor] = None
+        if edge_index.is_cuda:
+            # the native counting sorts of libgp_b200.so (gp_csr_from_coo): no ATen sort, no host round trip
+            self._alloc_native(edge_index.device, _persistent)
+            self.rebuild_(edge_index)
+            return
+        # host tensors (CPU tests, the partitioner): the same layout spelled with torch ops
+        src, dst = edge_index[0].int(), edge_index[1].int()
         perm = torch.sort(dst, stable=True).indices
         src_s, dst_s = src[perm], dst[perm]
         self.perm_dst64 = perm
@@ -65,10 +71,41 @@ class GraphCSR:
         src_sorted, perm_src = torch.sort(src_s, stable=True)
         self.perm_src = perm_src.int()
         self.rowptr_src = self._rowptr(src_sorted, num_nodes)
-        self._inv_perm: Optional[torch.Tensor] = None
         # attention view: rows = senders (edge_index[0]); the row-sorted entry p is entry perm_src[p] of
         # the receiver-sorted list, so its column is dst[perm_src[p]]
         self.att_col = self.dst[self.perm_src.long()].contiguous()
+
+    def _alloc_native(self, device, persistent: bool) -> None:
+        from . import ops
+        E, N = self.num_edges, self.num_nodes
+        i32 = lambda n: torch.empty(n, dtype=torch.int32, device=device)
+        self.perm_dst, self.src, self.dst, self.perm_src, self.att_col = i32(E), i32(E), i32(E), i32(E), i32(E)
+        self.rowptr_dst, self.rowptr_src = i32(N + 1), i32(N + 1)
+        self._ws = torch.empty(ops.csr_workspace_bytes(E, N), dtype=torch.uint8, device=device)
+        # persistent layouts (replayed CUDA graphs) keep the previous edge_index and skip the rebuild when it repeats
+        self._prev = torch.empty((2, E), dtype=torch.int64, device=device) if persistent else None
+        self._state = torch.zeros(2, dtype=torch.int32, device=device) if persistent else None
+        self._perm64 = torch.empty(E, dtype=torch.int64, device=device)
+
+    def rebuild_(self, edge_index: torch.Tensor) -> "GraphCSR":
+        """(Re)compute the layout in place from a CUDA edge_index of the same shape; every buffer keeps its address."""
+        from . import ops
+        assert edge_index.is_cuda and edge_index.shape == (2, self.num_edges)
+        ei = edge_index if (edge_index.dtype == torch.int64 and edge_index.is_contiguous()) else edge_index.long().contiguous()
+        out = dict(perm_dst=self.perm_dst, src=self.src, dst=self.dst, rowptr_dst=self.rowptr_dst, perm_src=self.perm_src,
+                   rowptr_src=self.rowptr_src, att_col=self.att_col)
+        ops.csr_from_coo(ei, self.num_nodes, out, self._ws, self._prev, self._state)
+        self._perm64.copy_(self.perm_dst)          # int64 copy for torch indexing of the raw edge features
+        self._inv_perm = None
+        return self
+
+    @property
+    def perm_dst64(self) -> torch.Tensor:
+        return self._perm64
+
+    @perm_dst64.setter
+    def perm_dst64(self, v: torch.Tensor) -> None:
+        self._perm64 = v
 
     @staticmethod
     def _rowptr(sorted_ids: torch.Tensor, n: int) -> torch.Tensor:
@@ -88,6 +125,7 @@ class GraphCSR:
 
 
 _CACHE: dict = {}
+_PERSISTENT: dict = {}       # (E, N, device) -> GraphCSR with fixed buffers, rebuilt in place (CUDA-graph replay)
 
 
 _CACHE_ENABLED = [True]
@@ -109,7 +147,16 @@ def get_csr(edge_index: torch.Tensor, num_nodes: int) -> GraphCSR:
     """GraphCSR of `edge_index`, cached on (storage pointer, version, shape) so a static topology
     (roll-outs, repeated batches) is sorted once."""
     if not _CACHE_ENABLED[0]:
-        return GraphCSR(edge_index, num_nodes)
+        if not edge_index.is_cuda:
+            return GraphCSR(edge_index, num_nodes)
+        # replayed steps: one layout object per shape, rebuilt in place from the current contents of the static input
+        # buffer -- and not rebuilt at all (device-side comparison) while the topology repeats
+        key = (int(edge_index.shape[1]), int(num_nodes), str(edge_index.device))
+        g = _PERSISTENT.get(key)
+        if g is None:
+            g = _PERSISTENT[key] = GraphCSR(edge_index, num_nodes, _persistent=True)
+            return g
+        return g.rebuild_(edge_index)
     key = (edge_index.data_ptr(), edge_index._version, tuple(edge_index.shape), int(num_nodes), str(edge_index.device))
     g = _CACHE.get(key)
     if g is None:

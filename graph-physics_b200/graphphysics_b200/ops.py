@@ -464,3 +464,49 @@ class CSRAttention(torch.autograd.Function):
         check(lib().gp_csr_attention_bwd(C.byref(a), C.c_void_p(stream_ptr())), "gp_csr_attention_bwd")
         _launched(2)
         return dq, dk, dv, None, None
+
+
+# ---------------------------------------------------------------------------------------------- graph layout / halo rows
+def csr_from_coo(edge_index: torch.Tensor, num_nodes: int, out: dict, workspace: torch.Tensor,
+                 prev: Optional[torch.Tensor] = None, state: Optional[torch.Tensor] = None) -> None:
+    """gp_csr_from_coo: receiver-sorted layout of a CUDA edge_index [2, E] int64 into the int32 tensors of `out`
+    (perm_dst, src, dst, rowptr_dst, perm_src, rowptr_src, att_col).  prev/state: skip when the topology is unchanged."""
+    assert edge_index.is_cuda and edge_index.dtype == torch.int64 and edge_index.is_contiguous()
+    lib().gp_csr_from_coo.restype = C.c_int
+    check(lib().gp_csr_from_coo(C.c_void_p(ptr(edge_index)), C.c_int64(edge_index.shape[1]), C.c_int32(num_nodes),
+                                C.c_void_p(ptr(out["perm_dst"])), C.c_void_p(ptr(out["src"])), C.c_void_p(ptr(out["dst"])),
+                                C.c_void_p(ptr(out["rowptr_dst"])), C.c_void_p(ptr(out["perm_src"])),
+                                C.c_void_p(ptr(out["rowptr_src"])), C.c_void_p(ptr(out["att_col"])), C.c_void_p(ptr(workspace)),
+                                C.c_void_p(ptr(prev)), C.c_void_p(ptr(state)), C.c_void_p(stream_ptr())), "gp_csr_from_coo")
+    _launched(21)
+
+
+def csr_workspace_bytes(num_edges: int, num_nodes: int) -> int:
+    lib().gp_csr_workspace_bytes.restype = C.c_int64
+    return int(lib().gp_csr_workspace_bytes(C.c_int64(num_edges), C.c_int32(num_nodes)))
+
+
+def halo_pack(x: torch.Tensor, idx: torch.Tensor, out: torch.Tensor) -> None:
+    """out[r] = x[idx[r]] (gp_halo_pack)."""
+    assert x.is_cuda and x.stride(1) == 1 and idx.dtype == torch.int32 and out.is_contiguous() and out.dtype == x.dtype
+    check(lib().gp_halo_pack(C.c_void_p(ptr(x)), C.c_int32(x.stride(0)), C.c_int32(x.element_size()), C.c_void_p(ptr(idx)),
+                             C.c_int32(idx.numel()), C.c_int32(x.shape[1]), C.c_void_p(ptr(out)), C.c_void_p(stream_ptr())), "gp_halo_pack")
+    _launched()
+
+
+def halo_unpack(x: torch.Tensor, idx: torch.Tensor, rows: torch.Tensor) -> None:
+    """x[idx[r]] = rows[r] (gp_halo_unpack)."""
+    assert x.is_cuda and x.stride(1) == 1 and idx.dtype == torch.int32 and rows.is_contiguous() and rows.dtype == x.dtype
+    check(lib().gp_halo_unpack(C.c_void_p(ptr(x)), C.c_int32(x.stride(0)), C.c_int32(x.element_size()), C.c_void_p(ptr(idx)),
+                               C.c_int32(idx.numel()), C.c_int32(x.shape[1]), C.c_void_p(ptr(rows)), C.c_void_p(stream_ptr())),
+          "gp_halo_unpack")
+    _launched()
+
+
+def halo_unpack_add(x: torch.Tensor, dst_rows: torch.Tensor, rowptr: torch.Tensor, order: torch.Tensor, rows: torch.Tensor) -> None:
+    """x[dst_rows[d]] += sum of rows[order[j]], j in [rowptr[d], rowptr[d+1])  (gp_halo_unpack_add, fp32, fixed order)."""
+    assert x.dtype == torch.float32 and rows.dtype == torch.float32 and x.stride(1) == 1 and rows.is_contiguous()
+    check(lib().gp_halo_unpack_add(C.c_void_p(ptr(x)), C.c_int32(x.stride(0)), C.c_void_p(ptr(dst_rows)), C.c_void_p(ptr(rowptr)),
+                                   C.c_void_p(ptr(order)), C.c_int32(dst_rows.numel()), C.c_int32(x.shape[1]), C.c_void_p(ptr(rows)),
+                                   C.c_void_p(stream_ptr())), "gp_halo_unpack_add")
+    _launched()

@@ -195,7 +195,8 @@ class Trainer:
             static = Data(**{k: torch.empty_like(getattr(batch, k), device=self.device) for k in fields})
             for k in fields:
                 getattr(static, k).copy_(getattr(batch, k), non_blocking=True)
-            self._training_step_eager(static)          # first step of this shape runs eagerly (allocations, smem attributes)
+            with no_csr_cache():                        # (allocates the persistent layout buffers outside the capture)
+                self._training_step_eager(static)      # first step of this shape runs eagerly (allocations, smem attributes)
             graph = torch.cuda.CUDAGraph()
             # with a process group, NCCL's watchdog thread polls CUDA events while we capture: only
             # this thread's calls belong to the capture
@@ -289,7 +290,8 @@ class Trainer:
                 pred.copy_(p)
                 last.copy_(p)
 
-            step()                                      # eager once: allocations, shared-memory attributes
+            with no_csr_cache():
+                step()                                  # eager once: allocations, shared-memory attributes
             graph = torch.cuda.CUDAGraph()
             with no_csr_cache(), torch.cuda.graph(graph):
                 step()

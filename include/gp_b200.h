@@ -282,6 +282,34 @@ int gp_csr_attention_fwd(const gp_attention_args* args, void* stream);
 int gp_csr_attention_bwd(const gp_attention_args* args, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Graph layout (integer work).  The reference hands COO edge lists (edge_index [2][E] int64, PyG order: sorted by
+ * sender) and aggregates at edge_index[1] (graphphysics/models/layers.py:926, 1016-1018, 1031-1037); the fused
+ * kernels want every receiver's edges contiguous.  gp_csr_from_coo builds, deterministically and without a host
+ * round trip (capturable in a CUDA graph):
+ *   perm_dst[p]   original edge id of sorted position p (STABLE sort by receiver)
+ *   src_sorted / dst_sorted [E]   endpoints in sorted order;   rowptr_dst [N+1]   receiver segments
+ *   perm_src[p]   positions of the sorted list, stably sorted by sender;   rowptr_src [N+1]   sender segments
+ *   att_col[p]    (optional) dst_sorted[perm_src[p]]: column of row-sorted entry p (attention kernels)
+ * workspace: gp_csr_workspace_bytes(E, N) bytes.  prev_edge_index ([2][E] int64) + state ([2] int32, zero-initialised),
+ * both optional and owned by the caller across calls: when given, the call first compares edge_index with the copy of
+ * the previous call and every kernel returns at once if nothing changed (static meshes under graph replay).
+ * --------------------------------------------------------------------------------------------- */
+int64_t gp_csr_workspace_bytes(int64_t num_edges, int32_t num_nodes);
+int gp_csr_from_coo(const int64_t* edge_index, int64_t num_edges, int32_t num_nodes, int32_t* perm_dst, int32_t* src_sorted,
+                    int32_t* dst_sorted, int32_t* rowptr_dst, int32_t* perm_src, int32_t* rowptr_src, int32_t* att_col,
+                    void* workspace, int64_t* prev_edge_index, int32_t* state, void* stream);
+
+/* Halo exchange of the node-partitioned mode: rows of a [.][ld] matrix (bf16: elem_bytes 2, fp32: 4).
+ *   gp_halo_pack:        out[r] = x[idx[r]]                      (send buffer, contiguous rows of `cols` elements)
+ *   gp_halo_unpack:      x[idx[r]] = in[r]                       (ghost rows overwritten by their owners' values)
+ *   gp_halo_unpack_add:  x[dst_rows[d]] += sum_{j in [rowptr[d], rowptr[d+1])} in[order[j]]   (fp32; the transpose of
+ *       pack for the backward: a row sent to several peers collects all of them in fixed order, no atomics) */
+int gp_halo_pack(const void* x, int32_t ld, int32_t elem_bytes, const int32_t* idx, int32_t n, int32_t cols, void* out, void* stream);
+int gp_halo_unpack(void* x, int32_t ld, int32_t elem_bytes, const int32_t* idx, int32_t n, int32_t cols, const void* in, void* stream);
+int gp_halo_unpack_add(float* x, int32_t ld, const int32_t* dst_rows, const int32_t* rowptr, const int32_t* order, int32_t n_dst,
+                       int32_t cols, const float* in, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Split-precision GEMM (tcgen05): the "tight" arithmetic mode (SURVEY §7 iii).  Every fp32 operand is split into
  * three bf16 terms hi + mid + lo on the fly (24 mantissa bits) and one product is six MMAs (fp32 accumulate in
  * TMEM, smallest terms first), i.e. fp32-grade products on the bf16 tensor path.  Replaces torch.nn.functional.linear inside build_mlp
