@@ -77,7 +77,7 @@ extern "C" int gp_sizeof_struct(const char* name) {
     if (!name) return -1;
 #define GP_SZ(T) if (!strcmp(name, #T)) return (int)sizeof(T);
     GP_SZ(gp_mlp_fwd_args) GP_SZ(gp_mlp_bwd_args) GP_SZ(gp_linear_bwd_args) GP_SZ(gp_pack_entry) GP_SZ(gp_reduce_seg)
-    GP_SZ(gp_attention_args) GP_SZ(gp_gemm3_args)
+    GP_SZ(gp_attention_args) GP_SZ(gp_gemm_args)
 #undef GP_SZ
     return -1;
 }

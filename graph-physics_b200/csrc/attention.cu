@@ -10,6 +10,8 @@
 // are strided across lanes, so the per-head dot product is a butterfly all-reduce over the lanes
 // that hold the same head.  fp32 throughout.  The backward is two gather passes (rows, then
 // columns) -- no atomics, bit-reproducible.
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 #include "../../include/gp_b200.h"
 
@@ -40,6 +42,24 @@ struct HeadReduce {
     }
 };
 
+// bf16 rows (q, k, v, y in the Transformer path: half the gathered bytes, SURVEY §8d E*(4H+8)) converted on load
+template <int VPT>
+__device__ __forceinline__ void load_row(const __nv_bfloat16* __restrict__ base, size_t row, int H, int lane, float (&out)[VPT]) {
+    const __nv_bfloat16* p = base + row * H + lane * VPT;
+    if constexpr (VPT == 4) {
+        const uint2 v = __ldg(reinterpret_cast<const uint2*>(p));
+        out[0] = __uint_as_float(v.x << 16); out[1] = __uint_as_float(v.x & 0xFFFF0000u);
+        out[2] = __uint_as_float(v.y << 16); out[3] = __uint_as_float(v.y & 0xFFFF0000u);
+    } else if constexpr (VPT == 2) {
+        const uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(p));
+        out[0] = __uint_as_float(v << 16); out[1] = __uint_as_float(v & 0xFFFF0000u);
+    } else {
+        out[0] = __bfloat162float(p[0]);
+    }
+}
+__device__ __forceinline__ void store_elem(float* p, float v) { *p = v; }
+__device__ __forceinline__ void store_elem(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+
 template <int VPT>
 __device__ __forceinline__ void load_row(const float* __restrict__ base, size_t row, int H, int lane, float (&out)[VPT]) {
     const float* p = base + row * H + lane * VPT;
@@ -54,10 +74,10 @@ __device__ __forceinline__ void load_row(const float* __restrict__ base, size_t 
     }
 }
 
-template <int VPT, int HH>
-__global__ void attn_fwd_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
+template <int VPT, int HH, typename T>
+__global__ void attn_fwd_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __restrict__ v,
                                 const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, int n, float scale,
-                                float* __restrict__ y, float* __restrict__ lse) {
+                                T* __restrict__ y, float* __restrict__ y32, float* __restrict__ lse) {
     constexpr int H = 32 * VPT;
     const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
@@ -87,16 +107,18 @@ __global__ void attn_fwd_kernel(const float* __restrict__ q, const float* __rest
 #pragma unroll
     for (int t = 0; t < VPT; ++t) {
         const int c = lane * VPT + t;
-        y[(size_t)i * H + c] = (e > b) ? acc[t] / s[t] : 0.f;
+        const float yv = (e > b) ? acc[t] / s[t] : 0.f;
+        store_elem(y + (size_t)i * H + c, yv);
+        if (y32) y32[(size_t)i * H + c] = yv;
         if (c < HH) lse[(size_t)i * HH + c] = (e > b) ? m[t] + __logf(s[t]) : 0.f;   // channel c < HH has head c
     }
 }
 
 // Backward pass 1 (rows): dq_i, and per stored entry the softmax weight a and ds = a * (dy.v - dy.y),
 // written at the entry's position in the COLUMN-sorted list (pos[p]) for pass 2.
-template <int VPT, int HH>
-__global__ void attn_bwd_rows_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
-                                     const float* __restrict__ y, const float* __restrict__ dy,
+template <int VPT, int HH, typename T>
+__global__ void attn_bwd_rows_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __restrict__ v,
+                                     const T* __restrict__ y, const float* __restrict__ y32, const float* __restrict__ dy,
                                      const float* __restrict__ lse, const int32_t* __restrict__ rowptr,
                                      const int32_t* __restrict__ col, const int32_t* __restrict__ pos, int n, float scale,
                                      float* __restrict__ dq, float* __restrict__ ea, float* __restrict__ eds) {
@@ -106,7 +128,8 @@ __global__ void attn_bwd_rows_kernel(const float* __restrict__ q, const float* _
     if (i >= n) return;
     float qv[VPT], yv[VPT], dyv[VPT], l[VPT], pr[VPT], D[VPT], dqa[VPT];
     load_row<VPT>(q, i, H, lane, qv);
-    load_row<VPT>(y, i, H, lane, yv);
+    if (y32) load_row<VPT>(y32, i, H, lane, yv);
+    else load_row<VPT>(y, i, H, lane, yv);
     load_row<VPT>(dy, i, H, lane, dyv);
 #pragma unroll
     for (int t = 0; t < VPT; ++t) {
@@ -144,8 +167,8 @@ __global__ void attn_bwd_rows_kernel(const float* __restrict__ q, const float* _
 
 // Backward pass 2 (columns): dk_j = sum_i ds_ij q_i / sqrt(d),  dv_j = sum_i a_ij dy_i over the entries of
 // column j (contiguous in the column-sorted list; `row` holds their row index).
-template <int VPT, int HH>
-__global__ void attn_bwd_cols_kernel(const float* __restrict__ q, const float* __restrict__ dy,
+template <int VPT, int HH, typename T>
+__global__ void attn_bwd_cols_kernel(const T* __restrict__ q, const float* __restrict__ dy,
                                      const float* __restrict__ ea, const float* __restrict__ eds,
                                      const int32_t* __restrict__ colptr, const int32_t* __restrict__ row, int n,
                                      float scale, float* __restrict__ dk, float* __restrict__ dv) {
@@ -177,18 +200,24 @@ __global__ void attn_bwd_cols_kernel(const float* __restrict__ q, const float* _
     }
 }
 
-template <int VPT, int HH>
-void launch_all(int which, const gp_attention_args& a, cudaStream_t st) {
+template <int VPT, int HH, typename T>
+void launch_typed(int which, const gp_attention_args& a, cudaStream_t st) {
     const int threads = 256, blocks = (int)(((size_t)a.n * 32 + threads - 1) / threads);
     const float scale = 1.f / sqrtf((float)(32 * VPT / HH));
+    const T *q = reinterpret_cast<const T*>(a.q), *k = reinterpret_cast<const T*>(a.k), *v = reinterpret_cast<const T*>(a.v);
+    T* y = reinterpret_cast<T*>(a.y);
     if (which == 0)
-        attn_fwd_kernel<VPT, HH><<<blocks, threads, 0, st>>>(a.q, a.k, a.v, a.rowptr, a.col, a.n, scale, a.y, a.lse);
+        attn_fwd_kernel<VPT, HH, T><<<blocks, threads, 0, st>>>(q, k, v, a.rowptr, a.col, a.n, scale, y, a.y_f32, a.lse);
     else if (which == 1)
-        attn_bwd_rows_kernel<VPT, HH><<<blocks, threads, 0, st>>>(a.q, a.k, a.v, a.y, a.dy, a.lse, a.rowptr, a.col, a.pos,
-                                                                a.n, scale, a.dq, a.edge_a, a.edge_ds);
+        attn_bwd_rows_kernel<VPT, HH, T><<<blocks, threads, 0, st>>>(q, k, v, y, a.y_f32, a.dy, a.lse, a.rowptr, a.col, a.pos, a.n, scale, a.dq,
+                                                                   a.edge_a, a.edge_ds);
     else
-        attn_bwd_cols_kernel<VPT, HH><<<blocks, threads, 0, st>>>(a.q, a.dy, a.edge_a, a.edge_ds, a.colptr, a.row, a.n,
-                                                                scale, a.dk, a.dv);
+        attn_bwd_cols_kernel<VPT, HH, T><<<blocks, threads, 0, st>>>(q, a.dy, a.edge_a, a.edge_ds, a.colptr, a.row, a.n, scale, a.dk, a.dv);
+}
+template <int VPT, int HH>
+void launch_all(int which, const gp_attention_args& a, cudaStream_t st) {
+    if (a.io_bf16) launch_typed<VPT, HH, __nv_bfloat16>(which, a, st);
+    else launch_typed<VPT, HH, float>(which, a, st);
 }
 
 template <int VPT>

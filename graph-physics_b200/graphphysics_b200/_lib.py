@@ -188,21 +188,26 @@ class AttentionArgs(C.Structure):
         ("dy", C.c_void_p), ("pos", C.c_void_p), ("colptr", C.c_void_p), ("row", C.c_void_p),
         ("dq", C.c_void_p), ("dk", C.c_void_p), ("dv", C.c_void_p),
         ("edge_a", C.c_void_p), ("edge_ds", C.c_void_p),
+        ("io_bf16", C.c_int32),
+        ("y_f32", C.c_void_p),
     ]
 
 
-class Gemm3Args(C.Structure):
+class GemmArgs(C.Structure):
     _fields_ = [
         ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32),
         ("a", C.c_void_p), ("a_sm", C.c_int64), ("a_sk", C.c_int64),
         ("b", C.c_void_p), ("b_sn", C.c_int64), ("b_sk", C.c_int64),
         ("c", C.c_void_p), ("c_sm", C.c_int64), ("c_sn", C.c_int64),
-        ("bias", C.c_void_p),
+        ("bias", C.c_void_p), ("resid", C.c_void_p),
+        ("a_bf16", C.c_int32), ("b_bf16", C.c_int32), ("c_bf16", C.c_int32),
         ("relu", C.c_int32), ("accumulate", C.c_int32),
+        ("terms", C.c_int32),
         ("split_k", C.c_int32),
         ("partials", C.c_void_p),
+        ("flags", C.c_int32),
     ]
 
 
 # header struct name -> ctypes class, beyond the core six (tests/test_boundary_cpu.py checks every one)
-EXTRA_STRUCTS = {"gp_gemm3_args": Gemm3Args}
+EXTRA_STRUCTS = {"gp_gemm_args": GemmArgs}

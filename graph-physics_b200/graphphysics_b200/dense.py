@@ -1,0 +1,377 @@
+"""Dense side of the graph-Transformer path on the native kernels (no library GEMM, no eager elementwise math):
+
+    Linear      y = x W^T + b [+ resid] [relu]          gp_gemm (tcgen05, bf16 operands, fp32 accumulate)
+    RMSNorm     one norm, or norm2 followed by the gated MLP's own norm           gp_rmsnorm_fwd / _bwd
+    GeluGate    GELU(a1) * a2                                                     gp_gelu_gate_fwd / _bwd
+    bias / scale gradients: per-block partial sums + fixed-order reduction        gp_colsum, gp_reduce_partials
+
+Three torch.autograd.Functions with hand-written backwards cover the model (graphphysics/models/layers.py:104-129,
+163-278, 637-697, 766-819):
+
+    attention_branch   [x +] proj(attention(q, k, v of [norm1](x)))       Attention.forward / first half of Transformer.forward
+    gated_branch       [x +] [W3] (GELU(W1 n) * (W2 n)), n = [norms](x)   GatedMLP.forward / second half of Transformer.forward
+    mlp4               build_mlp: Linear, ReLU x3, Linear, [RMSNorm]      nodes_encoder / decode_module
+
+Every bf16 tensor (norm outputs, q / k / v / y, the gate output, hidden activations) lives INSIDE one of these functions,
+so torch never sees a bf16 tensor that needs a gradient (it would cast that gradient to bf16): all gradients between
+kernels are fp32, rounded to bf16 only as MMA operands.  Arithmetic ("kernel specification", restated by
+oracle/gp_oracle.py mode="bf16"): GEMM operands -- activations, weights and, in the backward, the incoming gradient --
+rounded to bf16, fp32 accumulation; the residual stream x, norm statistics, GELU and all parameter-gradient sums in
+fp32.  terms = 3 (precision="tight") splits every fp32 operand into three bf16 terms instead and keeps all tensors fp32.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import ops
+from ._lib import AttentionArgs, GemmArgs, check, lib, ptr, stream_ptr
+
+
+# ------------------------------------------------------------------------------------------------ kernel wrappers (no autograd)
+def gemm(M: int, N: int, K: int, a: torch.Tensor, a_sm: int, a_sk: int, b: torch.Tensor, b_sn: int, b_sk: int, c: torch.Tensor,
+         c_sm: int, c_sn: int, *, bias: Optional[torch.Tensor] = None, resid: Optional[torch.Tensor] = None, relu: bool = False,
+         accumulate: bool = False, split_k: int = 1, terms: int = 1) -> None:
+    """C(m,n) = [C +] [resid +] bias[n] + sum_k A(m,k) B(n,k) with strided fp32 / bf16 operands (gp_gemm)."""
+    for t in (a, b, c):
+        assert t.is_cuda and t.dtype in (torch.float32, torch.bfloat16)
+    g = GemmArgs()
+    g.M, g.N, g.K = M, N, K
+    g.a, g.a_sm, g.a_sk = ptr(a), a_sm, a_sk
+    g.b, g.b_sn, g.b_sk = ptr(b), b_sn, b_sk
+    g.c, g.c_sm, g.c_sn = ptr(c), c_sm, c_sn
+    g.bias, g.resid = ptr(bias), ptr(resid)
+    g.a_bf16, g.b_bf16, g.c_bf16 = (int(t.dtype == torch.bfloat16) for t in (a, b, c))
+    g.relu, g.accumulate, g.terms, g.split_k = int(relu), int(accumulate), terms, split_k
+    part = None
+    if split_k > 1:
+        part = torch.empty(split_k * M * N, dtype=torch.float32, device=c.device)
+        g.partials = ptr(part)
+    check(lib().gp_gemm(C.byref(g), C.c_void_p(stream_ptr())), "gp_gemm")
+    ops._launched(2 if split_k > 1 else 1)
+
+
+def _reduce_rows(part: torch.Tensor, n_parts: int, cols: int) -> torch.Tensor:
+    out = torch.empty(cols, dtype=torch.float32, device=part.device)
+    ops.reduce_partials(part, n_parts, cols, 0, 1, cols, cols, out, cols, False)
+    return out
+
+
+def colsum(src: torch.Tensor, round_bf16: bool) -> torch.Tensor:
+    """Column sums of a contiguous fp32 [rows, cols] matrix (bias gradient), fixed order."""
+    rows, cols = src.shape
+    nb = int(lib().gp_colsum_blocks(C.c_int32(rows)))
+    part = torch.empty((nb, cols), dtype=torch.float32, device=src.device)
+    check(lib().gp_colsum(C.c_void_p(ptr(src)), C.c_int32(src.stride(0)), C.c_int32(rows), C.c_int32(cols), C.c_int32(int(round_bf16)),
+                          C.c_void_p(ptr(part)), C.c_void_p(stream_ptr())), "gp_colsum")
+    ops._launched()
+    return _reduce_rows(part, nb, cols)
+
+
+def _split_k(rows: int) -> int:
+    return max(1, min(128, (rows + 4095) // 4096))
+
+
+def lin_fwd(x, w, b, *, resid=None, relu=False, out_bf16=False, terms=1) -> torch.Tensor:
+    """y = x W^T + b [+ resid] [relu]; x [R, K] fp32 or bf16 (rows contiguous), w [N, K]."""
+    R, K = x.shape
+    N = w.shape[0]
+    assert w.shape[1] == K and w.stride(1) == 1 and x.stride(1) == 1
+    y = torch.empty((R, N), dtype=torch.bfloat16 if out_bf16 else torch.float32, device=x.device)
+    gemm(R, N, K, x, x.stride(0), 1, w, w.stride(0), 1, y, N, 1, bias=b, resid=resid, relu=relu, terms=terms)
+    return y
+
+
+def lin_dgrad(dy, w, *, out=None, terms=1) -> torch.Tensor:
+    """dx[r, k] (+)= sum_n dy[r, n] w[n, k]; accumulates into `out` when given."""
+    R, N = dy.shape
+    K = w.shape[1]
+    acc = out is not None
+    if out is None:
+        out = torch.empty((R, K), dtype=torch.float32, device=dy.device)
+    gemm(R, K, N, dy, N, 1, w, 1, w.stride(0), out, K, 1, accumulate=acc, terms=terms)
+    return out
+
+
+def lin_wgrad(dy, x, *, terms=1) -> torch.Tensor:
+    """dw[n, k] = sum_r dy[r, n] x[r, k] (split over CTAs along r, reduced in fixed order)."""
+    R, N = dy.shape
+    K = x.shape[1]
+    dw = torch.empty((N, K), dtype=torch.float32, device=dy.device)
+    gemm(N, K, R, dy, 1, N, x, 1, x.stride(0), dw, K, 1, split_k=_split_k(R), terms=terms)
+    return dw
+
+
+def bias_grad(dy, terms=1) -> torch.Tensor:
+    return colsum(dy, round_bf16=(terms == 1))
+
+
+def relu_mask_(d: torch.Tensor, h: torch.Tensor) -> None:
+    """d[i] = h[i] > 0 ? d[i] : 0 in place (d is a buffer this module allocated)."""
+    check(lib().gp_relu_bwd(C.c_void_p(ptr(d)), C.c_void_p(ptr(h)), C.c_int32(int(h.dtype == torch.bfloat16)), C.c_int64(d.numel()),
+                            C.c_void_p(stream_ptr())), "gp_relu_bwd")
+    ops._launched()
+
+
+def norm_fwd(x, s1, s2=None, out_bf16=True) -> torch.Tensor:
+    R, H = x.shape
+    out = torch.empty((R, H), dtype=torch.bfloat16 if out_bf16 else torch.float32, device=x.device)
+    check(lib().gp_rmsnorm_fwd(C.c_void_p(ptr(x)), C.c_int32(x.stride(0)), C.c_int32(R), C.c_int32(H), C.c_void_p(ptr(s1)),
+                               C.c_void_p(ptr(s2)), C.c_void_p(ptr(out) if out_bf16 else None), C.c_void_p(None if out_bf16 else ptr(out)),
+                               C.c_int32(H), C.c_void_p(stream_ptr())), "gp_rmsnorm_fwd")
+    ops._launched()
+    return out
+
+
+def norm_bwd(x, s1, s2, dy, add=None):
+    """dx = [add +] J^T dy through norm(x; s1) [then norm(.; s2)]; returns dx, dscale1, dscale2 (None without s2)."""
+    R, H = x.shape
+    nb = int(lib().gp_rmsnorm_bwd_blocks(C.c_int32(R)))
+    p1 = torch.empty((nb, H), dtype=torch.float32, device=x.device)
+    p2 = torch.empty((nb, H), dtype=torch.float32, device=x.device) if s2 is not None else None
+    dx = torch.empty((R, H), dtype=torch.float32, device=x.device)
+    check(lib().gp_rmsnorm_bwd(C.c_void_p(ptr(x)), C.c_int32(x.stride(0)), C.c_int32(R), C.c_int32(H), C.c_void_p(ptr(s1)),
+                               C.c_void_p(ptr(s2)), C.c_void_p(ptr(dy)), C.c_int32(dy.stride(0)), C.c_void_p(ptr(dx)), C.c_int32(H),
+                               C.c_void_p(ptr(add)), C.c_int32(add.stride(0) if add is not None else 0), C.c_void_p(ptr(p1)),
+                               C.c_void_p(ptr(p2)), C.c_void_p(stream_ptr())), "gp_rmsnorm_bwd")
+    ops._launched()
+    return dx, _reduce_rows(p1, nb, H), (_reduce_rows(p2, nb, H) if s2 is not None else None)
+
+
+def gelu_fwd(a1, a2, out_bf16=True) -> torch.Tensor:
+    g = torch.empty(a1.shape, dtype=torch.bfloat16 if out_bf16 else torch.float32, device=a1.device)
+    check(lib().gp_gelu_gate_fwd(C.c_void_p(ptr(a1)), C.c_void_p(ptr(a2)), C.c_int64(a1.numel()), C.c_void_p(ptr(g) if out_bf16 else None),
+                                 C.c_void_p(None if out_bf16 else ptr(g)), C.c_void_p(stream_ptr())), "gp_gelu_gate_fwd")
+    ops._launched()
+    return g
+
+
+def gelu_bwd(a1, a2, dg):
+    da1, da2 = torch.empty_like(a1), torch.empty_like(a2)
+    check(lib().gp_gelu_gate_bwd(C.c_void_p(ptr(a1)), C.c_void_p(ptr(a2)), C.c_void_p(ptr(dg)), C.c_int64(a1.numel()), C.c_void_p(ptr(da1)),
+                                 C.c_void_p(ptr(da2)), C.c_void_p(stream_ptr())), "gp_gelu_gate_bwd")
+    ops._launched()
+    return da1, da2
+
+
+def attn_fwd(q, k, v, g, num_heads: int):
+    """Adjacency-masked multi-head attention over the CSR rows of `g`; q, k, v [N, H] all fp32 or all bf16."""
+    n, h = q.shape
+    a = AttentionArgs()
+    a.io_bf16 = int(q.dtype == torch.bfloat16)
+    a.n, a.hidden, a.num_heads = n, h, num_heads
+    a.q, a.k, a.v = ptr(q), ptr(k), ptr(v)
+    a.rowptr, a.col = ptr(g.rowptr_src), ptr(g.att_col)
+    y = torch.empty_like(q)
+    y32 = torch.empty(q.shape, dtype=torch.float32, device=q.device) if a.io_bf16 else None
+    lse = torch.empty((n, num_heads), dtype=torch.float32, device=q.device)
+    a.y, a.lse, a.y_f32 = ptr(y), ptr(lse), ptr(y32)
+    check(lib().gp_csr_attention_fwd(C.byref(a), C.c_void_p(stream_ptr())), "gp_csr_attention_fwd")
+    ops._launched()
+    return y, y32, lse
+
+
+def attn_bwd(q, k, v, y, y32, lse, dy, g, num_heads: int):
+    n, h = q.shape
+    a = AttentionArgs()
+    a.io_bf16 = int(q.dtype == torch.bfloat16)
+    a.n, a.hidden, a.num_heads = n, h, num_heads
+    a.q, a.k, a.v, a.y, a.lse, a.dy, a.y_f32 = ptr(q), ptr(k), ptr(v), ptr(y), ptr(lse), ptr(dy), ptr(y32)
+    a.rowptr, a.col, a.pos = ptr(g.rowptr_src), ptr(g.att_col), ptr(g.perm_src)
+    a.colptr, a.row = ptr(g.rowptr_dst), ptr(g.src)
+    dq, dk, dv = (torch.empty(q.shape, dtype=torch.float32, device=q.device) for _ in range(3))
+    ea = torch.empty((g.num_edges, num_heads), dtype=torch.float32, device=q.device)
+    eds = torch.empty_like(ea)
+    a.dq, a.dk, a.dv, a.edge_a, a.edge_ds = ptr(dq), ptr(dk), ptr(dv), ptr(ea), ptr(eds)
+    check(lib().gp_csr_attention_bwd(C.byref(a), C.c_void_p(stream_ptr())), "gp_csr_attention_bwd")
+    ops._launched(2)
+    return dq, dk, dv
+
+
+def _f32(t: torch.Tensor) -> torch.Tensor:
+    if t.device.type != "cuda":
+        raise RuntimeError("graphphysics_b200 runs on CUDA devices only (there is no CPU fallback)")
+    return t.float().contiguous()
+
+
+# ------------------------------------------------------------------------------------------------ autograd functions
+class _AttentionBranch(torch.autograd.Function):
+    """out = [x +] proj(attention(q, k, v)), q / k / v = Linear([RMSNorm](x)) (layers.py:637-697, 766-790)."""
+
+    @staticmethod
+    def forward(ctx, x, sn, wq, bq, wk, bk, wv, bv, wp, bp, add_resid: bool, g, heads: int, terms: int):
+        x = _f32(x)
+        bf = terms == 1
+        n = norm_fwd(x, sn, None, out_bf16=bf) if sn is not None else x
+        q = lin_fwd(n, wq, bq, out_bf16=bf, terms=terms)
+        k = lin_fwd(n, wk, bk, out_bf16=bf, terms=terms)
+        v = lin_fwd(n, wv, bv, out_bf16=bf, terms=terms)
+        y, y32, lse = attn_fwd(q, k, v, g, heads)
+        out = lin_fwd(y, wp, bp, resid=x if add_resid else None, terms=terms)
+        ctx.save_for_backward(x, sn, n if sn is not None else None, q, k, v, y, y32, lse, wq, wk, wv, wp)
+        ctx.cfg = (add_resid, g, heads, terms, bq is not None, bk is not None, bv is not None, bp is not None)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, sn, n, q, k, v, y, y32, lse, wq, wk, wv, wp = ctx.saved_tensors
+        add_resid, g, heads, terms, hbq, hbk, hbv, hbp = ctx.cfg
+        if n is None:
+            n = x
+        dout = _f32(dout)
+        dy = lin_dgrad(dout, wp, terms=terms)
+        dwp, dbp = lin_wgrad(dout, y, terms=terms), (bias_grad(dout, terms) if hbp else None)
+        dq, dk, dv = attn_bwd(q, k, v, y, y32, lse, dy, g, heads)
+        dn = lin_dgrad(dq, wq, terms=terms)
+        lin_dgrad(dk, wk, out=dn, terms=terms)
+        lin_dgrad(dv, wv, out=dn, terms=terms)
+        dwq, dwk, dwv = lin_wgrad(dq, n, terms=terms), lin_wgrad(dk, n, terms=terms), lin_wgrad(dv, n, terms=terms)
+        dbq = bias_grad(dq, terms) if hbq else None
+        dbk = bias_grad(dk, terms) if hbk else None
+        dbv = bias_grad(dv, terms) if hbv else None
+        dsn = None
+        if sn is not None:
+            dx, dsn, _ = norm_bwd(x, sn, None, dn, add=dout if add_resid else None)
+        else:
+            assert not add_resid
+            dx = dn
+        return dx, dsn, dwq, dbq, dwk, dbk, dwv, dbv, dwp, dbp, None, None, None, None
+
+
+def attention_branch(x, norm_scale, att, g, add_resid: bool, terms: int = 1):
+    """`att`: a models.layers.Attention module (its q_proj / k_proj / v_proj / proj parameters)."""
+    return _AttentionBranch.apply(x, norm_scale, att.q_proj.weight, att.q_proj.bias, att.k_proj.weight, att.k_proj.bias,
+                                  att.v_proj.weight, att.v_proj.bias, att.proj.weight, att.proj.bias, add_resid, g, att.num_heads, terms)
+
+
+class _GatedBranch(torch.autograd.Function):
+    """out = [x +] [W3 .] (GELU(W1 n + b1) * (W2 n + b2)), n = [norm(norm(x; s1); s2)] (layers.py:213-278, 791-819)."""
+
+    @staticmethod
+    def forward(ctx, x, s1, s2, w1, b1, w2, b2, w3, b3, add_resid: bool, terms: int):
+        x = _f32(x)
+        bf = terms == 1
+        n = norm_fwd(x, s1, s2, out_bf16=bf) if s1 is not None else x
+        a1 = lin_fwd(n, w1, b1, terms=terms)
+        a2 = lin_fwd(n, w2, b2, terms=terms)
+        gate = gelu_fwd(a1, a2, out_bf16=(bf and w3 is not None))
+        out = lin_fwd(gate, w3, b3, resid=x if add_resid else None, terms=terms) if w3 is not None else gate
+        ctx.save_for_backward(x, s1, s2, n if s1 is not None else None, a1, a2, gate if w3 is not None else None, w1, w2, w3)
+        ctx.cfg = (add_resid, terms, b1 is not None, b2 is not None, b3 is not None)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, s1, s2, n, a1, a2, gate, w1, w2, w3 = ctx.saved_tensors
+        add_resid, terms, hb1, hb2, hb3 = ctx.cfg
+        if n is None:
+            n = x
+        dout = _f32(dout)
+        dw3 = db3 = None
+        if w3 is not None:
+            dg = lin_dgrad(dout, w3, terms=terms)
+            dw3, db3 = lin_wgrad(dout, gate, terms=terms), (bias_grad(dout, terms) if hb3 else None)
+        else:
+            dg = dout
+        da1, da2 = gelu_bwd(a1, a2, dg)
+        dn = lin_dgrad(da1, w1, terms=terms)
+        lin_dgrad(da2, w2, out=dn, terms=terms)
+        dw1, dw2 = lin_wgrad(da1, n, terms=terms), lin_wgrad(da2, n, terms=terms)
+        db1 = bias_grad(da1, terms) if hb1 else None
+        db2 = bias_grad(da2, terms) if hb2 else None
+        ds1 = ds2 = None
+        if s1 is not None:
+            dx, ds1, ds2 = norm_bwd(x, s1, s2, dn, add=dout if add_resid else None)
+        else:
+            assert not add_resid
+            dx = dn
+        return dx, ds1, ds2, dw1, db1, dw2, db2, dw3, db3, None, None
+
+
+def gated_branch(x, s1, s2, gmlp, out_linear, add_resid: bool, terms: int = 1):
+    """`gmlp`: a models.layers.GatedMLP; `out_linear`: the nn.Linear after it (None: return the gate itself, fp32)."""
+    w3, b3 = (out_linear.weight, out_linear.bias) if out_linear is not None else (None, None)
+    return _GatedBranch.apply(x, s1, s2, gmlp.linear1.weight, gmlp.linear1.bias, gmlp.linear2.weight, gmlp.linear2.bias, w3, b3,
+                              add_resid, terms)
+
+
+class _Mlp4(torch.autograd.Function):
+    """build_mlp (layers.py:163-210): Linear, ReLU, Linear, ReLU, Linear, ReLU, Linear, [RMSNorm]; hidden activations are
+    stored as bf16 (the next GEMM's operand; fp32 when terms = 3), the last Linear and the norm are fp32."""
+
+    @staticmethod
+    def forward(ctx, x, w0, b0, w1, b1, w2, b2, w3, b3, scale, terms: int):
+        x = _f32(x)
+        hb = terms == 1
+        h0 = lin_fwd(x, w0, b0, relu=True, out_bf16=hb, terms=terms)
+        h1 = lin_fwd(h0, w1, b1, relu=True, out_bf16=hb, terms=terms)
+        h2 = lin_fwd(h1, w2, b2, relu=True, out_bf16=hb, terms=terms)
+        y = lin_fwd(h2, w3, b3, terms=terms)
+        out = norm_fwd(y, scale, None, out_bf16=False) if scale is not None else y
+        ctx.save_for_backward(x, h0, h1, h2, y if scale is not None else None, scale, w0, w1, w2, w3)
+        ctx.terms = terms
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, h0, h1, h2, y, scale, w0, w1, w2, w3 = ctx.saved_tensors
+        terms = ctx.terms
+        d = _f32(dout)
+        dscale = None
+        if scale is not None:
+            d, dscale, _ = norm_bwd(y, scale, None, d)
+        grads = []
+        acts, ws = (x, h0, h1, h2), (w0, w1, w2, w3)
+        for i in (3, 2, 1, 0):
+            grads.append((lin_wgrad(d, acts[i], terms=terms), bias_grad(d, terms)))
+            if i > 0:
+                d = lin_dgrad(d, ws[i], terms=terms)
+                relu_mask_(d, acts[i])
+        dx = lin_dgrad(d, w0, terms=terms) if ctx.needs_input_grad[0] else None
+        (dw3, db3), (dw2, db2), (dw1, db1), (dw0, db0) = grads
+        return dx, dw0, db0, dw1, db1, dw2, db2, dw3, db3, dscale, None
+
+
+def mlp4(seq, x, terms: int = 1):
+    scale = seq[7].scale if len(seq) > 7 else None
+    return _Mlp4.apply(x, seq[0].weight, seq[0].bias, seq[2].weight, seq[2].bias, seq[4].weight, seq[4].bias, seq[6].weight,
+                       seq[6].bias, scale, terms)
+
+
+# small standalone functions (used by the unit tests and by RMSNorm-only callers); fp32 in, fp32 out under autograd
+class _RMSNorm(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, s1, s2, out_bf16: bool):
+        x = _f32(x)
+        ctx.save_for_backward(x, s1, s2)
+        return norm_fwd(x, s1, s2, out_bf16)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, s1, s2 = ctx.saved_tensors
+        dx, ds1, ds2 = norm_bwd(x, s1, s2, _f32(dy))
+        return dx, ds1, ds2, None
+
+
+def rms_norm(x, s1, s2=None, out_bf16: bool = False):
+    return _RMSNorm.apply(x, s1, s2, out_bf16)
+
+
+class _GeluGate(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a1, a2, out_bf16: bool):
+        a1, a2 = _f32(a1), _f32(a2)
+        ctx.save_for_backward(a1, a2)
+        return gelu_fwd(a1, a2, out_bf16)
+
+    @staticmethod
+    def backward(ctx, dg):
+        a1, a2 = ctx.saved_tensors
+        da1, da2 = gelu_bwd(a1, a2, _f32(dg))
+        return da1, da2, None
+
+
+def gelu_gate(a1, a2, out_bf16: bool = False):
+    return _GeluGate.apply(a1, a2, out_bf16)

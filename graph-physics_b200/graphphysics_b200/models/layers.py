@@ -56,6 +56,9 @@ class RMSNorm(nn.Module):
         self.scale = nn.Parameter(torch.ones(d))
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if x.is_cuda and self.d in (32, 64, 128) and self.eps == 1e-8:      # gp_rmsnorm_fwd / _bwd
+            from .. import dense
+            return dense.rms_norm(x.reshape(-1, self.d), self.scale).reshape(x.shape)
         rms = x.norm(2, dim=-1, keepdim=True) / math.sqrt(self.d)
         return self.scale * (x / (rms + self.eps))
 
@@ -203,9 +206,13 @@ class GatedMLP(nn.Module):
         self.linear1 = nn.Linear(in_size, expansion_factor * hidden_size)
         self.linear2 = nn.Linear(in_size, expansion_factor * hidden_size)
         self.activation = nn.GELU()
+        self.precision = "bf16"
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        return self.activation(self.linear1(x)) * self.linear2(x)
+        from .. import dense
+        if x.device.type != "cuda":
+            raise RuntimeError("graphphysics_b200 runs on CUDA devices only (there is no CPU fallback)")
+        return dense.gated_branch(x, None, None, self, None, add_resid=False, terms=3 if self.precision == "tight" else 1)
 
 
 def build_gated_mlp(in_size: int, hidden_size: int, out_size: int, expansion_factor: int = 3) -> nn.Module:
@@ -215,10 +222,11 @@ def build_gated_mlp(in_size: int, hidden_size: int, out_size: int, expansion_fac
 
 
 class Attention(nn.Module):
-    """Multi-head attention masked by the mesh adjacency (layers.py:564-697).  The projections are
-    plain dense layers (library GEMMs); scores, row softmax and the weighted sum -- the part the
-    reference sends to dgl.sparse bsddmm / softmax / bspmm -- run in the CSR attention kernels of
-    libgp_b200.so.  `adj` is the graph: a GraphCSR, or an edge_index tensor (2, E)."""
+    """Multi-head attention masked by the mesh adjacency (layers.py:564-697).  q / k / v / proj run on the tensor
+    cores (gp_gemm, bf16 operands, fp32 accumulate; q, k, v and y stored as bf16 in the reference's (N, d, heads)
+    layout); scores, row softmax and the weighted sum -- the part the reference sends to dgl.sparse bsddmm / softmax /
+    bspmm -- run in the CSR attention kernels of libgp_b200.so.  `adj` is the graph: a GraphCSR, or an edge_index
+    tensor (2, E)."""
 
     def __init__(self, input_dim=512, output_dim=512, num_heads=4, pos_dimension: int = 3, use_proj_bias: bool = True,
                  use_separate_proj_weight: bool = True, use_rope_embeddings: bool = False,
@@ -237,22 +245,24 @@ class Attention(nn.Module):
         self.m = 0
         self.register_buffer("rope_inv_freq", torch.empty(0, dtype=torch.float32), persistent=False)
         self.gate_proj = None
+        self.precision = "bf16"        # "tight": three-term split GEMMs, fp32 q / k / v / y (set by the owning model)
         if not use_separate_proj_weight:
             with torch.no_grad():
                 self.k_proj.weight = self.q_proj.weight
                 self.v_proj.weight = self.q_proj.weight
 
-    def forward(self, x: torch.Tensor, adj, pos: Optional[torch.Tensor] = None, return_attention: bool = False):
+    def _graph(self, x, adj):
         from ..graph import GraphCSR
-        from ..ops import CSRAttention
-        if return_attention:
-            raise NotImplementedError("return_attention=True is not supported (attention weights are never materialised)")
         if adj is None:
             raise ValueError("Attention needs the mesh adjacency (a GraphCSR or an edge_index tensor)")
-        g = adj if isinstance(adj, GraphCSR) else get_csr(adj, x.shape[0])
-        q, k, v = self.q_proj(x), self.k_proj(x), self.v_proj(x)
-        y = CSRAttention.apply(q, k, v, g, self.num_heads)
-        return self.proj(y)
+        return adj if isinstance(adj, GraphCSR) else get_csr(adj, x.shape[0])
+
+    def forward(self, x: torch.Tensor, adj, pos: Optional[torch.Tensor] = None, return_attention: bool = False):
+        from .. import dense
+        if return_attention:
+            raise NotImplementedError("return_attention=True is not supported (attention weights are never materialised)")
+        return dense.attention_branch(x, None, self, self._graph(x, adj), add_resid=False,
+                                      terms=3 if self.precision == "tight" else 1)
 
 
 class Transformer(nn.Module):
@@ -273,7 +283,23 @@ class Transformer(nn.Module):
         self.norm1, self.norm2 = RMSNorm(output_dim), RMSNorm(output_dim)
         self.gated_mlp = build_gated_mlp(in_size=output_dim, hidden_size=output_dim, out_size=output_dim)
         self.use_adjacency = True
+        self.set_precision("bf16")
+
+    def set_precision(self, precision: str) -> None:
+        """"bf16": bf16 MMA operands / bf16 q, k, v, y; "tight": three-term split GEMMs with fp32 tensors (csrc/gemm.cu)."""
+        if precision not in ("bf16", "tight"):
+            raise ValueError(f"precision must be 'bf16' or 'tight', got {precision!r}")
+        self.precision = self.attention.precision = self.gated_mlp[1].precision = precision
 
     def forward(self, x: torch.Tensor, adj, pos: Optional[torch.Tensor] = None, return_attention: bool = False):
-        x = x + self.attention(self.norm1(x), adj, pos=pos, return_attention=return_attention)
-        return x + self.gated_mlp(self.norm2(x))
+        """x (fp32 residual stream) -> x + Attn(norm1(x)) -> ... + W3(GELU(W1 n) * (W2 n)), n = norm_g(norm2(.)): seven
+        GEMMs, the CSR attention kernel and three row-wise kernels; both residual adds ride in a GEMM epilogue.  Two
+        autograd nodes (dense.attention_branch, dense.gated_branch) with hand-written backwards."""
+        from .. import dense
+        if return_attention:
+            raise NotImplementedError("return_attention=True is not supported (attention weights are never materialised)")
+        terms = 3 if self.precision == "tight" else 1
+        x = dense.attention_branch(x, self.norm1.scale, self.attention, self.attention._graph(x, adj), add_resid=True, terms=terms)
+        # the double norm: Transformer.norm2, then build_gated_mlp's own leading RMSNorm (layers.py:252-278)
+        return dense.gated_branch(x, self.norm2.scale, self.gated_mlp[0].scale, self.gated_mlp[1], self.gated_mlp[2],
+                                  add_resid=True, terms=terms)

@@ -70,14 +70,15 @@ class EncodeProcessDecode(nn.Module):
 class EncodeTransformDecode(nn.Module):
     """Encoder MLP, L graph-Transformer blocks over the mesh adjacency, decoder MLP
     (graphphysics/models/processors.py:218-384, the DGL branch).  Same constructor and state_dict
-    keys.  The adjacency-masked attention runs in the CSR kernels of libgp_b200.so; encoder, decoder,
-    projections and the gated MLP are dense layers executed as library GEMMs in fp32."""
+    keys.  Every dense layer -- encoder, q/k/v/proj, gated MLP, decoder -- is a tensor-core GEMM of libgp_b200.so
+    (gp_gemm, graphphysics_b200/dense.py), the adjacency-masked attention its CSR kernels, norms and the GELU gate its
+    row-wise kernels: no library GEMM and no eager elementwise math on the path."""
 
     def __init__(self, message_passing_num: int, node_input_size: int, output_size: int, hidden_size: int = 128,
                  num_heads: int = 4, only_processor: bool = False, use_proj_bias: bool = True,
                  use_separate_proj_weight: bool = True, use_rope_embeddings: bool = False,
                  use_gated_attention: bool = False, rope_pos_dimension: int = 3, rope_base: float = 10000.0,
-                 use_temporal_block: bool = False):
+                 use_temporal_block: bool = False, precision: str = None):
         super().__init__()
         from .layers import Transformer
         if use_temporal_block:
@@ -94,14 +95,21 @@ class EncodeTransformDecode(nn.Module):
                         use_gated_attention=use_gated_attention, pos_dimension=rope_pos_dimension, rope_base=rope_base)
             for _ in range(message_passing_num)])
         self.temporal_block = None
+        # "bf16": bf16 MMA operands, fp32 accumulate and residual stream -- the timed path; "tight": three-term split
+        # GEMMs (csrc/gemm.cu, terms = 3) with fp32 tensors, for rtol-1e-3 parity with the fp32 reference
+        self.precision = precision or os.environ.get("GP_B200_PRECISION", "bf16")
+        for blk in self.processor_list:
+            blk.set_precision(self.precision)
 
     def forward(self, graph) -> torch.Tensor:
         x = graph.x
         if x.device.type != "cuda":
             raise RuntimeError("graphphysics_b200 runs on CUDA devices only (there is no CPU fallback)")
+        from .. import dense
+        terms = 3 if self.precision == "tight" else 1
         g = get_csr(graph.edge_index, x.shape[0])          # processors.py:366: rows edge_index[0], cols edge_index[1]
         if not self.only_processor:
-            x = self.nodes_encoder(x)
+            x = dense.mlp4(self.nodes_encoder, x.float(), terms=terms)
         for block in self.processor_list:
             x = block(x, g, pos=getattr(graph, "pos", None))
-        return x if self.only_processor else self.decode_module(x)
+        return x if self.only_processor else dense.mlp4(self.decode_module, x, terms=terms)

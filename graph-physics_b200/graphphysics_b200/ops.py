@@ -427,42 +427,27 @@ from ._lib import AttentionArgs  # noqa: E402
 
 class CSRAttention(torch.autograd.Function):
     """y = masked multi-head attention(q, k, v) over the adjacency of `g` (rows = edge_index[0],
-    columns = edge_index[1]); gp_csr_attention_fwd / _bwd.  q, k, v: fp32 [N, H] contiguous."""
+    columns = edge_index[1]); gp_csr_attention_fwd / _bwd.  q, k, v: [N, H] contiguous, all fp32 or all bf16
+    (bf16: half the gathered bytes; y is then bf16 too, and an unrounded copy is kept for the backward)."""
 
     @staticmethod
     def forward(ctx, q, k, v, g, num_heads: int):
-        q, k, v = q.contiguous().float(), k.contiguous().float(), v.contiguous().float()
-        n, h = q.shape
-        a = AttentionArgs()
-        a.n, a.hidden, a.num_heads = n, h, num_heads
-        a.q, a.k, a.v = ptr(q), ptr(k), ptr(v)
-        a.rowptr, a.col = ptr(g.rowptr_src), ptr(g.att_col)
-        y = torch.empty_like(q)
-        lse = torch.empty((n, num_heads), dtype=torch.float32, device=q.device)
-        a.y, a.lse = ptr(y), ptr(lse)
-        check(lib().gp_csr_attention_fwd(C.byref(a), C.c_void_p(stream_ptr())), "gp_csr_attention_fwd")
-        _launched()
-        ctx.save_for_backward(q, k, v, y, lse)
+        from . import dense
+        bf = q.dtype == torch.bfloat16 and k.dtype == torch.bfloat16 and v.dtype == torch.bfloat16
+        if bf:
+            q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
+        else:
+            q, k, v = q.contiguous().float(), k.contiguous().float(), v.contiguous().float()
+        y, y32, lse = dense.attn_fwd(q, k, v, g, num_heads)
+        ctx.save_for_backward(q, k, v, y, y32, lse)
         ctx.g, ctx.num_heads = g, num_heads
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        q, k, v, y, lse = ctx.saved_tensors
-        g, nh = ctx.g, ctx.num_heads
-        n, h = q.shape
-        dy = dy.contiguous().float()
-        a = AttentionArgs()
-        a.n, a.hidden, a.num_heads = n, h, nh
-        a.q, a.k, a.v, a.y, a.lse, a.dy = ptr(q), ptr(k), ptr(v), ptr(y), ptr(lse), ptr(dy)
-        a.rowptr, a.col, a.pos = ptr(g.rowptr_src), ptr(g.att_col), ptr(g.perm_src)
-        a.colptr, a.row = ptr(g.rowptr_dst), ptr(g.src)
-        dq, dk, dv = torch.empty_like(q), torch.empty_like(q), torch.empty_like(q)
-        ea = torch.empty((g.num_edges, nh), dtype=torch.float32, device=q.device)
-        eds = torch.empty_like(ea)
-        a.dq, a.dk, a.dv, a.edge_a, a.edge_ds = ptr(dq), ptr(dk), ptr(dv), ptr(ea), ptr(eds)
-        check(lib().gp_csr_attention_bwd(C.byref(a), C.c_void_p(stream_ptr())), "gp_csr_attention_bwd")
-        _launched(2)
+        from . import dense
+        q, k, v, y, y32, lse = ctx.saved_tensors
+        dq, dk, dv = dense.attn_bwd(q, k, v, y, y32, lse, dy.contiguous().float(), ctx.g, ctx.num_heads)
         return dq, dk, dv, None, None
 
 

@@ -1,7 +1,7 @@
 """precision="tight": the encode-process-decode model evaluated with split-precision tensor-core GEMMs.
 
 Every dense contraction -- forward, dgrad and wgrad of every nn.Linear of build_mlp
-(graphphysics/models/layers.py:163-210) -- runs in gp_gemm3 (csrc/gemm3.cu): fp32 operands split into three bf16
+(graphphysics/models/layers.py:163-210) -- runs in gp_gemm with terms = 3 (csrc/gemm.cu): fp32 operands split into three bf16
 terms (hi + mid + lo, 24 mantissa bits), six tcgen05 MMAs per product, fp32 accumulate, fp32 tensors in HBM.  The algorithm is the one the
 fused bf16 kernels execute: the node-dependent column blocks of both first layers are applied once
 per node (P = x.[W1d; W1s; W1x]^T) and gathered as pre-activations.  Bias, ReLU, RMSNorm, gathers, the receiver sum
@@ -13,35 +13,20 @@ model section of the training JSON, or GP_B200_PRECISION=tight.
 """
 from __future__ import annotations
 
-import ctypes as C
 import math
 from typing import Optional
 
 import torch
 
-from ._lib import Gemm3Args, check, lib, ptr, stream_ptr
+from .dense import gemm as _gemm
 
 
 def gemm3(M: int, N: int, K: int, a: torch.Tensor, a_sm: int, a_sk: int, b: torch.Tensor, b_sn: int, b_sk: int,
           c: torch.Tensor, c_sm: int, c_sn: int, bias: Optional[torch.Tensor] = None, relu: bool = False,
           accumulate: bool = False, split_k: int = 1) -> None:
-    """C(m,n) = [C +] bias[n] + sum_k A(m,k) B(n,k) with strided fp32 operands (gp_gemm3)."""
+    """C(m,n) = [C +] bias[n] + sum_k A(m,k) B(n,k) with strided fp32 operands, three-term split (gp_gemm, terms = 3)."""
     assert a.dtype == b.dtype == c.dtype == torch.float32
-    args = Gemm3Args()
-    args.M, args.N, args.K = M, N, K
-    args.a, args.a_sm, args.a_sk = ptr(a), a_sm, a_sk
-    args.b, args.b_sn, args.b_sk = ptr(b), b_sn, b_sk
-    args.c, args.c_sm, args.c_sn = ptr(c), c_sm, c_sn
-    args.bias = ptr(bias)
-    args.relu, args.accumulate = int(relu), int(accumulate)
-    args.split_k = split_k
-    part = None
-    if split_k > 1:
-        part = torch.empty(split_k * M * N, dtype=torch.float32, device=c.device)
-        args.partials = ptr(part)
-    check(lib().gp_gemm3(C.byref(args), C.c_void_p(stream_ptr())), "gp_gemm3")
-    from . import ops
-    ops._launched(2 if split_k > 1 else 1)
+    _gemm(M, N, K, a, a_sm, a_sk, b, b_sn, b_sk, c, c_sm, c_sn, bias=bias, relu=relu, accumulate=accumulate, split_k=split_k, terms=3)
 
 
 class _Linear3(torch.autograd.Function):

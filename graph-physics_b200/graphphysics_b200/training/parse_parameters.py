@@ -34,7 +34,8 @@ def get_model(param: Dict[str, Any], only_processor: bool = False):
         from ..models.processors import EncodeTransformDecode
         return EncodeTransformDecode(message_passing_num=m["message_passing_num"], node_input_size=node_input_size,
                                      output_size=m["output_size"], hidden_size=m["hidden_size"],
-                                     num_heads=m["num_heads"], only_processor=only_processor, **common)
+                                     num_heads=m["num_heads"], only_processor=only_processor, precision=m.get("precision"),
+                                     **common)
     if model_type == "transolver":
         raise NotImplementedError("model type 'transolver' is outside the accelerated path (SURVEY §2)")
     raise ValueError(f"Model type '{model_type}' not supported.")

@@ -250,7 +250,7 @@ int gp_reduce_partials_multi(const float* partials, int32_t n_parts, int32_t str
 /* ---------------------------------------------------------------------------------------------
  * Adjacency-masked multi-head attention over a CSR graph: the DGL-sparse path of
  * graphphysics/models/layers.py:493-561 (bsddmm, row softmax, bspmm) as used by Attention.forward
- * (layers.py:637-697).  q, k, v, y, dy, dq, dk, dv are fp32 [n][hidden] with the reference's head
+ * (layers.py:637-697).  q, k, v, y (fp32, or bf16 with io_bf16) and dy, dq, dk, dv (fp32) are [n][hidden] with the reference's head
  * layout (channel c = d_idx*num_heads + h).  Rows are edge_index[0], columns edge_index[1].
  *   rowptr/col : the entries sorted by row (CSR);      pos[p] = index of row-sorted entry p in the
  *   colptr/row : the entries sorted by column (CSC);             column-sorted list
@@ -277,6 +277,9 @@ typedef struct gp_attention_args {
     float* dv;
     float* edge_a;
     float* edge_ds;
+    int32_t io_bf16; /* != 0: q, k, v and y are bf16 (raw uint16) instead of fp32 -- the Transformer path; everything else stays fp32 */
+    float* y_f32;    /* optional, with io_bf16: the forward also writes y unrounded here and the backward reads it (dy.y is the
+                        softmax-gradient offset of every entry of the row: kept exact, 4H bytes per NODE) */
 } gp_attention_args;
 int gp_csr_attention_fwd(const gp_attention_args* args, void* stream);
 int gp_csr_attention_bwd(const gp_attention_args* args, void* stream);
@@ -310,29 +313,62 @@ int gp_halo_unpack_add(float* x, int32_t ld, const int32_t* dst_rows, const int3
                        int32_t cols, const float* in, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
- * Split-precision GEMM (tcgen05): the "tight" arithmetic mode (SURVEY §7 iii).  Every fp32 operand is split into
- * three bf16 terms hi + mid + lo on the fly (24 mantissa bits) and one product is six MMAs (fp32 accumulate in
- * TMEM, smallest terms first), i.e. fp32-grade products on the bf16 tensor path.  Replaces torch.nn.functional.linear inside build_mlp
- * (graphphysics/models/layers.py:163-210) -- forward, dgrad and wgrad alike, by choice of strides -- when the
- * model is built with precision="tight"; brings the whole model within 1e-3 of the fp32 reference.
- *   C(m, n) = [C(m, n) +] bias[n] + sum_k A(m, k) * B(n, k),  then max(., 0) if relu
- *   A(m, k) = a[m*a_sm + k*a_sk],  B(n, k) = b[n*b_sn + k*b_sk],  C(m, n) = c[m*c_sm + n*c_sn]  (fp32, element strides)
+ * Strided row-tile GEMM (tcgen05): the dense building block of the graph-Transformer path and of the "tight" mode.
+ *   C(m, n) = [C(m, n) +] [resid(m, n) +] bias[n] + sum_k A(m, k) * B(n, k),  then max(., 0) if relu
+ *   A(m, k) = a[m*a_sm + k*a_sk],  B(n, k) = b[n*b_sn + k*b_sk],  C(m, n) = c[m*c_sm + n*c_sn]  (element strides)
+ * a / b / c are fp32 or bf16 (a_bf16 / b_bf16 / c_bf16 != 0); resid is fp32, indexed like C.  By choice of strides
+ * this is torch.nn.functional.linear (graphphysics/models/layers.py:163-210, 213-278, 637-697), its dgrad or its wgrad.
+ *   terms = 1: operands rounded to bf16, one MMA per k-step (Transformer block);
+ *   terms = 3: fp32 operands split into three bf16 terms hi + mid + lo (24 mantissa bits), six MMAs per k-step, smallest
+ *              terms first: fp32-grade products on the bf16 tensor path (precision="tight", SURVEY §7 iii).
  * split_k > 1 cuts K over CTAs (partials: split_k*M*N floats of scratch, reduced in fixed order).
+ * `flags` is filled by the library.
  * --------------------------------------------------------------------------------------------- */
-typedef struct gp_gemm3_args {
+typedef struct gp_gemm_args {
     int32_t M, N, K;
-    const float* a;
+    const void* a;
     int64_t a_sm, a_sk;
-    const float* b;
+    const void* b;
     int64_t b_sn, b_sk;
-    float* c;
+    void* c;
     int64_t c_sm, c_sn;
     const float* bias;
+    const float* resid;
+    int32_t a_bf16, b_bf16, c_bf16;
     int32_t relu, accumulate;
+    int32_t terms;
     int32_t split_k;
     float* partials;
-} gp_gemm3_args;
-int gp_gemm3(const gp_gemm3_args* args, void* stream);
+    int32_t flags;
+} gp_gemm_args;
+int gp_gemm(const gp_gemm_args* args, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Row-wise kernels of the graph-Transformer block (graphphysics/models/layers.py:104-129 RMSNorm, 213-249 GatedMLP,
+ * 766-819 Transformer.forward) around gp_gemm and gp_csr_attention_*.  fp32 arithmetic, no atomics; the *_blocks()
+ * helpers give the number of per-block partial rows that gp_reduce_partials then adds in fixed order.
+ *   gp_rmsnorm_fwd : y = s1*x/(rms(x)+1e-8); with scale2 the second norm of the gated MLP is applied on top
+ *                    (Transformer.norm2 followed by build_gated_mlp's own RMSNorm); output bf16 (MMA operand) or fp32
+ *   gp_rmsnorm_bwd : dx = [add +] J^T dy through the same one or two norms (recomputed from x; `add`, e.g. the gradient
+ *                    of the residual path, may be NULL or alias dx);
+ *                    part1 / part2: [gp_rmsnorm_bwd_blocks(rows)][hidden] partial sums of dscale1 / dscale2
+ *   gp_gelu_gate_* : g = GELU(a1) * a2 elementwise over n contiguous fp32 values (a1 = linear1(x), a2 = linear2(x)), exact
+ *                    (erf) GELU, bf16 result (the operand of the last Linear); backward
+ *   gp_relu_bwd    : d[i] = h[i] > 0 ? d[i] : 0 in place (h fp32 or bf16)
+ *   gp_colsum      : partials[gp_colsum_blocks(rows)][cols] of the column sums of src (bias gradients); round_bf16 sums
+ *                    the bf16-rounded values (the delta is a bf16 MMA operand of the matching dgrad / wgrad)
+ * --------------------------------------------------------------------------------------------- */
+int gp_rmsnorm_fwd(const float* x, int32_t ldx, int32_t rows, int32_t hidden, const float* scale1, const float* scale2,
+                   gp_bf16* out_bf16, float* out_f32, int32_t ld_out, void* stream);
+int gp_rmsnorm_bwd_blocks(int32_t rows);
+int gp_rmsnorm_bwd(const float* x, int32_t ldx, int32_t rows, int32_t hidden, const float* scale1, const float* scale2,
+                   const float* dy, int32_t ld_dy, float* dx, int32_t ld_dx, const float* add, int32_t ld_add, float* part1,
+                   float* part2, void* stream);
+int gp_gelu_gate_fwd(const float* a1, const float* a2, int64_t n, gp_bf16* g_bf16, float* g_f32, void* stream);
+int gp_gelu_gate_bwd(const float* a1, const float* a2, const float* dg, int64_t n, float* da1, float* da2, void* stream);
+int gp_relu_bwd(float* d, const void* h, int32_t h_bf16, int64_t n, void* stream);
+int gp_colsum_blocks(int32_t rows);
+int gp_colsum(const float* src, int32_t ld, int32_t rows, int32_t cols, int32_t round_bf16, float* partials, void* stream);
 
 #ifdef __cplusplus
 }

@@ -212,29 +212,41 @@ def attention(x, row, col, sd, prefix: str, num_heads: int, mode: Optional[str] 
 
 def transformer_block(x, row, col, sd, prefix: str, num_heads: int, mode: Optional[str] = None):
     """Transformer.forward (layers.py:766-819) with build_gated_mlp (layers.py:252-278, 213-249):
-    x += Attn(norm1(x));  x += W3( GELU(W1 n) * (W2 n) ),  n = RMSNorm_g(RMSNorm_2(x))."""
+    x += Attn(norm1(x));  x += W3( GELU(W1 n) * (W2 n) ),  n = RMSNorm_g(RMSNorm_2(x)).
+    Kernel mode: the residual stream x stays fp32 (both adds ride in a GEMM epilogue); the norm outputs, q / k / v / y and
+    the gate output are bf16 (MMA operands); the scale gradients are plain fp32 column sums (gp_rmsnorm_bwd)."""
     n1 = rms_norm(x, sd[f"{prefix}.norm1.scale"])
-    x = rnd(x + attention(rnd(n1, mode), row, col, sd, f"{prefix}.attention", num_heads, mode), mode)
+    x = x + attention(rnd(n1, mode), row, col, sd, f"{prefix}.attention", num_heads, mode)
     n2 = rms_norm(rms_norm(x, sd[f"{prefix}.norm2.scale"]), sd[f"{prefix}.gated_mlp.0.scale"])
     n2 = rnd(n2, mode)
     left = F.gelu(linear(n2, sd[f"{prefix}.gated_mlp.1.linear1.weight"], sd[f"{prefix}.gated_mlp.1.linear1.bias"], mode))
     right = linear(n2, sd[f"{prefix}.gated_mlp.1.linear2.weight"], sd[f"{prefix}.gated_mlp.1.linear2.bias"], mode)
     g = rnd(left * right, mode)
     out = linear(g, sd[f"{prefix}.gated_mlp.2.weight"], sd[f"{prefix}.gated_mlp.2.bias"], mode)
-    return rnd(x + out, mode)
+    return x + out
+
+
+def dense_mlp(x, sd, prefix: str, layer_norm: bool = True, mode: Optional[str] = None):
+    """build_mlp as the Transformer path runs it (graphphysics_b200/dense.py mlp4): one GEMM per Linear, hidden
+    activations stored as bf16, fp32 output and a plain fp32 RMSNorm."""
+    h = x
+    for i in range(4):
+        h = linear(h, sd[f"{prefix}.{2 * i}.weight"], sd[f"{prefix}.{2 * i}.bias"], mode)
+        if i < 3:
+            h = rnd(F.relu(h), mode)
+    return rms_norm(h, sd[f"{prefix}.7.scale"]) if layer_norm else h
 
 
 def etd_forward(sd, x_in, edge_index, num_layers: int, num_heads: int, mode: Optional[str] = None, prefix: str = ""):
     """EncodeTransformDecode.forward, DGL branch (processors.py:338-384): adjacency rows are
     edge_index[0], columns edge_index[1] (processors.py:366), no self loops added."""
     row, col = edge_index[0], edge_index[1]
-    x = rnd(mlp(x_in, sd, f"{prefix}nodes_encoder", mode=mode), mode)
+    x = dense_mlp(x_in, sd, f"{prefix}nodes_encoder", mode=mode)
     for i in range(num_layers):
         x = transformer_block(x, row, col, sd, f"{prefix}processor_list.{i}", num_heads, mode)
-    return mlp(x, sd, f"{prefix}decode_module", layer_norm=False, mode=mode)
+    return dense_mlp(x, sd, f"{prefix}decode_module", layer_norm=False, mode=mode)
 
 
-# --------------------------------------------------------------------------- normalizer / simulator / loss
 class Normalizer:
     """Normalizer (layers.py:281-408): running sum / sum of squares / count, frozen after
     max_accumulations calls; (x - mean) / max(std, eps)."""
