@@ -131,3 +131,26 @@ def kuhn_box_graph(nx: int, ny: int, nz: int):
     row, col = np.concatenate(rows), np.concatenate(cols)
     order = np.argsort(row * np.int64(nx * ny * nz) + col, kind="stable")
     return pos, np.stack([row[order], col[order]])
+
+
+def deforming_plate_sample(nx: int = 21, ny: int = 21, nz: int = 3, seed: int = 0):
+    """DeformingPlate-shaped sample (BASELINE.json configs[2]; no dataset access): a thin tetrahedral plate (~1.3k NORMAL
+    nodes, HANDLE nodes along one edge) and a small rigid OBSTACLE block hovering within the world-edge radius above it.
+    Returns numpy arrays: mesh_pos (N,3) fp32, tetra (T,4) int64, x_raw (N,4) = [world_pos, node_type], y (N,3) = the next
+    world_pos (the obstacle moves down, the plate gives way a little)."""
+    rng = np.random.default_rng(seed)
+    p, t = box_tet_mesh(nx, ny, nz)
+    p = p * np.array([0.5, 0.5, 0.02], np.float32)
+    o, to = box_tet_mesh(5, 5, 3)
+    o = o * np.array([0.08, 0.08, 0.04], np.float32) + np.array([0.21, 0.21, 0.03], np.float32)
+    pos = np.concatenate([p, o]).astype(np.float32)
+    tets = np.concatenate([t, to + len(p)])
+    ntype = np.full(len(pos), int(NodeType.NORMAL), np.int64)
+    ntype[: len(p)][p[:, 0] < 1e-6] = int(NodeType.HANDLE)
+    ntype[len(p):] = int(NodeType.OBSTACLE)
+    world = pos + np.concatenate([0.002 * rng.standard_normal(p.shape), np.zeros_like(o)]).astype(np.float32)
+    nxt = world.copy()
+    nxt[len(p):, 2] -= 0.002
+    nxt[: len(p)] += (0.0005 * rng.standard_normal(p.shape)).astype(np.float32)
+    x_raw = np.concatenate([world, ntype[:, None].astype(np.float32)], 1).astype(np.float32)
+    return pos, tets, x_raw, nxt.astype(np.float32)

@@ -370,6 +370,39 @@ int gp_relu_bwd(float* d, const void* h, int32_t h_bf16, int64_t n, void* stream
 int gp_colsum_blocks(int32_t rows);
 int gp_colsum(const float* src, int32_t ld, int32_t rows, int32_t cols, int32_t round_bf16, float* partials, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Graph construction on the device -- what the reference's preprocessing does on the host for every
+ * sample: graphphysics/dataset/preprocessing.py:410-424 T.FaceToEdge (+ graphphysics/utils/torch_graph.py:194-210
+ * tetrahedra -> triangles), :16-23 T.Cartesian + T.Distance, :92-140 add_world_edges (cKDTree.query_pairs + node-type
+ * mask + to_undirected), :143-175 add_world_pos_features, :177-238 add_noise.  All index arrays int64 like edge_index.
+ *   gp_cell_edge_candidates : cells (3 or 4 vertices; vertex-major [verts][n] like PyG `face`, or cell-major [n][verts])
+ *                             -> 6 (12) directed candidate pairs per cell in cand_row / cand_col
+ *   gp_coalesce_count       : buckets / marks the candidates, writes the number of unique directed pairs to *num_unique
+ *                             (device int32); gp_coalesce_write then writes them sorted by (row, col) -- PyG coalesce.
+ *                             workspace: gp_coalesce_workspace_bytes(n_cand, num_nodes), shared by the two calls
+ *   gp_edge_features        : out[e] = [pos[row]-pos[col] (dim values), ||pos[col]-pos[row]||_2], fp32, out row stride ld_out
+ *   gp_world_pairs_count    : OBSTACLE-NORMAL node pairs within `radius` (fp64 squared distance, <=); *num_pairs (device
+ *                             int32) = number of unordered pairs; gp_world_pairs_fill writes both directions of every
+ *                             pair (2 * num_pairs entries).  workspace: gp_world_pairs_workspace_bytes(num_nodes)
+ *   gp_add_noise            : x[r, col_start:col_end] += noise[r, :] * scale where x[r, node_type_col] == normal_type
+ * --------------------------------------------------------------------------------------------- */
+int gp_cell_edge_candidates(const int64_t* cells, int64_t n_cells, int32_t verts_per_cell, int32_t cell_major, int64_t* cand_row,
+                            int64_t* cand_col, void* stream);
+int64_t gp_coalesce_workspace_bytes(int64_t n_cand, int32_t num_nodes);
+int gp_coalesce_count(const int64_t* cand_row, const int64_t* cand_col, int64_t n_cand, int32_t num_nodes, void* workspace,
+                      int32_t* num_unique, void* stream);
+int gp_coalesce_write(const int64_t* cand_row, const int64_t* cand_col, int64_t n_cand, int32_t num_nodes, void* workspace,
+                      int64_t* out_row, int64_t* out_col, void* stream);
+int gp_edge_features(const float* pos, int32_t ld_pos, int32_t dim, const int64_t* row, const int64_t* col, int64_t num_edges,
+                     float* out, int32_t ld_out, void* stream);
+int64_t gp_world_pairs_workspace_bytes(int32_t num_nodes);
+int gp_world_pairs_count(const float* pos, int32_t ld_pos, const float* node_type, int32_t ld_type, int32_t num_nodes, double radius,
+                         int32_t normal_type, int32_t obstacle_type, void* workspace, int32_t* num_pairs, void* stream);
+int gp_world_pairs_fill(const float* pos, int32_t ld_pos, const float* node_type, int32_t ld_type, int32_t num_nodes, double radius,
+                        int32_t obstacle_type, void* workspace, int64_t* out_row, int64_t* out_col, void* stream);
+int gp_add_noise(float* x, int32_t ld, int32_t rows, int32_t col_start, int32_t col_end, int32_t node_type_col, int32_t normal_type,
+                 const float* noise, float scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -507,3 +507,38 @@ def grid_tet_mesh(nx: int, ny: int, nz: int):
         np.stack([v000, v010, v011, v111], -1), np.stack([v000, v011, v001, v111], -1),
         np.stack([v000, v001, v101, v111], -1), np.stack([v000, v101, v100, v111], -1)])
     return pos.astype(np.float32), tets.astype(np.int64)
+
+
+# --------------------------------------------------------------------------- preprocessing around the path
+def world_edges(edge_index: np.ndarray, world_pos: np.ndarray, node_type: np.ndarray, num_nodes: int, radius: float = 0.03) -> np.ndarray:
+    """add_world_edges (preprocessing.py:92-140): cKDTree.query_pairs(radius) on the fp32 world positions (scipy, the
+    reference's own third-party call: pairs i < j with distance <= radius), kept when one end is OBSTACLE and the other
+    NORMAL, concatenated in front of the mesh edges and passed through to_undirected (both directions, coalesced,
+    sorted by (row, col)).  Returns int64 (2, E)."""
+    from scipy.spatial import cKDTree
+    pairs = cKDTree(np.asarray(world_pos)).query_pairs(radius, output_type="ndarray").T.astype(np.int64)
+    t0, t1 = node_type[pairs[0]], node_type[pairs[1]]
+    keep = ((t0 == OBSTACLE) & (t1 == NORMAL)) | ((t0 == NORMAL) & (t1 == OBSTACLE))
+    ei = np.concatenate([pairs[:, keep], np.asarray(edge_index, dtype=np.int64)], axis=1)
+    both = np.concatenate([ei, ei[::-1]], axis=1)
+    key = np.unique(both[0] * np.int64(num_nodes) + both[1])
+    return np.stack([key // num_nodes, key % num_nodes])
+
+
+def world_pos_features(edge_attr: np.ndarray, world_pos: np.ndarray, edge_index: np.ndarray) -> np.ndarray:
+    """add_world_pos_features (preprocessing.py:143-175): [edge_attr, wp[senders]-wp[receivers], ||.||_2], fp32."""
+    s, r = edge_index
+    rel = (world_pos[s] - world_pos[r]).astype(np.float32)
+    back = (world_pos[r] - world_pos[s]).astype(np.float32)          # same magnitude; spelled like edge_features
+    nrm = np.linalg.norm(back, axis=-1, keepdims=True).astype(np.float32)
+    return np.concatenate([edge_attr.astype(np.float32), rel, nrm], -1)
+
+
+def add_noise(x: np.ndarray, noise: np.ndarray, start: int, end: int, scale: float, node_type_index: int, t: Optional[float] = None):
+    """add_noise (preprocessing.py:177-238) with the Gaussian draw passed in: x[:, start:end] += noise * scale on NORMAL
+    nodes (scale(t) = 10 * scale * (1 + cos(pi t)) under the curriculum); fp32."""
+    s = np.float32(10 * scale * (1 + math.cos(t * math.pi)) if t is not None else scale)
+    out = x.copy()
+    keep = (x[:, node_type_index] == NORMAL)[:, None]
+    out[:, start:end] = x[:, start:end] + np.where(keep, noise.astype(np.float32) * s, np.float32(0))
+    return out

@@ -1,0 +1,158 @@
+"""GPU: graph construction kernels (csrc/mesh_ops.cu, graphphysics_b200/preprocessing.py) against the CPU oracle, BIT-EXACT:
+FaceToEdge on the reference's own fixture meshes (11 070 / 291 144 directed edges, the counts the reference's tests pin:
+tests/graphphysics/dataset/test_xdmfdataset.py:31,46), Cartesian + Distance edge features, world edges (cKDTree radius
+search + node-type mask + to_undirected), world-position features, noise injection, and the whole build_preprocessing
+pipeline on a DeformingPlate-shaped sample (BASELINE.json configs[2])."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(__file__), "golden")
+DEV = "cuda:0"
+
+
+def _t(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+
+
+def test_face_to_edge_cylinder_and_aneurysm_bit_exact():
+    from oracle import gp_oracle as O
+    from graphphysics_b200 import preprocessing as P
+    from graphphysics_b200.graph import Data
+    c = np.load(os.path.join(G, "cylinder_mesh.npz"))
+    ref = O.face_to_edge(c["triangles"], 1923)
+    g = P.face_to_edge(Data(x=torch.zeros(1923, 1, device=DEV), face=_t(c["triangles"].T.astype(np.int64))))
+    assert g.edge_index.dtype == torch.int64 and tuple(g.edge_index.shape) == (2, 11070)
+    assert np.array_equal(g.edge_index.cpu().numpy(), ref)
+    a = np.load(os.path.join(G, "aneurysm_mesh.npz"))
+    ref = O.face_to_edge(O.tetra_to_faces(a["tets"]), 22535)
+    g = P.face_to_edge(Data(x=torch.zeros(22535, 1, device=DEV), tetra=_t(a["tets"].T.astype(np.int64))))
+    assert tuple(g.edge_index.shape) == (2, 291144)
+    assert np.array_equal(g.edge_index.cpu().numpy(), ref)
+    # the reference's loader hands FaceToEdge the four triangles of every tetrahedron (torch_graph.py:194-210): same result
+    cells = torch.from_numpy(a["tets"].T.astype(np.int64))
+    face = torch.cat([cells[0:3], cells[1:4], torch.stack([cells[2], cells[3], cells[0]]), torch.stack([cells[3], cells[0], cells[1]])], dim=1)
+    g2 = P.face_to_edge(Data(x=torch.zeros(22535, 1, device=DEV), face=face.to(DEV)))
+    assert torch.equal(g2.edge_index, g.edge_index)
+
+
+def test_coalesce_edge_cases():
+    from graphphysics_b200 import preprocessing as P
+    # duplicates, self loops, isolated nodes, one hub row with a long bucket, empty input
+    rng = np.random.default_rng(0)
+    n = 500
+    row = np.concatenate([rng.integers(0, n, 4000), np.full(3000, 7), np.arange(50), np.arange(50)])
+    col = np.concatenate([rng.integers(0, n, 4000), rng.integers(0, n, 3000), np.arange(50), np.arange(50)])
+    row[row == 11] = 12                                            # node 11 has no outgoing entries
+    key = np.unique(row.astype(np.int64) * n + col)
+    out = P.coalesce(_t(row.astype(np.int64)), _t(col.astype(np.int64)), n).cpu().numpy()
+    assert np.array_equal(out, np.stack([key // n, key % n]))
+    empty = P.coalesce(torch.zeros(0, dtype=torch.int64, device=DEV), torch.zeros(0, dtype=torch.int64, device=DEV), 5)
+    assert tuple(empty.shape) == (2, 0)
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_edge_features_bit_exact(dim):
+    from oracle import gp_oracle as O
+    from graphphysics_b200 import preprocessing as P
+    c = np.load(os.path.join(G, "cylinder_mesh.npz"))
+    pos = np.ascontiguousarray(c["points"][:, :dim])
+    if dim == 3:
+        pos = pos + np.random.default_rng(1).standard_normal(pos.shape).astype(np.float32) * 0.01
+    ei = O.face_to_edge(c["triangles"], 1923)
+    ref = O.edge_features(pos, ei).astype(np.float32)
+    got = P.edge_features(_t(pos), _t(ei)).cpu().numpy()
+    assert got.shape == (11070, dim + 1)
+    assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
+
+
+def _plate():
+    from graphphysics_b200.synthetic import deforming_plate_sample
+    return deforming_plate_sample(seed=3)
+
+
+def test_world_edges_bit_exact():
+    from oracle import gp_oracle as O
+    from graphphysics_b200 import preprocessing as P
+    from graphphysics_b200.graph import Data
+    pos, tets, x_raw, y = _plate()
+    n = len(pos)
+    mesh_ei = O.face_to_edge(O.tetra_to_faces(tets), n)
+    ref = O.world_edges(mesh_ei, x_raw[:, :3], x_raw[:, 3].astype(np.int64), n, 0.03)
+    assert ref.shape[1] > mesh_ei.shape[1] + 100                  # the sample does have world edges
+    g = Data(x=_t(x_raw), edge_index=_t(mesh_ei))
+    g = P.add_world_edges(g, 0, 3, 3, radius=0.03)
+    assert np.array_equal(g.edge_index.cpu().numpy(), ref)
+    # a lattice where many pairs sit EXACTLY at the radius (query_pairs is inclusive), and a cloud spread over few cells
+    k = np.arange(6)
+    lat = (np.stack(np.meshgrid(k, k, k, indexing="ij"), -1).reshape(-1, 3) * 0.25).astype(np.float32)
+    types = (np.arange(len(lat)) % 2).astype(np.int64)            # alternate NORMAL / OBSTACLE
+    none = np.zeros((2, 0), np.int64)
+    ref = O.world_edges(none, lat, types, len(lat), 0.25)
+    assert ref.shape[1] > 0
+    g = P.add_world_edges(Data(x=_t(np.concatenate([lat, types[:, None].astype(np.float32)], 1)), edge_index=_t(none)), 0, 3, 3, radius=0.25)
+    assert np.array_equal(g.edge_index.cpu().numpy(), ref)
+    rng = np.random.default_rng(5)
+    cloud = (rng.random((4000, 3)) * np.array([40.0, 1.0, 0.2])).astype(np.float32)
+    types = rng.integers(0, 3, 4000).astype(np.int64)             # NORMAL / OBSTACLE / AIRFOIL (ignored)
+    ref = O.world_edges(none, cloud, types, 4000, 0.11)
+    g = P.add_world_edges(Data(x=_t(np.concatenate([cloud, types[:, None].astype(np.float32)], 1)), edge_index=_t(none)), 0, 3, 3, radius=0.11)
+    assert np.array_equal(g.edge_index.cpu().numpy(), ref)
+
+
+def test_noise_and_world_pos_features_bit_exact():
+    from oracle import gp_oracle as O
+    from graphphysics_b200 import preprocessing as P
+    from graphphysics_b200.graph import Data
+    pos, tets, x_raw, y = _plate()
+    n = len(pos)
+    noise = np.random.default_rng(2).standard_normal((n, 3)).astype(np.float32)
+    for t in (None, 0.3):
+        ref = O.add_noise(x_raw, noise, 0, 3, 0.003, 3, t=t)
+        x = _t(x_raw.copy())
+        import math
+        scale = 10 * 0.003 * (1 + math.cos(t * math.pi)) if t is not None else 0.003
+        P.apply_noise_(x, _t(noise), 0, 3, scale, 3)
+        assert np.array_equal(x.cpu().numpy().view(np.uint32), ref.view(np.uint32))
+    # the transform itself: only NORMAL rows move, the node-type column is untouched, the draw has the right scale
+    g = P.add_noise(Data(x=_t(x_raw.copy())), [0], [3], 0.003, 3, generator=torch.Generator(device=DEV).manual_seed(0))
+    d = g.x.cpu().numpy() - x_raw
+    normal = x_raw[:, 3] == 0
+    assert np.all(d[~normal] == 0) and np.all(d[:, 3] == 0) and 0.002 < d[normal, :3].std() < 0.004
+    ei = O.face_to_edge(O.tetra_to_faces(tets), n)
+    ea = O.edge_features(pos, ei).astype(np.float32)
+    ref = O.world_pos_features(ea, x_raw[:, :3], ei)
+    g = P.add_world_pos_features(Data(x=_t(x_raw), edge_index=_t(ei), edge_attr=_t(ea)), 0, 3)
+    assert np.array_equal(g.edge_attr.cpu().numpy().view(np.uint32), ref.view(np.uint32))
+
+
+def test_build_preprocessing_plate_pipeline():
+    """plate.json's pipeline (world_pos_parameters on): obstacle displacement features, FaceToEdge, world edges, edge
+    features -- every stage equal to the oracle's, and the result feeds the model."""
+    from oracle import gp_oracle as O
+    from graphphysics_b200 import preprocessing as P
+    from graphphysics_b200.graph import Data
+    pos, tets, x_raw, y = _plate()
+    n = len(pos)
+    pipe = P.build_preprocessing(world_pos_parameters={"world_pos_index_start": 0, "world_pos_index_end": 3, "node_type_index": 6})
+    g = pipe(Data(x=_t(x_raw), y=_t(y), pos=_t(pos), tetra=_t(tets.T.astype(np.int64))))
+    # add_obstacles_next_pos (preprocessing.py:47-89)
+    disp = y - x_raw[:, :3]
+    obs = x_raw[:, 3] == 1
+    disp[~obs] = disp[obs].mean(0)
+    assert np.allclose(g.x.cpu().numpy(), np.concatenate([x_raw[:, :3], disp, x_raw[:, 3:]], 1), atol=1e-7)
+    ref_ei = O.world_edges(O.face_to_edge(O.tetra_to_faces(tets), n), x_raw[:, :3], x_raw[:, 3].astype(np.int64), n, 0.03)
+    assert np.array_equal(g.edge_index.cpu().numpy(), ref_ei)
+    ref_ea = O.edge_features(pos, ref_ei).astype(np.float32)
+    assert np.array_equal(g.edge_attr.cpu().numpy().view(np.uint32), ref_ea.view(np.uint32))
+    # one model step on the constructed graph (plate.json is the transformer; config 3 also names the epd variant)
+    from graphphysics_b200.models.processors import EncodeProcessDecode, EncodeTransformDecode
+    torch.manual_seed(0)
+    feat = torch.randn(n, 6 + 9, device=DEV)
+    out = EncodeTransformDecode(2, 15, 3, hidden_size=64, num_heads=4).to(DEV)(Data(x=feat, edge_index=g.edge_index))
+    assert tuple(out.shape) == (n, 3) and torch.isfinite(out).all()
+    out = EncodeProcessDecode(2, 15, 4, 3, hidden_size=128).to(DEV)(Data(x=feat, edge_index=g.edge_index, edge_attr=g.edge_attr))
+    assert tuple(out.shape) == (n, 3) and torch.isfinite(out).all()

@@ -186,3 +186,22 @@ def test_cylinder_json_verbatim_matches_reference():
         net, tgt, outp = tr.forward(frames[3], ys[3], ea, ei, training=False)
     np.testing.assert_allclose(net.numpy(), z["eval_net"], rtol=5e-3, atol=5e-5)
     np.testing.assert_allclose(outp.numpy(), z["eval_outputs"], rtol=5e-3, atol=5e-5)
+
+
+def test_oracle_world_edges_against_brute_force():
+    """oracle.world_edges calls scipy's cKDTree like the reference (preprocessing.py:112-117); pin it against a brute-force
+    fp64 all-pairs evaluation of the same definition (distance <= radius, OBSTACLE-NORMAL ends, undirected, coalesced)."""
+    from oracle import gp_oracle as O
+    rng = np.random.default_rng(0)
+    n = 600
+    pos = (rng.random((n, 3)) * np.array([0.5, 0.5, 0.1])).astype(np.float32)
+    t = rng.integers(0, 3, n)
+    mesh = np.stack([rng.integers(0, n, 200), rng.integers(0, n, 200)])
+    got = O.world_edges(mesh, pos, t, n, 0.03)
+    p64 = pos.astype(np.float64)
+    d2 = ((p64[:, None, :] - p64[None, :, :]) ** 2).sum(-1)
+    i, j = np.nonzero((d2 <= 0.03 ** 2) & (t[:, None] == O.OBSTACLE) & (t[None, :] == O.NORMAL))
+    row = np.concatenate([i, j, mesh[0], mesh[1]])
+    col = np.concatenate([j, i, mesh[1], mesh[0]])
+    key = np.unique(row.astype(np.int64) * n + col)
+    assert np.array_equal(got, np.stack([key // n, key % n]))
