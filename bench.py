@@ -128,6 +128,113 @@ def run_reference(args, sample_graphs: int = BATCH, budget_s: float = 150.0, max
             "ms_per_step": dt * 1e3}
 
 
+def secondary_configs(dev, steps: int = 10, warmup: int = 3):
+    """The other BASELINE.json configurations that fit one GPU, each as a full training step through Trainer with
+    CUDA-graph replay (outside the headline's timed regions; `--no-secondary` skips them):
+      configs[0]  cylinder.json verbatim (epd, 5 layers, hidden 32) on the reference's mock cylinder mesh
+      configs[2]  DeformingPlate-shaped sample with world edges (graph built on the device), epd 15 x 128, edge_in 4
+      configs[3]  coarse-aneurysm.json (transformer, 10 blocks, hidden 64, 4 heads) on the reference's mock aneurysm mesh
+    The attention kernel gets its own roofline line: E * (4H + 8) algorithmic bytes per forward launch."""
+    import numpy as np
+    from graphphysics_b200 import ops
+    from graphphysics_b200 import preprocessing as P
+    from graphphysics_b200.graph import Data
+    from graphphysics_b200.synthetic import deforming_plate_sample
+    from graphphysics_b200.training.loop import Trainer
+    hbm_peak, _, peak_src = peaks()
+    gold = os.path.join(ROOT, "tests", "golden")
+    cfgs = json.load(open(os.path.join(gold, "training_configs.json")))
+    out = {}
+
+    def ev_time(fn, n):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    def run(name, cfg, batch, extra=None, tags=()):
+        tr = Trainer(cfg, learning_rate=1e-4, num_steps=100000, warmup=1000, device=dev, seed=0)
+        prof = None
+        if tags:                                     # per-kernel device time: eager steps, CUDA events on the launching stream
+            for _ in range(2):
+                tr.training_step(batch)
+            ops.PROFILE.reset(tags=tags)
+            ops.COUNTERS["launches"] = 0
+            for _ in range(3):
+                tr.training_step(batch)
+            prof = ops.PROFILE.summary()
+            ops.PROFILE.reset(tags=())
+            launches = ops.COUNTERS["launches"] // 3
+        tr.enable_cuda_graph(True)
+        for _ in range(warmup):
+            tr.training_step(batch)
+        ms = ev_time(lambda: tr.training_step(batch), steps)
+        E, L = int(batch.edge_index.shape[1]), cfg["model"]["message_passing_num"]
+        rec = {"ms_per_step": ms, "train_steps_per_s": 1e3 / ms, "edges_per_s_per_layer": E * L / (ms * 1e-3),
+               "nodes": int(batch.x.shape[0]), "directed_edges": E, "model": cfg["model"]["type"], "layers": L,
+               "hidden": cfg["model"]["hidden_size"], "launch": "cuda-graph replay", "loss": float(tr._loss[0])}
+        if prof:
+            rec["kernels_ms_per_step"] = {k: v["total_ms"] / 3 for k, v in prof.items()}
+            rec["gpu_launches"] = launches
+        if extra:
+            rec.update(extra)
+        out[name] = rec
+        return tr, prof
+
+    try:        # ---- configs[0]: cylinder.json
+        c = np.load(os.path.join(gold, "cylinder_mesh.npz"))
+        pos = torch.from_numpy(np.ascontiguousarray(c["points"][:, :2])).to(dev)
+        g = P.face_to_edge(Data(x=pos, face=torch.from_numpy(c["triangles"].T.astype(np.int64)).to(dev)))
+        ea = P.edge_features(pos, g.edge_index)
+        vel = torch.from_numpy(c["velocity"]).to(dev)
+        n = pos.shape[0]
+        x = torch.cat([vel[0], torch.zeros(n, 2, device=dev)], 1)
+        b = Data(x=x, y=vel[1].contiguous(), pos=pos, edge_index=g.edge_index, edge_attr=ea)
+        run("cylinder.json (configs[0])", cfgs["cylinder"], b)
+    except Exception as exc:
+        out["cylinder.json (configs[0])"] = {"error": str(exc)[:300]}
+    try:        # ---- configs[2]: plate with world edges, graph construction on the device
+        pos, tets, x_raw, y = deforming_plate_sample(seed=0)
+        to = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+        raw = Data(x=to(x_raw), y=to(y), pos=to(pos), tetra=to(tets.T.astype(np.int64)))
+        pipe = P.build_preprocessing(world_pos_parameters={"world_pos_index_start": 0, "world_pos_index_end": 3, "node_type_index": 6})
+        g = pipe(raw.clone())
+        ms_pre = ev_time(lambda: pipe(raw.clone()), 10)
+        cfg = {"model": {"type": "epd", "message_passing_num": 15, "hidden_size": 128, "node_input_size": 6, "output_size": 3, "edge_input_size": 4},
+               "index": {"feature_index_start": 0, "feature_index_end": 6, "output_index_start": 0, "output_index_end": 3, "node_type_index": 6}}
+        run("DeformingPlate-shaped, epd 15x128 with world edges (configs[2])", cfg, g,
+            extra={"graph_construction_ms": ms_pre,
+                   "graph_construction": "FaceToEdge + world-edge radius search + coalesce + edge features on the device, per sample"})
+    except Exception as exc:
+        out["DeformingPlate-shaped (configs[2])"] = {"error": str(exc)[:300]}
+    try:        # ---- configs[3]: coarse-aneurysm transformer
+        a = np.load(os.path.join(gold, "aneurysm_mesh.npz"))
+        n = a["points"].shape[0]
+        ei = P.cells_to_edge_index(torch.from_numpy(a["tets"].T.astype(np.int64)).to(dev), n)
+        gen = torch.Generator(device=dev).manual_seed(0)
+        x = torch.randn(n, 15, device=dev, generator=gen)
+        x[:, 14] = 0.0
+        b = Data(x=x, y=torch.randn(n, 3, device=dev, generator=gen), pos=torch.from_numpy(a["points"]).to(dev), edge_index=ei)
+        cfg = cfgs["coarse-aneurysm"]
+        _, prof = run("coarse-aneurysm.json (configs[3])", cfg, b, tags=("attn_fwd", "attn_bwd", "gemm"))
+        E, H, L = int(ei.shape[1]), cfg["model"]["hidden_size"], cfg["model"]["message_passing_num"]
+        if prof and "attn_fwd" in prof:
+            avg_ms = prof["attn_fwd"]["total_ms"] / prof["attn_fwd"]["calls"]
+            alg = E * (4 * H + 8)
+            ach = alg / (avg_ms * 1e-3) / 1e9
+            out["coarse-aneurysm.json (configs[3])"]["attention_roofline"] = {
+                "bound": "hbm", "kernel": "csr_attention_fwd (bf16 q/k/v)", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
+                "frac": ach / hbm_peak, "algorithmic_bytes": alg, "avg_launch_ms": avg_ms, "peak_source": peak_src,
+                "note": "E*(4H+8) bytes per launch (SURVEY 8d); the 23 MB of k / v rows live in L2, so HBM is not what bounds this launch"}
+    except Exception as exc:
+        out["coarse-aneurysm.json (configs[3])"] = {"error": str(exc)[:300]}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -141,6 +248,7 @@ def main():
     ap.add_argument("--ref-graphs", dest="ref_graphs", type=int, default=BATCH,
                     help="--impl reference: graphs per step (default: the whole batch; smaller only for smoke tests)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the secondary single-GPU configurations (configs[0], [2], [3])")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying a CUDA graph")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -295,6 +403,11 @@ def main():
                                    "directed_edges": int(one.edge_index.shape[1]), "launch": "cuda-graph replay" if graphed else "eager"}
             except Exception as exc:       # never let the side figure break the contract line
                 line["rollout"] = {"error": str(exc)[:200]}
+        if world == 1 and not args.no_secondary:
+            try:
+                line["other_configs"] = secondary_configs(dev)
+            except Exception as exc:
+                line["other_configs"] = {"error": str(exc)[:300]}
         if world == 1 and not args.no_cpu_baseline:
             # bounded sample (about 10-30 s of CPU work): 8 of the 32 graphs per step, 1 warm-up + 2 timed steps
             cb = run_reference(args, sample_graphs=8, budget_s=30.0, max_steps=2)

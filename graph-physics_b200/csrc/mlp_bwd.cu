@@ -748,14 +748,27 @@ __global__ void __launch_bounds__(BwdCfg<H>::NT, 1) mlp_bwd_kernel(const gp_mlp_
     if (tid < 32) tmem_dealloc(tmem, 512);
 }
 
-__global__ void reduce_partials_kernel(const float* __restrict__ partials, int n_parts, int stride, int offset, int rows,
-                                       int cols, int ld_part, float* __restrict__ dst, int ld_dst, int accumulate) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= rows * cols) return;
-    const int r = i / cols, c = i - r * cols;
-    const float* src = partials + offset + (size_t)r * ld_part + c;
+// Block = 32 outputs x 8 groups: group g adds the partial blocks p = g, g + 8, ... in ascending order, then the eight
+// group sums are added in fixed order (bit-reproducible; an eighth of the dependent-load chain of a serial sum).
+__global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ partials, int n_parts, int stride, int offset,
+                                                              int rows, int cols, int ld_part, float* __restrict__ dst, int ld_dst,
+                                                              int accumulate) {
+    __shared__ float sh[8][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int i = blockIdx.x * 32 + tx;
+    const bool in = i < rows * cols;
+    const int r = in ? i / cols : 0, c = in ? i - r * cols : 0;
     float acc = 0.f;
-    for (int pi = 0; pi < n_parts; ++pi) acc += src[(size_t)pi * stride];
+    if (in) {
+        const float* src = partials + offset + (size_t)r * ld_part + c;
+        for (int pi = ty; pi < n_parts; pi += 8) acc += src[(size_t)pi * stride];
+    }
+    sh[ty][tx] = acc;
+    __syncthreads();
+    if (ty != 0 || !in) return;
+    acc = 0.f;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) acc += sh[g][tx];
     float* d = dst + (size_t)r * ld_dst + c;
     *d = accumulate ? (*d + acc) : acc;
 }
@@ -934,7 +947,7 @@ extern "C" int gp_reduce_partials(const float* partials, int32_t n_parts, int32_
                                   void* stream) {
     const int total = rows * cols;
     if (total <= 0) return 0;
-    reduce_partials_kernel<<<(total + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+    reduce_partials_kernel<<<(total + 31) / 32, 256, 0, static_cast<cudaStream_t>(stream)>>>(
         partials, n_parts, stride, offset, rows, cols, ld_part, dst, ld_dst, accumulate);
     GP_CHECK_CUDA(cudaGetLastError());
     return 0;

@@ -192,8 +192,8 @@ extern "C" int gp_rmsnorm_fwd(const float* x, int32_t ldx, int32_t rows, int32_t
 }
 
 extern "C" int gp_rmsnorm_bwd_blocks(int32_t rows) {
-    const int b = (rows + 255) / 256;
-    return b < 1 ? 1 : (b > 296 ? 296 : b);
+    const int b = (rows + 63) / 64;      // 8 rows per warp: short dependent chains, every SM busy
+    return b < 1 ? 1 : (b > 1184 ? 1184 : b);
 }
 
 extern "C" int gp_rmsnorm_bwd(const float* x, int32_t ldx, int32_t rows, int32_t hidden, const float* scale1, const float* scale2,

@@ -206,6 +206,7 @@ class GemmArgs(C.Structure):
         ("split_k", C.c_int32),
         ("partials", C.c_void_p),
         ("flags", C.c_int32),
+        ("b_ones", C.c_int32),
     ]
 
 

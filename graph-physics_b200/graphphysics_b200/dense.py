@@ -33,8 +33,9 @@ from ._lib import AttentionArgs, GemmArgs, check, lib, ptr, stream_ptr
 # ------------------------------------------------------------------------------------------------ kernel wrappers (no autograd)
 def gemm(M: int, N: int, K: int, a: torch.Tensor, a_sm: int, a_sk: int, b: torch.Tensor, b_sn: int, b_sk: int, c: torch.Tensor,
          c_sm: int, c_sn: int, *, bias: Optional[torch.Tensor] = None, resid: Optional[torch.Tensor] = None, relu: bool = False,
-         accumulate: bool = False, split_k: int = 1, terms: int = 1) -> None:
-    """C(m,n) = [C +] [resid +] bias[n] + sum_k A(m,k) B(n,k) with strided fp32 / bf16 operands (gp_gemm)."""
+         accumulate: bool = False, split_k: int = 1, terms: int = 1, b_ones: bool = False) -> None:
+    """C(m,n) = [C +] [resid +] bias[n] + sum_k A(m,k) B(n,k) with strided fp32 / bf16 operands (gp_gemm).  b_ones: row N-1
+    of B is not in memory and reads as 1.0."""
     for t in (a, b, c):
         assert t.is_cuda and t.dtype in (torch.float32, torch.bfloat16)
     g = GemmArgs()
@@ -44,12 +45,14 @@ def gemm(M: int, N: int, K: int, a: torch.Tensor, a_sm: int, a_sk: int, b: torch
     g.c, g.c_sm, g.c_sn = ptr(c), c_sm, c_sn
     g.bias, g.resid = ptr(bias), ptr(resid)
     g.a_bf16, g.b_bf16, g.c_bf16 = (int(t.dtype == torch.bfloat16) for t in (a, b, c))
-    g.relu, g.accumulate, g.terms, g.split_k = int(relu), int(accumulate), terms, split_k
+    g.relu, g.accumulate, g.terms, g.split_k, g.b_ones = int(relu), int(accumulate), terms, split_k, int(b_ones)
     part = None
     if split_k > 1:
-        part = torch.empty(split_k * M * N, dtype=torch.float32, device=c.device)
+        part = torch.empty(split_k * M * ((N + 3) // 4 * 4), dtype=torch.float32, device=c.device)
         g.partials = ptr(part)
+    ev = ops.PROFILE.begin("gemm")
     check(lib().gp_gemm(C.byref(g), C.c_void_p(stream_ptr())), "gp_gemm")
+    ops.PROFILE.end("gemm", ev)
     ops._launched(2 if split_k > 1 else 1)
 
 
@@ -70,8 +73,11 @@ def colsum(src: torch.Tensor, round_bf16: bool) -> torch.Tensor:
     return _reduce_rows(part, nb, cols)
 
 
-def _split_k(rows: int) -> int:
-    return max(1, min(128, (rows + 4095) // 4096))
+def _split_k(rows: int, tiles: int = 1) -> int:
+    """CTAs along the contraction of a wgrad: up to four co-resident CTAs per SM (one 64-row chunk per CTA at least), so
+    the load -> MMA -> store chain of one CTA hides behind the others'."""
+    chunks = (rows + 63) // 64
+    return max(1, min(chunks, 592 // max(tiles, 1), 1024))
 
 
 def lin_fwd(x, w, b, *, resid=None, relu=False, out_bf16=False, terms=1) -> torch.Tensor:
@@ -95,13 +101,21 @@ def lin_dgrad(dy, w, *, out=None, terms=1) -> torch.Tensor:
     return out
 
 
-def lin_wgrad(dy, x, *, terms=1) -> torch.Tensor:
-    """dw[n, k] = sum_r dy[r, n] x[r, k] (split over CTAs along r, reduced in fixed order)."""
+def lin_wgrad(dy, x, *, bias: bool = False, terms=1):
+    """dw[n, k] = sum_r dy[r, n] x[r, k] (split over CTAs along r, reduced in fixed order).  bias=True: x is read with one
+    more column of ones, so column K of the same product is db[n] = sum_r dy[r, n] -- returns (dw, db), views of one buffer."""
     R, N = dy.shape
     K = x.shape[1]
-    dw = torch.empty((N, K), dtype=torch.float32, device=dy.device)
-    gemm(N, K, R, dy, 1, N, x, 1, x.stride(0), dw, K, 1, split_k=_split_k(R), terms=terms)
-    return dw
+    if not bias:
+        dw = torch.empty((N, K), dtype=torch.float32, device=dy.device)
+        tiles = ((N + 127) // 128) * ((K + 127) // 128)
+        gemm(N, K, R, dy, 1, N, x, 1, x.stride(0), dw, K, 1, split_k=_split_k(R, tiles), terms=terms)
+        return dw
+    ld = K + 8                                                   # padded row: 16-byte aligned rows for the vector stores
+    buf = torch.empty((N, ld), dtype=torch.float32, device=dy.device)
+    tiles = ((N + 127) // 128) * ((K + 1 + 127) // 128)
+    gemm(N, K + 1, R, dy, 1, N, x, 1, x.stride(0), buf, ld, 1, split_k=_split_k(R, tiles), terms=terms, b_ones=True)
+    return buf[:, :K], buf[:, K]
 
 
 def bias_grad(dy, terms=1) -> torch.Tensor:
@@ -168,7 +182,9 @@ def attn_fwd(q, k, v, g, num_heads: int):
     y32 = torch.empty(q.shape, dtype=torch.float32, device=q.device) if a.io_bf16 else None
     lse = torch.empty((n, num_heads), dtype=torch.float32, device=q.device)
     a.y, a.lse, a.y_f32 = ptr(y), ptr(lse), ptr(y32)
+    ev = ops.PROFILE.begin("attn_fwd")
     check(lib().gp_csr_attention_fwd(C.byref(a), C.c_void_p(stream_ptr())), "gp_csr_attention_fwd")
+    ops.PROFILE.end("attn_fwd", ev)
     ops._launched()
     return y, y32, lse
 
@@ -185,7 +201,9 @@ def attn_bwd(q, k, v, y, y32, lse, dy, g, num_heads: int):
     ea = torch.empty((g.num_edges, num_heads), dtype=torch.float32, device=q.device)
     eds = torch.empty_like(ea)
     a.dq, a.dk, a.dv, a.edge_a, a.edge_ds = ptr(dq), ptr(dk), ptr(dv), ptr(ea), ptr(eds)
+    ev = ops.PROFILE.begin("attn_bwd")
     check(lib().gp_csr_attention_bwd(C.byref(a), C.c_void_p(stream_ptr())), "gp_csr_attention_bwd")
+    ops.PROFILE.end("attn_bwd", ev)
     ops._launched(2)
     return dq, dk, dv
 
@@ -222,15 +240,14 @@ class _AttentionBranch(torch.autograd.Function):
             n = x
         dout = _f32(dout)
         dy = lin_dgrad(dout, wp, terms=terms)
-        dwp, dbp = lin_wgrad(dout, y, terms=terms), (bias_grad(dout, terms) if hbp else None)
+        dwp, dbp = lin_wgrad(dout, y, bias=True, terms=terms) if hbp else (lin_wgrad(dout, y, terms=terms), None)
         dq, dk, dv = attn_bwd(q, k, v, y, y32, lse, dy, g, heads)
         dn = lin_dgrad(dq, wq, terms=terms)
         lin_dgrad(dk, wk, out=dn, terms=terms)
         lin_dgrad(dv, wv, out=dn, terms=terms)
-        dwq, dwk, dwv = lin_wgrad(dq, n, terms=terms), lin_wgrad(dk, n, terms=terms), lin_wgrad(dv, n, terms=terms)
-        dbq = bias_grad(dq, terms) if hbq else None
-        dbk = bias_grad(dk, terms) if hbk else None
-        dbv = bias_grad(dv, terms) if hbv else None
+        dwq, dbq = lin_wgrad(dq, n, bias=True, terms=terms) if hbq else (lin_wgrad(dq, n, terms=terms), None)
+        dwk, dbk = lin_wgrad(dk, n, bias=True, terms=terms) if hbk else (lin_wgrad(dk, n, terms=terms), None)
+        dwv, dbv = lin_wgrad(dv, n, bias=True, terms=terms) if hbv else (lin_wgrad(dv, n, terms=terms), None)
         dsn = None
         if sn is not None:
             dx, dsn, _ = norm_bwd(x, sn, None, dn, add=dout if add_resid else None)
@@ -272,15 +289,14 @@ class _GatedBranch(torch.autograd.Function):
         dw3 = db3 = None
         if w3 is not None:
             dg = lin_dgrad(dout, w3, terms=terms)
-            dw3, db3 = lin_wgrad(dout, gate, terms=terms), (bias_grad(dout, terms) if hb3 else None)
+            dw3, db3 = lin_wgrad(dout, gate, bias=True, terms=terms) if hb3 else (lin_wgrad(dout, gate, terms=terms), None)
         else:
             dg = dout
         da1, da2 = gelu_bwd(a1, a2, dg)
         dn = lin_dgrad(da1, w1, terms=terms)
         lin_dgrad(da2, w2, out=dn, terms=terms)
-        dw1, dw2 = lin_wgrad(da1, n, terms=terms), lin_wgrad(da2, n, terms=terms)
-        db1 = bias_grad(da1, terms) if hb1 else None
-        db2 = bias_grad(da2, terms) if hb2 else None
+        dw1, db1 = lin_wgrad(da1, n, bias=True, terms=terms) if hb1 else (lin_wgrad(da1, n, terms=terms), None)
+        dw2, db2 = lin_wgrad(da2, n, bias=True, terms=terms) if hb2 else (lin_wgrad(da2, n, terms=terms), None)
         ds1 = ds2 = None
         if s1 is not None:
             dx, ds1, ds2 = norm_bwd(x, s1, s2, dn, add=dout if add_resid else None)
@@ -325,7 +341,7 @@ class _Mlp4(torch.autograd.Function):
         grads = []
         acts, ws = (x, h0, h1, h2), (w0, w1, w2, w3)
         for i in (3, 2, 1, 0):
-            grads.append((lin_wgrad(d, acts[i], terms=terms), bias_grad(d, terms)))
+            grads.append(lin_wgrad(d, acts[i], bias=True, terms=terms))
             if i > 0:
                 d = lin_dgrad(d, ws[i], terms=terms)
                 relu_mask_(d, acts[i])

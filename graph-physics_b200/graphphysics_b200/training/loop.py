@@ -32,10 +32,18 @@ class Trainer:
     def __init__(self, parameters: Dict[str, Any], learning_rate: float, num_steps: int, warmup: int,
                  device: torch.device, masks: Sequence[int] = (NodeType.NORMAL, NodeType.OUTFLOW),
                  gradient_clip_val: float = 1.0, weight_decay: float = 1e-4, betas=(0.9, 0.95), eps: float = 1e-8,
-                 process_group=None, seed: Optional[int] = None):
+                 process_group=None, seed: Optional[int] = None, inject_noise: bool = False):
         if seed is not None:
             torch.manual_seed(seed)
         self.param = parameters
+        # training noise (graphphysics/dataset/preprocessing.py:177-238, wired by get_preprocessing from the JSON section
+        # transformations.preprocessing): drawn and applied on the device at the start of every step, inside the
+        # captured graph when the step is replayed
+        self.noise = None
+        pre = parameters.get("transformations", {}).get("preprocessing", {}) if inject_noise else {}
+        if pre.get("noise", 0):
+            self.noise = dict(noise_index_start=pre["noise_index_start"], noise_index_end=pre["noise_index_end"],
+                              noise_scale=pre["noise"], node_type_index=parameters["index"]["node_type_index"])
         self.device = device
         model = get_model(parameters)
         self.model = get_simulator(parameters, model, device)       # the reference calls the Simulator `model`
@@ -218,6 +226,10 @@ class Trainer:
         sim.train()
         if not batch.x.is_cuda:
             batch = batch.to(self.device, non_blocking=True)
+        if self.noise is not None:
+            from ..preprocessing import add_noise
+            batch = batch.clone() if not self.use_cuda_graph else batch      # (the replayed step owns its static batch)
+            add_noise(batch, **self.noise)
         node_type = batch.x[:, sim.node_type_index]
         if self.pg is not None:
             from ..dist.ddp import accumulate_normalizers_globally

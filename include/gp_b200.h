@@ -321,7 +321,7 @@ int gp_halo_unpack_add(float* x, int32_t ld, const int32_t* dst_rows, const int3
  *   terms = 1: operands rounded to bf16, one MMA per k-step (Transformer block);
  *   terms = 3: fp32 operands split into three bf16 terms hi + mid + lo (24 mantissa bits), six MMAs per k-step, smallest
  *              terms first: fp32-grade products on the bf16 tensor path (precision="tight", SURVEY §7 iii).
- * split_k > 1 cuts K over CTAs (partials: split_k*M*N floats of scratch, reduced in fixed order).
+ * split_k > 1 cuts K over CTAs (partials: split_k * M * ((N + 3) & ~3) floats of scratch, reduced in fixed order).
  * `flags` is filled by the library.
  * --------------------------------------------------------------------------------------------- */
 typedef struct gp_gemm_args {
@@ -339,7 +339,9 @@ typedef struct gp_gemm_args {
     int32_t terms;
     int32_t split_k;
     float* partials;
-    int32_t flags;
+    int32_t flags;   /* filled in by gp_gemm (staging modes) */
+    int32_t b_ones;  /* != 0: B has one more row than its memory, reading as 1.0: row N-1 of the result's N axis is sum_k A(m,k)
+                        (a bias gradient as the last column of a weight gradient); N counts that row */
 } gp_gemm_args;
 int gp_gemm(const gp_gemm_args* args, void* stream);
 

@@ -52,6 +52,26 @@ def test_gemm_bf16_operands(M, N, K, split, a_bf16, c_bf16):
             assert l2_rel(c2, ref2) < 1e-5, pattern
 
 
+@pytest.mark.parametrize("R,N,K", [(1000, 64, 64), (5000, 192, 64), (700, 64, 192), (300, 3, 23), (22535, 64, 128)])
+@pytest.mark.parametrize("terms", [1, 3])
+def test_wgrad_with_bias_column(R, N, K, terms):
+    """lin_wgrad(bias=True): x read with one more column of ones, so the same split-K product returns dW and db."""
+    from graphphysics_b200 import dense
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(R + N)
+    dy, x = torch.randn(R, N, generator=g), torch.randn(R, K, generator=g)
+    rd = (lambda t: t.double()) if terms == 3 else _bf
+    ref_w, ref_b = rd(dy).t() @ rd(x), rd(dy).sum(0)
+    for xb in ([False, True] if terms == 1 else [False]):
+        xd = (x.to(torch.bfloat16) if xb else x).to(dev)
+        dw, db = dense.lin_wgrad(dy.to(dev), xd, bias=True, terms=terms)
+        tol = 2e-5 if terms == 3 else 2e-6
+        assert tuple(dw.shape) == (N, K) and tuple(db.shape) == (N,)
+        assert l2_rel(dw, ref_w) < tol and l2_rel(db, ref_b) < tol, (l2_rel(dw, ref_w), l2_rel(db, ref_b))
+        dw2 = dense.lin_wgrad(dy.to(dev), xd, terms=terms)          # (its split over CTAs may differ: not bit-equal)
+        assert l2_rel(dw2, dw) < 1e-5
+
+
 @pytest.mark.parametrize("hidden", [32, 64, 128])
 @pytest.mark.parametrize("double_norm", [False, True])
 def test_rmsnorm_forward_backward(hidden, double_norm):

@@ -85,3 +85,32 @@ def test_trainer_resume_is_bit_identical(graphed):
     for k in sa:
         assert torch.equal(sa[k], sb[k]), k
     assert torch.equal(a.exp_avg, b2.exp_avg) and torch.equal(a.exp_avg_sq, b2.exp_avg_sq)
+
+
+@pytest.mark.parametrize("graphed", [False, True])
+def test_training_noise_injection(graphed):
+    """transformations.preprocessing noise (preprocessing.py:177-238) drawn and applied on the device inside the step
+    (SURVEY §8f N2): the caller's batch is left alone, a fresh draw is used every step (also under CUDA-graph replay),
+    and a zero scale reproduces the noise-free run bit for bit."""
+    from graphphysics_b200.training.loop import Trainer
+    dev = torch.device("cuda:0")
+
+    def run(scale, inject):
+        cfg = copy.deepcopy(CFG)
+        cfg["transformations"] = {"preprocessing": {"noise": scale, "noise_index_start": [0], "noise_index_end": [2]}}
+        tr = Trainer(cfg, learning_rate=0.0, num_steps=100, warmup=1, device=dev, seed=0, inject_noise=inject)   # lr 0: weights stay
+        if graphed:
+            tr.enable_cuda_graph()
+        b = _batch().to(dev)
+        x0 = b.x.clone()
+        losses = [float(tr.training_step(b)) for _ in range(4)]
+        assert torch.equal(b.x, x0)
+        return losses
+
+    clean = run(0.02, False)
+    noisy = run(0.02, True)
+    assert all(np.isfinite(noisy))
+    # lr = 0 and a repeated batch: without noise every step repeats (normaliser statistics aside), with noise the
+    # loss moves from step to step because every step draws again
+    assert len(set(noisy[1:])) == 3, noisy
+    assert noisy != clean
