@@ -235,6 +235,75 @@ def secondary_configs(dev, steps: int = 10, warmup: int = 3):
     return out
 
 
+def partition_block(dev, pg, world: int, rank: int, side: int = 72, steps: int = 3, warmup: int = 2):
+    """Strong scaling of the FULL training step on one large mesh, node-partitioned with halo exchange (SURVEY §8e.2,
+    BASELINE.json configs[4] scaled to what one GPU holds): a side^3 Kuhn-triangulated box (14 neighbours per interior
+    node), EPD 15 x 128.  Every rank first times the unpartitioned step on the whole mesh by itself (the 1-GPU
+    reference, same build, same box), then the ranks split the mesh (recursive coordinate bisection, an edge lives
+    with its receiver, ghost rows exchanged per message-passing step by gp_halo_* kernels + NCCL all-to-all-v) and run
+    the same step captured in one CUDA graph.  Device time, max over ranks."""
+    import gc
+    import numpy as np
+    import torch.distributed as dist
+    from graphphysics_b200.graph import Data
+    from graphphysics_b200.synthetic import kuhn_box_graph, mesh_edge_attr
+    from graphphysics_b200.training.loop import Trainer
+    cfg = {"model": dict(CONFIG["model"], node_input_size=3, output_size=3, edge_input_size=4),
+           "index": {"feature_index_start": 0, "feature_index_end": 3, "output_index_start": 0, "output_index_end": 3, "node_type_index": 3}}
+    pos, ei = kuhn_box_graph(side, side, side)
+    n, E = pos.shape[0], ei.shape[1]
+    rng = np.random.default_rng(0)
+    vel = rng.standard_normal((n, 3)).astype(np.float32)
+    x = np.concatenate([vel, np.zeros((n, 2), np.float32)], 1)
+    batch = Data(x=torch.from_numpy(x), y=torch.from_numpy(vel + 0.1 * rng.standard_normal((n, 3)).astype(np.float32)),
+                 pos=torch.from_numpy(pos), edge_index=torch.from_numpy(ei), edge_attr=torch.from_numpy(mesh_edge_attr(pos, ei))).to(dev)
+
+    def timed(tr, k):
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            tr.training_step(batch)
+        e1.record()
+        dist.barrier()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1) / k], device=dev)
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    tr1 = Trainer(cfg, learning_rate=1e-4, num_steps=100000, warmup=1000, device=dev, seed=0)
+    tr1.enable_cuda_graph(True)
+    for _ in range(warmup):
+        tr1.training_step(batch)
+    ms1 = timed(tr1, steps)
+    mem1 = torch.cuda.max_memory_allocated(dev) / 2 ** 30
+    loss1 = float(tr1._loss[0])
+    del tr1
+    from graphphysics_b200 import graph as _g
+    _g._PERSISTENT.clear(); _g._CACHE.clear()
+    gc.collect()
+    torch.cuda.empty_cache()
+    torch.cuda.reset_peak_memory_stats(dev)
+    trp = Trainer(cfg, learning_rate=1e-4, num_steps=100000, warmup=1000, device=dev, process_group=pg, seed=0)
+    trp.enable_node_partition(batch.pos, batch.edge_index)
+    trp.enable_cuda_graph(True)
+    for _ in range(warmup):
+        trp.training_step(batch)
+    msn = timed(trp, steps)
+    lg = trp._part.lg
+    stats = torch.tensor([lg.num_owned, len(lg.ghosts), len(lg.edge_ids)], device=dev, dtype=torch.float32)
+    mx = stats.clone()
+    dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+    return {"mesh": f"{side}^3 Kuhn box, {n} nodes, {E} directed edges, EPD 15 x 128, full training step", "scaling": "strong",
+            "ms_per_step_1gpu": ms1, "ms_per_step": msn, "n_gpus": world, "speedup": ms1 / msn, "efficiency": ms1 / (world * msn),
+            "edges_per_s_per_layer": E * CONFIG["model"]["message_passing_num"] / (msn * 1e-3),
+            "max_owned_nodes": int(mx[0]), "max_ghost_nodes": int(mx[1]), "max_local_edges": int(mx[2]),
+            "gib_1gpu": mem1, "gib_per_gpu": torch.cuda.max_memory_allocated(dev) / 2 ** 30,
+            "loss_1gpu": loss1, "loss": float(trp._loss[0]), "launch": "cuda-graph replay, halo exchange inside the graph",
+            "timing": "CUDA events, barrier + synchronize on both sides, max over ranks"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -248,6 +317,9 @@ def main():
     ap.add_argument("--ref-graphs", dest="ref_graphs", type=int, default=BATCH,
                     help="--impl reference: graphs per step (default: the whole batch; smaller only for smoke tests)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-partition", action="store_true", help="--gpus N > 1: skip the node-partition strong-scaling block")
+    ap.add_argument("--partition-side", dest="partition_side", type=int, default=72,
+                    help="--gpus N > 1: side of the box mesh of the node-partition block (side^3 nodes)")
     ap.add_argument("--no-secondary", action="store_true", help="skip the secondary single-GPU configurations (configs[0], [2], [3])")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying a CUDA graph")
     args = ap.parse_args()
@@ -412,6 +484,15 @@ def main():
             # bounded sample (about 10-30 s of CPU work): 8 of the 32 graphs per step, 1 warm-up + 2 timed steps
             cb = run_reference(args, sample_graphs=8, budget_s=30.0, max_steps=2)
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    part = None
+    if world > 1 and not args.no_partition:
+        try:
+            part = partition_block(dev, pg, world, rank, side=args.partition_side)
+        except Exception as exc:
+            part = {"error": str(exc)[:300]}
+    if rank == 0 and part is not None:
+        line["partition"] = part
+    if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
         # The captured steps hold NCCL work; tearing the communicator down under them can block, and

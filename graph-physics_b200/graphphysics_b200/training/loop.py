@@ -130,14 +130,14 @@ class Trainer:
         see the SAME batch."""
         import numpy as np
         import torch.distributed as dist
-        from ..dist.partition import build_local_graphs, partition_nodes
+        from ..dist.partition import build_local_graph, partition_nodes
         from ..dist.partitioned import PartitionedEPD
         if self.pg is None or not self.fused:
             raise ValueError("enable_node_partition needs a process group and the fused EPD model")
         world, rank = dist.get_world_size(self.pg), dist.get_rank(self.pg)
         pos_np = pos.detach().cpu().numpy() if torch.is_tensor(pos) else np.asarray(pos)
         ei_np = edge_index.detach().cpu().numpy() if torch.is_tensor(edge_index) else np.asarray(edge_index)
-        lg = build_local_graphs(ei_np, partition_nodes(pos_np, world), world)[rank]
+        lg = build_local_graph(ei_np, partition_nodes(pos_np, world), world, rank)
         self._part = PartitionedEPD(self.processor, lg, world, self.pg)
         self._owned = torch.from_numpy(lg.owned).to(self.device)
 
@@ -154,15 +154,16 @@ class Trainer:
         graph, target = sim._build_input_graph(batch, True)
         mask = prepare_mask(node_type, self.loss_masks)[self._owned].contiguous()
         out, ctx = part.forward(graph.x, graph.edge_attr, save=True)
-        counts = torch.stack([mask.sum().float(), mask.sum().float()])
-        dist.all_reduce(counts[1:], group=self.pg)
-        n_loc, n_all = (float(v) for v in counts.tolist())                 # one host read per step in this mode
-        d_out = torch.zeros_like(out)
-        if n_loc > 0:
-            ops.masked_mse(out, target[self._owned].contiguous(), mask, self._loss, d_out, grad_scale=n_loc / n_all)
-            self._loss.mul_(n_loc / n_all)
-        else:
-            self._loss.zero_()                                             # this part holds no node of the loss
+        # loss = mean over the masked nodes of ALL ranks = sum_r (n_r / n_all) * loss_r; everything stays on the device
+        # (no host read: the step can be captured), a rank without masked nodes contributes exactly zero
+        n_loc = mask.sum().to(torch.float32).reshape(1)
+        n_all = n_loc.clone()
+        dist.all_reduce(n_all, group=self.pg)
+        ratio = n_loc / n_all
+        d_out = torch.empty_like(out)
+        ops.masked_mse(out, target[self._owned].contiguous(), mask, self._loss, d_out)
+        d_out.mul_(ratio)                                                  # (all-zero rows when n_loc == 0)
+        self._loss.copy_(torch.where(n_loc > 0, self._loss * ratio, torch.zeros_like(ratio)))
         dist.all_reduce(self._loss, group=self.pg)
         part.backward(ctx, d_out)                                          # weight gradients summed over ranks
         self.optimizer_step()
@@ -191,10 +192,9 @@ class Trainer:
             for v in batch.__dict__.values():           # the side stream allocated these tensors
                 if torch.is_tensor(v):
                     v.record_stream(torch.cuda.current_stream(self.device))
-        if self._part is not None:
-            return self._partitioned_step(batch)
+        step = self._partitioned_step if self._part is not None else self._training_step_eager
         if not self.use_cuda_graph:
-            return self._training_step_eager(batch)
+            return step(batch)
         from ..graph import Data, no_csr_cache
         fields = [k for k in ("x", "y", "pos", "edge_index", "edge_attr") if getattr(batch, k) is not None]
         key = tuple((k, tuple(getattr(batch, k).shape), getattr(batch, k).dtype) for k in fields)
@@ -204,13 +204,13 @@ class Trainer:
             for k in fields:
                 getattr(static, k).copy_(getattr(batch, k), non_blocking=True)
             with no_csr_cache():                        # (allocates the persistent layout buffers outside the capture)
-                self._training_step_eager(static)      # first step of this shape runs eagerly (allocations, smem attributes)
+                step(static)                            # first step of this shape runs eagerly (allocations, smem attributes)
             graph = torch.cuda.CUDAGraph()
             # with a process group, NCCL's watchdog thread polls CUDA events while we capture: only
             # this thread's calls belong to the capture
             mode = "thread_local" if self.pg is not None else "global"
             with no_csr_cache(), torch.cuda.graph(graph, capture_error_mode=mode):
-                self._training_step_eager(static)
+                step(static)
             self.step_index -= 1                        # the capture pass enqueued nothing; undo its host-side count
             self._graphs[key] = (graph, static, fields)
             return self._loss[0]

@@ -58,6 +58,14 @@ def test_partition_and_halo_maps_bit_exact():
             for q in lg.recv:
                 assert np.array_equal(lg.recv[q], r["recv"][q])
             assert (lg.edge_index_local[1] < lg.num_owned).all()                    # receivers are owned
+        from graphphysics_b200.dist.partition import build_local_graph
+        for p in range(parts):                                                       # the O(E) per-rank builder gives the same maps
+            one = build_local_graph(ei, owner, parts, p)
+            assert np.array_equal(one.owned, lgs[p].owned) and np.array_equal(one.ghosts, lgs[p].ghosts)
+            assert np.array_equal(one.edge_ids, lgs[p].edge_ids) and np.array_equal(one.edge_index_local, lgs[p].edge_index_local)
+            assert set(one.send) == set(lgs[p].send) and set(one.recv) == set(lgs[p].recv)
+            assert all(np.array_equal(one.send[q], lgs[p].send[q]) for q in one.send)
+            assert all(np.array_equal(one.recv[q], lgs[p].recv[q]) for q in one.recv)
         for p in range(parts):                                                       # send/recv lists mirror each other
             for q, idx in lgs[p].recv.items():
                 glob_p = np.concatenate([lgs[p].owned, lgs[p].ghosts])[idx]
