@@ -318,8 +318,8 @@ def main():
                     help="--impl reference: graphs per step (default: the whole batch; smaller only for smoke tests)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-partition", action="store_true", help="--gpus N > 1: skip the node-partition strong-scaling block")
-    ap.add_argument("--partition-side", dest="partition_side", type=int, default=72,
-                    help="--gpus N > 1: side of the box mesh of the node-partition block (side^3 nodes)")
+    ap.add_argument("--partition-side", dest="partition_side", type=int, default=0,
+                    help="--gpus N > 1: side of the box mesh of the node-partition block (side^3 nodes; 0 = by job size)")
     ap.add_argument("--no-secondary", action="store_true", help="skip the secondary single-GPU configurations (configs[0], [2], [3])")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying a CUDA graph")
     args = ap.parse_args()
@@ -487,7 +487,14 @@ def main():
     part = None
     if world > 1 and not args.no_partition:
         try:
-            part = partition_block(dev, pg, world, rank, side=args.partition_side)
+            # the mesh grows with the job (each line carries its own 1-GPU reference on the same mesh): 373k nodes at 2
+            # GPUs, 681k at 4, the 1M-node / 13.8M-edge mesh of BASELINE.json configs[4] at 8 -- when the unpartitioned
+            # reference step (~145 GiB of activations at 1M nodes) fits next to what this process already holds
+            side = args.partition_side or {2: 72, 4: 88}.get(world, 100 if world >= 8 else 72)
+            free_gib = torch.cuda.mem_get_info(dev)[0] / 2 ** 30
+            if side >= 100 and free_gib < 168:
+                side = 88
+            part = partition_block(dev, pg, world, rank, side=side)
         except Exception as exc:
             part = {"error": str(exc)[:300]}
     if rank == 0 and part is not None:

@@ -774,7 +774,7 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __res
 }
 
 struct ReduceSegs {
-    gp_reduce_seg s[16];
+    gp_reduce_seg s[32];
     int n;
 };
 // Block = 32 lanes x 8 partial-groups: thread (tx, ty) adds the partial blocks p = ty, ty+8, ... in
@@ -955,7 +955,7 @@ extern "C" int gp_reduce_partials(const float* partials, int32_t n_parts, int32_
 
 extern "C" int gp_reduce_partials_multi(const float* partials, int32_t n_parts, int32_t stride,
                                         const gp_reduce_seg* segs_host, int32_t n_segs, void* stream) {
-    GP_REQUIRE(n_segs >= 0 && n_segs <= 16, "gp_reduce_partials_multi: at most 16 segments");
+    GP_REQUIRE(n_segs >= 0 && n_segs <= 32, "gp_reduce_partials_multi: at most 32 segments");
     if (n_segs == 0) return 0;
     ReduceSegs segs;
     segs.n = n_segs;

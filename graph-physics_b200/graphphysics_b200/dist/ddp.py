@@ -21,18 +21,21 @@ def allreduce_mean_(flat_grad: torch.Tensor, group=None) -> None:
     flat_grad.mul_(1.0 / dist.get_world_size(group))
 
 
-def _accumulate_global(norm, data: torch.Tensor, group) -> None:
-    """Normalizer._accumulate (layers.py:363-377) with the sums taken over all ranks."""
+def _local_stats(norm, data: torch.Tensor):
+    """[sum, sum of squares, count] of the local rows, or None when the normaliser is frozen / absent."""
     if norm is None:
-        return
+        return None
     if norm._host_calls is None:
         norm._host_calls = int(norm._num_accumulations.item())
     if norm._host_calls >= norm._max_accumulations:
-        return
+        return None
     d = data.detach()
-    stats = torch.cat([d.sum(0), (d ** 2).sum(0), torch.full((1,), float(d.shape[0]), dtype=d.dtype, device=d.device)])   # (no H2D copy: capturable)
-    dist.all_reduce(stats, op=dist.ReduceOp.SUM, group=group)
-    k = d.shape[1]
+    return torch.cat([d.sum(0), (d ** 2).sum(0), torch.full((1,), float(d.shape[0]), dtype=d.dtype, device=d.device)])   # (no H2D copy: capturable)
+
+
+def _apply_stats(norm, stats: torch.Tensor) -> None:
+    """Normalizer._accumulate (layers.py:363-377) with the sums taken over all ranks."""
+    k = (stats.numel() - 1) // 2
     gate = (norm._num_accumulations < norm._max_accumulations).to(torch.float32)     # device-side freeze (graph replay)
     norm._acc_sum += gate * stats[:k][None]
     norm._acc_sum_squared += gate * stats[k:2 * k][None]
@@ -43,10 +46,20 @@ def _accumulate_global(norm, data: torch.Tensor, group) -> None:
 
 def accumulate_normalizers_globally(sim, batch, group=None) -> None:
     """What Simulator._build_input_graph(is_training=True) accumulates (simulator.py:145-167), over the
-    global batch.  Call before building the input graph with accumulate=False."""
+    global batch: the statistics of all three normalisers travel in ONE all-reduce.  Call before building the
+    input graph with accumulate=False."""
     pre = batch.x[:, sim.output_index_start:sim.output_index_end]
-    _accumulate_global(sim._output_normalizer, batch.y - pre, group)
-    nf = sim._build_node_features(batch, sim._get_one_hot_type(batch)).float()
-    _accumulate_global(sim._node_normalizer, nf, group)
+    items = [(sim._output_normalizer, batch.y - pre)]
+    if sim._node_normalizer is not None:
+        items.append((sim._node_normalizer, sim._build_node_features(batch, sim._get_one_hot_type(batch)).float()))
     if sim._edge_normalizer is not None:
-        _accumulate_global(sim._edge_normalizer, batch.edge_attr, group)
+        items.append((sim._edge_normalizer, batch.edge_attr))
+    live = [(n, st) for n, st in ((n, _local_stats(n, d)) for n, d in items) if st is not None]
+    if not live:
+        return
+    buf = torch.cat([st for _, st in live])
+    dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
+    off = 0
+    for n, st in live:
+        _apply_stats(n, buf[off:off + st.numel()])
+        off += st.numel()

@@ -349,12 +349,23 @@ class EPDEngine:
                                   delta_a_out=delta_a_out, tag=(tag + "_A") if tag else None, **kw)
         self._reduce_stage(gridA, ka, H, s, 0, 1, False)
 
-    def _backward(self, ctx, d_out: torch.Tensor, dE_sorted: Optional[torch.Tensor] = None, before_block=None):
+    def grad_range(self, prefix: str):
+        """[lo, hi) of the flat buffers covered by the parameters whose name starts with `prefix` (contiguous: the
+        buffers follow named_parameters order)."""
+        names = [n for n in self.offsets if n.startswith(prefix)]
+        lo = min(self.offsets[n] for n in names)
+        hi = max(self.offsets[n] + self.numels[n] for n in names)
+        return lo, hi
+
+    def _backward(self, ctx, d_out: torch.Tensor, dE_sorted: Optional[torch.Tensor] = None, before_block=None, grads_ready=None):
         """Fills self.gflat with d loss / d parameters.  d_out is d loss / d output ([N,out] fp32, or
         [N,H] with only_processor); dE_sorted (bf16, receiver-sorted) is the gradient of the last
         edge latent when somebody consumes it.  Returns (dX_in, dE_in_sorted) for only_processor.
         `before_block(dX)` (optional) runs on the fp32 gradient of a block's node output before that
-        block's backward -- the transpose of forward's `after_block` (reverse halo exchange)."""
+        block's backward -- the transpose of forward's `after_block` (reverse halo exchange).
+        `grads_ready(lo, hi)` (optional) is called as soon as gflat[lo:hi] is final (decoder, then every processor
+        layer from the last to the first, then the encoders): data-parallel training all-reduces that slice while the
+        backward of the earlier layers is still running."""
         H, dev = self.H, self.device
         g: GraphCSR = ctx["g"]
         N, E = g.num_nodes, g.num_edges
@@ -367,6 +378,9 @@ class EPDEngine:
             Gp[:, :out_size] = d_out
             dX = torch.empty((N, H), dtype=torch.float32, device=dev)
             self._mlp_backward(self.dec, N, a_in=ctx["x_last"], ka=H, h2=ctx["h2d"], top=dict(delta_b=Gp), out=dX)
+            if grads_ready is not None:
+                self._flush_reduce()
+                grads_ready(*self.grad_range("decode_module."))
         # nobody consumes the last edge latent: its gradient is zero.  An explicit zero tile keeps the top
         # layer on the same specialised kernel as the others (a memset is cheaper than the general path).
         dE = dE_sorted if dE_sorted is not None else torch.zeros((E, H), dtype=bf, device=dev)
@@ -402,6 +416,8 @@ class EPDEngine:
                 (2 * H * H, H, H, H, gp + 4 * self.offsets[pn], 2 * H, False),
             ])
             self._flush_reduce()      # one reduction launch per processor layer
+            if grads_ready is not None:
+                grads_ready(*self.grad_range(f"processor_list.{l}."))
             dX, dE = dX_new, dE_new
         if self.only_processor:
             self._flush_reduce()
@@ -409,6 +425,10 @@ class EPDEngine:
         self._mlp_backward(self.enc_n, N, a_in=ctx["xin_p"], ka=ctx["xin_p"].shape[1], h2=ctx["h2n0"], top=dict(gy=dX))
         self._mlp_backward(self.enc_e, E, a_in=ctx["ea_p"], ka=ctx["ea_p"].shape[1], h2=ctx["h2e0"], top=dict(gy=dE))
         self._flush_reduce()
+        if grads_ready is not None:
+            lo_n, hi_n = self.grad_range("nodes_encoder.")
+            lo_e, hi_e = self.grad_range("edges_encoder.")
+            grads_ready(min(lo_n, lo_e), max(hi_n, hi_e))
         return None, None
 
     # ------------------------------------------------------------------ optimizer helpers

@@ -352,9 +352,9 @@ def reduce_multi(partials: Optional[torch.Tensor], n_parts: int, stride: int, se
     """segs: list of (offset, rows, cols, ld_part, dst_ptr(int), ld_dst, accumulate) -- reduced from the
     call-level `partials` (n_parts blocks of `stride` floats) -- optionally extended by
     (partials_ptr(int), n_parts, stride) for a segment that lives in another partial buffer.
-    At most 16 segments per launch (longer lists are split)."""
-    for lo in range(0, len(segs), 16):
-        chunk = segs[lo:lo + 16]
+    At most 32 segments per launch (longer lists are split; one processor layer's backward queues 21)."""
+    for lo in range(0, len(segs), 32):
+        chunk = segs[lo:lo + 32]
         arr = (ReduceSeg * len(chunk))()
         for i, sg in enumerate(chunk):
             off, rows, cols, ldp, dst, ldd, acc = sg[:7]

@@ -234,7 +234,7 @@ typedef struct gp_pack_entry {
 int gp_pack_weights(const float* params, gp_bf16* packed, const gp_pack_entry* table, int32_t n_entries, void* stream);
 int gp_cast_bf16(const float* src, gp_bf16* dst, int64_t n, void* stream);
 
-/* One launch for the gradient pieces of one or several stages (at most 16 segments): for each segment s,
+/* One launch for the gradient pieces of one or several stages (at most 32 segments): for each segment s,
  * dst_s[r*ld_dst + c] (+)= sum_p partials_s[p*stride_s + offset_s + r*ld_part_s + c], p < n_parts_s.
  * A segment with partials == NULL uses the call-level partials / n_parts / stride. */
 typedef struct gp_reduce_seg {
