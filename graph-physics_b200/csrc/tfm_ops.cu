@@ -130,6 +130,59 @@ __global__ void rmsnorm_bwd_kernel(const float* __restrict__ x, int ldx, int row
     }
 }
 
+
+// ---- any width (the 2H / 3H-wide norm in front of the gated edge / node MLP, layers.py:252-278): one norm, columns strided over the lanes
+__global__ void rmsnorm_fwd_generic_kernel(const float* __restrict__ x, int ldx, int rows, int H, const float* __restrict__ s1,
+                                           __nv_bfloat16* __restrict__ out_bf16, float* __restrict__ out_f32, int ld_out) {
+    const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (r >= rows) return;
+    const float* xr = x + (size_t)r * ldx;
+    float ss = 0.f;
+    for (int c = lane; c < H; c += 32) ss = fmaf(xr[c], xr[c], ss);
+    const float inv = 1.f / (sqrtf(warp_sum(ss) / (float)H) + 1e-8f);
+    for (int c = lane; c < H; c += 32) {
+        const float v = s1[c] * (xr[c] * inv);
+        if (out_bf16) out_bf16[(size_t)r * ld_out + c] = __float2bfloat16_rn(v);
+        else out_f32[(size_t)r * ld_out + c] = v;
+    }
+}
+__global__ void rmsnorm_bwd_generic_kernel(const float* __restrict__ x, int ldx, int rows, int H, const float* __restrict__ s1,
+                                           const float* __restrict__ dy, int ld_dy, float* dx, int ld_dx, const float* add, int ld_add,
+                                           float* __restrict__ part1) {
+    extern __shared__ float shg[];              // [8 warps][H]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* mine = shg + (size_t)warp * H;
+    for (int c = lane; c < H; c += 32) mine[c] = 0.f;
+    const int rows_per_block = (rows + gridDim.x - 1) / gridDim.x;
+    const int r_begin = blockIdx.x * rows_per_block, r_end = min(rows, r_begin + rows_per_block);
+    for (int r = r_begin + warp; r < r_end; r += 8) {
+        const float* xr = x + (size_t)r * ldx;
+        const float* g = dy + (size_t)r * ld_dy;
+        float ss = 0.f, dot = 0.f;
+        for (int c = lane; c < H; c += 32) {
+            ss = fmaf(xr[c], xr[c], ss);
+            dot = fmaf(g[c] * s1[c], xr[c], dot);
+        }
+        ss = warp_sum(ss);
+        dot = warp_sum(dot);
+        const float rms = sqrtf(ss / (float)H);
+        const float inv = 1.f / (rms + 1e-8f);
+        const float coef = rms > 0.f ? dot * inv * inv / (rms * H) : 0.f;
+        for (int c = lane; c < H; c += 32) {
+            mine[c] += g[c] * (xr[c] * inv);
+            const float a = add ? add[(size_t)r * ld_add + c] : 0.f;
+            dx[(size_t)r * ld_dx + c] = a + fmaf(s1[c] * g[c], inv, -(coef * xr[c]));
+        }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < H; c += blockDim.x) {
+        float a = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) a += shg[(size_t)w * H + c];
+        part1[(size_t)blockIdx.x * H + c] = a;
+    }
+}
+
 __device__ __forceinline__ float gelu_exact(float a) { return 0.5f * a * (1.f + erff(a * 0.70710678118654752f)); }
 __device__ __forceinline__ float gelu_grad(float a) {
     return 0.5f * (1.f + erff(a * 0.70710678118654752f)) + a * 0.39894228040143268f * __expf(-0.5f * a * a);
@@ -185,7 +238,9 @@ extern "C" int gp_rmsnorm_fwd(const float* x, int32_t ldx, int32_t rows, int32_t
         case 32: rmsnorm_fwd_kernel<1><<<blocks, threads, 0, st>>>(x, ldx, rows, scale1, scale2, ob, out_f32, ld_out); break;
         case 64: rmsnorm_fwd_kernel<2><<<blocks, threads, 0, st>>>(x, ldx, rows, scale1, scale2, ob, out_f32, ld_out); break;
         case 128: rmsnorm_fwd_kernel<4><<<blocks, threads, 0, st>>>(x, ldx, rows, scale1, scale2, ob, out_f32, ld_out); break;
-        default: gp::set_error("gp_rmsnorm_fwd: hidden must be 32, 64 or 128 (got %d)", hidden); return -1;
+        default:
+            GP_REQUIRE(scale2 == nullptr && hidden > 0 && hidden <= 1024, "gp_rmsnorm_fwd: the double norm needs hidden 32, 64 or 128 (got %d)", hidden);
+            rmsnorm_fwd_generic_kernel<<<blocks, threads, 0, st>>>(x, ldx, rows, hidden, scale1, ob, out_f32, ld_out);
     }
     GP_CHECK_CUDA(cudaGetLastError());
     return 0;
@@ -207,7 +262,10 @@ extern "C" int gp_rmsnorm_bwd(const float* x, int32_t ldx, int32_t rows, int32_t
         case 32: rmsnorm_bwd_kernel<1><<<blocks, 256, 0, st>>>(x, ldx, rows, scale1, scale2, dy, ld_dy, dx, ld_dx, add, ld_add, part1, part2); break;
         case 64: rmsnorm_bwd_kernel<2><<<blocks, 256, 0, st>>>(x, ldx, rows, scale1, scale2, dy, ld_dy, dx, ld_dx, add, ld_add, part1, part2); break;
         case 128: rmsnorm_bwd_kernel<4><<<blocks, 256, 0, st>>>(x, ldx, rows, scale1, scale2, dy, ld_dy, dx, ld_dx, add, ld_add, part1, part2); break;
-        default: gp::set_error("gp_rmsnorm_bwd: hidden must be 32, 64 or 128 (got %d)", hidden); return -1;
+        default:
+            GP_REQUIRE(scale2 == nullptr && hidden > 0 && hidden <= 1024, "gp_rmsnorm_bwd: the double norm needs hidden 32, 64 or 128 (got %d)", hidden);
+            rmsnorm_bwd_generic_kernel<<<blocks, 256, (size_t)8 * hidden * sizeof(float), st>>>(x, ldx, rows, hidden, scale1, dy, ld_dy, dx, ld_dx, add,
+                                                                                             ld_add, part1);
     }
     GP_CHECK_CUDA(cudaGetLastError());
     return 0;

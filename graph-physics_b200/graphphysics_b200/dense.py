@@ -154,16 +154,30 @@ def norm_bwd(x, s1, s2, dy, add=None):
     return dx, _reduce_rows(p1, nb, H), (_reduce_rows(p2, nb, H) if s2 is not None else None)
 
 
-def gelu_fwd(a1, a2, out_bf16=True) -> torch.Tensor:
+def gelu_fwd(a1, a2, out_bf16=True, kind: int = 3) -> torch.Tensor:
+    """act(a1) * a2; kind 3 = GELU (gp_gelu_gate_fwd), 2 = SiLU (gp_glu_fwd)."""
     g = torch.empty(a1.shape, dtype=torch.bfloat16 if out_bf16 else torch.float32, device=a1.device)
+    if kind != 3:
+        R, G = a1.shape
+        check(lib().gp_glu_fwd(C.c_void_p(ptr(a1)), C.c_void_p(ptr(a2)), C.c_int32(G), C.c_int64(R), C.c_int32(G), C.c_int32(kind),
+                               C.c_void_p(ptr(g) if out_bf16 else None), C.c_void_p(None if out_bf16 else ptr(g)), C.c_void_p(stream_ptr())),
+              "gp_glu_fwd")
+        ops._launched()
+        return g
     check(lib().gp_gelu_gate_fwd(C.c_void_p(ptr(a1)), C.c_void_p(ptr(a2)), C.c_int64(a1.numel()), C.c_void_p(ptr(g) if out_bf16 else None),
                                  C.c_void_p(None if out_bf16 else ptr(g)), C.c_void_p(stream_ptr())), "gp_gelu_gate_fwd")
     ops._launched()
     return g
 
 
-def gelu_bwd(a1, a2, dg):
+def gelu_bwd(a1, a2, dg, kind: int = 3):
     da1, da2 = torch.empty_like(a1), torch.empty_like(a2)
+    if kind != 3:
+        R, G = a1.shape
+        check(lib().gp_glu_bwd(C.c_void_p(ptr(a1)), C.c_void_p(ptr(a2)), C.c_int32(G), C.c_void_p(ptr(dg)), C.c_int64(R), C.c_int32(G),
+                               C.c_int32(kind), C.c_void_p(ptr(da1)), C.c_void_p(ptr(da2)), C.c_int32(G), C.c_void_p(stream_ptr())), "gp_glu_bwd")
+        ops._launched()
+        return da1, da2
     check(lib().gp_gelu_gate_bwd(C.c_void_p(ptr(a1)), C.c_void_p(ptr(a2)), C.c_void_p(ptr(dg)), C.c_int64(a1.numel()), C.c_void_p(ptr(da1)),
                                  C.c_void_p(ptr(da2)), C.c_void_p(stream_ptr())), "gp_gelu_gate_bwd")
     ops._launched()
@@ -215,36 +229,88 @@ def _f32(t: torch.Tensor) -> torch.Tensor:
 
 
 # ------------------------------------------------------------------------------------------------ autograd functions
+def _rope_nodes_(t: torch.Tensor, pos: torch.Tensor, head_dim: int, heads: int, m: int, base: float, inverse: bool) -> None:
+    """Rotary embedding of per-node q / k rows ((N, head_dim, heads) layout, fp32) in place (layers.py:420-491)."""
+    check(lib().gp_rope_nodes(C.c_void_p(ptr(t)), C.c_void_p(ptr(pos)), C.c_int32(pos.stride(0)), C.c_int64(t.shape[0]), C.c_int32(head_dim),
+                              C.c_int32(heads), C.c_int32(pos.shape[1]), C.c_int32(m), C.c_float(base), C.c_int32(int(inverse)),
+                              C.c_void_p(stream_ptr())), "gp_rope_nodes")
+    ops._launched()
+
+
+def _to_bf16(t: torch.Tensor) -> torch.Tensor:
+    out = torch.empty(t.shape, dtype=torch.bfloat16, device=t.device)
+    ops.cast_bf16(t, out)
+    return out
+
+
 class _AttentionBranch(torch.autograd.Function):
-    """out = [x +] proj(attention(q, k, v)), q / k / v = Linear([RMSNorm](x)) (layers.py:637-697, 766-790)."""
+    """out = [x +] proj(gate * attention(rope(q), rope(k), v)), q / k / v = Linear([RMSNorm](x)) (layers.py:637-697, 766-790);
+    `rope` = (pos, m, base) or None, the gate (wg, bg) optional."""
 
     @staticmethod
-    def forward(ctx, x, sn, wq, bq, wk, bk, wv, bv, wp, bp, add_resid: bool, g, heads: int, terms: int):
+    def forward(ctx, x, sn, wq, bq, wk, bk, wv, bv, wp, bp, wg, bg, add_resid: bool, g, heads: int, terms: int, rope):
         x = _f32(x)
         bf = terms == 1
         n = norm_fwd(x, sn, None, out_bf16=bf) if sn is not None else x
-        q = lin_fwd(n, wq, bq, out_bf16=bf, terms=terms)
-        k = lin_fwd(n, wk, bk, out_bf16=bf, terms=terms)
+        H = wq.shape[0]
+        if rope is not None:
+            pos, m, base = rope
+            q = lin_fwd(n, wq, bq, terms=terms)
+            k = lin_fwd(n, wk, bk, terms=terms)
+            _rope_nodes_(q, pos, H // heads, heads, m, base, False)
+            _rope_nodes_(k, pos, H // heads, heads, m, base, False)
+            if bf:
+                q, k = _to_bf16(q), _to_bf16(k)
+        else:
+            q = lin_fwd(n, wq, bq, out_bf16=bf, terms=terms)
+            k = lin_fwd(n, wk, bk, out_bf16=bf, terms=terms)
         v = lin_fwd(n, wv, bv, out_bf16=bf, terms=terms)
         y, y32, lse = attn_fwd(q, k, v, g, heads)
-        out = lin_fwd(y, wp, bp, resid=x if add_resid else None, terms=terms)
-        ctx.save_for_backward(x, sn, n if sn is not None else None, q, k, v, y, y32, lse, wq, wk, wv, wp)
-        ctx.cfg = (add_resid, g, heads, terms, bq is not None, bk is not None, bv is not None, bp is not None)
+        gl = None
+        yin = y
+        if wg is not None:                       # gated attention (layers.py:684-689): y * sigmoid(gate_proj(x))
+            gl = lin_fwd(n, wg, bg, terms=terms)
+            ysrc = y32 if y32 is not None else y
+            yin = torch.empty_like(ysrc)
+            check(lib().gp_sigmoid_mul_fwd(C.c_void_p(ptr(gl)), C.c_void_p(ptr(ysrc)), C.c_int64(ysrc.numel()), C.c_void_p(ptr(yin)),
+                                           C.c_void_p(stream_ptr())), "gp_sigmoid_mul_fwd")
+            ops._launched()
+        out = lin_fwd(yin, wp, bp, resid=x if add_resid else None, terms=terms)
+        ctx.save_for_backward(x, sn, n if sn is not None else None, q, k, v, y, y32, lse, wq, wk, wv, wp, wg, gl, yin if wg is not None else None,
+                              rope[0] if rope is not None else None)
+        ctx.cfg = (add_resid, g, heads, terms, bq is not None, bk is not None, bv is not None, bp is not None, bg is not None,
+                   (rope[1], rope[2]) if rope is not None else None)
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        x, sn, n, q, k, v, y, y32, lse, wq, wk, wv, wp = ctx.saved_tensors
-        add_resid, g, heads, terms, hbq, hbk, hbv, hbp = ctx.cfg
+        x, sn, n, q, k, v, y, y32, lse, wq, wk, wv, wp, wg, gl, yin, pos = ctx.saved_tensors
+        add_resid, g, heads, terms, hbq, hbk, hbv, hbp, hbg, rope = ctx.cfg
         if n is None:
             n = x
         dout = _f32(dout)
         dy = lin_dgrad(dout, wp, terms=terms)
-        dwp, dbp = lin_wgrad(dout, y, bias=True, terms=terms) if hbp else (lin_wgrad(dout, y, terms=terms), None)
+        proj_in = yin if wg is not None else y
+        dwp, dbp = lin_wgrad(dout, proj_in, bias=True, terms=terms) if hbp else (lin_wgrad(dout, proj_in, terms=terms), None)
+        dgl = dwg = dbg = None
+        if wg is not None:
+            ysrc = y32 if y32 is not None else y
+            dgl, dy2 = torch.empty_like(gl), torch.empty_like(dy)
+            check(lib().gp_sigmoid_mul_bwd(C.c_void_p(ptr(gl)), C.c_void_p(ptr(ysrc)), C.c_void_p(ptr(dy)), C.c_int64(dy.numel()),
+                                           C.c_void_p(ptr(dgl)), C.c_void_p(ptr(dy2)), C.c_void_p(stream_ptr())), "gp_sigmoid_mul_bwd")
+            ops._launched()
+            dy = dy2
+            dwg, dbg = lin_wgrad(dgl, n, bias=True, terms=terms) if hbg else (lin_wgrad(dgl, n, terms=terms), None)
         dq, dk, dv = attn_bwd(q, k, v, y, y32, lse, dy, g, heads)
+        if rope is not None:                     # the rotation is orthogonal: its transpose is the inverse rotation
+            H = wq.shape[0]
+            _rope_nodes_(dq, pos, H // heads, heads, rope[0], rope[1], True)
+            _rope_nodes_(dk, pos, H // heads, heads, rope[0], rope[1], True)
         dn = lin_dgrad(dq, wq, terms=terms)
         lin_dgrad(dk, wk, out=dn, terms=terms)
         lin_dgrad(dv, wv, out=dn, terms=terms)
+        if dgl is not None:
+            lin_dgrad(dgl, wg, out=dn, terms=terms)
         dwq, dbq = lin_wgrad(dq, n, bias=True, terms=terms) if hbq else (lin_wgrad(dq, n, terms=terms), None)
         dwk, dbk = lin_wgrad(dk, n, bias=True, terms=terms) if hbk else (lin_wgrad(dk, n, terms=terms), None)
         dwv, dbv = lin_wgrad(dv, n, bias=True, terms=terms) if hbv else (lin_wgrad(dv, n, terms=terms), None)
@@ -254,35 +320,41 @@ class _AttentionBranch(torch.autograd.Function):
         else:
             assert not add_resid
             dx = dn
-        return dx, dsn, dwq, dbq, dwk, dbk, dwv, dbv, dwp, dbp, None, None, None, None
+        return dx, dsn, dwq, dbq, dwk, dbk, dwv, dbv, dwp, dbp, dwg, dbg, None, None, None, None, None
 
 
-def attention_branch(x, norm_scale, att, g, add_resid: bool, terms: int = 1):
-    """`att`: a models.layers.Attention module (its q_proj / k_proj / v_proj / proj parameters)."""
+def attention_branch(x, norm_scale, att, g, add_resid: bool, terms: int = 1, pos=None):
+    """`att`: a models.layers.Attention module (its q_proj / k_proj / v_proj / proj [/ gate_proj] parameters); `pos`: node
+    positions when the module uses rotary embeddings."""
+    rope = None
+    if pos is not None and att.m > 0:
+        rope = (pos[:, :att.pos_dimension].float().contiguous(), int(att.m), float(att.rope_base))
+    wg, bg = (att.gate_proj.weight, att.gate_proj.bias) if att.gate_proj is not None else (None, None)
     return _AttentionBranch.apply(x, norm_scale, att.q_proj.weight, att.q_proj.bias, att.k_proj.weight, att.k_proj.bias,
-                                  att.v_proj.weight, att.v_proj.bias, att.proj.weight, att.proj.bias, add_resid, g, att.num_heads, terms)
+                                  att.v_proj.weight, att.v_proj.bias, att.proj.weight, att.proj.bias, wg, bg, add_resid, g, att.num_heads,
+                                  terms, rope)
 
 
 class _GatedBranch(torch.autograd.Function):
     """out = [x +] [W3 .] (GELU(W1 n + b1) * (W2 n + b2)), n = [norm(norm(x; s1); s2)] (layers.py:213-278, 791-819)."""
 
     @staticmethod
-    def forward(ctx, x, s1, s2, w1, b1, w2, b2, w3, b3, add_resid: bool, terms: int):
+    def forward(ctx, x, s1, s2, w1, b1, w2, b2, w3, b3, add_resid: bool, terms: int, kind: int):
         x = _f32(x)
         bf = terms == 1
         n = norm_fwd(x, s1, s2, out_bf16=bf) if s1 is not None else x
         a1 = lin_fwd(n, w1, b1, terms=terms)
         a2 = lin_fwd(n, w2, b2, terms=terms)
-        gate = gelu_fwd(a1, a2, out_bf16=(bf and w3 is not None))
+        gate = gelu_fwd(a1, a2, out_bf16=(bf and w3 is not None), kind=kind)
         out = lin_fwd(gate, w3, b3, resid=x if add_resid else None, terms=terms) if w3 is not None else gate
         ctx.save_for_backward(x, s1, s2, n if s1 is not None else None, a1, a2, gate if w3 is not None else None, w1, w2, w3)
-        ctx.cfg = (add_resid, terms, b1 is not None, b2 is not None, b3 is not None)
+        ctx.cfg = (add_resid, terms, b1 is not None, b2 is not None, b3 is not None, kind)
         return out
 
     @staticmethod
     def backward(ctx, dout):
         x, s1, s2, n, a1, a2, gate, w1, w2, w3 = ctx.saved_tensors
-        add_resid, terms, hb1, hb2, hb3 = ctx.cfg
+        add_resid, terms, hb1, hb2, hb3, kind = ctx.cfg
         if n is None:
             n = x
         dout = _f32(dout)
@@ -292,7 +364,7 @@ class _GatedBranch(torch.autograd.Function):
             dw3, db3 = lin_wgrad(dout, gate, bias=True, terms=terms) if hb3 else (lin_wgrad(dout, gate, terms=terms), None)
         else:
             dg = dout
-        da1, da2 = gelu_bwd(a1, a2, dg)
+        da1, da2 = gelu_bwd(a1, a2, dg, kind=kind)
         dn = lin_dgrad(da1, w1, terms=terms)
         lin_dgrad(da2, w2, out=dn, terms=terms)
         dw1, db1 = lin_wgrad(da1, n, bias=True, terms=terms) if hb1 else (lin_wgrad(da1, n, terms=terms), None)
@@ -303,14 +375,15 @@ class _GatedBranch(torch.autograd.Function):
         else:
             assert not add_resid
             dx = dn
-        return dx, ds1, ds2, dw1, db1, dw2, db2, dw3, db3, None, None
+        return dx, ds1, ds2, dw1, db1, dw2, db2, dw3, db3, None, None, None
 
 
-def gated_branch(x, s1, s2, gmlp, out_linear, add_resid: bool, terms: int = 1):
-    """`gmlp`: a models.layers.GatedMLP; `out_linear`: the nn.Linear after it (None: return the gate itself, fp32)."""
+def gated_branch(x, s1, s2, gmlp, out_linear, add_resid: bool, terms: int = 1, act: str = "gelu"):
+    """`gmlp`: a models.layers.GatedMLP; `out_linear`: the nn.Linear after it (None: return the gate itself, fp32); `act`:
+    "gelu", or "silu" under the reference's global SiLU switch (layers.py:232-233)."""
     w3, b3 = (out_linear.weight, out_linear.bias) if out_linear is not None else (None, None)
     return _GatedBranch.apply(x, s1, s2, gmlp.linear1.weight, gmlp.linear1.bias, gmlp.linear2.weight, gmlp.linear2.bias, w3, b3,
-                              add_resid, terms)
+                              add_resid, terms, 2 if act == "silu" else 3)
 
 
 class _Mlp4(torch.autograd.Function):

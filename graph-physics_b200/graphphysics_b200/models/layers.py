@@ -2,9 +2,11 @@
 (graphphysics/models/layers.py), executing on the sm_100a kernels of libgp_b200.so.
 
 Covered here: RMSNorm (73-129), build_mlp (163-210), Normalizer (281-408), GraphNetBlock
-(890-1102).  The variant flags that no BASELINE config turns on (SiLU, gated MLP, RoPE, gate;
-SURVEY §8f N3) are accepted by the constructors and rejected at construction time with
-NotImplementedError instead of silently computing something else.
+(890-1149), GatedMLP / Attention / Transformer (213-278, 564-819).  The default configuration of every
+shipped training_config runs on the fused kernels; the variant flags (SiLU, gated MLP, relative RoPE,
+aggregation gate, gated attention, RoPE on q / k) run on the general path of
+graphphysics_b200/variants.py and dense.py -- the same native kernels, composed per layer.  Only
+TemporalAttention (use_temporal_block) is rejected with NotImplementedError.
 """
 from __future__ import annotations
 
@@ -158,23 +160,41 @@ class _ProcessorStack(nn.Module):
 
 
 class GraphNetBlock(nn.Module):
-    """One message-passing step (layers.py:890-1102):
-        e' = e + MLP_e([e, x[dst], x[src]]);  agg[n] = sum_{dst=n} (e'-e);  x' = x + MLP_n([x, agg]).
-    Same constructor and state_dict keys as the reference (edge_block.*, node_block.*)."""
+    """One message-passing step (layers.py:890-1149):
+        e' = e + MLP_e([e, x[dst], rope(x[src])]);  agg[n] = gate(x) * sum_{dst=n} (e'-e);  x' = x + MLP_n([x, agg]).
+    Same constructor and state_dict keys as the reference (edge_block.*, node_block.*, gate_proj.*, gate_pos).  The default
+    flags run on the fused kernels; use_rope / use_gated_mlp / use_gate / the global SiLU switch on the general path of
+    graphphysics_b200/variants.py."""
 
     def __init__(self, hidden_size: int, nb_of_layers: int = 4, layer_norm: bool = True, use_rope: bool = False,
                  rope_axes: int = 3, rope_base: float = 10000.0, use_gated_mlp: bool = False, use_gate: bool = False):
         super().__init__()
-        if use_rope or use_gated_mlp or use_gate:
-            raise NotImplementedError("use_rope / use_gated_mlp / use_gate are not implemented on the sm_100a path "
-                                      "(off in every shipped training_config; SURVEY §8f N3)")
-        if nb_of_layers != 4 or not layer_norm:
-            raise NotImplementedError("the fused kernels implement the 4-layer, RMS-normalised MLP the reference uses")
         self.hidden_size = hidden_size
         self.use_gated_mlp, self.use_rope, self.use_gate = use_gated_mlp, use_rope, use_gate
         self.rope_axes, self.rope_base = rope_axes, rope_base
-        self.edge_block = build_mlp(3 * hidden_size, hidden_size, hidden_size, nb_of_layers, layer_norm)
-        self.node_block = build_mlp(2 * hidden_size, hidden_size, hidden_size, nb_of_layers, layer_norm)
+        self.act = "silu" if use_silu_activation() else "relu"
+        self.variant = use_rope or use_gated_mlp or use_gate or self.act != "relu"
+        if not self.variant and (nb_of_layers != 4 or not layer_norm):
+            raise NotImplementedError("the fused kernels implement the 4-layer, RMS-normalised MLP the reference uses")
+        if use_gated_mlp:
+            self.edge_block = build_gated_mlp(in_size=3 * hidden_size, hidden_size=hidden_size, out_size=hidden_size)
+            self.node_block = build_gated_mlp(in_size=2 * hidden_size, hidden_size=hidden_size, out_size=hidden_size)
+        else:
+            self.edge_block = build_mlp(3 * hidden_size, hidden_size, hidden_size, nb_of_layers, layer_norm)
+            self.node_block = build_mlp(2 * hidden_size, hidden_size, hidden_size, nb_of_layers, layer_norm)
+        if use_rope:
+            if rope_axes not in (2, 3):
+                raise ValueError("rope_axes must be 2 or 3 when use_rope=True.")
+            self._pair_count = hidden_size // (2 * rope_axes)
+            self._rope_dim = self._pair_count * 2 * rope_axes
+            if self._pair_count == 0:
+                raise ValueError(f"hidden_size={hidden_size} too small for rope_axes={rope_axes}; need at least 2 * rope_axes channels.")
+        else:
+            self._pair_count, self._rope_dim = 0, 0
+        if use_gate:
+            self.gate_proj = nn.Linear(hidden_size, hidden_size, bias=True)
+            self.gate_pos = nn.Parameter(torch.zeros(hidden_size))
+        self.precision = "bf16"
         self._engine = None
 
     def _get_engine(self):
@@ -187,9 +207,16 @@ class GraphNetBlock(nn.Module):
 
     def forward(self, x: torch.Tensor, edge_index: torch.Tensor, edge_attr: torch.Tensor, size=None,
                 pos: Optional[torch.Tensor] = None, phi: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+        g = get_csr(edge_index, x.shape[0])
+        if self.variant:
+            from .. import variants
+            if not x.is_cuda:
+                raise RuntimeError("graphphysics_b200 runs on CUDA devices only (there is no CPU fallback)")
+            x2, e2 = variants.graph_net_block_forward(self, x.float(), edge_attr.float()[g.perm_dst64], g, pos, phi, self.act,
+                                                      3 if self.precision == "tight" else 1)
+            return x2, e2[g.inv_perm_dst64]
         from ..engine import BlockFunction
         eng = self._get_engine()
-        g = get_csr(edge_index, x.shape[0])
         return BlockFunction.apply(eng.flat, x, edge_attr, eng, g)
 
 
@@ -201,18 +228,17 @@ class GatedMLP(nn.Module):
 
     def __init__(self, in_size: int, hidden_size: int, expansion_factor: int):
         super().__init__()
-        if use_silu_activation():
-            raise NotImplementedError("SiLU gating is not implemented on the sm_100a path (SURVEY §8f N3)")
         self.linear1 = nn.Linear(in_size, expansion_factor * hidden_size)
         self.linear2 = nn.Linear(in_size, expansion_factor * hidden_size)
-        self.activation = nn.GELU()
+        self.act = "silu" if use_silu_activation() else "gelu"
+        self.activation = nn.SiLU() if self.act == "silu" else nn.GELU()
         self.precision = "bf16"
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         from .. import dense
         if x.device.type != "cuda":
             raise RuntimeError("graphphysics_b200 runs on CUDA devices only (there is no CPU fallback)")
-        return dense.gated_branch(x, None, None, self, None, add_resid=False, terms=3 if self.precision == "tight" else 1)
+        return dense.gated_branch(x, None, None, self, None, add_resid=False, terms=3 if self.precision == "tight" else 1, act=self.act)
 
 
 def build_gated_mlp(in_size: int, hidden_size: int, out_size: int, expansion_factor: int = 3) -> nn.Module:
@@ -233,8 +259,6 @@ class Attention(nn.Module):
                  use_gated_attention: bool = False, rope_base: float = 10000.0):
         super().__init__()
         assert output_dim % num_heads == 0, "Output dimension must be divisible by number of heads."
-        if use_rope_embeddings or use_gated_attention:
-            raise NotImplementedError("RoPE / gated attention are not implemented on the sm_100a path (SURVEY §8f N3)")
         self.hidden_size, self.num_heads, self.head_dim = output_dim, num_heads, output_dim // num_heads
         self.use_rope_embeddings, self.use_gated_attention = use_rope_embeddings, use_gated_attention
         self.pos_dimension, self.rope_base = pos_dimension, rope_base
@@ -242,9 +266,15 @@ class Attention(nn.Module):
         self.k_proj = nn.Linear(input_dim, output_dim, bias=use_proj_bias)
         self.v_proj = nn.Linear(input_dim, output_dim, bias=use_proj_bias)
         self.proj = nn.Linear(output_dim, output_dim, bias=use_proj_bias)
-        self.m = 0
-        self.register_buffer("rope_inv_freq", torch.empty(0, dtype=torch.float32), persistent=False)
-        self.gate_proj = None
+        if use_rope_embeddings:
+            self.m = self.head_dim // max(pos_dimension * 2, 1)
+            step = math.log(rope_base) / max(self.m, 1)          # _make_inv_freq (layers.py:410-417)
+            inv = torch.exp(-torch.arange(self.m, dtype=torch.float32) * step) if self.m > 0 else torch.empty(0)
+            self.register_buffer("rope_inv_freq", inv, persistent=True)
+        else:
+            self.m = 0
+            self.register_buffer("rope_inv_freq", torch.empty(0, dtype=torch.float32), persistent=False)
+        self.gate_proj = nn.Linear(input_dim, output_dim, bias=use_proj_bias) if use_gated_attention else None
         self.precision = "bf16"        # "tight": three-term split GEMMs, fp32 q / k / v / y (set by the owning model)
         if not use_separate_proj_weight:
             with torch.no_grad():
@@ -262,7 +292,14 @@ class Attention(nn.Module):
         if return_attention:
             raise NotImplementedError("return_attention=True is not supported (attention weights are never materialised)")
         return dense.attention_branch(x, None, self, self._graph(x, adj), add_resid=False,
-                                      terms=3 if self.precision == "tight" else 1)
+                                      terms=3 if self.precision == "tight" else 1, pos=self._rope_pos(pos))
+
+    def _rope_pos(self, pos):
+        if not self.use_rope_embeddings:
+            return None
+        if pos is None:
+            raise ValueError("RoPE embeddings require positional information when enabled.")
+        return pos
 
 
 class Transformer(nn.Module):
@@ -299,7 +336,8 @@ class Transformer(nn.Module):
         if return_attention:
             raise NotImplementedError("return_attention=True is not supported (attention weights are never materialised)")
         terms = 3 if self.precision == "tight" else 1
-        x = dense.attention_branch(x, self.norm1.scale, self.attention, self.attention._graph(x, adj), add_resid=True, terms=terms)
+        x = dense.attention_branch(x, self.norm1.scale, self.attention, self.attention._graph(x, adj), add_resid=True, terms=terms,
+                                   pos=self.attention._rope_pos(pos))
         # the double norm: Transformer.norm2, then build_gated_mlp's own leading RMSNorm (layers.py:252-278)
         return dense.gated_branch(x, self.norm2.scale, self.gated_mlp[0].scale, self.gated_mlp[1], self.gated_mlp[2],
-                                  add_resid=True, terms=terms)
+                                  add_resid=True, terms=terms, act=self.gated_mlp[1].act)

@@ -10,7 +10,7 @@ import torch
 import torch.nn as nn
 
 from ..graph import get_csr
-from .layers import GraphNetBlock, build_mlp
+from .layers import GraphNetBlock, build_mlp, use_silu_activation
 
 
 class EncodeProcessDecode(nn.Module):
@@ -43,6 +43,13 @@ class EncodeProcessDecode(nn.Module):
                           rope_axes=rope_pos_dimension, rope_base=rope_base, use_gate=use_gated_attention)
             for _ in range(message_passing_num)])
         self._engine = None
+        self.act = "silu" if use_silu_activation() else "relu"
+        # any variant flag (or the global SiLU switch) takes the model off the fused kernels onto the general path
+        self.variant = bool(use_rope_embeddings or use_gated_attention or use_gated_mlp or self.act != "relu")
+        if self.use_rope and self.rope_axes not in (2, 3):
+            raise ValueError("rope_pos_dimension must be 2 or 3 when use_rope_embeddings=True.")
+        for blk in self.processor_list:
+            blk.precision = self.precision
 
     @property
     def engine(self):
@@ -52,6 +59,9 @@ class EncodeProcessDecode(nn.Module):
         return self._engine
 
     def forward(self, graph) -> torch.Tensor:
+        if self.variant:
+            from ..variants import epd_forward as variant_forward
+            return variant_forward(self, graph, self.act)
         if self.precision == "tight":
             from ..tight import epd_forward
             return epd_forward(self, graph)
@@ -100,6 +110,7 @@ class EncodeTransformDecode(nn.Module):
         self.precision = precision or os.environ.get("GP_B200_PRECISION", "bf16")
         for blk in self.processor_list:
             blk.set_precision(self.precision)
+        self.act = "silu" if use_silu_activation() else "relu"
 
     def forward(self, graph) -> torch.Tensor:
         x = graph.x
@@ -108,8 +119,16 @@ class EncodeTransformDecode(nn.Module):
         from .. import dense
         terms = 3 if self.precision == "tight" else 1
         g = get_csr(graph.edge_index, x.shape[0])          # processors.py:366: rows edge_index[0], cols edge_index[1]
+        pos = getattr(graph, "pos", None)
+        if self.use_rope_embeddings and pos is None:
+            raise ValueError("use_rope_embeddings=True requires 'pos' attribute in the input graph.")
+        if self.act != "relu":                                   # SiLU encoder / decoder: the general MLP path
+            from .. import variants
+            enc = lambda seq, t: variants.mlp_seq(seq, t, self.act, terms)
+        else:
+            enc = lambda seq, t: dense.mlp4(seq, t, terms=terms)
         if not self.only_processor:
-            x = dense.mlp4(self.nodes_encoder, x.float(), terms=terms)
+            x = enc(self.nodes_encoder, x.float())
         for block in self.processor_list:
-            x = block(x, g, pos=getattr(graph, "pos", None))
-        return x if self.only_processor else dense.mlp4(self.decode_module, x, terms=terms)
+            x = block(x, g, pos=pos)
+        return x if self.only_processor else enc(self.decode_module, x)

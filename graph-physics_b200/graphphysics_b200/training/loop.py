@@ -60,7 +60,8 @@ class Trainer:
         self.step_index = 0
         # EPD on the fused kernels: engine-driven forward/backward, no autograd tape (precision="tight" and the
         # Transformer run under autograd over flat parameter / gradient buffers)
-        self.fused = hasattr(type(self.processor), "engine") and getattr(self.processor, "precision", "bf16") == "bf16"
+        self.fused = (hasattr(type(self.processor), "engine") and getattr(self.processor, "precision", "bf16") == "bf16"
+                      and not getattr(self.processor, "variant", False))
         self._flat = None if self.fused else None
         if not self.fused:
             from ..engine import FlatParams

@@ -17,9 +17,7 @@ def get_model(param: Dict[str, Any], only_processor: bool = False):
     model_type = m.get("type", "")
     node_input_size = param["model"]["node_input_size"] + NodeType.SIZE     # parse_parameters.py:96
     training = param.get("training", {})
-    if m.get("use_silu_activation", False):
-        raise NotImplementedError("use_silu_activation is not implemented on the sm_100a path (SURVEY §8f N3)")
-    set_use_silu_activation(False)
+    set_use_silu_activation(bool(m.get("use_silu_activation", False)))
     set_memory_optimized_training(training.get("enable_vram_optimizations", False))
     common = dict(use_rope_embeddings=m.get("use_rope_embeddings", False),
                   use_gated_attention=m.get("use_gated_attention", False),

@@ -405,6 +405,35 @@ int gp_world_pairs_fill(const float* pos, int32_t ld_pos, const float* node_type
 int gp_add_noise(float* x, int32_t ld, int32_t rows, int32_t col_start, int32_t col_end, int32_t node_type_col, int32_t normal_type,
                  const float* noise, float scale, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Variant flags of the path (graphphysics/models/layers.py:213-249 GatedMLP with SiLU / GELU, 410-491 RoPE on
+ * q / k, 637-697 gated attention, 989-1149 GraphNetBlock with use_rope / use_gate): row-wise fp32 kernels around gp_gemm.
+ *   kind: 1 ReLU, 2 SiLU, 3 GELU (exact).  gp_act_bwd multiplies d in place by act'(z).  gp_glu_*: g = act(a1) * a2 on
+ *   [rows, cols] blocks with row stride ld.  gp_sigmoid_mul_*: out = v * sigmoid(logits).  gp_add_outer: logits[r, c] +=
+ *   phi[r] * vec[c].  gp_rope_rel: relative rotary embedding of gathered sender rows by pos[src] - pos[dst]; gp_rope_nodes:
+ *   rotary embedding of per-node q / k in the (N, head_dim, heads) layout, in place; `inverse` applies the transpose (the
+ *   backward).  gp_concat_rows / gp_split_cols: [a | b | c] per row and its transpose (column block copy / accumulate).
+ * --------------------------------------------------------------------------------------------- */
+int gp_act_fwd(const float* z, int64_t n, int32_t kind, gp_bf16* out_bf16, float* out_f32, void* stream);
+int gp_act_bwd(const float* z, int64_t n, int32_t kind, float* d, void* stream);
+int gp_glu_fwd(const float* a1, const float* a2, int32_t ld, int64_t rows, int32_t cols, int32_t kind, gp_bf16* out_bf16, float* out_f32,
+               void* stream);
+int gp_glu_bwd(const float* a1, const float* a2, int32_t ld, const float* dg, int64_t rows, int32_t cols, int32_t kind, float* da1,
+               float* da2, int32_t ld_d, void* stream);
+int gp_sigmoid_mul_fwd(const float* logits, const float* v, int64_t n, float* out, void* stream);
+int gp_sigmoid_mul_bwd(const float* logits, const float* v, const float* dout, int64_t n, float* dlogits, float* dv, void* stream);
+int gp_add_outer(float* logits, const float* phi, const float* vec, int64_t rows, int32_t cols, void* stream);
+int gp_rope_rel(const float* x, const float* pos, int32_t ld_pos, const int32_t* src, const int32_t* dst, int64_t num_edges, int32_t hidden,
+                int32_t axes, int32_t pair_count, float base, int32_t inverse, float* out, void* stream);
+int gp_rope_nodes(float* t, const float* pos, int32_t ld_pos, int64_t num_nodes, int32_t head_dim, int32_t num_heads, int32_t pos_dim,
+                  int32_t m, float base, int32_t inverse, void* stream);
+int gp_concat_rows(const float* a, int32_t wa, const float* b, int32_t wb, const float* c, int32_t wc, int64_t rows, float* out, void* stream);
+int gp_split_cols(const float* d, int32_t width, int32_t col0, int32_t w, int64_t rows, float* out, int32_t accumulate, void* stream);
+/* out[n] = sum_{p in [rowptr[n], rowptr[n+1])} src[perm ? perm[p] : p]  (fp32 rows, ascending p: the receiver sum of the variant
+ * path and the transpose of its row gathers) */
+int gp_segsum_rows_f32(const float* src, int32_t ld, const int32_t* perm, const int32_t* rowptr, int64_t num_segments, int32_t hidden,
+                       float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

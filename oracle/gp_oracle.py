@@ -542,3 +542,128 @@ def add_noise(x: np.ndarray, noise: np.ndarray, start: int, end: int, scale: flo
     keep = (x[:, node_type_index] == NORMAL)[:, None]
     out[:, start:end] = x[:, start:end] + np.where(keep, noise.astype(np.float32) * s, np.float32(0))
     return out
+
+
+# --------------------------------------------------------------------------- variant flags
+def gated_mlp_seq(x, sd, prefix: str, act: str = "gelu", mode: Optional[str] = None):
+    """build_gated_mlp (layers.py:252-278): RMSNorm -> GatedMLP (act(W1 n) * (W2 n), layers.py:213-249) -> Linear."""
+    n = rnd(rms_norm(x, sd[f"{prefix}.0.scale"]), mode)
+    left = _ACT[act](linear(n, sd[f"{prefix}.1.linear1.weight"], sd[f"{prefix}.1.linear1.bias"], mode))
+    right = linear(n, sd[f"{prefix}.1.linear2.weight"], sd[f"{prefix}.1.linear2.bias"], mode)
+    return linear(rnd(left * right, mode), sd[f"{prefix}.2.weight"], sd[f"{prefix}.2.bias"], mode)
+
+
+def rope_rel(x_src, delta_pos, axes: int, base: float = 10000.0):
+    """GraphNetBlock._apply_rope_rel (layers.py:1104-1149): per axis, `pair_count` (even, odd) channel pairs rotated by
+    theta = delta[axis] * base^(-i / pair_count); the remaining channels pass through."""
+    E, H = x_src.shape
+    pc = H // (2 * axes)
+    if pc == 0:
+        return x_src
+    inv = torch.pow(torch.tensor(base, dtype=torch.float32), -torch.arange(pc, dtype=torch.float32) / max(float(pc), 1.0))
+    parts, start = [], 0
+    for a in range(axes):
+        seg = x_src[:, start:start + 2 * pc].reshape(E, pc, 2)
+        theta = delta_pos[:, a].to(inv.dtype).unsqueeze(1) * inv.unsqueeze(0)
+        c, s = torch.cos(theta).to(x_src.dtype), torch.sin(theta).to(x_src.dtype)
+        ev, od = seg[..., 0], seg[..., 1]
+        parts.append(torch.stack([ev * c - od * s, ev * s + od * c], -1).reshape(E, 2 * pc))
+        start += 2 * pc
+    return torch.cat(parts + [x_src[:, axes * 2 * pc:]], -1)
+
+
+def graph_net_block_variant(x, e, src, dst, sd, prefix: str, *, act: str = "relu", gated_mlp: bool = False, gate: bool = False,
+                            rope_axes: int = 0, rope_base: float = 10000.0, pos=None, phi=None, mode: Optional[str] = None):
+    """GraphNetBlock.forward with its constructor flags (layers.py:989-1102).  Kernel mode (`mode="bf16"`): GEMM operands
+    and the gradients entering them rounded to bf16, everything else in the working precision -- the arithmetic of
+    graphphysics_b200/variants.py."""
+    x_i, x_j = x[dst], x[src]
+    if rope_axes:
+        x_j = rope_rel(x_j, pos[src, :rope_axes] - pos[dst, :rope_axes], rope_axes, rope_base)
+    cat = torch.cat([e, x_i, x_j], -1)
+    if gated_mlp:
+        e_upd = gated_mlp_seq(cat, sd, f"{prefix}.edge_block", "silu" if act == "silu" else "gelu", mode)
+    else:
+        e_upd = dense_mlp_act(cat, sd, f"{prefix}.edge_block", act, mode)
+    agg = torch.zeros_like(x).index_add_(0, dst, e_upd)
+    if gate:
+        logits = linear(x, sd[f"{prefix}.gate_proj.weight"], sd[f"{prefix}.gate_proj.bias"], mode)
+        if phi is not None:
+            logits = logits + phi.reshape(-1, 1).to(logits.dtype) * sd[f"{prefix}.gate_pos"].reshape(1, -1)
+        agg = agg * torch.sigmoid(logits)
+    cat_n = torch.cat([x, agg], -1)
+    if gated_mlp:
+        x_upd = gated_mlp_seq(cat_n, sd, f"{prefix}.node_block", "silu" if act == "silu" else "gelu", mode)
+    else:
+        x_upd = dense_mlp_act(cat_n, sd, f"{prefix}.node_block", act, mode)
+    return x + x_upd, e + e_upd
+
+
+def dense_mlp_act(x, sd, prefix: str, act: str = "relu", mode: Optional[str] = None, layer_norm: bool = True):
+    """build_mlp with a selectable activation, one GEMM per Linear (hidden activations are MMA operands)."""
+    h = x
+    for i in range(4):
+        h = linear(h, sd[f"{prefix}.{2 * i}.weight"], sd[f"{prefix}.{2 * i}.bias"], mode)
+        if i < 3:
+            h = _ACT[act](h)
+    return rms_norm(h, sd[f"{prefix}.7.scale"]) if layer_norm else h
+
+
+def epd_forward_variant(sd, x_in, edge_attr, edge_index, num_layers: int, *, act: str = "relu", gated_mlp: bool = False,
+                        gate: bool = False, rope_axes: int = 0, rope_base: float = 10000.0, pos=None, phi=None,
+                        mode: Optional[str] = None):
+    """EncodeProcessDecode.forward with the variant flags (processors.py:162-215)."""
+    src, dst = edge_index[0], edge_index[1]
+    x = dense_mlp_act(x_in, sd, "nodes_encoder", act, mode)
+    e = dense_mlp_act(edge_attr, sd, "edges_encoder", act, mode)
+    for i in range(num_layers):
+        x, e = graph_net_block_variant(x, e, src, dst, sd, f"processor_list.{i}", act=act, gated_mlp=gated_mlp, gate=gate,
+                                       rope_axes=rope_axes, rope_base=rope_base, pos=pos, phi=phi if gate else None, mode=mode)
+    return dense_mlp_act(x, sd, "decode_module", act, mode, layer_norm=False)
+
+
+def rope_nodes(q, k, pos, inv_freq):
+    """_apply_rope_with_inv (layers.py:420-491): q, k (N, D, Hh); per position axis a and frequency i the channel pair
+    (d_even, d_odd) = (a*2m + 2i, a*2m + 2i + 1) of every head is rotated by pos[:, a] * inv_freq[i]."""
+    N, D, Hh = q.shape
+    pd = pos.shape[1]
+    m = D // (pd * 2)
+    if m == 0:
+        return q, k
+    ang = pos[:, :pd].to(torch.float32).unsqueeze(-1) * inv_freq.to(torch.float32).view(1, 1, m)
+    s, c = torch.sin(ang).to(q.dtype), torch.cos(ang).to(q.dtype)
+
+    def ap(t):
+        part = t[:, :pd * 2 * m, :].reshape(N, pd, m, 2, Hh)
+        ev, od = part[..., 0, :], part[..., 1, :]
+        rot = torch.stack((ev * c.unsqueeze(-1) - od * s.unsqueeze(-1), ev * s.unsqueeze(-1) + od * c.unsqueeze(-1)), 3).reshape(N, pd * 2 * m, Hh)
+        return torch.cat([rot, t[:, pd * 2 * m:, :]], 1)
+
+    return ap(q), ap(k)
+
+
+def etd_forward_variant(sd, x_in, edge_index, num_layers: int, num_heads: int, *, act: str = "relu", gated_attention: bool = False,
+                        rope: bool = False, rope_base: float = 10000.0, pos=None, mode: Optional[str] = None):
+    """EncodeTransformDecode.forward with use_gated_attention / use_rope_embeddings / SiLU (processors.py:338-384,
+    layers.py:637-697, 766-819)."""
+    row, col = edge_index[0], edge_index[1]
+    x = dense_mlp_act(x_in, sd, "nodes_encoder", act, mode)
+    N, H = x.shape
+    d = H // num_heads
+    for i in range(num_layers):
+        p = f"processor_list.{i}"
+        n1 = rnd(rms_norm(x, sd[f"{p}.norm1.scale"]), mode)
+        q, k, v = (linear(n1, sd[f"{p}.attention.{w}_proj.weight"], sd.get(f"{p}.attention.{w}_proj.bias"), mode) for w in "qkv")
+        q, k, v = (t.reshape(N, d, num_heads) for t in (q, k, v))
+        if rope:
+            m = d // max(pos.shape[1] * 2, 1)
+            inv = torch.exp(-torch.arange(m, dtype=torch.float32) * (math.log(rope_base) / max(m, 1)))      # _make_inv_freq
+            q, k = rope_nodes(q, k, pos, inv)
+        q, k, v = (rnd(t, mode) for t in (q, k, v))
+        y = sparse_attention(q, k, v, row, col, N)
+        if gated_attention:
+            gl = linear(n1, sd[f"{p}.attention.gate_proj.weight"], sd.get(f"{p}.attention.gate_proj.bias"), mode)
+            y = y * torch.sigmoid(gl).reshape(N, d, num_heads)
+        x = x + linear(rnd(y.reshape(N, H), mode), sd[f"{p}.attention.proj.weight"], sd.get(f"{p}.attention.proj.bias"), mode)
+        x = x + gated_mlp_seq(rms_norm(x, sd[f"{p}.norm2.scale"]), sd, f"{p}.gated_mlp", "silu" if act == "silu" else "gelu", mode)
+    return dense_mlp_act(x, sd, "decode_module", act, mode, layer_norm=False)

@@ -167,8 +167,28 @@ def test_shipped_training_configs_parse_verbatim():
         assert sim._edge_normalizer is None and sim.node_input_size == nin + 9
     with pytest.raises(ValueError):
         get_model({"model": {"type": "nope", "node_input_size": 1}})
+    # variant flags build the reference's modules and route to the general path
+    from graphphysics_b200.models import layers as L
+    var = json.loads(json.dumps(cfgs["cylinder"]))
+    var["model"].update(use_silu_activation=True, use_gated_mlp=True, use_gated_attention=True, use_rope_embeddings=True,
+                        rope_pos_dimension=2)
+    try:
+        v = get_model(var)
+        assert v.variant and isinstance(v.nodes_encoder[1], torch.nn.SiLU)
+        keys = set(v.state_dict().keys())
+        assert {"processor_list.0.gate_proj.weight", "processor_list.0.gate_pos", "processor_list.0.edge_block.1.linear1.weight",
+                "processor_list.0.edge_block.0.scale", "processor_list.0.node_block.2.bias"} <= keys
+        assert v.processor_list[0].edge_block[0].scale.numel() == 3 * 32 and v.processor_list[0]._pair_count == 32 // 4
+    finally:
+        L.set_use_silu_activation(False)
+    assert not get_model(cfgs["cylinder"]).variant
+    tv = json.loads(json.dumps(cfgs["coarse-aneurysm"]))
+    tv["model"].update(use_gated_attention=True, use_rope_embeddings=True)
+    t = get_model(tv)
+    assert t.processor_list[0].attention.gate_proj is not None and t.processor_list[0].attention.m == 16 // 6
+    assert "processor_list.0.attention.rope_inv_freq" in t.state_dict()
     bad = json.loads(json.dumps(cfgs["cylinder"]))
-    bad["model"]["use_silu_activation"] = True
+    bad["training"] = {"use_temporal_block": True}
     with pytest.raises(NotImplementedError):
         get_model(bad)
 

@@ -9,6 +9,7 @@ import torch
 
 from oracle import gp_oracle as O
 from oracle.cpu_train import CpuTrainer
+from tests.util import l2_rel
 
 G = os.path.join(os.path.dirname(__file__), "golden")
 
@@ -205,3 +206,46 @@ def test_oracle_world_edges_against_brute_force():
     col = np.concatenate([j, i, mesh[1], mesh[0]])
     key = np.unique(row.astype(np.int64) * n + col)
     assert np.array_equal(got, np.stack([key // n, key % n]))
+
+
+EPD_VARIANTS = {"epd_silu": dict(act="silu"), "epd_gated_mlp": dict(gated_mlp=True), "epd_gated_mlp_silu": dict(act="silu", gated_mlp=True),
+                "epd_gate": dict(gate=True), "epd_rope": dict(rope_axes=2),
+                "epd_all": dict(act="silu", gated_mlp=True, gate=True, rope_axes=2)}
+ETD_VARIANTS = {"etd_gated_attention": dict(gated_attention=True), "etd_rope": dict(rope=True), "etd_silu": dict(act="silu"),
+                "etd_shared_qkv": dict()}
+
+
+def _variant_case(z, name):
+    sd = {k[len(name) + 4:]: torch.from_numpy(z[k]).double().requires_grad_(True) for k in z.files if k.startswith(name + "/sd/")}
+    grads = {k[len(name) + 6:]: z[k] for k in z.files if k.startswith(name + "/grad/")}
+    return sd, grads
+
+
+def test_oracle_variant_flags_against_reference_golden():
+    """SiLU / gated MLP / aggregation gate / relative RoPE (EncodeProcessDecode) and gated attention / RoPE / SiLU / shared
+    q-k-v weights (EncodeTransformDecode): the oracle reproduces the UNMODIFIED reference's outputs (1e-5) and parameter
+    gradients (1e-4; tests/golden/variants.npz, oracle/make_golden_variants.py)."""
+    from oracle import gp_oracle as O
+    z = np.load(os.path.join(G, "variants.npz"))
+    ei, ea, pos = torch.from_numpy(z["edge_index"]), torch.from_numpy(z["edge_attr"]).double(), torch.from_numpy(z["pos"]).double()
+    for name, kw in EPD_VARIANTS.items():
+        sd, grads = _variant_case(z, name)
+        out = O.epd_forward_variant(sd, torch.from_numpy(z["x_epd"]).double(), ea, ei, 2, pos=pos, phi=torch.from_numpy(z["phi"]).double(), **kw)
+        assert l2_rel(out, torch.from_numpy(z[name + "/out"])) < 1e-5, name
+        (out * torch.from_numpy(z["G_epd"]).double()).sum().backward()
+        for k, g in grads.items():
+            assert l2_rel(sd[k].grad, torch.from_numpy(g)) < 2e-4, (name, k)
+    for name, kw in ETD_VARIANTS.items():
+        sd, grads = _variant_case(z, name)
+        shared = name == "etd_shared_qkv"
+        out = O.etd_forward_variant(sd, torch.from_numpy(z["x_etd"]).double(), ei, 2, 4, pos=pos, **kw)
+        assert l2_rel(out, torch.from_numpy(z[name + "/out"])) < 1e-5, name
+        (out * torch.from_numpy(z["G_etd"]).double()).sum().backward()
+        biggest = max(float(np.linalg.norm(g)) for g in grads.values())
+        for k, g in grads.items():
+            if float(np.linalg.norm(g)) < 1e-7 * biggest:                 # k_proj.bias without RoPE: analytically zero
+                continue
+            got = sd[k].grad
+            if shared and k.endswith("attention.q_proj.weight"):       # one Parameter behind q / k / v: its gradient is the sum
+                got = got + sd[k.replace("q_proj", "k_proj")].grad + sd[k.replace("q_proj", "v_proj")].grad
+            assert l2_rel(got, torch.from_numpy(g)) < 2e-4, (name, k)
