@@ -431,16 +431,16 @@ def main():
                  "edge_bwd_A": E * (10 * H + 8) + 2 * N * H}
     alg_flops = {"edge_fwd": E * 8 * H * H, "edge_bwd_B": E * 12 * H * H, "edge_bwd_A": E * 10 * H * H}
     # dram__bytes_read.sum + dram__bytes_write.sum per launch of the same kernels on this workload, from the
-    # `ncu --set full` captures summarised in profiles/r01_final_summary.md (below the algorithmic bytes: the
+    # `ncu --set full` captures summarised in profiles/r02_final_summary.md (at or below the algorithmic bytes: the
     # gathered rows and the residual tile hit L2)
-    ncu_dram_bytes = {"edge_fwd": 220.5e6, "edge_bwd_B": 284.2e6, "edge_bwd_A": 517.7e6} if (E, N, H) == (372752, 64424, 128) else {}
+    ncu_dram_bytes = {"edge_fwd": 295.5e6, "edge_bwd_B": 284.3e6, "edge_bwd_A": 520.4e6} if (E, N, H) == (372752, 64424, 128) else {}
     roof = None
     if prof:
         top = max(prof, key=lambda k: prof[k]["total_ms"])
         avg_ms = prof[top]["total_ms"] / max(prof[top]["calls"], 1)
         ach = alg_bytes[top] / (avg_ms * 1e-3) / 1e9
         roof = {"bound": "hbm", "kernel": top, "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-                "traffic": ncu_dram_bytes.get(top), "traffic_source": "profiles/r01_final_summary.md (ncu --set full, per launch, bytes)",
+                "traffic": ncu_dram_bytes.get(top), "traffic_source": "profiles/r02_final_summary.md (ncu --set full, per launch, bytes)",
                 "algorithmic_bytes": alg_bytes[top], "peak_source": peak_src, "avg_launch_ms": avg_ms,
                 "share_of_step": (prof[top]["total_ms"] / n_prof) / (ms_res / args.steps),
                 "tensor": {"achieved_tflops": alg_flops[top] / (avg_ms * 1e-3) / 1e12, "peak_tflops": tf_peak,
@@ -486,13 +486,22 @@ def main():
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
     part = None
     if world > 1 and not args.no_partition:
+        # release the headline trainer (activations, captured graphs) first: the partition block's 1-GPU reference step
+        # wants the whole device
+        import gc
+        from graphphysics_b200 import graph as _g
+        tr = resident = None
+        _g._PERSISTENT.clear()
+        _g._CACHE.clear()
+        gc.collect()
+        torch.cuda.empty_cache()
         try:
             # the mesh grows with the job (each line carries its own 1-GPU reference on the same mesh): 373k nodes at 2
             # GPUs, 681k at 4, the 1M-node / 13.8M-edge mesh of BASELINE.json configs[4] at 8 -- when the unpartitioned
             # reference step (~145 GiB of activations at 1M nodes) fits next to what this process already holds
             side = args.partition_side or {2: 72, 4: 88}.get(world, 100 if world >= 8 else 72)
             free_gib = torch.cuda.mem_get_info(dev)[0] / 2 ** 30
-            if side >= 100 and free_gib < 168:
+            if side >= 100 and free_gib < 160:
                 side = 88
             part = partition_block(dev, pg, world, rank, side=side)
         except Exception as exc:
