@@ -69,6 +69,23 @@ bool tma_map_2d(CUtensorMap* map, const void* base, long long rows, int cols, lo
     *map = m;
     return true;
 }
+// Row-gather map for cp.async.bulk.tensor.2d ... tile::gather4: box = 64 columns x ONE row (a {64, 4} box faults; probe/
+// gather4_probe.cu), each instruction names four row coordinates and lands 4 x 128 bytes in the SW128 tile layout.
+bool tma_map_rows(CUtensorMap* map, const void* base, long long rows, int cols, long long ld) {
+    EncodeTiledFn enc = encode_tiled();
+    if (!enc || !base || rows <= 0 || cols <= 0) return false;
+    if ((reinterpret_cast<uintptr_t>(base) & 15u) || (ld * 2) % 16 != 0 || ld < cols) return false;
+    const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+    const cuuint32_t box[2] = {64, 1}, estr[2] = {1, 1};
+    CUtensorMap m;
+    const CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return false;
+    *map = m;
+    return true;
+}
 }  // namespace gp
 
 extern "C" int gp_version(void) { return 200; }

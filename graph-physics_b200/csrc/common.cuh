@@ -17,6 +17,8 @@ int max_smem_optin();
 // false (map untouched) when the tensor cannot be described (alignment) -- callers then use
 // their per-thread copy path.
 bool tma_map_2d(CUtensorMap* map, const void* base, long long rows, int cols, long long ld);
+// the same matrix described for row gathers (tile::gather4): box = 64 columns x 1 row
+bool tma_map_rows(CUtensorMap* map, const void* base, long long rows, int cols, long long ld);
 
 // Launch-overlap switch (gp_set_launch_overlap): when on, the persistent MLP kernels are launched with
 // programmatic stream serialization, so their prologue (weight staging, TMEM allocation) overlaps the tail

@@ -58,8 +58,9 @@ constexpr uint32_t kSlotCols = 192, kColAct = 128;      // TMEM columns of a slo
 static_assert(kSmemBytes <= 232448, "shared memory budget of one CTA");
 
 struct Fwd2Maps {
-    CUtensorMap e, h2;
+    CUtensorMap e, h2, psrc;
     uint32_t save_h2;
+    uint32_t gather4;      // sender rows P[src] by TMA tile::gather4 (psrc valid) instead of cp.async
 };
 
 struct Bars {
@@ -133,6 +134,13 @@ __device__ __forceinline__ void mma2_ts(uint32_t tmem_d, uint32_t tmem_a, uint64
 __device__ __forceinline__ void mma2_commit_both(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                  ::"r"(smem_u32(bar)), "h"((uint16_t)3)
+                 : "memory");
+}
+// four indexed rows (64 columns each) of the gather map -> 4 x 128 bytes of an SW128 tile, completion on `bar`
+__device__ __forceinline__ void tma_gather4(uint32_t smem_dst, const void* tmap, int32_t col, int32_t r0, int32_t r1, int32_t r2, int32_t r3,
+                                            uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+                 ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(col), "r"(r0), "r"(r1), "r"(r2), "r"(r3)
                  : "memory");
 }
 __device__ __forceinline__ void named_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
@@ -258,7 +266,7 @@ edge_fwd2_kernel(const gp_mlp_fwd_args p, const __grid_constant__ Fwd2Maps maps)
             mbar_init(&B.tma_e[s], 1);
             mbar_init(&B.u_full[s], 4);
             mbar_init(&B.u_empty[s], 4);
-            mbar_init(&B.g_full[s], 64);      // two producer warps x 32 lanes (cp.async completions); one barrier pair per
+            mbar_init(&B.g_full[s], maps.gather4 ? 2 : 64);      // cp.async: two producer warps x 32 lanes; TMA: one expect_tx per warp
             mbar_init(&B.g_empty[s], 4);      // consuming slot: each slot sees its own phases in order
         }
         fence_mbar_init();
@@ -578,6 +586,22 @@ edge_fwd2_kernel(const gp_mlp_fwd_args p, const __grid_constant__ Fwd2Maps maps)
             PROF_TICK(13);       // producer: issue (previous tile) + index loads
             if (j > 0) mbar_wait(&B.g_empty[(j - 1) & 1], ((j - 1) >> 1) & 1);      // the previous tile's rows have been consumed
             PROF_TICK(14);       // producer: waiting for the staging buffer
+            if (maps.gather4) {
+                // TMA row gather: lane = (column block, group of four rows); one instruction lands 4 x 128 bytes in the
+                // tile layout, the copy engine does the address arithmetic and the swizzle
+                if (lane == 0) mbar_arrive_expect_tx(&B.g_full[j & 1], 64 * H * 2);
+                const int gq = lane & 15, blk = lane >> 4;
+                const int rl = 4 * gq;                                     // first of this lane's four rows within the warp's 64
+                int ix[4];
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {        // (both halves are shuffled: the selection belongs to the receiving lane)
+                    const int lo = __shfl_sync(0xffffffffu, my[0], (rl + t) & 31), hi = __shfl_sync(0xffffffffu, my[1], (rl + t) & 31);
+                    ix[t] = rl < 32 ? lo : hi;
+                }
+                const int i0 = ix[0], i1 = ix[1], i2 = ix[2], i3 = ix[3];
+                tma_gather4(g_u + blk * 16384 + (pw * 64 + rl) * 128, &maps.psrc, blk * 64, i0, i1, i2, i3, &B.g_full[j & 1]);
+                continue;
+            }
 #pragma unroll 8
             for (int jj = 0; jj < 32; ++jj) {
                 const int rl = 2 * jj + (lane >> 4), ch = lane & 15;       // row within this warp's 64
@@ -615,6 +639,10 @@ int try_edge_fwd2(const gp_mlp_fwd_args& a, cudaStream_t st) {
         if (!gp::tma_map_2d(&maps.h2, a.save_h2, a.rows, H, H)) return 0;
         maps.save_h2 = 1;
     }
+    // sender rows by TMA tile::gather4 (GP_EDGE_FWD_GATHER4=0 keeps the cp.async producers).  The row bound of the map is
+    // an upper limit only (the argument block does not carry the node count; every index is valid by contract).
+    static const bool g4_off = getenv("GP_EDGE_FWD_GATHER4") != nullptr && getenv("GP_EDGE_FWD_GATHER4")[0] == '0';
+    if (!g4_off && gp::tma_map_rows(&maps.psrc, a.init + a.init_off1, 1ll << 30, H, a.ld_init)) maps.gather4 = 1;
     static bool attr_set = false;
     if (!attr_set) {
         if (cudaFuncSetAttribute(edge_fwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes) != cudaSuccess) {
