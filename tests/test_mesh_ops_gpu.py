@@ -156,3 +156,22 @@ def test_build_preprocessing_plate_pipeline():
     assert tuple(out.shape) == (n, 3) and torch.isfinite(out).all()
     out = EncodeProcessDecode(2, 15, 4, 3, hidden_size=128).to(DEV)(Data(x=feat, edge_index=g.edge_index, edge_attr=g.edge_attr))
     assert tuple(out.shape) == (n, 3) and torch.isfinite(out).all()
+
+
+def test_xdmf_archive_to_training_step():
+    """The reference's own XDMF test archive -> graph on the device -> one training step: I/O (graphphysics_b200.io, no meshio /
+    h5py), graph construction (FaceToEdge + edge features kernels) and the fused model, end to end."""
+    from graphphysics_b200 import preprocessing as P
+    from graphphysics_b200.io.xdmf import XDMFTrajectory
+    from graphphysics_b200.training.loop import Trainer
+    meta = {"dt": 0.01, "features": {"velocity_x": {"type": "dynamic", "dtype": "float32"}, "velocity_y": {"type": "dynamic", "dtype": "float32"}}}
+    traj = XDMFTrajectory(os.path.join(G, "mock_xdmf", "mock.xdmf"), meta, targets=["velocity_x", "velocity_y"])
+    g = traj[0].to(DEV)                                   # x = [vx, vy, time = 0]: column 2 doubles as an all-NORMAL node type
+    g.pos = g.pos[:, :2].contiguous()
+    g = P.build_preprocessing()(g)
+    assert tuple(g.edge_index.shape) == (2, 11070) and tuple(g.edge_attr.shape) == (11070, 3)
+    cfg = {"model": {"type": "epd", "message_passing_num": 2, "hidden_size": 128, "node_input_size": 2, "output_size": 2, "edge_input_size": 3},
+           "index": {"feature_index_start": 0, "feature_index_end": 2, "output_index_start": 0, "output_index_end": 2, "node_type_index": 2}}
+    tr = Trainer(cfg, learning_rate=1e-3, num_steps=100, warmup=2, device=torch.device(DEV), seed=0)
+    losses = [float(tr.training_step(g)) for _ in range(6)]
+    assert all(np.isfinite(losses)) and losses[-1] < losses[0], losses
