@@ -77,21 +77,21 @@ __device__ __forceinline__ void load_row(const float* __restrict__ base, size_t 
 template <int VPT, int HH, typename T>
 __global__ void attn_fwd_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __restrict__ v,
                                 const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, int n, float scale,
-                                T* __restrict__ y, float* __restrict__ y32, float* __restrict__ lse) {
+                                T* __restrict__ y, float* __restrict__ y32, float* __restrict__ lse, int ldq) {
     constexpr int H = 32 * VPT;
     const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (i >= n) return;
     float qv[VPT], m[VPT], s[VPT], acc[VPT];
-    load_row<VPT>(q, i, H, lane, qv);
+    load_row<VPT>(q, i, ldq, lane, qv);
 #pragma unroll
     for (int t = 0; t < VPT; ++t) { qv[t] *= scale; m[t] = -INFINITY; s[t] = 0.f; acc[t] = 0.f; }
     const int b = rowptr[i], e = rowptr[i + 1];
     for (int p = b; p < e; ++p) {
         const int j = __ldg(col + p);
         float kv[VPT], vv[VPT], pr[VPT], dot[VPT];
-        load_row<VPT>(k, j, H, lane, kv);
-        load_row<VPT>(v, j, H, lane, vv);
+        load_row<VPT>(k, j, ldq, lane, kv);
+        load_row<VPT>(v, j, ldq, lane, vv);
 #pragma unroll
         for (int t = 0; t < VPT; ++t) pr[t] = qv[t] * kv[t];
         HeadReduce<VPT, HH>::run(pr, dot);
@@ -121,13 +121,13 @@ __global__ void attn_bwd_rows_kernel(const T* __restrict__ q, const T* __restric
                                      const T* __restrict__ y, const float* __restrict__ y32, const float* __restrict__ dy,
                                      const float* __restrict__ lse, const int32_t* __restrict__ rowptr,
                                      const int32_t* __restrict__ col, const int32_t* __restrict__ pos, int n, float scale,
-                                     float* __restrict__ dq, float* __restrict__ ea, float* __restrict__ eds) {
+                                     float* __restrict__ dq, float* __restrict__ ea, float* __restrict__ eds, int ldq, int ldg) {
     constexpr int H = 32 * VPT;
     const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (i >= n) return;
     float qv[VPT], yv[VPT], dyv[VPT], l[VPT], pr[VPT], D[VPT], dqa[VPT];
-    load_row<VPT>(q, i, H, lane, qv);
+    load_row<VPT>(q, i, ldq, lane, qv);
     if (y32) load_row<VPT>(y32, i, H, lane, yv);
     else load_row<VPT>(y, i, H, lane, yv);
     load_row<VPT>(dy, i, H, lane, dyv);
@@ -143,8 +143,8 @@ __global__ void attn_bwd_rows_kernel(const T* __restrict__ q, const T* __restric
     for (int p = b; p < e; ++p) {
         const int j = __ldg(col + p);
         float kv[VPT], vv[VPT], dot[VPT], dp[VPT];
-        load_row<VPT>(k, j, H, lane, kv);
-        load_row<VPT>(v, j, H, lane, vv);
+        load_row<VPT>(k, j, ldq, lane, kv);
+        load_row<VPT>(v, j, ldq, lane, vv);
 #pragma unroll
         for (int t = 0; t < VPT; ++t) pr[t] = qv[t] * kv[t];
         HeadReduce<VPT, HH>::run(pr, dot);
@@ -162,7 +162,7 @@ __global__ void attn_bwd_rows_kernel(const T* __restrict__ q, const T* __restric
         }
     }
 #pragma unroll
-    for (int t = 0; t < VPT; ++t) dq[(size_t)i * H + lane * VPT + t] = dqa[t];
+    for (int t = 0; t < VPT; ++t) dq[(size_t)i * ldg + lane * VPT + t] = dqa[t];
 }
 
 // Backward pass 2 (columns): dk_j = sum_i ds_ij q_i / sqrt(d),  dv_j = sum_i a_ij dy_i over the entries of
@@ -171,7 +171,7 @@ template <int VPT, int HH, typename T>
 __global__ void attn_bwd_cols_kernel(const T* __restrict__ q, const float* __restrict__ dy,
                                      const float* __restrict__ ea, const float* __restrict__ eds,
                                      const int32_t* __restrict__ colptr, const int32_t* __restrict__ row, int n,
-                                     float scale, float* __restrict__ dk, float* __restrict__ dv) {
+                                     float scale, float* __restrict__ dk, float* __restrict__ dv, int ldq, int ldg) {
     constexpr int H = 32 * VPT;
     const int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
@@ -183,7 +183,7 @@ __global__ void attn_bwd_cols_kernel(const T* __restrict__ q, const float* __res
     for (int p = b; p < e; ++p) {
         const int i = __ldg(row + p);
         float qv[VPT], dyv[VPT];
-        load_row<VPT>(q, i, H, lane, qv);
+        load_row<VPT>(q, i, ldq, lane, qv);
         load_row<VPT>(dy, i, H, lane, dyv);
 #pragma unroll
         for (int t = 0; t < VPT; ++t) {
@@ -195,8 +195,8 @@ __global__ void attn_bwd_cols_kernel(const T* __restrict__ q, const float* __res
     }
 #pragma unroll
     for (int t = 0; t < VPT; ++t) {
-        dk[(size_t)j * H + lane * VPT + t] = dka[t];
-        dv[(size_t)j * H + lane * VPT + t] = dva[t];
+        dk[(size_t)j * ldg + lane * VPT + t] = dka[t];
+        dv[(size_t)j * ldg + lane * VPT + t] = dva[t];
     }
 }
 
@@ -206,13 +206,15 @@ void launch_typed(int which, const gp_attention_args& a, cudaStream_t st) {
     const float scale = 1.f / sqrtf((float)(32 * VPT / HH));
     const T *q = reinterpret_cast<const T*>(a.q), *k = reinterpret_cast<const T*>(a.k), *v = reinterpret_cast<const T*>(a.v);
     T* y = reinterpret_cast<T*>(a.y);
+    const int ldq = a.ld_qkv > 0 ? a.ld_qkv : 32 * VPT, ldg = a.ld_dqkv > 0 ? a.ld_dqkv : 32 * VPT;
     if (which == 0)
-        attn_fwd_kernel<VPT, HH, T><<<blocks, threads, 0, st>>>(q, k, v, a.rowptr, a.col, a.n, scale, y, a.y_f32, a.lse);
+        attn_fwd_kernel<VPT, HH, T><<<blocks, threads, 0, st>>>(q, k, v, a.rowptr, a.col, a.n, scale, y, a.y_f32, a.lse, ldq);
     else if (which == 1)
         attn_bwd_rows_kernel<VPT, HH, T><<<blocks, threads, 0, st>>>(q, k, v, y, a.y_f32, a.dy, a.lse, a.rowptr, a.col, a.pos, a.n, scale, a.dq,
-                                                                   a.edge_a, a.edge_ds);
+                                                                   a.edge_a, a.edge_ds, ldq, ldg);
     else
-        attn_bwd_cols_kernel<VPT, HH, T><<<blocks, threads, 0, st>>>(q, a.dy, a.edge_a, a.edge_ds, a.colptr, a.row, a.n, scale, a.dk, a.dv);
+        attn_bwd_cols_kernel<VPT, HH, T><<<blocks, threads, 0, st>>>(q, a.dy, a.edge_a, a.edge_ds, a.colptr, a.row, a.n, scale, a.dk, a.dv, ldq,
+                                                                   ldg);
 }
 template <int VPT, int HH>
 void launch_all(int which, const gp_attention_args& a, cudaStream_t st) {

@@ -189,6 +189,7 @@ class AttentionArgs(C.Structure):
         ("dq", C.c_void_p), ("dk", C.c_void_p), ("dv", C.c_void_p),
         ("edge_a", C.c_void_p), ("edge_ds", C.c_void_p),
         ("io_bf16", C.c_int32),
+        ("ld_qkv", C.c_int32), ("ld_dqkv", C.c_int32),
         ("y_f32", C.c_void_p),
     ]
 

@@ -157,9 +157,10 @@ def norm_bwd(x, s1, s2, dy, add=None):
 def gelu_fwd(a1, a2, out_bf16=True, kind: int = 3) -> torch.Tensor:
     """act(a1) * a2; kind 3 = GELU (gp_gelu_gate_fwd), 2 = SiLU (gp_glu_fwd)."""
     g = torch.empty(a1.shape, dtype=torch.bfloat16 if out_bf16 else torch.float32, device=a1.device)
-    if kind != 3:
+    if kind != 3 or not a1.is_contiguous():      # SiLU gating, or a1 | a2 as column blocks of one buffer (row stride ld)
         R, G = a1.shape
-        check(lib().gp_glu_fwd(C.c_void_p(ptr(a1)), C.c_void_p(ptr(a2)), C.c_int32(G), C.c_int64(R), C.c_int32(G), C.c_int32(kind),
+        assert a1.stride() == a2.stride() and a1.stride(1) == 1
+        check(lib().gp_glu_fwd(C.c_void_p(ptr(a1)), C.c_void_p(ptr(a2)), C.c_int32(a1.stride(0)), C.c_int64(R), C.c_int32(G), C.c_int32(kind),
                                C.c_void_p(ptr(g) if out_bf16 else None), C.c_void_p(None if out_bf16 else ptr(g)), C.c_void_p(stream_ptr())),
               "gp_glu_fwd")
         ops._launched()
@@ -170,12 +171,18 @@ def gelu_fwd(a1, a2, out_bf16=True, kind: int = 3) -> torch.Tensor:
     return g
 
 
-def gelu_bwd(a1, a2, dg, kind: int = 3):
-    da1, da2 = torch.empty_like(a1), torch.empty_like(a2)
-    if kind != 3:
-        R, G = a1.shape
-        check(lib().gp_glu_bwd(C.c_void_p(ptr(a1)), C.c_void_p(ptr(a2)), C.c_int32(G), C.c_void_p(ptr(dg)), C.c_int64(R), C.c_int32(G),
-                               C.c_int32(kind), C.c_void_p(ptr(da1)), C.c_void_p(ptr(da2)), C.c_int32(G), C.c_void_p(stream_ptr())), "gp_glu_bwd")
+def gelu_bwd(a1, a2, dg, kind: int = 3, fused_out: bool = False):
+    """fused_out: da1 | da2 are the column blocks of ONE [R, 2G] buffer (returned as two views)."""
+    R, G = a1.shape
+    if fused_out:
+        da12 = torch.empty((R, 2 * G), dtype=torch.float32, device=a1.device)
+        da1, da2 = da12[:, :G], da12[:, G:]
+    else:
+        da1, da2 = torch.empty((R, G), dtype=torch.float32, device=a1.device), torch.empty((R, G), dtype=torch.float32, device=a1.device)
+    if kind != 3 or fused_out or not a1.is_contiguous():
+        check(lib().gp_glu_bwd(C.c_void_p(ptr(a1)), C.c_void_p(ptr(a2)), C.c_int32(a1.stride(0)), C.c_void_p(ptr(dg)), C.c_int64(R), C.c_int32(G),
+                               C.c_int32(kind), C.c_void_p(ptr(da1)), C.c_void_p(ptr(da2)), C.c_int32(da1.stride(0)), C.c_void_p(stream_ptr())),
+              "gp_glu_bwd")
         ops._launched()
         return da1, da2
     check(lib().gp_gelu_gate_bwd(C.c_void_p(ptr(a1)), C.c_void_p(ptr(a2)), C.c_void_p(ptr(dg)), C.c_int64(a1.numel()), C.c_void_p(ptr(da1)),
@@ -191,8 +198,10 @@ def attn_fwd(q, k, v, g, num_heads: int):
     a.io_bf16 = int(q.dtype == torch.bfloat16)
     a.n, a.hidden, a.num_heads = n, h, num_heads
     a.q, a.k, a.v = ptr(q), ptr(k), ptr(v)
+    assert q.stride(1) == 1 and q.stride() == k.stride() == v.stride()
+    a.ld_qkv = q.stride(0)                      # h, or 3h when q | k | v are column blocks of one buffer
     a.rowptr, a.col = ptr(g.rowptr_src), ptr(g.att_col)
-    y = torch.empty_like(q)
+    y = torch.empty((n, h), dtype=q.dtype, device=q.device)
     y32 = torch.empty(q.shape, dtype=torch.float32, device=q.device) if a.io_bf16 else None
     lse = torch.empty((n, num_heads), dtype=torch.float32, device=q.device)
     a.y, a.lse, a.y_f32 = ptr(y), ptr(lse), ptr(y32)
@@ -203,15 +212,22 @@ def attn_fwd(q, k, v, g, num_heads: int):
     return y, y32, lse
 
 
-def attn_bwd(q, k, v, y, y32, lse, dy, g, num_heads: int):
+def attn_bwd(q, k, v, y, y32, lse, dy, g, num_heads: int, fused_out: bool = False):
+    """fused_out: dq | dk | dv are written as the column blocks of ONE [N, 3h] buffer (returned as three views)."""
     n, h = q.shape
     a = AttentionArgs()
     a.io_bf16 = int(q.dtype == torch.bfloat16)
     a.n, a.hidden, a.num_heads = n, h, num_heads
+    a.ld_qkv = q.stride(0)
     a.q, a.k, a.v, a.y, a.lse, a.dy, a.y_f32 = ptr(q), ptr(k), ptr(v), ptr(y), ptr(lse), ptr(dy), ptr(y32)
     a.rowptr, a.col, a.pos = ptr(g.rowptr_src), ptr(g.att_col), ptr(g.perm_src)
     a.colptr, a.row = ptr(g.rowptr_dst), ptr(g.src)
-    dq, dk, dv = (torch.empty(q.shape, dtype=torch.float32, device=q.device) for _ in range(3))
+    if fused_out:
+        dqkv = torch.empty((n, 3 * h), dtype=torch.float32, device=q.device)
+        dq, dk, dv = dqkv[:, :h], dqkv[:, h:2 * h], dqkv[:, 2 * h:]
+        a.ld_dqkv = 3 * h
+    else:
+        dq, dk, dv = (torch.empty((n, h), dtype=torch.float32, device=q.device) for _ in range(3))
     ea = torch.empty((g.num_edges, num_heads), dtype=torch.float32, device=q.device)
     eds = torch.empty_like(ea)
     a.dq, a.dk, a.dv, a.edge_a, a.edge_ds = ptr(dq), ptr(dk), ptr(dv), ptr(ea), ptr(eds)
@@ -220,6 +236,23 @@ def attn_bwd(q, k, v, y, y32, lse, dy, g, num_heads: int):
     ops.PROFILE.end("attn_bwd", ev)
     ops._launched(2)
     return dq, dk, dv
+
+
+def _stackable(ws, bs) -> bool:
+    """The weights (and, if present, the biases) are consecutive slices of one buffer -- engine.FlatParams lays q / k / v
+    and linear1 / linear2 out that way -- so they read as one stacked matrix / vector."""
+    from .engine import _adjacent
+    if any(w.shape != ws[0].shape or not w.is_contiguous() for w in ws) or not _adjacent(*ws):
+        return False
+    if all(b is None for b in bs):
+        return True
+    return all(b is not None for b in bs) and _adjacent(*bs)
+
+
+def _stack(first: torch.Tensor, k: int) -> torch.Tensor:
+    """View of `k` adjacent equal-shaped tensors starting at `first` as one tensor stacked along dim 0."""
+    shape = (k * first.shape[0],) + tuple(first.shape[1:])
+    return torch.as_strided(first.detach(), shape, first.stride())
 
 
 def _f32(t: torch.Tensor) -> torch.Tensor:
@@ -253,7 +286,11 @@ class _AttentionBranch(torch.autograd.Function):
         bf = terms == 1
         n = norm_fwd(x, sn, None, out_bf16=bf) if sn is not None else x
         H = wq.shape[0]
-        if rope is not None:
+        fused = rope is None and _stackable((wq, wk, wv), (bq, bk, bv))
+        if fused:                                # q | k | v = n [Wq; Wk; Wv]^T: ONE GEMM into one [N, 3H] buffer
+            qkv = lin_fwd(n, _stack(wq, 3), _stack(bq, 3) if bq is not None else None, out_bf16=bf, terms=terms)
+            q, k, v = qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:]
+        elif rope is not None:
             pos, m, base = rope
             q = lin_fwd(n, wq, bq, terms=terms)
             k = lin_fwd(n, wk, bk, terms=terms)
@@ -264,7 +301,8 @@ class _AttentionBranch(torch.autograd.Function):
         else:
             q = lin_fwd(n, wq, bq, out_bf16=bf, terms=terms)
             k = lin_fwd(n, wk, bk, out_bf16=bf, terms=terms)
-        v = lin_fwd(n, wv, bv, out_bf16=bf, terms=terms)
+        if not fused:
+            v = lin_fwd(n, wv, bv, out_bf16=bf, terms=terms)
         y, y32, lse = attn_fwd(q, k, v, g, heads)
         gl = None
         yin = y
@@ -279,13 +317,13 @@ class _AttentionBranch(torch.autograd.Function):
         ctx.save_for_backward(x, sn, n if sn is not None else None, q, k, v, y, y32, lse, wq, wk, wv, wp, wg, gl, yin if wg is not None else None,
                               rope[0] if rope is not None else None)
         ctx.cfg = (add_resid, g, heads, terms, bq is not None, bk is not None, bv is not None, bp is not None, bg is not None,
-                   (rope[1], rope[2]) if rope is not None else None)
+                   (rope[1], rope[2]) if rope is not None else None, fused)
         return out
 
     @staticmethod
     def backward(ctx, dout):
         x, sn, n, q, k, v, y, y32, lse, wq, wk, wv, wp, wg, gl, yin, pos = ctx.saved_tensors
-        add_resid, g, heads, terms, hbq, hbk, hbv, hbp, hbg, rope = ctx.cfg
+        add_resid, g, heads, terms, hbq, hbk, hbv, hbp, hbg, rope, fused = ctx.cfg
         if n is None:
             n = x
         dout = _f32(dout)
@@ -301,7 +339,26 @@ class _AttentionBranch(torch.autograd.Function):
             ops._launched()
             dy = dy2
             dwg, dbg = lin_wgrad(dgl, n, bias=True, terms=terms) if hbg else (lin_wgrad(dgl, n, terms=terms), None)
-        dq, dk, dv = attn_bwd(q, k, v, y, y32, lse, dy, g, heads)
+        dq, dk, dv = attn_bwd(q, k, v, y, y32, lse, dy, g, heads, fused_out=fused)
+        if fused:                                # one dgrad over K = 3H, one wgrad for [Wq; Wk; Wv] (+ the bias column)
+            H = wq.shape[0]
+            dqkv = dq._base if dq._base is not None else dq
+            dn = lin_dgrad(dqkv, _stack(wq, 3), terms=terms)
+            if dgl is not None:
+                lin_dgrad(dgl, wg, out=dn, terms=terms)
+            if hbq:
+                dw, db = lin_wgrad(dqkv, n, bias=True, terms=terms)
+                dbq, dbk, dbv = db[:H], db[H:2 * H], db[2 * H:]
+            else:
+                dw, dbq, dbk, dbv = lin_wgrad(dqkv, n, terms=terms), None, None, None
+            dwq, dwk, dwv = dw[:H], dw[H:2 * H], dw[2 * H:]
+            dsn = None
+            if sn is not None:
+                dx, dsn, _ = norm_bwd(x, sn, None, dn, add=dout if add_resid else None)
+            else:
+                assert not add_resid
+                dx = dn
+            return dx, dsn, dwq, dbq, dwk, dbk, dwv, dbv, dwp, dbp, dwg, dbg, None, None, None, None, None
         if rope is not None:                     # the rotation is orthogonal: its transpose is the inverse rotation
             H = wq.shape[0]
             _rope_nodes_(dq, pos, H // heads, heads, rope[0], rope[1], True)
@@ -343,18 +400,24 @@ class _GatedBranch(torch.autograd.Function):
         x = _f32(x)
         bf = terms == 1
         n = norm_fwd(x, s1, s2, out_bf16=bf) if s1 is not None else x
-        a1 = lin_fwd(n, w1, b1, terms=terms)
-        a2 = lin_fwd(n, w2, b2, terms=terms)
+        fused = _stackable((w1, w2), (b1, b2))
+        if fused:                                # [a1 | a2] = n [W1; W2]^T: one GEMM, the gate reads the two column blocks
+            G = w1.shape[0]
+            a12 = lin_fwd(n, _stack(w1, 2), _stack(b1, 2) if b1 is not None else None, terms=terms)
+            a1, a2 = a12[:, :G], a12[:, G:]
+        else:
+            a1 = lin_fwd(n, w1, b1, terms=terms)
+            a2 = lin_fwd(n, w2, b2, terms=terms)
         gate = gelu_fwd(a1, a2, out_bf16=(bf and w3 is not None), kind=kind)
         out = lin_fwd(gate, w3, b3, resid=x if add_resid else None, terms=terms) if w3 is not None else gate
         ctx.save_for_backward(x, s1, s2, n if s1 is not None else None, a1, a2, gate if w3 is not None else None, w1, w2, w3)
-        ctx.cfg = (add_resid, terms, b1 is not None, b2 is not None, b3 is not None, kind)
+        ctx.cfg = (add_resid, terms, b1 is not None, b2 is not None, b3 is not None, kind, fused)
         return out
 
     @staticmethod
     def backward(ctx, dout):
         x, s1, s2, n, a1, a2, gate, w1, w2, w3 = ctx.saved_tensors
-        add_resid, terms, hb1, hb2, hb3, kind = ctx.cfg
+        add_resid, terms, hb1, hb2, hb3, kind, fused = ctx.cfg
         if n is None:
             n = x
         dout = _f32(dout)
@@ -364,11 +427,22 @@ class _GatedBranch(torch.autograd.Function):
             dw3, db3 = lin_wgrad(dout, gate, bias=True, terms=terms) if hb3 else (lin_wgrad(dout, gate, terms=terms), None)
         else:
             dg = dout
-        da1, da2 = gelu_bwd(a1, a2, dg, kind=kind)
-        dn = lin_dgrad(da1, w1, terms=terms)
-        lin_dgrad(da2, w2, out=dn, terms=terms)
-        dw1, db1 = lin_wgrad(da1, n, bias=True, terms=terms) if hb1 else (lin_wgrad(da1, n, terms=terms), None)
-        dw2, db2 = lin_wgrad(da2, n, bias=True, terms=terms) if hb2 else (lin_wgrad(da2, n, terms=terms), None)
+        da1, da2 = gelu_bwd(a1, a2, dg, kind=kind, fused_out=fused)
+        if fused:
+            G = w1.shape[0]
+            da12 = da1._base
+            dn = lin_dgrad(da12, _stack(w1, 2), terms=terms)
+            if hb1:
+                dw, db = lin_wgrad(da12, n, bias=True, terms=terms)
+                db1, db2 = db[:G], db[G:]
+            else:
+                dw, db1, db2 = lin_wgrad(da12, n, terms=terms), None, None
+            dw1, dw2 = dw[:G], dw[G:]
+        else:
+            dn = lin_dgrad(da1, w1, terms=terms)
+            lin_dgrad(da2, w2, out=dn, terms=terms)
+            dw1, db1 = lin_wgrad(da1, n, bias=True, terms=terms) if hb1 else (lin_wgrad(da1, n, terms=terms), None)
+            dw2, db2 = lin_wgrad(da2, n, bias=True, terms=terms) if hb2 else (lin_wgrad(da2, n, terms=terms), None)
         ds1 = ds2 = None
         if s1 is not None:
             dx, ds1, ds2 = norm_bwd(x, s1, s2, dn, add=dout if add_resid else None)

@@ -75,6 +75,36 @@ class EPDEngine:
         self._sq_ws = torch.empty(256, dtype=torch.float32, device=self.device)
         self.sqnorm = torch.zeros(1, dtype=torch.float32, device=self.device)
 
+    @staticmethod
+    def _group_fusable(model: nn.Module, params):
+        """Order the parameters so that the weights (and the biases) of layers that read the same input sit next to each
+        other in the flat buffer: q / k / v of an Attention and linear1 / linear2 of a GatedMLP then ARE one stacked
+        [3H, H] / [6H, H] matrix, and graphphysics_b200.dense runs each group as a single GEMM (forward, dgrad, wgrad)."""
+        from .models.layers import Attention, GatedMLP
+        groups = []
+        for m in model.modules():
+            if isinstance(m, Attention) and m.q_proj.weight is not m.k_proj.weight:
+                lins = (m.q_proj, m.k_proj, m.v_proj)
+            elif isinstance(m, GatedMLP):
+                lins = (m.linear1, m.linear2)
+            else:
+                continue
+            groups.append([l.weight for l in lins])
+            if all(l.bias is not None for l in lins):
+                groups.append([l.bias for l in lins])
+        grouped = {id(p) for g in groups for p in g}
+        if len(grouped) != sum(len(g) for g in groups):          # a parameter shared between groups: leave the order alone
+            return params
+        known = {id(p) for p in params}
+        head = {id(g[0]): g for g in groups if all(id(p) in known for p in g)}
+        out = []
+        for p in params:
+            if id(p) in head:
+                out.extend(head[id(p)])
+            elif id(p) not in grouped or not any(id(p) == id(q) for g in head.values() for q in g):
+                out.append(p)
+        return out
+
     # ------------------------------------------------------------------ parameters
     def _build_flat(self):
         named = list(self.model.named_parameters())
@@ -437,6 +467,12 @@ class EPDEngine:
         return self.sqnorm
 
 
+def _adjacent(*ts) -> bool:
+    """True when the tensors are consecutive slices of one buffer (so they read as one stacked matrix / vector)."""
+    return all(b.data_ptr() == a.data_ptr() + a.numel() * a.element_size() and
+               b.untyped_storage().data_ptr() == a.untyped_storage().data_ptr() for a, b in zip(ts, ts[1:]))
+
+
 class FlatParams:
     """Flat fp32 parameter / gradient buffers for a model that runs under torch autograd (the
     Transformer path): every nn.Parameter becomes a view of `flat`, every `.grad` a view of `gflat`,
@@ -449,6 +485,7 @@ class FlatParams:
             if id(p) not in seen:
                 seen.add(id(p))
                 uniq.append(p)
+        uniq = self._group_fusable(model, uniq)
         self.device = uniq[0].device
         total = sum((p.numel() + 15) // 16 * 16 for p in uniq)
         self.flat = torch.zeros(total, dtype=torch.float32, device=self.device)
@@ -462,6 +499,36 @@ class FlatParams:
             off += (n + 15) // 16 * 16
         self._sq_ws = torch.empty(256, dtype=torch.float32, device=self.device)
         self.sqnorm = torch.zeros(1, dtype=torch.float32, device=self.device)
+
+    @staticmethod
+    def _group_fusable(model: nn.Module, params):
+        """Order the parameters so that the weights (and the biases) of layers that read the same input sit next to each
+        other in the flat buffer: q / k / v of an Attention and linear1 / linear2 of a GatedMLP then ARE one stacked
+        [3H, H] / [6H, H] matrix, and graphphysics_b200.dense runs each group as a single GEMM (forward, dgrad, wgrad)."""
+        from .models.layers import Attention, GatedMLP
+        groups = []
+        for m in model.modules():
+            if isinstance(m, Attention) and m.q_proj.weight is not m.k_proj.weight:
+                lins = (m.q_proj, m.k_proj, m.v_proj)
+            elif isinstance(m, GatedMLP):
+                lins = (m.linear1, m.linear2)
+            else:
+                continue
+            groups.append([l.weight for l in lins])
+            if all(l.bias is not None for l in lins):
+                groups.append([l.bias for l in lins])
+        grouped = {id(p) for g in groups for p in g}
+        if len(grouped) != sum(len(g) for g in groups):          # a parameter shared between groups: leave the order alone
+            return params
+        known = {id(p) for p in params}
+        head = {id(g[0]): g for g in groups if all(id(p) in known for p in g)}
+        out = []
+        for p in params:
+            if id(p) in head:
+                out.extend(head[id(p)])
+            elif id(p) not in grouped or not any(id(p) == id(q) for g in head.values() for q in g):
+                out.append(p)
+        return out
 
     def zero_grad(self):
         self.gflat.zero_()

@@ -211,6 +211,9 @@ class Trainer:
                 getattr(static, k).copy_(getattr(batch, k), non_blocking=True)
             with no_csr_cache():                        # (allocates the persistent layout buffers outside the capture)
                 step(static)                            # first step of this shape runs eagerly (allocations, smem attributes)
+            if self.noise is not None:                  # the eager pass added its noise to the static batch in place
+                for k in fields:
+                    getattr(static, k).copy_(getattr(batch, k), non_blocking=True)
             graph = torch.cuda.CUDAGraph()
             # with a process group, NCCL's watchdog thread polls CUDA events while we capture: only
             # this thread's calls belong to the capture

@@ -278,6 +278,8 @@ typedef struct gp_attention_args {
     float* edge_a;
     float* edge_ds;
     int32_t io_bf16; /* != 0: q, k, v and y are bf16 (raw uint16) instead of fp32 -- the Transformer path; everything else stays fp32 */
+    int32_t ld_qkv;  /* row stride (elements) of q, k, v; 0 = hidden.  > hidden: q | k | v are column blocks of one [N, 3*hidden] buffer */
+    int32_t ld_dqkv; /* row stride of dq, dk, dv; 0 = hidden */
     float* y_f32;    /* optional, with io_bf16: the forward also writes y unrounded here and the backward reads it (dy.y is the
                         softmax-gradient offset of every entry of the row: kept exact, 4H bytes per NODE) */
 } gp_attention_args;

@@ -127,10 +127,12 @@ def _mesh_graph(n_side=14, seed=0):
     return len(pos), torch.from_numpy(ei).long()
 
 
+@pytest.mark.parametrize("flat", [False, True])
 @pytest.mark.parametrize("hidden,heads", [(64, 4), (128, 4), (32, 2)])
-def test_transformer_block_against_kernel_mode_oracle(hidden, heads):
+def test_transformer_block_against_kernel_mode_oracle(hidden, heads, flat):
     """One Transformer block (norm1 -> q/k/v -> masked attention -> proj + x -> double norm -> gated MLP -> W3 + x):
-    output and every gradient vs the oracle in kernel mode, l2 <= 1e-3."""
+    output and every gradient vs the oracle in kernel mode, l2 <= 1e-3.  flat: the parameters live in one flat buffer
+    (engine.FlatParams, what the Trainer uses), q / k / v and linear1 / linear2 adjacent -> the stacked single-GEMM paths."""
     from oracle import gp_oracle as O
     from graphphysics_b200.models.layers import Transformer
     dev = torch.device("cuda:0")
@@ -148,6 +150,13 @@ def test_transformer_block_against_kernel_mode_oracle(hidden, heads):
     ref = O.transformer_block(x64, ei[0], ei[1], sd, "b", heads, mode="bf16")
     (ref * dy.double()).sum().backward()
     blk = blk.to(dev)
+    if flat:
+        from graphphysics_b200.dense import _stackable
+        from graphphysics_b200.engine import FlatParams
+        fp = FlatParams(blk)
+        a, m = blk.attention, blk.gated_mlp[1]
+        assert _stackable((a.q_proj.weight, a.k_proj.weight, a.v_proj.weight), (a.q_proj.bias, a.k_proj.bias, a.v_proj.bias))
+        assert _stackable((m.linear1.weight, m.linear2.weight), (m.linear1.bias, m.linear2.bias))
     xd = x.to(dev).requires_grad_(True)
     out = blk(xd, ei.to(dev))
     (out * dy.to(dev)).sum().backward()
