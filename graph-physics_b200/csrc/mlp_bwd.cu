@@ -203,7 +203,11 @@ __global__ void __launch_bounds__(BwdCfg<H>::NT, 1) mlp_bwd_kernel(const gp_mlp_
     const int soff = stage1 ? p.init_off1 : p.init_off0;
     const bool du_smem = F ? kTGy[MODE] : (norm && p.gy_bf16 != nullptr);     // upstream gradient tile staged in qb (+ gathered rows in db)
 
-    const bool prof = p.prof != nullptr && tid == 0;
+#ifdef GP_MLP_PROF
+    const bool prof = p.prof != nullptr && tid == 0;      // phase timing (scratch/phase*.py): lib/libgp_b200_prof.so only
+#else
+    constexpr bool prof = false;                        // the product build carries no profiling code
+#endif
     long long tk = 0;
     auto tick = [&](int slot) {
         if (prof) {

@@ -138,7 +138,11 @@ __global__ void __launch_bounds__(kSlotThreads * NG, 1) mlp_fwd_kernel(const gp_
     const int n_tiles = (p.rows + 127) >> 7;
     const int tile_stride = gridDim.x * NG;
 
-    const bool prof = p.prof != nullptr && t == 0;
+#ifdef GP_MLP_PROF
+    const bool prof = p.prof != nullptr && t == 0;      // phase timing (scratch/phase*.py): lib/libgp_b200_prof.so only
+#else
+    constexpr bool prof = false;                        // the product build carries no profiling code
+#endif
     long long tk = 0;
     auto tick = [&](int slot) {   // accumulate cycles since the previous tick into counter `slot`
         if (prof) {

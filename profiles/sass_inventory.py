@@ -41,8 +41,9 @@ def main():
         rows.append((short(n), c, k))
     print("# SASS inventory of `libgp_b200.so` (sm_100a), round 2\n")
     print("`python profiles/sass_inventory.py` (cuobjdump -sass).  Library totals: " + ", ".join(f"{o} {tot[o]}" for o in OPS) + ".\n")
-    print("The only global reductions (`REDG` / `ATOMG`) are integer: 64-bit cycle counters of the optional phase profiling in the MLP "
-          "kernels (`p.prof`, NULL in the product path) and the bucket counters of the graph-layout / mesh kernels. No float atomics, no `HMMA`.\n")
+    print("The only global reductions (`REDG` / `ATOMG`) are integer: the bucket counters of the graph-layout / mesh kernels "
+          "(`gp_csr_from_coo`, `gp_coalesce_*`, `gp_world_pairs_*`). The phase-profiling counters of the MLP kernels exist only in the "
+          "`-DGP_MLP_PROF` tuning build. No float atomics, no `HMMA`.\n")
     print("| kernel | instructions | " + " | ".join(OPS[:9]) + " |\n|---|---|" + "---|" * 9)
     for n, c, _ in sorted(rows, key=lambda r: -r[1]["n"]):
         if any(c[o] for o in OPS[:8]):
