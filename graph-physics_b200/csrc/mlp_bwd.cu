@@ -920,7 +920,11 @@ extern "C" int gp_mlp_bwd_layout(int hidden, int ka, int nb, int32_t* out6) {
 extern "C" int gp_mlp_bwd_stage(const gp_mlp_bwd_args* args, int hidden, int32_t* grid_out, void* stream) {
     GP_REQUIRE(args != nullptr, "gp_mlp_bwd_stage: null args");
     const gp_mlp_bwd_args& a = *args;
-    GP_REQUIRE(a.rows > 0, "gp_mlp_bwd_stage: rows must be positive");
+    GP_REQUIRE(a.rows >= 0, "gp_mlp_bwd_stage: rows must not be negative");
+    if (a.rows == 0) {           // an edge-less graph: no rows, no partial blocks (the reductions then write zeros)
+        if (grid_out) *grid_out = 0;
+        return 0;
+    }
     GP_REQUIRE(a.ka > 0 && a.ka % 16 == 0 && a.ka <= 128, "gp_mlp_bwd_stage: bad ka=%d", a.ka);
     GP_REQUIRE(a.nb > 0 && a.nb % 16 == 0 && a.nb <= 128, "gp_mlp_bwd_stage: bad nb=%d", a.nb);
     GP_REQUIRE((a.a_bf16 != nullptr) != (a.a_f32 != nullptr), "gp_mlp_bwd_stage: exactly one of a_bf16 / a_f32");
@@ -973,7 +977,8 @@ extern "C" int gp_reduce_partials_multi(const float* partials, int32_t n_parts, 
             g.n_parts = n_parts;
             g.stride = stride;
         }
-        GP_REQUIRE(g.partials != nullptr && g.n_parts > 0, "gp_reduce_partials_multi: segment %d has no partials", i);
+        // n_parts == 0 is legal (a stage over zero rows wrote no partial block): the segment's sum is zero
+        GP_REQUIRE(g.partials != nullptr && g.n_parts >= 0, "gp_reduce_partials_multi: segment %d has no partials", i);
         const int t = g.rows * g.cols;
         if (t > max_total) max_total = t;
         vec4 = vec4 && g.stride % 4 == 0 && (reinterpret_cast<uintptr_t>(g.partials) & 15u) == 0 && g.cols % 4 == 0 &&
