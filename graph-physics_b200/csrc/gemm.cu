@@ -337,8 +337,10 @@ __global__ void __launch_bounds__(256) gemm_reduce_kernel(const gp_gemm_args p, 
 extern "C" int gp_gemm(const gp_gemm_args* args, void* stream) {
     GP_REQUIRE(args != nullptr, "gp_gemm: null args");
     gp_gemm_args a = *args;
-    GP_REQUIRE(a.M > 0 && a.N > 0 && a.K >= 0, "gp_gemm: bad shape M=%d N=%d K=%d", a.M, a.N, a.K);
-    GP_REQUIRE(a.a && a.b && a.c, "gp_gemm: null operand");
+    GP_REQUIRE(a.M >= 0 && a.N >= 0 && a.K >= 0, "gp_gemm: bad shape M=%d N=%d K=%d", a.M, a.N, a.K);
+    if (a.M == 0 || a.N == 0) return 0;                      // an empty output (e.g. the edge MLP of an edge-less graph)
+    // K == 0 (a weight gradient over zero rows) is legal: the product is zero, the epilogue still runs; A / B may be NULL then
+    GP_REQUIRE(a.c && (a.K == 0 || (a.a && a.b)), "gp_gemm: null operand");
     GP_REQUIRE(a.terms == 1 || a.terms == 3, "gp_gemm: terms must be 1 (bf16 operands) or 3 (three-term split)");
     GP_REQUIRE(a.split_k >= 1 && a.split_k <= 1024, "gp_gemm: split_k must be in [1, 1024]");
     GP_REQUIRE(a.split_k == 1 || a.partials != nullptr, "gp_gemm: split_k > 1 needs a partials buffer of split_k * M * ((N + 3) & ~3) floats");

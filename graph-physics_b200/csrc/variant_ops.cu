@@ -166,7 +166,7 @@ __global__ void segsum_f32_kernel(const float* __restrict__ src, int ld, const i
 extern "C" int gp_segsum_rows_f32(const float* src, int32_t ld, const int32_t* perm, const int32_t* rowptr, int64_t num_segments, int32_t hidden,
                                   float* out, void* stream) {
     if (num_segments <= 0 || hidden <= 0) return 0;
-    GP_REQUIRE(src && rowptr && out, "gp_segsum_rows_f32: null pointer");
+    GP_REQUIRE(rowptr && out, "gp_segsum_rows_f32: null pointer");        // (src is NULL when there are no rows to add: all sums are zero)
     segsum_f32_kernel<<<nblk(num_segments * hidden), kTB, 0, ST(stream)>>>(src, ld, perm, rowptr, num_segments, hidden, out);
     GP_CHECK_CUDA(cudaGetLastError());
     return 0;

@@ -175,3 +175,28 @@ def test_xdmf_archive_to_training_step():
     tr = Trainer(cfg, learning_rate=1e-3, num_steps=100, warmup=2, device=torch.device(DEV), seed=0)
     losses = [float(tr.training_step(g)) for _ in range(6)]
     assert all(np.isfinite(losses)) and losses[-1] < losses[0], losses
+
+
+def test_graph_construction_edge_cases():
+    """One triangle, one tetrahedron, a mesh with unused nodes, no obstacle nodes (no world edges), radius below every distance."""
+    from oracle import gp_oracle as O
+    from graphphysics_b200 import preprocessing as P
+    from graphphysics_b200.graph import Data
+    tri = np.array([[0, 1, 2]], np.int64)
+    g = P.face_to_edge(Data(x=torch.zeros(3, 1, device=DEV), face=_t(tri.T)))
+    assert np.array_equal(g.edge_index.cpu().numpy(), O.face_to_edge(tri, 3)) and g.edge_index.shape[1] == 6
+    tet = np.array([[3, 1, 0, 2]], np.int64)
+    g = P.face_to_edge(Data(x=torch.zeros(6, 1, device=DEV), tetra=_t(tet.T)))          # nodes 4, 5 unused
+    assert np.array_equal(g.edge_index.cpu().numpy(), O.face_to_edge(O.tetra_to_faces(tet), 6)) and g.edge_index.shape[1] == 12
+    pos = np.random.default_rng(0).random((6, 3)).astype(np.float32)
+    ea = P.edge_features(_t(pos), g.edge_index).cpu().numpy()
+    assert np.array_equal(ea.view(np.uint32), O.edge_features(pos, g.edge_index.cpu().numpy()).astype(np.float32).view(np.uint32))
+    x = np.concatenate([pos, np.zeros((6, 1), np.float32)], 1)                           # all NORMAL: no world edges
+    g2 = P.add_world_edges(Data(x=_t(x), edge_index=g.edge_index.clone()), 0, 3, 3, radius=10.0)
+    assert torch.equal(g2.edge_index, g.edge_index)
+    x[0, 3] = 1.0                                                                        # one obstacle, radius smaller than any distance
+    g3 = P.add_world_edges(Data(x=_t(x), edge_index=g.edge_index.clone()), 0, 3, 3, radius=1e-6)
+    assert torch.equal(g3.edge_index, g.edge_index)
+    g4 = P.add_world_edges(Data(x=_t(x), edge_index=g.edge_index.clone()), 0, 3, 3, radius=10.0)
+    ref = O.world_edges(g.edge_index.cpu().numpy(), pos, x[:, 3].astype(np.int64), 6, 10.0)
+    assert np.array_equal(g4.edge_index.cpu().numpy(), ref) and g4.edge_index.shape[1] > 12

@@ -138,3 +138,24 @@ def test_variant_model_trains_through_trainer():
     batch = cylinder_flow_batch(2, nx=20, ny=10, seed=0).to(DEV)
     losses = [float(tr.training_step(batch)) for _ in range(8)]
     assert all(np.isfinite(losses)) and losses[-1] < losses[0], losses
+
+
+@pytest.mark.parametrize("n_nodes,n_edges", [(6, 9), (50, 0), (130, 257)])
+def test_variant_path_edge_case_graphs(n_nodes, n_edges):
+    """The general (variant) path on tiny, tile-boundary and edge-less graphs: equals the kernel-mode oracle, finite gradients."""
+    from oracle import gp_oracle as O
+    from graphphysics_b200.graph import Data
+    from graphphysics_b200.models.processors import EncodeProcessDecode
+    rng = np.random.default_rng(n_nodes + n_edges)
+    key = rng.choice(n_nodes * n_nodes, size=n_edges, replace=False) if n_edges else np.zeros(0, np.int64)
+    ei = torch.from_numpy(np.stack([key // n_nodes, key % n_nodes]).astype(np.int64))
+    torch.manual_seed(n_edges)
+    m = EncodeProcessDecode(2, 11, 3, 2, hidden_size=32, use_gated_mlp=True, use_gated_attention=True, use_rope_embeddings=True, rope_pos_dimension=2)
+    sd = {k: v.detach().clone().double() for k, v in m.state_dict().items()}
+    x, ea, pos, phi, G_ = torch.randn(n_nodes, 11), torch.randn(n_edges, 3), torch.rand(n_nodes, 2), torch.rand(n_nodes), torch.randn(n_nodes, 2)
+    ref = O.epd_forward_variant(sd, x.double(), ea.double(), ei, 2, gated_mlp=True, gate=True, rope_axes=2, pos=pos.double(), phi=phi.double(), mode="bf16")
+    m = m.to(DEV)
+    out = m(Data(x=x.to(DEV), edge_index=ei.to(DEV), edge_attr=ea.to(DEV), pos=pos.to(DEV), phi=phi.to(DEV)))
+    assert l2_rel(out, ref) < 3e-3, l2_rel(out, ref)
+    (out * G_.to(DEV)).sum().backward()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in m.parameters())
