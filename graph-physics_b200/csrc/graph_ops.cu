@@ -210,7 +210,7 @@ extern "C" int gp_csr_from_coo(const int64_t* edge_index, int64_t num_edges, int
                num_nodes);
     GP_REQUIRE(rowptr_dst && rowptr_src && workspace, "gp_csr_from_coo: null output");
     GP_REQUIRE(num_edges == 0 || (edge_index && perm_dst && src_sorted && dst_sorted && perm_src), "gp_csr_from_coo: null edge array");
-    GP_REQUIRE((prev_edge_index == nullptr) == (state == nullptr), "gp_csr_from_coo: prev_edge_index and state go together");
+    GP_REQUIRE(num_edges == 0 || (prev_edge_index == nullptr) == (state == nullptr), "gp_csr_from_coo: prev_edge_index and state go together");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int E = (int)num_edges, N = num_nodes, tb = 256;
     int32_t* ws = static_cast<int32_t*>(workspace);
