@@ -59,6 +59,10 @@ class EPDEngine:
         # tile buffer until the copy engine has read it) than the backward gains from skipping the
         # recompute: 15.4 vs 14.3 ms/step on the benchmark.  Kept as an option.
         self.save_all = os.environ.get("GP_B200_SAVE_ALL", "0") == "1"
+        # activation checkpointing: segments of this many processor layers (0 = keep every layer's activations).  On by
+        # the reference's switch training.enable_vram_optimizations (set_memory_optimized_training), or GP_B200_CHECKPOINT=k
+        from .models.layers import use_memory_optimized_training
+        self.checkpoint_every = int(os.environ.get("GP_B200_CHECKPOINT", "0")) or (4 if use_memory_optimized_training() else 0)
         # the engine packs the operand copies of the weights once per step, several launches before any MLP
         # kernel reads them, so the kernels may overlap their prologue with the previous kernel's tail
         self._overlap = os.environ.get("GP_B200_NO_PDL") is None
@@ -305,11 +309,19 @@ class EPDEngine:
             if save:
                 ctx.update(xin_p=xin_p, ea_p=ea_p, h2n0=h2n0, h2e0=h2e0)
         bnd = torch.empty(ops.seg_bnd_size(E, H), dtype=torch.float32, device=dev)
+        # memory-optimised training (the reference's enable_vram_optimizations / torch checkpointing, layers.py:24-36,
+        # 803-814): keep only the inputs (x, e) of every `ckpt`-th layer; the backward re-runs the forward of one
+        # segment at a time to rebuild what the layers in it need (bit-identical: every kernel is deterministic)
+        ckpt = self.checkpoint_every if (save and after_block is None) else 0
+        if save:
+            ctx["ckpt"] = ckpt
         for l in range(self.L):
-            x2, e2, saved = self.run_block(l, x, e, g, bnd, save)
+            if ckpt and l % ckpt == 0:
+                ctx["layers"].append((x, e))
+            x2, e2, saved = self.run_block(l, x, e, g, bnd, save and not ckpt)
             if after_block is not None:
                 after_block(x2)
-            if save:
+            if save and not ckpt:
                 ctx["layers"].append(saved)
             x, e = x2, e2
         if self.only_processor:
@@ -416,8 +428,21 @@ class EPDEngine:
         dE = dE_sorted if dE_sorted is not None else torch.zeros((E, H), dtype=bf, device=dev)
         bnd = torch.empty(ops.seg_bnd_size(E, H, backward=True), dtype=torch.float32, device=dev)
         gp = self.gflat.data_ptr()
+        ckpt = ctx.get("ckpt", 0)
+        seg_saved, fwd_bnd = {}, None
         for l in reversed(range(self.L)):
-            x, e, P, agg, h2e, h2n = ctx["layers"][l]
+            if ckpt:
+                if l not in seg_saved:                    # rebuild the saved activations of the segment that holds layer l
+                    seg_saved.clear()
+                    s0 = (l // ckpt) * ckpt
+                    xs, es = ctx["layers"][s0 // ckpt]
+                    if fwd_bnd is None:
+                        fwd_bnd = torch.empty(ops.seg_bnd_size(E, H), dtype=torch.float32, device=dev)
+                    for ll in range(s0, l + 1):
+                        xs, es, seg_saved[ll] = self.run_block(ll, xs, es, g, fwd_bnd, True)
+                x, e, P, agg, h2e, h2n = seg_saved.pop(l)
+            else:
+                x, e, P, agg, h2e, h2n = ctx["layers"][l]
             if before_block is not None:
                 before_block(dX)
             # node MLP:  x' = x + norm(MLP([x, agg]))

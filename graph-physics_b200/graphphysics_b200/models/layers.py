@@ -32,9 +32,11 @@ def use_silu_activation() -> bool:
 
 
 def set_memory_optimized_training(enabled: bool) -> None:
-    """The reference toggles bf16 autocast + checkpointing here (layers.py:24-36).  This
-    implementation always computes in bf16 with fp32 accumulation and always recomputes in
-    backward, so the flag is only recorded."""
+    """The reference toggles bf16 autocast + activation checkpointing here (layers.py:24-36, 803-814).  The
+    arithmetic here is bf16 operands / fp32 accumulate either way; the flag switches the encode-process-decode
+    engine to checkpointed training: only the inputs of every 4th message-passing layer are kept, the backward
+    re-runs one segment's forward at a time (engine.checkpoint_every) -- about 40 % of the activation memory for
+    one extra forward pass, bit-identical gradients."""
     global _MEMORY_OPTIMIZED_TRAINING
     _MEMORY_OPTIMIZED_TRAINING = bool(enabled)
 

@@ -139,3 +139,36 @@ def test_trainer_on_degenerate_batches(graphed, precision):
         assert all(np.isfinite(losses)), (n, losses)
         r = tr.rollout([b])
         assert np.isfinite(r["val_1step_rmse"]) and tuple(r["predictions"][0].shape) == (n, 2)
+
+
+def test_checkpointed_training_is_bit_identical_and_smaller():
+    """training.enable_vram_optimizations (the reference's memory-optimised training, layers.py:24-36): the engine keeps only
+    every 4th layer's inputs and re-runs segments in the backward -- gradients bit-identical, peak memory lower."""
+    from graphphysics_b200.graph import Data
+    from graphphysics_b200.models import layers as L
+    from graphphysics_b200.models.processors import EncodeProcessDecode
+    from graphphysics_b200.synthetic import cylinder_flow_batch
+    dev = torch.device("cuda:0")
+    b = cylinder_flow_batch(8, seed=0).to(dev)
+    torch.manual_seed(0)
+    x, G_ = torch.randn(b.x.shape[0], 11, device=dev), torch.randn(b.x.shape[0], 2, device=dev)
+    res = {}
+    for flag in (False, True):
+        L.set_memory_optimized_training(flag)
+        try:
+            torch.manual_seed(1)
+            m = EncodeProcessDecode(10, 11, 3, 2, hidden_size=128).to(dev)
+            assert m.engine.checkpoint_every == (4 if flag else 0)
+        finally:
+            L.set_memory_optimized_training(False)
+        torch.cuda.synchronize()
+        torch.cuda.reset_peak_memory_stats(dev)
+        base = torch.cuda.memory_allocated(dev)
+        out = m(Data(x=x, edge_index=b.edge_index, edge_attr=b.edge_attr))
+        (out * G_).sum().backward()
+        torch.cuda.synchronize()
+        res[flag] = (out.detach().clone(), {k: v.clone() for k, v in m.engine.grads_by_name().items()}, torch.cuda.max_memory_allocated(dev) - base)
+        del m, out
+    assert torch.equal(res[True][0], res[False][0])
+    assert all(torch.equal(res[True][1][k], res[False][1][k]) for k in res[False][1])
+    assert res[True][2] < 0.7 * res[False][2], (res[True][2], res[False][2])
