@@ -5,8 +5,8 @@ Covered here: RMSNorm (73-129), build_mlp (163-210), Normalizer (281-408), Graph
 (890-1149), GatedMLP / Attention / Transformer (213-278, 564-819).  The default configuration of every
 shipped training_config runs on the fused kernels; the variant flags (SiLU, gated MLP, relative RoPE,
 aggregation gate, gated attention, RoPE on q / k) run on the general path of
-graphphysics_b200/variants.py and dense.py -- the same native kernels, composed per layer.  Only
-TemporalAttention (use_temporal_block) is rejected with NotImplementedError.
+graphphysics_b200/variants.py and dense.py -- the same native kernels, composed per layer; so does
+TemporalAttention (822-887, use_temporal_block).
 """
 from __future__ import annotations
 
@@ -343,3 +343,38 @@ class Transformer(nn.Module):
         # the double norm: Transformer.norm2, then build_gated_mlp's own leading RMSNorm (layers.py:252-278)
         return dense.gated_branch(x, self.norm2.scale, self.gated_mlp[0].scale, self.gated_mlp[1], self.gated_mlp[2],
                                   add_resid=True, terms=terms, act=self.gated_mlp[1].act)
+
+
+class TemporalAttention(nn.Module):
+    """Temporal corrector (graphphysics/models/layers.py:822-887): adjacency-masked cross-attention with queries and
+    values from the last block's output `h_pred` and keys from its input `h_prev`, a sigmoid gate on [h_pred | h_prev],
+    the residual onto h_prev and a two-layer SiLU mixer on [h_corr | h_prev].  Same constructor and state_dict keys
+    (q_proj / k_proj / v_proj / out_proj / gate.{0,2} / mixer.{0,2}).  Every Linear is gp_gemm, the attention the CSR
+    kernels of csrc/attention.cu, SiLU / sigmoid-multiply / concatenation the row kernels of csrc/variant_ops.cu
+    (composed in graphphysics_b200/variants.py::temporal_attention_forward)."""
+
+    def __init__(self, hidden_size: int, num_heads: int = 4, use_gate: bool = True):
+        super().__init__()
+        assert hidden_size % num_heads == 0, "hidden_size must be divisible by num_heads"
+        self.h, self.H, self.d = hidden_size, num_heads, hidden_size // num_heads
+        self.use_gate = use_gate
+        self.q_proj = nn.Linear(self.h, self.h, bias=True)
+        self.k_proj = nn.Linear(self.h, self.h, bias=True)
+        self.v_proj = nn.Linear(self.h, self.h, bias=True)
+        self.out_proj = nn.Linear(self.h, self.h, bias=True)
+        if use_gate:
+            self.gate = nn.Sequential(nn.Linear(2 * self.h, self.h), nn.SiLU(), nn.Linear(self.h, self.h), nn.Sigmoid())
+        self.mixer = nn.Sequential(nn.Linear(2 * self.h, self.h), nn.SiLU(), nn.Linear(self.h, self.h))
+        self.precision = "bf16"
+
+    def forward(self, h_prev: torch.Tensor, h_pred: torch.Tensor, adj=None) -> torch.Tensor:
+        """adj: a GraphCSR, or an edge_index [2, E] (rows = queries edge_index[0], columns = keys edge_index[1], as
+        dglsp.spmatrix(indices=edge_index) at processors.py:183 / 366)."""
+        from ..graph import GraphCSR
+        from ..variants import temporal_attention_forward
+        if adj is None:
+            raise ValueError("TemporalAttention needs the adjacency (the reference's DGL sparse matrix)")
+        if not h_prev.is_cuda:
+            raise RuntimeError("graphphysics_b200 runs on CUDA devices only (there is no CPU fallback)")
+        g = adj if isinstance(adj, GraphCSR) else get_csr(adj, h_prev.shape[0])
+        return temporal_attention_forward(self, h_prev, h_pred, g, 3 if self.precision == "tight" else 1)

@@ -10,7 +10,7 @@ import torch
 import torch.nn as nn
 
 from ..graph import get_csr
-from .layers import GraphNetBlock, build_mlp, use_silu_activation
+from .layers import GraphNetBlock, TemporalAttention, build_mlp, use_silu_activation
 
 
 class EncodeProcessDecode(nn.Module):
@@ -19,8 +19,6 @@ class EncodeProcessDecode(nn.Module):
                  use_gated_attention: bool = False, use_gated_mlp: bool = False, rope_pos_dimension: int = 3,
                  rope_base: float = 10000.0, use_temporal_block: bool = False, precision: str = None):
         super().__init__()
-        if use_temporal_block:
-            raise NotImplementedError("use_temporal_block is not implemented on the sm_100a path (SURVEY §8f N3)")
         # "bf16": the fused kernels (bf16 MMA operands and storage, fp32 accumulate) -- the timed path;
         # "tight": split-precision GEMMs (bf16 hi+lo, three MMAs per product, fp32 storage), graphphysics_b200/tight.py
         self.precision = precision or os.environ.get("GP_B200_PRECISION", "bf16")
@@ -34,6 +32,8 @@ class EncodeProcessDecode(nn.Module):
         self.use_rope = use_rope_embeddings
         self.use_gate = use_gated_attention
         self.rope_axes, self.rope_base = rope_pos_dimension, rope_base
+        # created first, as in processors.py:122-126 (same default initialisation under a seed)
+        self.temporal_block = TemporalAttention(hidden_size=hidden_size) if use_temporal_block else None
         if not only_processor:
             self.nodes_encoder = build_mlp(node_input_size, hidden_size, hidden_size)
             self.edges_encoder = build_mlp(edge_input_size, hidden_size, hidden_size)
@@ -45,11 +45,13 @@ class EncodeProcessDecode(nn.Module):
         self._engine = None
         self.act = "silu" if use_silu_activation() else "relu"
         # any variant flag (or the global SiLU switch) takes the model off the fused kernels onto the general path
-        self.variant = bool(use_rope_embeddings or use_gated_attention or use_gated_mlp or self.act != "relu")
+        self.variant = bool(use_rope_embeddings or use_gated_attention or use_gated_mlp or use_temporal_block or self.act != "relu")
         if self.use_rope and self.rope_axes not in (2, 3):
             raise ValueError("rope_pos_dimension must be 2 or 3 when use_rope_embeddings=True.")
         for blk in self.processor_list:
             blk.precision = self.precision
+        if self.temporal_block is not None:
+            self.temporal_block.precision = self.precision
 
     @property
     def engine(self):
@@ -91,8 +93,6 @@ class EncodeTransformDecode(nn.Module):
                  use_temporal_block: bool = False, precision: str = None):
         super().__init__()
         from .layers import Transformer
-        if use_temporal_block:
-            raise NotImplementedError("use_temporal_block is not implemented on the sm_100a path (SURVEY §8f N3)")
         self.hidden_size, self.only_processor, self.d = hidden_size, only_processor, output_size
         self.use_rope_embeddings, self.use_gated_attention = use_rope_embeddings, use_gated_attention
         self.use_temporal_block = use_temporal_block
@@ -104,12 +104,15 @@ class EncodeTransformDecode(nn.Module):
                         use_separate_proj_weight=use_separate_proj_weight, use_rope_embeddings=use_rope_embeddings,
                         use_gated_attention=use_gated_attention, pos_dimension=rope_pos_dimension, rope_base=rope_base)
             for _ in range(message_passing_num)])
-        self.temporal_block = None
+        self.temporal_block = (TemporalAttention(hidden_size=hidden_size, num_heads=num_heads)
+                               if use_temporal_block else None)                                            # processors.py:332-336
         # "bf16": bf16 MMA operands, fp32 accumulate and residual stream -- the timed path; "tight": three-term split
         # GEMMs (csrc/gemm.cu, terms = 3) with fp32 tensors, for rtol-1e-3 parity with the fp32 reference
         self.precision = precision or os.environ.get("GP_B200_PRECISION", "bf16")
         for blk in self.processor_list:
             blk.set_precision(self.precision)
+        if self.temporal_block is not None:
+            self.temporal_block.precision = self.precision
         self.act = "silu" if use_silu_activation() else "relu"
 
     def forward(self, graph) -> torch.Tensor:
@@ -129,6 +132,10 @@ class EncodeTransformDecode(nn.Module):
             enc = lambda seq, t: dense.mlp4(seq, t, terms=terms)
         if not self.only_processor:
             x = enc(self.nodes_encoder, x.float())
+        prev_x = x
         for block in self.processor_list:
+            prev_x = x
             x = block(x, g, pos=pos)
+        if self.temporal_block is not None:                      # processors.py:376-377
+            x = self.temporal_block(prev_x, x, g)
         return x if self.only_processor else enc(self.decode_module, x)

@@ -296,6 +296,20 @@ def graph_net_block_forward(block, x, e_sorted, g, pos, phi, act: str, terms: in
     return x + x_upd, e_sorted + e_upd
 
 
+def temporal_attention_forward(blk, h_prev, h_pred, g, terms: int = 1):
+    """TemporalAttention.forward (layers.py:861-887).  q, v from h_pred, k from h_prev; (N, H) -> (N, head_dim, heads)
+    is the channel layout the attention kernels use (c = d * heads + h)."""
+    h_prev, h_pred = dense._f32(h_prev), dense._f32(h_pred)
+    q, k, v = linear(h_pred, blk.q_proj, terms), linear(h_prev, blk.k_proj, terms), linear(h_pred, blk.v_proj, terms)
+    out = linear(ops.CSRAttention.apply(q, k, v, g, blk.H), blk.out_proj, terms)
+    if blk.use_gate:
+        z = _Act.apply(linear(_Concat.apply(h_pred, h_prev, None), blk.gate[0], terms), ACT_KIND["silu"])
+        out = _SigmoidMul.apply(linear(z, blk.gate[2], terms), out)
+    h_corr = h_prev + out
+    z = _Act.apply(linear(_Concat.apply(h_corr, h_prev, None), blk.mixer[0], terms), ACT_KIND["silu"])
+    return h_corr + linear(z, blk.mixer[2], terms)
+
+
 def epd_forward(model, graph, act: str):
     """EncodeProcessDecode.forward with variant flags (processors.py:162-215)."""
     from .graph import get_csr
@@ -313,8 +327,12 @@ def epd_forward(model, graph, act: str):
     if model.use_rope and pos is None:
         raise ValueError("Graph data must contain `pos` when use_rope_embeddings=True.")
     phi = getattr(graph, "phi", None) if model.use_gate else None
+    prev_x = x
     for blk in model.processor_list:
+        prev_x = x
         x, e = graph_net_block_forward(blk, x, e, g, pos, phi, act, terms)
+    if model.temporal_block is not None:                    # processors.py:204-209: (input, output) of the last block
+        x = temporal_attention_forward(model.temporal_block, prev_x, x, g, terms)
     if model.only_processor:
         return x
     return mlp_seq(model.decode_module, x, act, terms)

@@ -609,16 +609,36 @@ def dense_mlp_act(x, sd, prefix: str, act: str = "relu", mode: Optional[str] = N
     return rms_norm(h, sd[f"{prefix}.7.scale"]) if layer_norm else h
 
 
+def temporal_attention(h_prev, h_pred, row, col, sd, prefix: str, num_heads: int = 4, use_gate: bool = True, mode: Optional[str] = None):
+    """TemporalAttention.forward (layers.py:861-887): q, v = Linear(h_pred), k = Linear(h_prev), heads innermost;
+    scaled_dot_product_attention over the adjacency; out_proj; sigmoid gate MLP on [h_pred | h_prev]; residual onto
+    h_prev; SiLU mixer on [h_corr | h_prev].  Kernel mode rounds GEMM operands only (q / k / v stay fp32)."""
+    N, H = h_prev.shape
+    d = H // num_heads
+    lin = lambda x, n: linear(x, sd[f"{prefix}.{n}.weight"], sd[f"{prefix}.{n}.bias"], mode)
+    q, k, v = lin(h_pred, "q_proj"), lin(h_prev, "k_proj"), lin(h_pred, "v_proj")
+    y = sparse_attention(*(t.reshape(N, d, num_heads) for t in (q, k, v)), row, col, N).reshape(N, H)
+    out = lin(y, "out_proj")
+    if use_gate:
+        out = torch.sigmoid(lin(F.silu(lin(torch.cat([h_pred, h_prev], -1), "gate.0")), "gate.2")) * out
+    h_corr = h_prev + out
+    return h_corr + lin(F.silu(lin(torch.cat([h_corr, h_prev], -1), "mixer.0")), "mixer.2")
+
+
 def epd_forward_variant(sd, x_in, edge_attr, edge_index, num_layers: int, *, act: str = "relu", gated_mlp: bool = False,
                         gate: bool = False, rope_axes: int = 0, rope_base: float = 10000.0, pos=None, phi=None,
-                        mode: Optional[str] = None):
+                        temporal: bool = False, mode: Optional[str] = None):
     """EncodeProcessDecode.forward with the variant flags (processors.py:162-215)."""
     src, dst = edge_index[0], edge_index[1]
     x = dense_mlp_act(x_in, sd, "nodes_encoder", act, mode)
     e = dense_mlp_act(edge_attr, sd, "edges_encoder", act, mode)
+    prev_x = x
     for i in range(num_layers):
+        prev_x = x
         x, e = graph_net_block_variant(x, e, src, dst, sd, f"processor_list.{i}", act=act, gated_mlp=gated_mlp, gate=gate,
                                        rope_axes=rope_axes, rope_base=rope_base, pos=pos, phi=phi if gate else None, mode=mode)
+    if temporal:                                                          # processors.py:204-209
+        x = temporal_attention(prev_x, x, src, dst, sd, "temporal_block", 4, True, mode)
     return dense_mlp_act(x, sd, "decode_module", act, mode, layer_norm=False)
 
 
@@ -643,14 +663,16 @@ def rope_nodes(q, k, pos, inv_freq):
 
 
 def etd_forward_variant(sd, x_in, edge_index, num_layers: int, num_heads: int, *, act: str = "relu", gated_attention: bool = False,
-                        rope: bool = False, rope_base: float = 10000.0, pos=None, mode: Optional[str] = None):
+                        rope: bool = False, rope_base: float = 10000.0, pos=None, temporal: bool = False, mode: Optional[str] = None):
     """EncodeTransformDecode.forward with use_gated_attention / use_rope_embeddings / SiLU (processors.py:338-384,
     layers.py:637-697, 766-819)."""
     row, col = edge_index[0], edge_index[1]
     x = dense_mlp_act(x_in, sd, "nodes_encoder", act, mode)
     N, H = x.shape
     d = H // num_heads
+    prev_x = x
     for i in range(num_layers):
+        prev_x = x
         p = f"processor_list.{i}"
         n1 = rnd(rms_norm(x, sd[f"{p}.norm1.scale"]), mode)
         q, k, v = (linear(n1, sd[f"{p}.attention.{w}_proj.weight"], sd.get(f"{p}.attention.{w}_proj.bias"), mode) for w in "qkv")
@@ -666,4 +688,6 @@ def etd_forward_variant(sd, x_in, edge_index, num_layers: int, num_heads: int, *
             y = y * torch.sigmoid(gl).reshape(N, d, num_heads)
         x = x + linear(rnd(y.reshape(N, H), mode), sd[f"{p}.attention.proj.weight"], sd.get(f"{p}.attention.proj.bias"), mode)
         x = x + gated_mlp_seq(rms_norm(x, sd[f"{p}.norm2.scale"]), sd, f"{p}.gated_mlp", "silu" if act == "silu" else "gelu", mode)
+    if temporal:                                                          # processors.py:376-377
+        x = temporal_attention(prev_x, x, row, col, sd, "temporal_block", num_heads, True, mode)
     return dense_mlp_act(x, sd, "decode_module", act, mode, layer_norm=False)

@@ -4,7 +4,8 @@
 
 EncodeProcessDecode with use_silu_activation / use_gated_mlp / use_gated_attention (the aggregation gate of
 GraphNetBlock, layers.py:1091-1098) / use_rope_embeddings (relative RoPE on the senders, layers.py:1020-1026, 1104-1149)
-and EncodeTransformDecode with use_gated_attention / use_rope_embeddings / SiLU gating (layers.py:637-697, 213-249):
+and EncodeTransformDecode with use_gated_attention / use_rope_embeddings / SiLU gating (layers.py:637-697, 213-249),
+both also with use_temporal_block (TemporalAttention, layers.py:822-887):
 inputs, weights, output and the gradients of sum(out * G) for every parameter, on the small mesh of the other goldens."""
 from __future__ import annotations
 
@@ -28,12 +29,14 @@ EPD_CASES = {
     "epd_gate": dict(silu=False, kw=dict(use_gated_attention=True)),
     "epd_rope": dict(silu=False, kw=dict(use_rope_embeddings=True, rope_pos_dimension=2)),
     "epd_all": dict(silu=True, kw=dict(use_gated_mlp=True, use_gated_attention=True, use_rope_embeddings=True, rope_pos_dimension=2)),
+    "epd_temporal": dict(silu=False, kw=dict(use_temporal_block=True)),
 }
 ETD_CASES = {
     "etd_gated_attention": dict(silu=False, kw=dict(use_gated_attention=True)),
     "etd_rope": dict(silu=False, kw=dict(use_rope_embeddings=True, rope_pos_dimension=2)),
     "etd_silu": dict(silu=True, kw={}),
     "etd_shared_qkv": dict(silu=False, kw=dict(use_separate_proj_weight=False)),
+    "etd_temporal": dict(silu=False, kw=dict(use_temporal_block=True)),
 }
 
 

@@ -187,10 +187,13 @@ def test_shipped_training_configs_parse_verbatim():
     t = get_model(tv)
     assert t.processor_list[0].attention.gate_proj is not None and t.processor_list[0].attention.m == 16 // 6
     assert "processor_list.0.attention.rope_inv_freq" in t.state_dict()
-    bad = json.loads(json.dumps(cfgs["cylinder"]))
-    bad["training"] = {"use_temporal_block": True}
-    with pytest.raises(NotImplementedError):
-        get_model(bad)
+    for base in ("cylinder", "coarse-aneurysm"):                        # training.use_temporal_block (parse_parameters.py:103)
+        tb = json.loads(json.dumps(cfgs[base]))
+        tb["training"] = {"use_temporal_block": True}
+        m = get_model(tb)
+        assert {"temporal_block.q_proj.weight", "temporal_block.out_proj.bias", "temporal_block.gate.0.weight",
+                "temporal_block.gate.2.bias", "temporal_block.mixer.0.weight", "temporal_block.mixer.2.bias"} <= set(m.state_dict().keys())
+        assert m.temporal_block.gate[0].weight.shape == (m.hidden_size, 2 * m.hidden_size)
 
 
 def test_kuhn_box_graph_equals_tetra_mesh_edges():

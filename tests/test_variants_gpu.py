@@ -1,5 +1,6 @@
 """GPU: the variant flags of the path -- use_silu_activation, use_gated_mlp, use_gated_attention (aggregation
-gate with phi / gated attention), use_rope_embeddings (relative RoPE on senders / RoPE on q, k), shared q-k-v weights --
+gate with phi / gated attention), use_rope_embeddings (relative RoPE on senders / RoPE on q, k), shared q-k-v weights,
+use_temporal_block (TemporalAttention after the last block) --
 against the golden outputs and gradients of the UNMODIFIED reference (tests/golden/variants.npz,
 oracle/make_golden_variants.py):
 
@@ -25,11 +26,13 @@ EPD = {"epd_silu": (dict(), True, dict(act="silu")),
        "epd_gate": (dict(use_gated_attention=True), False, dict(gate=True)),
        "epd_rope": (dict(use_rope_embeddings=True, rope_pos_dimension=2), False, dict(rope_axes=2)),
        "epd_all": (dict(use_gated_mlp=True, use_gated_attention=True, use_rope_embeddings=True, rope_pos_dimension=2), True,
-                   dict(act="silu", gated_mlp=True, gate=True, rope_axes=2))}
+                   dict(act="silu", gated_mlp=True, gate=True, rope_axes=2)),
+       "epd_temporal": (dict(use_temporal_block=True), False, dict(temporal=True))}
 ETD = {"etd_gated_attention": (dict(use_gated_attention=True), False, dict(gated_attention=True)),
        "etd_rope": (dict(use_rope_embeddings=True, rope_pos_dimension=2), False, dict(rope=True)),
        "etd_silu": (dict(), True, dict(act="silu")),
-       "etd_shared_qkv": (dict(use_separate_proj_weight=False), False, dict())}
+       "etd_shared_qkv": (dict(use_separate_proj_weight=False), False, dict()),
+       "etd_temporal": (dict(use_temporal_block=True), False, dict(temporal=True))}
 
 
 def _load(z, name):
