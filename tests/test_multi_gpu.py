@@ -198,3 +198,51 @@ def test_trainer_node_partition_matches_single_gpu_training():
         assert np.allclose(l_part, l_ref, rtol=1e-2), (l_part, l_ref)
         assert drift < 1e-2, drift
 
+
+
+def _partition_transformer_worker(rank, world):
+    """EncodeTransformDecode through the node partition (attention rows live with their query node, ghost keys / values
+    recomputed locally, fp32 latent halo before every block) vs the unpartitioned model: output on the owned nodes and
+    the gradient of  sum_n <out[n], G[n]>  for every parameter."""
+    from graphphysics_b200.dist.partition import build_local_graphs, partition_nodes
+    from graphphysics_b200.dist.partitioned import PartitionedETD
+    from graphphysics_b200.graph import Data
+    from graphphysics_b200.models.processors import EncodeTransformDecode
+    from graphphysics_b200.synthetic import box_tet_mesh, faces_of_cells, mesh_edges
+    dev = torch.device("cuda", rank)
+    pos, tets = box_tet_mesh(12, 10, 8)
+    ei = mesh_edges(faces_of_cells(tets), len(pos))
+    res = []
+    for kw in (dict(), dict(use_gated_attention=True, use_rope_embeddings=True, use_temporal_block=True)):
+        torch.manual_seed(0)
+        model = EncodeTransformDecode(3, 14, 3, hidden_size=64, num_heads=4, precision="tight", **kw).to(dev)
+        gen = torch.Generator().manual_seed(1)
+        x = torch.randn(len(pos), 14, generator=gen).to(dev)
+        G = torch.randn(len(pos), 3, generator=gen).to(dev)
+        ei_d, pos_d = torch.from_numpy(ei).to(dev), torch.from_numpy(pos).float().to(dev)
+        full = model(Data(x=x, edge_index=ei_d, pos=pos_d))
+        (full * G).sum().backward()
+        ref = {k: p.grad.clone() for k, p in model.named_parameters()}
+        model.zero_grad(set_to_none=True)
+        owner = partition_nodes(pos, world)
+        lg = build_local_graphs(np.ascontiguousarray(ei[::-1]), owner, world)[rank]
+        part = PartitionedETD(model, lg, world, dist.group.WORLD)
+        out = part.forward(x, pos_d)
+        own = torch.from_numpy(lg.owned).to(dev)
+        (out * G[own]).sum().backward()
+        part.reduce_gradients()
+        e_out = float((out.detach() - full.detach()[own]).norm() / full.detach()[own].norm())
+        big = max(float(v.norm()) for v in ref.values())
+        e_grad = max(float((p.grad - ref[k]).norm() / ref[k].norm()) for k, p in model.named_parameters()
+                     if float(ref[k].norm()) > 1e-6 * big)
+        res.append((e_out, e_grad, int(sum(len(v) for v in lg.recv.values()))))
+    return res
+
+
+def test_node_partitioned_transformer_equals_unpartitioned():
+    _need_two()
+    for per_rank in _spawn(_partition_transformer_worker):
+        for e_out, e_grad, halo in per_rank:
+            assert halo > 0
+            # tight arithmetic (fp32-grade products): what is left is fp32 summation order
+            assert e_out < 1e-4 and e_grad < 1e-3, (e_out, e_grad)
