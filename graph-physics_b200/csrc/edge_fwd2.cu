@@ -8,11 +8,13 @@
 // (64 KB) and one tcgen05.mma.cta_group::2 instruction multiplies BOTH CTAs' 128-row tiles by the full matrix.
 // The freed 64 KB become three more tile buffers per CTA, and the tile loop is split into roles that overlap:
 //
-//   warps  0-7   epilogue, two tile slots of 128 threads (thread = row of the tile = TMEM lane, 128 registers):
-//                accumulator pre-load from the gathered rows, ReLU / bf16 conversion between layers, RMSNorm
-//   warps  8-15  drain, 128 threads per slot: segment walk over the normalised update u, e' = e + u, stores
-//   warps 16-17  MMA issue (leader CTA): one thread per slot waits for BOTH CTAs' operands and issues the pair MMAs
-//   warps 18-19  gather producers: cp.async of the sender rows P[src] of the NEXT tile into a staging buffer
+//   warps  0-15  epilogue, two tile slots of 256 threads (thread = (row of the tile = TMEM lane, column half): the four
+//                layers of a tile are one dependent chain per slot, so its length is what bounds the kernel -- two
+//                threads per row halve every step of it): accumulator pre-load from the gathered rows, ReLU / bf16
+//                conversion between layers, RMSNorm
+//   warps 16-23  drain, 128 threads per slot: segment walk over the normalised update u, e' = e + u, stores
+//   warps 24-25  MMA issue (leader CTA): one thread per slot waits for BOTH CTAs' operands and issues the pair MMAs
+//   warps 26-27  gather producers: the sender rows P[src] of the NEXT tile into a staging buffer (TMA gather4 / cp.async)
 //
 // Buffers per CTA: ACT[slot] (layer operand, rewritten in place by the epilogues; the next tile's e arrives here by
 // TMA while the RMSNorm epilogue of the current one runs), U[slot] (normalised update, handed to the drain warps so
@@ -31,13 +33,22 @@ namespace gp {
 int try_edge_fwd2(const gp_mlp_fwd_args& a, cudaStream_t st);
 }
 
+// registers per thread of the three roles after setmaxnreg (16 epilogue, 8 drain, 4 control warps; 28 x 72 in total)
+#ifndef GP_FWD2_REGS_EPI
+#define GP_FWD2_REGS_EPI 80
+#define GP_FWD2_REGS_DRAIN 72
+#define GP_FWD2_REGS_CTRL 40
+#endif
+static_assert(16 * GP_FWD2_REGS_EPI + 8 * GP_FWD2_REGS_DRAIN + 4 * GP_FWD2_REGS_CTRL <= 28 * 72, "register budget of the CTA");
+
 namespace {
 using namespace gp;
 
 constexpr int H = 128;
-constexpr int kEpi = 128;                    // epilogue threads per slot: thread = row of the tile = TMEM lane
+constexpr int kEpi = 256;                    // epilogue threads per slot: (row of the tile = TMEM lane) x (column half)
 constexpr int kDrain = 128;                  // drain threads per slot
-constexpr int kNT = 2 * kEpi + 2 * kDrain + 128;      // 640: 8 epilogue + 8 drain + 4 control warps
+constexpr int kNT = 2 * kEpi + 2 * kDrain + 128;      // 896: 16 epilogue + 8 drain + 4 control warps
+constexpr int kWDrain = 2 * kEpi / 32, kWMma = kWDrain + 2 * kDrain / 32, kWProd = kWMma + 2;     // first warp of each role
 constexpr int kTile = 128 * H * 2;           // 32 KB
 constexpr int kWHalf = 64 * H * 2;           // 16 KB: rows [rank*64, +64) of one weight matrix
 
@@ -255,19 +266,26 @@ edge_fwd2_kernel(const gp_mlp_fwd_args p, const __grid_constant__ Fwd2Maps maps)
 
     // ---- prologue (parameters only): weights, barriers, TMEM
     if ((smem_u32(smem) & 1023u) != 0) __trap();
+#ifdef GP_FWD2_PROF
+    long long t_entry = 0;
+    if (p.prof && blockIdx.x == 0 && tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_entry));
+#define PROF_STAMP(slot_) do { if (p.prof && blockIdx.x == 0 && tid == 0) { long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); p.prof[slot_] = (unsigned long long)(t_ - t_entry); } } while (0)
+#else
+#define PROF_STAMP(slot_) do { } while (0)
+#endif
     for (int l = 0; l < 4; ++l) stage_weight(smem + kOffW + l * kWHalf, p.w[l] + (size_t)rank * 64 * H, 64, H);
     cp_async_commit();
     float* sbias = reinterpret_cast<float*>(smem + kOffBias);
     for (int i = tid; i < 5 * H; i += kNT) sbias[i] = i < 4 * H ? p.bias[i >> 7][i & 127] : p.norm_scale[i - 4 * H];
     if (tid == 0) {
         for (int s = 0; s < 2; ++s) {
-            mbar_init(&B.a_ready[s], 8);      // 4 epilogue warps x 2 CTAs
+            mbar_init(&B.a_ready[s], 16);     // 8 epilogue warps x 2 CTAs
             mbar_init(&B.mma_done[s], 1);
             mbar_init(&B.tma_e[s], 1);
-            mbar_init(&B.u_full[s], 4);
-            mbar_init(&B.u_empty[s], 4);
+            mbar_init(&B.u_full[s], 8);       // epilogue warps of the slot
+            mbar_init(&B.u_empty[s], 4);      // drain warps of the slot
             mbar_init(&B.g_full[s], maps.gather4 ? 2 : 64);      // cp.async: two producer warps x 32 lanes; TMA: one expect_tx per warp
-            mbar_init(&B.g_empty[s], 4);      // consuming slot: each slot sees its own phases in order
+            mbar_init(&B.g_empty[s], 8);      // consuming slot: each slot sees its own phases in order
         }
         fence_mbar_init();
     }
@@ -286,32 +304,35 @@ edge_fwd2_kernel(const gp_mlp_fwd_args p, const __grid_constant__ Fwd2Maps maps)
     pdl_wait();
     pdl_launch_dependents();
 
-    // Register budget per role: the launch gives every warp 96 registers per thread and setmaxnreg only moves
-    // registers inside the CTA's own allocation (640 x 96): 8 x 128 + 8 x 80 + 4 x 64 = 20 x 96 exactly.
-    if (warp < 8) {
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 128;");
-    } else if (warp < 16) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
+    // Register budget per role: the launch gives every warp 72 registers per thread and setmaxnreg only moves
+    // registers inside the CTA's own allocation (896 x 72): 16 x EPI + 8 x DRAIN + 4 x CTRL = 28 x 72 exactly.
+    if (warp < kWDrain) {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(GP_FWD2_REGS_EPI));
+    } else if (warp < kWMma) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(GP_FWD2_REGS_DRAIN));
     } else {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(GP_FWD2_REGS_CTRL));
     }
 
-    if (warp < 8) {
+    if (warp < kWDrain) {
         // =========================================================================== epilogue slots
-        const int s = warp >> 2;                 // slot
-        const int row = tid & 127;               // row of the tile == TMEM lane
+        const int s = warp >> 3;                 // slot
+        const int hf = (warp >> 2) & 1;          // column half of the row this thread works on
+        const int cb = hf * 64;
+        const int row = (warp & 3) * 32 + lane;  // row of the tile == TMEM lane (warp w may touch lanes [32 (w % 4), +32))
         uint8_t* act = smem + kOffAct + s * kTile;
         uint8_t* ubuf = smem + kOffU + s * kTile;
         const uint8_t* gbuf = smem + kOffG;
-        const uint32_t act_u = smem_u32(smem + kOffAct) + (uint32_t)(warp >> 2) * kTile;
-        const uint32_t tacc = tmem_addr(tmem_base, (row >> 5) * 32, s * kSlotCols);
+        const uint32_t act_u = smem_u32(smem + kOffAct) + (uint32_t)s * kTile;
+        const uint32_t tacc = tmem_addr(tmem_base, (warp & 3) * 32, s * kSlotCols);
         const uint32_t tact = tacc + kColAct;
         const uint32_t a_ready_leader = mapa_u32(smem_u32(&B.a_ready[s]), 0);
         uint32_t ph_mma = 0;
-        const bool issuer = ((warp & 3) == 0) && lane == 0;      // the thread that issues this slot's bulk copies
+        const bool issuer = ((warp & 7) == 0) && lane == 0;      // the thread that issues this slot's bulk copies
         auto dst_of = [&](int qq) { return __ldg(p.idx0 + min(((2 * qq + (int)rank) << 7) + row, p.rows - 1)); };
 
         PROF_DECL(tid == 0);
+        PROF_STAMP(24);      // ns from kernel entry to the start of the tile loop (prologue)
         int q = cid * 2 + s;
         if (q < n_pairs && issuer) {
             const int R0 = (2 * q + (int)rank) << 7;
@@ -325,36 +346,38 @@ edge_fwd2_kernel(const gp_mlp_fwd_args p, const __grid_constant__ Fwd2Maps maps)
             const bool has_next = q + q_stride < n_pairs;
             // ---- accumulator pre-load: b1 + P[src][H:2H] (staged rows; the buffer goes back to the producers right
             //      after this pass) + P[dst][0:H] (sorted: read directly, requested before the wait)
-            const gp_bf16* pd = p.init + (size_t)i_dst_next * p.ld_init + p.init_off0;
-            uint4 dq[16];
+            const gp_bf16* pd = p.init + (size_t)i_dst_next * p.ld_init + p.init_off0 + cb;
+            uint4 dq[8];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) dq[i] = ldg16(pd + i * 8);
+            for (int i = 0; i < 8; ++i) dq[i] = ldg16(pd + i * 8);
             PROF_COUNT(15);
             PROF_TICK(0);        // tile bookkeeping + requests
             mbar_wait(&B.g_full[s], k & 1);
             PROF_TICK(1);        // waiting for the staged sender rows
 #pragma unroll
-            for (int c2 = 0; c2 < H; c2 += 32) {
+            for (int c2 = cb; c2 < cb + 64; c2 += 32) {
                 float f[32];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) *reinterpret_cast<float4*>(f + 4 * i) = *reinterpret_cast<const float4*>(sbias + c2 + 4 * i);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     acc8(*reinterpret_cast<const uint4*>(gbuf + sw128_off(128, row, c2 + i * 8)), f + 8 * i);
-                    acc8(dq[c2 / 8 + i], f + 8 * i);
+                    acc8(dq[(c2 - cb) / 8 + i], f + 8 * i);
                 }
                 tmem_st16(tacc + c2, *reinterpret_cast<const uint32_t(*)[16]>(f));
                 tmem_st16(tacc + c2 + 16, *reinterpret_cast<const uint32_t(*)[16]>(f + 16));
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&B.g_empty[s]);
-            if (has_next) i_dst_next = dst_of(q + q_stride);
             tmem_st_wait();
             tc_fence_before();
             PROF_TICK(2);        // accumulator pre-load
             mbar_wait(&B.tma_e[s], k & 1);       // this tile's e is in ACT (bulk copy issued a tile ago)
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(a_ready_leader);
+            // the next tile's receiver index: requested here, so that its latency (and the store, should the value be
+            // spilled) falls into the wait for the first MMA instead of into the chain
+            if (has_next) i_dst_next = dst_of(q + q_stride);
             PROF_TICK(3);        // waiting for the e tile
 
             // ---- layers
@@ -370,14 +393,14 @@ edge_fwd2_kernel(const gp_mlp_fwd_args p, const __grid_constant__ Fwd2Maps maps)
                     // there to global memory by one bulk store (it is the input of backward stage B).
                     const float* bn = sbias + (l + 1) * H;
                     const bool to_smem = (l == 1) && maps.save_h2;
-#pragma unroll 1
-                    for (int c2 = 0; c2 < H; c2 += 64) {
-                        uint32_t v[64];
 #pragma unroll
-                        for (int c = 0; c < 64; c += 16) tmem_ld16(tacc + c2 + c, *reinterpret_cast<uint32_t(*)[16]>(&v[c]));
+                    for (int c2 = cb; c2 < cb + 64; c2 += 32) {
+                        uint32_t v[32];
+                        tmem_ld16(tacc + c2, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
+                        tmem_ld16(tacc + c2 + 16, *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
                         tmem_ld_wait();
 #pragma unroll
-                        for (int c = 0; c < 64; c += 16) {
+                        for (int c = 0; c < 32; c += 16) {
                             uint32_t b16[16];
 #pragma unroll
                             for (int i = 0; i < 4; ++i) {
@@ -386,14 +409,13 @@ edge_fwd2_kernel(const gp_mlp_fwd_args p, const __grid_constant__ Fwd2Maps maps)
                             }
                             tmem_st16(tacc + c2 + c, b16);
                         }
-                        uint32_t hp[32];          // 64 bf16 values: column j of the operand holds elements (2j, 2j+1)
+                        uint32_t hp[16];          // 32 bf16 values: column j of the operand holds elements (2j, 2j+1)
 #pragma unroll
-                        for (int c = 0; c < 64; c += 2) hp[c >> 1] = pack_bf16_relu(__uint_as_float(v[c]), __uint_as_float(v[c + 1]));
+                        for (int c = 0; c < 32; c += 2) hp[c >> 1] = pack_bf16_relu(__uint_as_float(v[c]), __uint_as_float(v[c + 1]));
                         tmem_st16(tact + (c2 >> 1), *reinterpret_cast<const uint32_t(*)[16]>(&hp[0]));
-                        tmem_st16(tact + (c2 >> 1) + 16, *reinterpret_cast<const uint32_t(*)[16]>(&hp[16]));
                         if (to_smem) {
 #pragma unroll
-                            for (int c = 0; c < 64; c += 8)
+                            for (int c = 0; c < 32; c += 8)
                                 *reinterpret_cast<uint4*>(act + sw128_off(128, row, c2 + c)) =
                                     make_uint4(hp[c >> 1], hp[(c >> 1) + 1], hp[(c >> 1) + 2], hp[(c >> 1) + 3]);
                         }
@@ -426,17 +448,19 @@ edge_fwd2_kernel(const gp_mlp_fwd_args p, const __grid_constant__ Fwd2Maps maps)
                         tma_load_2d(act_u, &maps.e, 0, Rn, &B.tma_e[s]);
                         tma_load_2d(act_u + 16384, &maps.e, 64, Rn, &B.tma_e[s]);
                     }
+                    // Both threads of a row read the WHOLE row for the sum of squares (tensor-memory reads are cheap; an
+                    // exchange would cost a slot barrier and shared memory that is not there) and then scale their own half.
                     // (two 64-column partial sums added at the end: the summation order of the single-CTA kernel, whose
                     //  two column halves belong to different threads -- the kernels stay bit-identical)
                     float ssh[2] = {0.f, 0.f};
 #pragma unroll
-                    for (int c2 = 0; c2 < H; c2 += 64) {
-                        uint32_t v[64];
-#pragma unroll
-                        for (int c = 0; c < 64; c += 16) tmem_ld16(tacc + c2 + c, *reinterpret_cast<uint32_t(*)[16]>(&v[c]));
+                    for (int c2 = 0; c2 < H; c2 += 32) {
+                        uint32_t v[32];
+                        tmem_ld16(tacc + c2, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
+                        tmem_ld16(tacc + c2 + 16, *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
                         tmem_ld_wait();
 #pragma unroll
-                        for (int c = 0; c < 64; ++c) {
+                        for (int c = 0; c < 32; ++c) {
                             const float m = __uint_as_float(v[c]);
                             ssh[c2 >> 6] = fmaf(m, m, ssh[c2 >> 6]);
                         }
@@ -447,8 +471,8 @@ edge_fwd2_kernel(const gp_mlp_fwd_args p, const __grid_constant__ Fwd2Maps maps)
                     if (k > 0) mbar_wait(&B.u_empty[s], (k - 1) & 1);     // the drain warps are done with the previous u
                     PROF_TICK(7);    // waiting for the drain warps
                     const float* sc = sbias + 4 * H;
-#pragma unroll 2
-                    for (int c2 = 0; c2 < H; c2 += 32) {
+#pragma unroll
+                    for (int c2 = cb; c2 < cb + 64; c2 += 32) {
                         uint32_t v[32];
                         tmem_ld16(tacc + c2, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
                         tmem_ld16(tacc + c2 + 16, *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
@@ -471,9 +495,10 @@ edge_fwd2_kernel(const gp_mlp_fwd_args p, const __grid_constant__ Fwd2Maps maps)
             }
         }
         if (maps.save_h2 && issuer) tma_store_wait_all();
-    } else if (warp < 16) {
+        PROF_STAMP(25);      // ... to the end of this thread's tile loop
+    } else if (warp < kWMma) {
         // =========================================================================== drain: segment sum + e' = e + u
-        const int s = (warp - 8) >> 2;
+        const int s = (warp - kWDrain) >> 2;
         const int d = (tid - 2 * kEpi) & (kDrain - 1);
         const uint8_t* ubuf = smem + kOffU + s * kTile;
         constexpr int KC = H / 8;
@@ -525,10 +550,10 @@ edge_fwd2_kernel(const gp_mlp_fwd_args p, const __grid_constant__ Fwd2Maps maps)
             if (lane == 0) mbar_arrive(&B.u_empty[s]);
             PROF_TICK(12);       // drain: segment walk
         }
-    } else if (warp < 18) {
+    } else if (warp < kWProd) {
         // =========================================================================== MMA issue (leader CTA)
         if (rank == 0) {
-            const int s = warp - 16;
+            const int s = warp - kWMma;
             const uint32_t act_u = smem_u32(smem + kOffAct) + (uint32_t)s * kTile;
             const uint32_t w_u = smem_u32(smem + kOffW);
             const uint32_t idesc = idesc_bf16(H, false, false, 256);
@@ -563,11 +588,11 @@ edge_fwd2_kernel(const gp_mlp_fwd_args p, const __grid_constant__ Fwd2Maps maps)
                 }
             }
         }
-    } else if (warp < 20) {
+    } else {
         // =========================================================================== gather producers: P[src] rows -> G
         // two warps, 64 rows each; the rows are pulled into L2 before the staging buffer is free, so the copies that
         // follow the hand-over are L2 hits
-        const int pw = warp - 18;
+        const int pw = warp - kWProd;
         const uint32_t g_u = smem_u32(smem + kOffG);
         PROF_DECL(lane == 0 && pw == 0);
         for (int j = 0;; ++j) {
@@ -618,6 +643,7 @@ edge_fwd2_kernel(const gp_mlp_fwd_args p, const __grid_constant__ Fwd2Maps maps)
     __syncthreads();
     cluster_sync_all();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    PROF_STAMP(26);          // ... to the exit of CTA 0
 }
 }  // namespace
 

@@ -32,4 +32,5 @@ for it in range(3):
     for i, n in ((16, "epi: l=2 wait h2 store read"), (17, "epi: hidden convert (x3)"), (18, "epi: fences (x3)"), (19, "epi: l=1 sync + store issue"),
                  (20, "pre: requests + wait accumulator"), (21, "pre: wait staged rows"), (22, "pre: sums + TMEM stores")):
         print(f"    {n:32s} {p[i]/tiles:9.0f}")
+    print(f"    timeline of CTA 0 (ns from entry): loop start {p[24]}, loop end {p[25]}, exit {p[26]}")
     print(f"    {'epilogue total':32s} {(sum(p[:9])+sum(p[16:20]))/tiles:9.0f}   drain total {sum(p[9:13])/tiles:9.0f}   producer total {sum(p[13:15])/tiles:9.0f}")
