@@ -210,7 +210,11 @@ int launch(const gp_linear_bwd_args& a, int32_t* grid_out, cudaStream_t st) {
             if (a.src_bf16[s] && gp::tma_map_2d(&maps.src[s], a.src_bf16[s], a.rows, H, a.ld_src[s])) maps.use |= 2u << s;
     }
     const int n_tiles = (a.rows + 127) / 128;
-    const int grid = n_tiles < gp::sm_count() ? n_tiles : gp::sm_count();
+    int grid = n_tiles < gp::sm_count() ? n_tiles : gp::sm_count();
+    if (grid > 0) {           // minimal number of tile rounds with the fewest CTAs (each dumps a block of partials)
+        const int rounds = (n_tiles + grid - 1) / grid;
+        grid = (n_tiles + rounds - 1) / rounds;
+    }
     GP_CHECK_CUDA(gp::launch_kernel(linear_bwd_kernel<H>, dim3(grid), dim3(256), smem, st, a, maps));
     if (grid_out) *grid_out = grid;
     return 0;

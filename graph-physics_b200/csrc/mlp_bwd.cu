@@ -890,7 +890,13 @@ int launch_bwd(const gp_mlp_bwd_args& a, int32_t* grid_out, cudaStream_t st) {
         smem_set[fast] = (int)smem;
     }
     const int n_tiles = (a.rows + 127) / 128;
+    // as many CTAs as keep the number of tile rounds minimal, not more: every CTA dumps (and the reduction re-reads)
+    // a full block of partial weight gradients (503 node tiles: 126 CTAs x 4 tiles instead of 148 x 3.4)
     int grid = n_tiles < gp::sm_count() ? n_tiles : gp::sm_count();
+    if (grid > 0) {
+        const int rounds = (n_tiles + grid - 1) / grid;
+        grid = (n_tiles + rounds - 1) / rounds;
+    }
     const dim3 g3(grid), b3(BwdCfg<H>::NT);
     cudaError_t le;
     if (fast == 1)
