@@ -441,7 +441,7 @@ def main():
     # dram__bytes_read.sum + dram__bytes_write.sum per launch of the same kernels on this workload, from the
     # `ncu --set full` captures summarised in profiles/r02_final_summary.md (at or below the algorithmic bytes: the
     # gathered rows and the residual tile hit L2)
-    ncu_dram_bytes = {"edge_fwd": 295.5e6, "edge_bwd_B": 284.3e6, "edge_bwd_A": 520.4e6} if (E, N, H) == (372752, 64424, 128) else {}
+    ncu_dram_bytes = {"edge_fwd": 299.3e6, "edge_bwd_B": 284.3e6, "edge_bwd_A": 520.4e6} if (E, N, H) == (372752, 64424, 128) else {}
     roof = None
     if prof:
         top = max(prof, key=lambda k: prof[k]["total_ms"])
@@ -454,6 +454,7 @@ def main():
                 "tensor": {"achieved_tflops": alg_flops[top] / (avg_ms * 1e-3) / 1e12, "peak_tflops": tf_peak,
                            "frac": alg_flops[top] / (avg_ms * 1e-3) / 1e12 / tf_peak},
                 "kernels_ms_per_step": {k: v["total_ms"] / n_prof for k, v in prof.items()},
+                "kernels_frac": {k: alg_bytes[k] / (v["total_ms"] / max(v["calls"], 1) * 1e-3) / 1e9 / hbm_peak for k, v in prof.items()},
                 "measured_in": f"{n_prof} eager steps, CUDA events around the three edge kernels on their stream; the host is kept ahead of "
                                f"the device (spin kernel before each step) so the events bracket device time only"}
 
