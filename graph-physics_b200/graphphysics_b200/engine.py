@@ -73,7 +73,14 @@ class EPDEngine:
         # still pending, so one reduction launch serves a whole processor layer (5 kernels).
         stride_max = max(ops.bwd_layout(H, 128, 128)[5], 3 * H * H)
         self._region_elems = ops.sm_count() * stride_max
-        self.partials_all = torch.empty(self.kNRegions * self._region_elems, dtype=torch.float32, device=self.device)
+        # The reduction of a layer runs on a side stream under the next layer's backward kernels (their grids leave SMs
+        # free; nothing on the main chain needs the reduced gradient before the optimizer): two sets of regions, so the
+        # next layer writes the other set while this one is being reduced.  GP_B200_SIDE_REDUCE=0: in-stream.
+        self._side_reduce = os.environ.get("GP_B200_SIDE_REDUCE", "1") != "0"
+        self._side_stream = torch.cuda.Stream(device=self.device) if self._side_reduce else None
+        self._side_stream2 = torch.cuda.Stream(device=self.device) if self._side_reduce else None
+        self._set, self._set_events = 0, [None, None]
+        self.partials_all = torch.empty(2 * self.kNRegions * self._region_elems, dtype=torch.float32, device=self.device)
         self._pending: list = []
         self._region = 0
         self._sq_ws = torch.empty(256, dtype=torch.float32, device=self.device)
@@ -304,8 +311,10 @@ class EPDEngine:
             x = torch.empty((N, H), dtype=bf, device=dev)
             e = torch.empty((E, H), dtype=bf, device=dev)
             h2n0, h2e0 = self._saved(N, save), self._saved(E, save)
-            self._mlp(self.enc_n, N, xin_p, xin_p.shape[1], x, H, **self._save_kw(h2n0))
+            with self._beside():        # the node encoder (N rows) runs beside the edge encoder (E rows)
+                self._mlp(self.enc_n, N, xin_p, xin_p.shape[1], x, H, **self._save_kw(h2n0))
             self._mlp(self.enc_e, E, ea_p, ea_p.shape[1], e, H, **self._save_kw(h2e0))
+            self._rejoin()
             if save:
                 ctx.update(xin_p=xin_p, ea_p=ea_p, h2n0=h2n0, h2e0=h2e0)
         bnd = torch.empty(ops.seg_bnd_size(E, H), dtype=torch.float32, device=dev)
@@ -343,18 +352,51 @@ class EPDEngine:
         `_flush_reduce`)."""
         if self._region >= self.kNRegions:
             self._flush_reduce()
-        return self.partials_all[self._region * self._region_elems:(self._region + 1) * self._region_elems]
+        r = self._set * self.kNRegions + self._region
+        return self.partials_all[r * self._region_elems:(r + 1) * self._region_elems]
 
     def _queue_reduce(self, grid: int, stride: int, segs) -> None:
         """Queue the reduction of the launch that just wrote the current region, and move on to the next."""
-        base = self.partials_all.data_ptr() + 4 * self._region * self._region_elems
+        base = self.partials_all.data_ptr() + 4 * (self._set * self.kNRegions + self._region) * self._region_elems
         self._pending += [tuple(sg) + (base, grid, stride) for sg in segs]
         self._region += 1
 
     def _flush_reduce(self) -> None:
         if self._pending:
-            ops.reduce_multi(None, 0, 0, self._pending)
+            if self._side_reduce:
+                cur, side = torch.cuda.current_stream(self.device), self._side_stream
+                side.wait_stream(cur)
+                with torch.cuda.stream(side):
+                    ops.reduce_multi(None, 0, 0, self._pending)
+                ev = torch.cuda.Event()
+                ev.record(side)
+                self._set_events[self._set] = ev
+                self._set ^= 1
+                if self._set_events[self._set] is not None:      # the set written next: its last reduction must have read it
+                    cur.wait_event(self._set_events[self._set])
+            else:
+                ops.reduce_multi(None, 0, 0, self._pending)
         self._pending, self._region = [], 0
+
+    def _beside(self):
+        """Context: launches inside go to the second side stream (after everything queued on the current stream so
+        far); `_rejoin()` makes the current stream wait for them.  Without side streams: a no-op."""
+        import contextlib
+        if not self._side_reduce:
+            return contextlib.nullcontext()
+        self._side_stream2.wait_stream(torch.cuda.current_stream(self.device))
+        return torch.cuda.stream(self._side_stream2)
+
+    def _rejoin(self) -> None:
+        if self._side_reduce:
+            torch.cuda.current_stream(self.device).wait_stream(self._side_stream2)
+
+    def _join_reduce(self) -> None:
+        """Every queued reduction has run and the flat gradient buffer is final for the current stream."""
+        self._flush_reduce()
+        if self._side_reduce:
+            torch.cuda.current_stream(self.device).wait_stream(self._side_stream)
+            self._set_events = [None, None]
 
     def _reduce_stage(self, grid, ka, nb, s: _MLPSlots, ia: int, ib: int, with_scale: bool):
         """Per-CTA partial blocks of a stage over layers (ia, ib) of MLP `s` -> flat gradient buffer."""
@@ -421,7 +463,7 @@ class EPDEngine:
             dX = torch.empty((N, H), dtype=torch.float32, device=dev)
             self._mlp_backward(self.dec, N, a_in=ctx["x_last"], ka=H, h2=ctx["h2d"], top=dict(delta_b=Gp), out=dX)
             if grads_ready is not None:
-                self._flush_reduce()
+                self._join_reduce()
                 grads_ready(*self.grad_range("decode_module."))
         # nobody consumes the last edge latent: its gradient is zero.  An explicit zero tile keeps the top
         # layer on the same specialised kernel as the others (a memset is cheaper than the general path).
@@ -458,9 +500,11 @@ class EPDEngine:
                                out=dE_new, out_resid=dE, delta_a_out=d1, seg=(g.dst, dPd, bnd),
                                first=dict(init=P, init_off0=0, init_off1=H, idx0=g.dst, idx1=g.src, two_inits=True),
                                tag="edge_bwd")
-            ops.seg_fixup(g.rowptr_dst, H, bnd, dPd, backward=True)
             dPs = torch.empty((N, H), dtype=bf, device=dev)
+            with self._beside():      # the receiver-side fix-up (a few CTAs) runs beside the sender-side segment sum
+                ops.seg_fixup(g.rowptr_dst, H, bnd, dPd, backward=True)
             ops.segsum_gather(d1, g.perm_src, g.rowptr_src, H, dPs)
+            self._rejoin()            # both feed linear_bwd
             # projection P = x . Wp^T, plus the residual path of x
             dX_new = torch.empty((N, H), dtype=torch.float32, device=dev)
             grid = ops.linear_bwd(N, H, [dPd, dPs, dQ], self.proj[l], x, dX, dX_new, self.partials)
@@ -472,14 +516,17 @@ class EPDEngine:
             ])
             self._flush_reduce()      # one reduction launch per processor layer
             if grads_ready is not None:
+                self._join_reduce()
                 grads_ready(*self.grad_range(f"processor_list.{l}."))
             dX, dE = dX_new, dE_new
         if self.only_processor:
-            self._flush_reduce()
+            self._join_reduce()
             return dX, dE
-        self._mlp_backward(self.enc_n, N, a_in=ctx["xin_p"], ka=ctx["xin_p"].shape[1], h2=ctx["h2n0"], top=dict(gy=dX))
+        with self._beside():
+            self._mlp_backward(self.enc_n, N, a_in=ctx["xin_p"], ka=ctx["xin_p"].shape[1], h2=ctx["h2n0"], top=dict(gy=dX))
         self._mlp_backward(self.enc_e, E, a_in=ctx["ea_p"], ka=ctx["ea_p"].shape[1], h2=ctx["h2e0"], top=dict(gy=dE))
-        self._flush_reduce()
+        self._rejoin()
+        self._join_reduce()
         if grads_ready is not None:
             lo_n, hi_n = self.grad_range("nodes_encoder.")
             lo_e, hi_e = self.grad_range("edges_encoder.")
