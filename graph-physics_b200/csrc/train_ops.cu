@@ -220,3 +220,182 @@ extern "C" int gp_cast_bf16(const float* src, gp_bf16* dst, int64_t n, void* str
     GP_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Online feature normaliser (graphphysics/models/layers.py:281-408) and the Simulator's node-feature assembly
+// (graphphysics/models/simulator.py:112-143) as three / one launches instead of ~20 elementwise ones per normaliser.
+//   stats  : per-block column sums of x and x*x over a strided row range (fixed-shape trees: deterministic)
+//   update : fixed-order sum of the block partials -> [sum | sum of squares | rows]; optionally the gated accumulation
+//            of Normalizer._accumulate (layers.py:363-377; the gate repeats the freeze test of :347 on the device)
+//   apply  : (x - mean) / max(std, eps)   or the inverse   x * max(std, eps) + mean,  mean / std from the accumulators
+//            with the operation order of layers.py:379-408
+namespace {
+constexpr int kNormBlocks = 296, kNormThreads = 256, kNormMaxSize = 64;
+
+__global__ void __launch_bounds__(kNormThreads) norm_stats_kernel(const float* __restrict__ x, long long rows, int size, long long ld,
+                                                                  float* __restrict__ partials) {
+    // thread -> (column, row phase): consecutive threads read consecutive columns of a row (rows are `size` floats wide)
+    __shared__ float sh[2][kNormThreads];
+    const int per = kNormThreads / size;                 // rows per pass of this block
+    const int c = threadIdx.x % size, rp = threadIdx.x / size;
+    float s = 0.f, q = 0.f;
+    if (rp < per)
+        for (long long r = (long long)blockIdx.x * per + rp; r < rows; r += (long long)gridDim.x * per) {
+            const float v = x[r * ld + c];
+            s += v;
+            q = fmaf(v, v, q);
+        }
+    sh[0][threadIdx.x] = s;
+    sh[1][threadIdx.x] = q;
+    __syncthreads();
+    if (threadIdx.x < size) {
+        float ts = 0.f, tq = 0.f;
+        for (int k = 0; k < per; ++k) {                   // fixed order
+            ts += sh[0][k * size + threadIdx.x];
+            tq += sh[1][k * size + threadIdx.x];
+        }
+        partials[(size_t)blockIdx.x * 2 * size + threadIdx.x] = ts;
+        partials[(size_t)blockIdx.x * 2 * size + size + threadIdx.x] = tq;
+    }
+}
+
+__global__ void norm_update_kernel(const float* __restrict__ partials, int n_blocks, int size, float rows, float* __restrict__ stats,
+                                   float* acc_sum, float* acc_sq, float* acc_count, float* num_acc, float max_acc) {
+    const int c = threadIdx.x;
+    float v = 0.f;
+    if (c < 2 * size)
+        for (int b = 0; b < n_blocks; ++b) v += partials[(size_t)b * 2 * size + c];
+    if (stats) {
+        if (c < 2 * size) stats[c] = v;
+        if (c == 0) stats[2 * size] = rows;
+    }
+    if (num_acc) {
+        const float gate = (num_acc[0] < max_acc) ? 1.f : 0.f;
+        __syncthreads();                                  // every thread has read the counter before it moves
+        if (c < size) acc_sum[c] += gate * v;
+        else if (c < 2 * size) acc_sq[c - size] += gate * v;
+        if (c == 0) {
+            acc_count[0] += gate * rows;
+            num_acc[0] += gate;
+        }
+    }
+}
+
+__global__ void norm_accumulate_kernel(const float* __restrict__ stats, int size, float* acc_sum, float* acc_sq, float* acc_count,
+                                       float* num_acc, float max_acc) {
+    const int c = threadIdx.x;
+    const float gate = (num_acc[0] < max_acc) ? 1.f : 0.f;
+    __syncthreads();
+    if (c < size) acc_sum[c] += gate * stats[c];
+    else if (c < 2 * size) acc_sq[c - size] += gate * stats[c];
+    if (c == 0) {
+        acc_count[0] += gate * stats[2 * size];
+        num_acc[0] += gate;
+    }
+}
+
+__global__ void norm_apply_kernel(const float* __restrict__ x, long long rows, int size, long long ld, const float* __restrict__ acc_sum,
+                                  const float* __restrict__ acc_sq, const float* __restrict__ acc_count, float eps, int inverse,
+                                  float* __restrict__ out, long long ld_out) {
+    __shared__ float s_mean[kNormMaxSize], s_std[kNormMaxSize];
+    if (threadIdx.x < size) {
+        const float cnt = fmaxf(acc_count[0], 1.f);
+        const float mean = __fdiv_rn(acc_sum[threadIdx.x], cnt);
+        const float var = __fsub_rn(__fdiv_rn(acc_sq[threadIdx.x], cnt), __fmul_rn(mean, mean));
+        s_mean[threadIdx.x] = mean;
+        s_std[threadIdx.x] = fmaxf(__fsqrt_rn(fmaxf(var, 0.f)), eps);
+    }
+    __syncthreads();
+    const long long n = rows * size;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / size;
+        const int c = (int)(i - r * size);
+        const float v = x[r * ld + c];
+        out[r * ld_out + c] = inverse ? __fadd_rn(__fmul_rn(v, s_std[c]), s_mean[c]) : __fdiv_rn(__fsub_rn(v, s_mean[c]), s_std[c]);
+    }
+}
+
+// out[r] = [ x[r, f0:f1] | one_hot(x[r, type_col], n_types) ]   (simulator.py:112-143)
+__global__ void node_features_kernel(const float* __restrict__ x, long long rows, long long ld, int f0, int f1, int type_col, int n_types,
+                                     float* __restrict__ out) {
+    const int w = (f1 - f0) + n_types;
+    const long long n = rows * w;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / w;
+        const int c = (int)(i - r * w);
+        float v;
+        if (c < f1 - f0) v = x[r * ld + f0 + c];
+        else v = ((int)x[r * ld + type_col] == c - (f1 - f0)) ? 1.f : 0.f;
+        out[i] = v;
+    }
+}
+int norm_grid(long long n) {
+    long long b = (n + 255) / 256;
+    if (b > gp::sm_count() * 8) b = gp::sm_count() * 8;
+    return b < 1 ? 1 : (int)b;
+}
+}  // namespace
+
+extern "C" int32_t gp_normalizer_blocks(void) { return kNormBlocks; }
+
+extern "C" int gp_normalizer_stats(const float* x, int64_t rows, int32_t size, int64_t ld, float* partials, void* stream) {
+    if (size < 1 || size > kNormMaxSize || rows < 0 || !partials || (rows > 0 && !x)) {
+        gp::set_error("gp_normalizer_stats: bad arguments (size 1..%d)", kNormMaxSize);
+        return -1;
+    }
+    norm_stats_kernel<<<kNormBlocks, kNormThreads, 0, static_cast<cudaStream_t>(stream)>>>(x, rows, size, ld, partials);
+    GP_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int gp_normalizer_update(const float* partials, int32_t size, int64_t rows, float* stats, float* acc_sum, float* acc_sum_squared,
+                                    float* acc_count, float* num_accumulations, float max_accumulations, void* stream) {
+    if (size < 1 || size > kNormMaxSize || !partials || (num_accumulations && (!acc_sum || !acc_sum_squared || !acc_count))) {
+        gp::set_error("gp_normalizer_update: bad arguments");
+        return -1;
+    }
+    norm_update_kernel<<<1, 2 * kNormMaxSize, 0, static_cast<cudaStream_t>(stream)>>>(partials, kNormBlocks, size, (float)rows, stats, acc_sum,
+                                                                                      acc_sum_squared, acc_count, num_accumulations,
+                                                                                      max_accumulations);
+    GP_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int gp_normalizer_accumulate(const float* stats, int32_t size, float* acc_sum, float* acc_sum_squared, float* acc_count,
+                                        float* num_accumulations, float max_accumulations, void* stream) {
+    if (size < 1 || size > kNormMaxSize || !stats || !acc_sum || !acc_sum_squared || !acc_count || !num_accumulations) {
+        gp::set_error("gp_normalizer_accumulate: bad arguments");
+        return -1;
+    }
+    norm_accumulate_kernel<<<1, 2 * kNormMaxSize, 0, static_cast<cudaStream_t>(stream)>>>(stats, size, acc_sum, acc_sum_squared, acc_count,
+                                                                                          num_accumulations, max_accumulations);
+    GP_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int gp_normalizer_apply(const float* x, int64_t rows, int32_t size, int64_t ld, const float* acc_sum, const float* acc_sum_squared,
+                                   const float* acc_count, float std_epsilon, int32_t inverse, float* out, int64_t ld_out, void* stream) {
+    if (size < 1 || size > kNormMaxSize || rows < 0 || !acc_sum || !acc_sum_squared || !acc_count || (rows > 0 && (!x || !out))) {
+        gp::set_error("gp_normalizer_apply: bad arguments (size 1..%d)", kNormMaxSize);
+        return -1;
+    }
+    if (rows == 0) return 0;
+    norm_apply_kernel<<<norm_grid(rows * size), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, rows, size, ld, acc_sum, acc_sum_squared,
+                                                                                             acc_count, std_epsilon, inverse, out, ld_out);
+    GP_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int gp_node_features(const float* x, int64_t rows, int64_t ld, int32_t feature_start, int32_t feature_end, int32_t node_type_col,
+                                int32_t num_types, float* out, void* stream) {
+    if (rows < 0 || feature_end < feature_start || num_types < 0 || (rows > 0 && (!x || !out))) {
+        gp::set_error("gp_node_features: bad arguments");
+        return -1;
+    }
+    if (rows == 0) return 0;
+    const long long n = rows * (long long)((feature_end - feature_start) + num_types);
+    node_features_kernel<<<norm_grid(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, rows, ld, feature_start, feature_end, node_type_col,
+                                                                                       num_types, out);
+    GP_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}

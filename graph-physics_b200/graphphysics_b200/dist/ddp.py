@@ -30,12 +30,20 @@ def _local_stats(norm, data: torch.Tensor):
     if norm._host_calls >= norm._max_accumulations:
         return None
     d = data.detach()
+    if norm._native(d):
+        from .. import ops
+        return ops.normalizer_update(ops.normalizer_stats(d), d.shape[0], want_stats=True)
     return torch.cat([d.sum(0), (d ** 2).sum(0), torch.full((1,), float(d.shape[0]), dtype=d.dtype, device=d.device)])   # (no H2D copy: capturable)
 
 
 def _apply_stats(norm, stats: torch.Tensor) -> None:
     """Normalizer._accumulate (layers.py:363-377) with the sums taken over all ranks."""
     k = (stats.numel() - 1) // 2
+    if stats.is_cuda and norm._acc_sum.is_cuda:
+        from .. import ops
+        ops.normalizer_accumulate(stats.contiguous(), norm)
+        norm._host_calls += 1
+        return
     gate = (norm._num_accumulations < norm._max_accumulations).to(torch.float32)     # device-side freeze (graph replay)
     norm._acc_sum += gate * stats[:k][None]
     norm._acc_sum_squared += gate * stats[k:2 * k][None]
@@ -51,7 +59,7 @@ def accumulate_normalizers_globally(sim, batch, group=None) -> None:
     pre = batch.x[:, sim.output_index_start:sim.output_index_end]
     items = [(sim._output_normalizer, batch.y - pre)]
     if sim._node_normalizer is not None:
-        items.append((sim._node_normalizer, sim._build_node_features(batch, sim._get_one_hot_type(batch)).float()))
+        items.append((sim._node_normalizer, sim.node_features(batch)))
     if sim._edge_normalizer is not None:
         items.append((sim._edge_normalizer, batch.edge_attr))
     live = [(n, st) for n, st in ((n, _local_stats(n, d)) for n, d in items) if st is not None]

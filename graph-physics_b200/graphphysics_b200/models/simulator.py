@@ -48,10 +48,18 @@ class Simulator(nn.Module):
     def _build_node_features(self, inputs, one_hot_type: torch.Tensor) -> torch.Tensor:
         return torch.cat([inputs.x[:, self.feature_index_start:self.feature_index_end], one_hot_type], dim=1)
 
+    def node_features(self, inputs) -> torch.Tensor:
+        """[features | one-hot node type] (simulator.py:112-143): one kernel for CUDA fp32 inputs (gp_node_features)."""
+        x = inputs.x
+        if x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 and x.stride(1) == 1:
+            from .. import ops
+            return ops.node_features(x, self.feature_index_start, self.feature_index_end, self.node_type_index, NodeType.SIZE)
+        return self._build_node_features(inputs, self._get_one_hot_type(inputs)).float()
+
     # simulator.py:145-176
     def _build_input_graph(self, inputs, is_training: bool):
         target_delta_normalized = self._get_target_normalized(inputs, is_training)
-        node_features = self._node_normalizer(self._build_node_features(inputs, self._get_one_hot_type(inputs)), is_training)
+        node_features = self._node_normalizer(self.node_features(inputs), is_training)
         edge_attr = inputs.edge_attr
         if self._edge_normalizer is not None:
             edge_attr = self._edge_normalizer(edge_attr, is_training)

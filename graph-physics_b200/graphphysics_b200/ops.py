@@ -495,3 +495,57 @@ def halo_unpack_add(x: torch.Tensor, dst_rows: torch.Tensor, rowptr: torch.Tenso
                                    C.c_void_p(ptr(order)), C.c_int32(dst_rows.numel()), C.c_int32(x.shape[1]), C.c_void_p(ptr(rows)),
                                    C.c_void_p(stream_ptr())), "gp_halo_unpack_add")
     _launched()
+
+
+# ---------------------------------------------------------------------------------------------- normaliser / node features
+def normalizer_stats(x: torch.Tensor) -> torch.Tensor:
+    """Per-block column sums of x and x^2 (gp_normalizer_stats): [blocks, 2 * size] fp32."""
+    lib().gp_normalizer_blocks.restype = C.c_int32
+    part = torch.empty((lib().gp_normalizer_blocks(), 2 * x.shape[1]), dtype=torch.float32, device=x.device)
+    check(lib().gp_normalizer_stats(C.c_void_p(ptr(x)), C.c_int64(x.shape[0]), C.c_int32(x.shape[1]), C.c_int64(x.stride(0)),
+                                    C.c_void_p(ptr(part)), C.c_void_p(stream_ptr())), "gp_normalizer_stats")
+    _launched()
+    return part
+
+
+def normalizer_update(part: torch.Tensor, rows: int, norm=None, want_stats: bool = False) -> Optional[torch.Tensor]:
+    """Sum the block partials; with `norm` also Normalizer._accumulate (gated on the device); with want_stats return
+    [sum | sum of squares | rows]."""
+    size = part.shape[1] // 2
+    stats = torch.empty(2 * size + 1, dtype=torch.float32, device=part.device) if want_stats else None
+    acc = (norm._acc_sum, norm._acc_sum_squared, norm._acc_count, norm._num_accumulations) if norm is not None else (None,) * 4
+    check(lib().gp_normalizer_update(C.c_void_p(ptr(part)), C.c_int32(size), C.c_int64(rows), C.c_void_p(ptr(stats)),
+                                     *(C.c_void_p(ptr(t)) for t in acc), C.c_float(float(norm._max_accumulations) if norm is not None else 0.0),
+                                     C.c_void_p(stream_ptr())), "gp_normalizer_update")
+    _launched()
+    return stats
+
+
+def normalizer_accumulate(stats: torch.Tensor, norm) -> None:
+    """Normalizer._accumulate from a [sum | sum of squares | rows] vector (gp_normalizer_accumulate)."""
+    size = (stats.numel() - 1) // 2
+    check(lib().gp_normalizer_accumulate(C.c_void_p(ptr(stats)), C.c_int32(size), C.c_void_p(ptr(norm._acc_sum)),
+                                         C.c_void_p(ptr(norm._acc_sum_squared)), C.c_void_p(ptr(norm._acc_count)),
+                                         C.c_void_p(ptr(norm._num_accumulations)), C.c_float(float(norm._max_accumulations)),
+                                         C.c_void_p(stream_ptr())), "gp_normalizer_accumulate")
+    _launched()
+
+
+def normalizer_apply(norm, x: torch.Tensor, inverse: bool = False) -> torch.Tensor:
+    """(x - mean) / max(std, eps) or its inverse from the accumulators of `norm` (gp_normalizer_apply)."""
+    out = torch.empty((x.shape[0], x.shape[1]), dtype=torch.float32, device=x.device)
+    check(lib().gp_normalizer_apply(C.c_void_p(ptr(x)), C.c_int64(x.shape[0]), C.c_int32(x.shape[1]), C.c_int64(x.stride(0)),
+                                    C.c_void_p(ptr(norm._acc_sum)), C.c_void_p(ptr(norm._acc_sum_squared)), C.c_void_p(ptr(norm._acc_count)),
+                                    C.c_float(norm._eps_host), C.c_int32(int(inverse)), C.c_void_p(ptr(out)), C.c_int64(out.stride(0)),
+                                    C.c_void_p(stream_ptr())), "gp_normalizer_apply")
+    _launched()
+    return out
+
+
+def node_features(x: torch.Tensor, f0: int, f1: int, type_col: int, num_types: int) -> torch.Tensor:
+    """[x[:, f0:f1] | one_hot(x[:, type_col], num_types)] in one launch (gp_node_features)."""
+    out = torch.empty((x.shape[0], (f1 - f0) + num_types), dtype=torch.float32, device=x.device)
+    check(lib().gp_node_features(C.c_void_p(ptr(x)), C.c_int64(x.shape[0]), C.c_int64(x.stride(0)), C.c_int32(f0), C.c_int32(f1),
+                                 C.c_int32(type_col), C.c_int32(num_types), C.c_void_p(ptr(out)), C.c_void_p(stream_ptr())), "gp_node_features")
+    _launched()
+    return out

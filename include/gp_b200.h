@@ -408,6 +408,28 @@ int gp_add_noise(float* x, int32_t ld, int32_t rows, int32_t col_start, int32_t 
                  const float* noise, float scale, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Online feature normaliser and the Simulator's node features (graphphysics/models/layers.py:281-408 Normalizer,
+ * graphphysics/models/simulator.py:112-143 one-hot node type + feature slice).  fp32, rows of `size` <= 64 values.
+ *   gp_normalizer_stats      : per-block column sums of x and x^2 -> partials [gp_normalizer_blocks()][2 * size]
+ *   gp_normalizer_update     : fixed-order sum of the partials -> stats [sum | sum of squares | rows] (2 * size + 1 floats,
+ *                              may be NULL) and, when num_accumulations is given, Normalizer._accumulate (layers.py:363-377)
+ *                              gated on the device by num_accumulations < max_accumulations (the freeze of layers.py:347)
+ *   gp_normalizer_accumulate : the same accumulation from a stats vector (e.g. summed over ranks by an all-reduce)
+ *   gp_normalizer_apply      : out = (x - mean) / max(std, eps), or with inverse != 0  out = x * max(std, eps) + mean
+ *   gp_node_features         : out[r] = [ x[r, feature_start:feature_end] | one_hot(x[r, node_type_col], num_types) ]
+ * --------------------------------------------------------------------------------------------- */
+int32_t gp_normalizer_blocks(void);
+int gp_normalizer_stats(const float* x, int64_t rows, int32_t size, int64_t ld, float* partials, void* stream);
+int gp_normalizer_update(const float* partials, int32_t size, int64_t rows, float* stats, float* acc_sum, float* acc_sum_squared,
+                         float* acc_count, float* num_accumulations, float max_accumulations, void* stream);
+int gp_normalizer_accumulate(const float* stats, int32_t size, float* acc_sum, float* acc_sum_squared, float* acc_count,
+                             float* num_accumulations, float max_accumulations, void* stream);
+int gp_normalizer_apply(const float* x, int64_t rows, int32_t size, int64_t ld, const float* acc_sum, const float* acc_sum_squared,
+                        const float* acc_count, float std_epsilon, int32_t inverse, float* out, int64_t ld_out, void* stream);
+int gp_node_features(const float* x, int64_t rows, int64_t ld, int32_t feature_start, int32_t feature_end, int32_t node_type_col,
+                     int32_t num_types, float* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Variant flags of the path (graphphysics/models/layers.py:213-249 GatedMLP with SiLU / GELU, 410-491 RoPE on
  * q / k, 637-697 gated attention, 989-1149 GraphNetBlock with use_rope / use_gate): row-wise fp32 kernels around gp_gemm.
  *   kind: 1 ReLU, 2 SiLU, 3 GELU (exact).  gp_act_bwd multiplies d in place by act'(z).  gp_glu_*: g = act(a1) * a2 on
