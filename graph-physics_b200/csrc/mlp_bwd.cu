@@ -78,6 +78,10 @@ __global__ void __launch_bounds__(BwdCfg<H>::NT, 1) mlp_bwd_kernel(const gp_mlp_
 
     const int tid = threadIdx.x;
     const int row = tid & 127, part = tid >> 7;
+#ifdef GP_MLP_PROF
+    long long t_entry = 0;
+    if (p.prof && blockIdx.x == 0 && tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_entry));
+#endif
     // option tables of the specialised instantiations:    general, edge B, edge A, node B, node A
     constexpr bool F = MODE != 0, F1 = MODE == 1;
     constexpr bool kNorm[5]   = {false, true,  false, true,  false};
@@ -205,7 +209,11 @@ __global__ void __launch_bounds__(BwdCfg<H>::NT, 1) mlp_bwd_kernel(const gp_mlp_
 
 #ifdef GP_MLP_PROF
     const bool prof = p.prof != nullptr && tid == 0;      // phase timing (scratch/phase*.py): lib/libgp_b200_prof.so only
+#define BWD_STAMP(slot_) do { if (prof && blockIdx.x == 0) { long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); p.prof[slot_] = (unsigned long long)(t_ - t_entry); } } while (0)
 #else
+#define BWD_STAMP(slot_) do { } while (0)
+#endif
+#ifndef GP_MLP_PROF
     constexpr bool prof = false;                        // the product build carries no profiling code
 #endif
     long long tk = 0;
@@ -232,6 +240,7 @@ __global__ void __launch_bounds__(BwdCfg<H>::NT, 1) mlp_bwd_kernel(const gp_mlp_
         }
     };
     if ((int)blockIdx.x < n_tiles) load_idx(blockIdx.x);
+    BWD_STAMP(16);        // ns from kernel entry: prologue done (weights staged, previous kernel finished)
     bool first = true;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, first = false) {
         if (prof) { tk = clock64(); atomicAdd(p.prof + 15, 1ull); }
@@ -289,6 +298,19 @@ __global__ void __launch_bounds__(BwdCfg<H>::NT, 1) mlp_bwd_kernel(const gp_mlp_
                 const int i = tid + j * NT;
                 const int r = i / KC, ch = i % KC;
                 cp_async16(qb_s + sw128_off(128, r, ch * 8), p.gy_bf16 + (size_t)min(R0 + r, p.rows - 1) * p.ld_gy + ch * 8);
+            }
+        }
+        if (MODE == 3) {
+            // node stage B: the fp32 upstream gradient tile, coalesced, into the two buffers that are idle until E2 writes
+            // delta_b / q into them: columns 0-63 -> qb, 64-127 -> db, rows of 256 bytes with their sixteen 16-byte chunks
+            // swizzled by the row (thread = row reads of E2 are then conflict-free).  Read row-per-thread straight from
+            // global memory, these 64 KB cost 11 k of the tile's 22 k cycles (32 lines per load instruction).
+#pragma unroll
+            for (int j = 0; j < 4096 / NT; ++j) {
+                const int i = tid + j * NT;
+                const int r = i >> 5, ch = i & 31;
+                const uint32_t dst = ((ch & 16) ? db_s : qb_s) + r * 256 + (((ch & 15) ^ (r & 15)) << 4);
+                cp_async16(dst, p.gy_f32 + (size_t)min(R0 + r, p.rows - 1) * p.ld_gy + ch * 4);
             }
         }
         if (has_init) {   // gathered pre-activation rows of the randomly indexed source -> ha
@@ -418,6 +440,8 @@ __global__ void __launch_bounds__(BwdCfg<H>::NT, 1) mlp_bwd_kernel(const gp_mlp_
                     }
                 }
             }
+            if (MODE == 3)      // the next tile's fp32 gradient rows: 512 lines, one per thread
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(p.gy_f32 + (size_t)min(Rn + (tid >> 2), p.rows - 1) * p.ld_gy + (tid & 3) * 32));
             if (has_init && stage1 && tid < 128)
                 for (int c = 0; c < H; c += 64)
                     asm volatile("prefetch.global.L2 [%0];" ::"l"(p.init + (size_t)i0n * p.ld_init + p.init_off0 + c));
@@ -465,6 +489,13 @@ __global__ void __launch_bounds__(BwdCfg<H>::NT, 1) mlp_bwd_kernel(const gp_mlp_
                 if (du_smem) {
                     unpack8(*reinterpret_cast<const uint4*>(qb + sw128_off(128, row, c0)), du);
                     if (f_gather) acc8(*reinterpret_cast<const uint4*>(db + sw128_off(128, row, c0)), du);
+                } else if (MODE == 3) {      // staged in P0 (see there)
+                    const uint8_t* base = (c0 >= 64 ? db : qb) + row * 256;
+                    const int cc = (c0 & 63) >> 2;
+                    const float4 t0 = *reinterpret_cast<const float4*>(base + ((cc ^ (row & 15)) << 4));
+                    const float4 t1 = *reinterpret_cast<const float4*>(base + (((cc + 1) ^ (row & 15)) << 4));
+                    du[0] = t0.x; du[1] = t0.y; du[2] = t0.z; du[3] = t0.w;
+                    du[4] = t1.x; du[5] = t1.y; du[6] = t1.z; du[7] = t1.w;
                 } else {
                     if (f_gyf32) {
                         const float4* gp_ = reinterpret_cast<const float4*>(p.gy_f32 + (size_t)crow * p.ld_gy + c0);
@@ -720,6 +751,7 @@ __global__ void __launch_bounds__(BwdCfg<H>::NT, 1) mlp_bwd_kernel(const gp_mlp_
         tick(11);     // E4 + output
     }
 
+    BWD_STAMP(17);        // ... tile loop done
     if ((t_da || t_out) && warp == 0 && elect_one()) tma_store_wait_all();
     __syncthreads();      // the staging tile below reuses buffers the last bulk stores were reading
     // ---- dump the weight-gradient accumulators of this CTA (lane r <-> output row r)
@@ -749,6 +781,7 @@ __global__ void __launch_bounds__(BwdCfg<H>::NT, 1) mlp_bwd_kernel(const gp_mlp_
     }
     tc_fence_before();
     __syncthreads();
+    BWD_STAMP(18);        // ... partial blocks written
     if (tid < 32) tmem_dealloc(tmem, 512);
 }
 
