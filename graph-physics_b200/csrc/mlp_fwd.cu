@@ -199,6 +199,16 @@ __global__ void __launch_bounds__(kSlotThreads * NG, 1) mlp_fwd_kernel(const gp_
         const int grow = R0 + row;
         const bool valid = grow < p.rows;
 
+        // the residual rows are read at the very end of the tile (output pass): pull them into L2 now.  In the node update
+        // they are x, which this kernel has not touched yet (the layer-0 operand is agg): read cold, the output pass took
+        // 5 k of the tile's 22 k cycles
+        if (f_resid && f_ybf) {
+            constexpr int kLines = 128 * (H * 2 / 128 > 0 ? H * 2 / 128 : 1);
+            for (int i = t; i < kLines; i += kSlotThreads) {
+                const int r = i / (kLines / 128), part_ = i % (kLines / 128);
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(p.resid + (size_t)min(R0 + r, p.rows - 1) * p.ld_out + part_ * 64));
+            }
+        }
         // (a) segment ids of the tile (+ one row of context on each side): requested now, stored
         //     to shared memory later so their latency is not exposed
         int sid_me = -1, sid_prev = -1, sid_next = -1;
