@@ -141,6 +141,24 @@ __global__ void __launch_bounds__(256, 1) linear_bwd_kernel(const gp_linear_bwd_
             }
             mma_commit(&mma_bar);
         }
+        // the next tile of this CTA: everything its loads will ask for goes to L2 now (bulk tiles by the copy engine, the
+        // fp32 rows one prefetch per 128-byte line), so that they wait on L2 instead of HBM
+        if (tile + (int)gridDim.x < n_tiles) {
+            const int Rn = (tile + (int)gridDim.x) << 7;
+            if (warp == 0 && elect_one()) {
+                if (maps.use & 1u)
+                    for (int b = 0; b < (H + 63) >> 6; ++b) tma_prefetch_2d(&maps.x, b * 64, Rn);
+#pragma unroll
+                for (int s = 0; s < 3; ++s)
+                    if (s < S && (maps.use & (2u << s)))
+                        for (int b = 0; b < (H + 63) >> 6; ++b) tma_prefetch_2d(&maps.src[s], b * 64, Rn);
+            }
+            if (p.dx_in) {
+                constexpr int LPR = (H * 4 / 128) > 0 ? H * 4 / 128 : 1;       // 128-byte lines per fp32 row
+                for (int i = tid; i < 128 * LPR; i += 256)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(p.dx_in + (size_t)min(Rn + i / LPR, p.rows - 1) * H + (i % LPR) * 32));
+            }
+        }
         // while the tensor core runs: the incoming dX rows of this tile (row-major chunks)
         float4 din[FPT];
         if (p.dx_in) {
