@@ -246,6 +246,8 @@ __global__ void segsum_gather_kernel(const gp_bf16* __restrict__ src, int ld, co
     const int lane = threadIdx.x & 31;
     if (seg >= num_segments) return;
     const int b = rowptr[seg], e = rowptr[seg + 1];
+    pdl_wait();                 // (the layout is older than the previous kernel; its rows are read from here on)
+    pdl_launch_dependents();
     float acc[VPT];
 #pragma unroll
     for (int i = 0; i < VPT; ++i) acc[i] = 0.f;
@@ -328,12 +330,11 @@ static int segsum_gather_launch(const gp_bf16* src, int32_t ld, const int32_t* p
     const int blocks = (int)(((size_t)num_segments * 32 + threads - 1) / threads);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     switch (hidden) {
-        case 128: segsum_gather_kernel<4, OutT><<<blocks, threads, 0, st>>>(src, ld, perm, rowptr, num_segments, out); break;
-        case 64: segsum_gather_kernel<2, OutT><<<blocks, threads, 0, st>>>(src, ld, perm, rowptr, num_segments, out); break;
-        case 32: segsum_gather_kernel<1, OutT><<<blocks, threads, 0, st>>>(src, ld, perm, rowptr, num_segments, out); break;
+        case 128: GP_CHECK_CUDA(gp::launch_kernel(segsum_gather_kernel<4, OutT>, dim3(blocks), dim3(threads), 0, st, src, (int)ld, perm, rowptr, (int)num_segments, out)); break;
+        case 64: GP_CHECK_CUDA(gp::launch_kernel(segsum_gather_kernel<2, OutT>, dim3(blocks), dim3(threads), 0, st, src, (int)ld, perm, rowptr, (int)num_segments, out)); break;
+        case 32: GP_CHECK_CUDA(gp::launch_kernel(segsum_gather_kernel<1, OutT>, dim3(blocks), dim3(threads), 0, st, src, (int)ld, perm, rowptr, (int)num_segments, out)); break;
         default: gp::set_error("gp_segsum_gather: unsupported hidden size %d", hidden); return -1;
     }
-    GP_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
 

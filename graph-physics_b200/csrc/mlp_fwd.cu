@@ -505,6 +505,9 @@ __global__ void __launch_bounds__(256) seg_fixup_kernel(const int32_t* __restric
         e = rowptr[seg + 1];
         flagged = (s == e) || ((s >> sub_shift) != ((e - 1) >> sub_shift));
     }
+    // the graph layout above is older than the previous kernel; its boundary partials are read from here on
+    pdl_wait();
+    pdl_launch_dependents();
     unsigned todo = __ballot_sync(0xffffffffu, flagged);
     const int c4 = lane * 4;
     while (todo) {
@@ -626,9 +629,8 @@ static int seg_fixup_launch(const int32_t* rowptr, int32_t num_segments, int32_t
     while ((1 << shift) < sub_rows) ++shift;
     const int threads = 256;
     const int blocks = (num_segments + threads - 1) / threads;
-    seg_fixup_kernel<OutT><<<blocks, threads, 0, static_cast<cudaStream_t>(stream)>>>(rowptr, num_segments, hidden, shift,
-                                                                                       seg_bnd, seg_out);
-    GP_CHECK_CUDA(cudaGetLastError());
+    GP_CHECK_CUDA(gp::launch_kernel(seg_fixup_kernel<OutT>, dim3(blocks), dim3(threads), 0, static_cast<cudaStream_t>(stream), rowptr,
+                                    (int)num_segments, (int)hidden, shift, seg_bnd, seg_out));
     return 0;
 }
 
