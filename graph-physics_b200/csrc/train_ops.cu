@@ -259,19 +259,37 @@ __global__ void __launch_bounds__(kNormThreads) norm_stats_kernel(const float* _
     }
 }
 
-__global__ void norm_update_kernel(const float* __restrict__ partials, int n_blocks, int size, float rows, float* __restrict__ stats,
-                                   float* acc_sum, float* acc_sq, float* acc_count, float* num_acc, float max_acc) {
-    const int c = threadIdx.x;
+__global__ void __launch_bounds__(1024) norm_update_kernel(const float* __restrict__ partials, int n_blocks, int size, float rows,
+                                                           float* __restrict__ stats, float* acc_sum, float* acc_sq, float* acc_count,
+                                                           float* num_acc, float max_acc) {
+    // thread (group g, column c): group g adds the block partials g, g + 8, ... in ascending order (independent loads, four
+    // in flight), then the eight group sums are added in fixed order -- a serial walk over all blocks is one long chain of
+    // L2 latencies (16 us for 296 blocks)
+    __shared__ float sh[8][2 * kNormMaxSize];
+    const int c = threadIdx.x & (2 * kNormMaxSize - 1), g = threadIdx.x / (2 * kNormMaxSize);
     float v = 0.f;
-    if (c < 2 * size)
-        for (int b = 0; b < n_blocks; ++b) v += partials[(size_t)b * 2 * size + c];
+    if (c < 2 * size) {
+        int b = g;
+        for (; b + 24 < n_blocks; b += 32) {
+            const float p0 = partials[(size_t)b * 2 * size + c], p1 = partials[(size_t)(b + 8) * 2 * size + c];
+            const float p2 = partials[(size_t)(b + 16) * 2 * size + c], p3 = partials[(size_t)(b + 24) * 2 * size + c];
+            v += p0; v += p1; v += p2; v += p3;
+        }
+        for (; b < n_blocks; b += 8) v += partials[(size_t)b * 2 * size + c];
+    }
+    sh[g][c] = v;
+    __syncthreads();
+    if (g != 0) return;
+    v = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v += sh[k][c];
     if (stats) {
         if (c < 2 * size) stats[c] = v;
         if (c == 0) stats[2 * size] = rows;
     }
     if (num_acc) {
         const float gate = (num_acc[0] < max_acc) ? 1.f : 0.f;
-        __syncthreads();                                  // every thread has read the counter before it moves
+        asm volatile("bar.sync 1, %0;" ::"n"(2 * kNormMaxSize) : "memory");      // group 0: everyone has read the counter before it moves
         if (c < size) acc_sum[c] += gate * v;
         else if (c < 2 * size) acc_sq[c - size] += gate * v;
         if (c == 0) {
@@ -354,7 +372,7 @@ extern "C" int gp_normalizer_update(const float* partials, int32_t size, int64_t
         gp::set_error("gp_normalizer_update: bad arguments");
         return -1;
     }
-    norm_update_kernel<<<1, 2 * kNormMaxSize, 0, static_cast<cudaStream_t>(stream)>>>(partials, kNormBlocks, size, (float)rows, stats, acc_sum,
+    norm_update_kernel<<<1, 16 * kNormMaxSize, 0, static_cast<cudaStream_t>(stream)>>>(partials, kNormBlocks, size, (float)rows, stats, acc_sum,
                                                                                       acc_sum_squared, acc_count, num_accumulations,
                                                                                       max_accumulations);
     GP_CHECK_CUDA(cudaGetLastError());
