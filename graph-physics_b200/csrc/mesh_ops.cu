@@ -414,6 +414,44 @@ extern "C" int gp_world_pairs_fill(const float* pos, int32_t ld_pos, const float
     return 0;
 }
 
+// k-hop adjacency, one hop (graphphysics/utils/torch_graph.py:14-54: adj_k <- adj_k + adj_k . adj without self loops): every
+// entry (i, j) of adj_k contributes itself and (i, l) for every neighbour l of j in adj; a would-be self loop (l == i) is
+// written as (i, j) again, so no compaction is needed before gp_coalesce_*.  offsets = exclusive prefix sum over the entries of
+// 1 + deg_adj(col); adj is given as CSR over its rows (rowptr, col sorted by row).
+namespace {
+__global__ void khop_candidates_kernel(const int64_t* __restrict__ rowk, const int64_t* __restrict__ colk, long long nk,
+                                       const int64_t* __restrict__ rowptr, const int64_t* __restrict__ adj_col,
+                                       const int64_t* __restrict__ offsets, int64_t* __restrict__ cand_row, int64_t* __restrict__ cand_col) {
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < nk; e += (long long)gridDim.x * blockDim.x) {
+        const int64_t i = rowk[e], j = colk[e];
+        int64_t o = offsets[e];
+        cand_row[o] = i;
+        cand_col[o] = j;
+        ++o;
+        for (int64_t q = rowptr[j]; q < rowptr[j + 1]; ++q, ++o) {
+            const int64_t l = adj_col[q];
+            cand_row[o] = i;
+            cand_col[o] = (l == i) ? j : l;
+        }
+    }
+}
+}  // namespace
+
+extern "C" int gp_khop_candidates(const int64_t* rowk, const int64_t* colk, int64_t num_entries, const int64_t* adj_rowptr,
+                                  const int64_t* adj_col, const int64_t* offsets, int64_t* cand_row, int64_t* cand_col, void* stream) {
+    if (num_entries < 0 || (num_entries > 0 && (!rowk || !colk || !adj_rowptr || !adj_col || !offsets || !cand_row || !cand_col))) {
+        gp::set_error("gp_khop_candidates: bad arguments");
+        return -1;
+    }
+    if (num_entries == 0) return 0;
+    long long blocks = (num_entries + 255) / 256;
+    if (blocks > gp::sm_count() * 16) blocks = gp::sm_count() * 16;
+    khop_candidates_kernel<<<(int)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(rowk, colk, num_entries, adj_rowptr, adj_col, offsets,
+                                                                                      cand_row, cand_col);
+    GP_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
 extern "C" int gp_add_noise(float* x, int32_t ld, int32_t rows, int32_t col_start, int32_t col_end, int32_t node_type_col, int32_t normal_type,
                             const float* noise, float scale, void* stream) {
     const int width = col_end - col_start;

@@ -78,6 +78,47 @@ def face_to_edge(graph):
     return graph
 
 
+def k_hop_edge_index(edge_index: torch.Tensor, num_hops: int, num_nodes: int) -> torch.Tensor:
+    """compute_k_hop_edge_index (graphphysics/utils/torch_graph.py:14-54): the pattern of adj_k <- adj_k + adj_k . adj with
+    self loops removed, (num_hops - 1) times, sorted by (row, col).  Per hop: gp_khop_candidates + the coalesce kernels."""
+    _cuda(edge_index, "edge_index")
+    ei = edge_index.long().contiguous()
+    adj = coalesce(ei[0], ei[1], num_nodes)                          # sorted by (row, col), duplicates merged
+    if num_hops <= 1:
+        return adj
+    deg = torch.bincount(adj[0], minlength=num_nodes)
+    rowptr = torch.zeros(num_nodes + 1, dtype=torch.int64, device=ei.device)
+    rowptr[1:] = torch.cumsum(deg, 0)
+    adj_col = adj[1].contiguous()
+    cur = adj
+    for _ in range(num_hops - 1):
+        cur = cur[:, cur[0] != cur[1]]                                # (a self loop in the input adjacency)
+        rk, ck = cur[0].contiguous(), cur[1].contiguous()
+        per = 1 + deg[ck]
+        offsets = torch.cumsum(per, 0) - per
+        total = int(per.sum().item())                                 # size of the candidate list: one host round trip per hop
+        cand = torch.empty((2, total), dtype=torch.int64, device=ei.device)
+        check(lib().gp_khop_candidates(C.c_void_p(ptr(rk)), C.c_void_p(ptr(ck)), C.c_int64(rk.numel()), C.c_void_p(ptr(rowptr)),
+                                       C.c_void_p(ptr(adj_col)), C.c_void_p(ptr(offsets)), C.c_void_p(ptr(cand[0])), C.c_void_p(ptr(cand[1])),
+                                       C.c_void_p(stream_ptr())), "gp_khop_candidates")
+        ops._launched()
+        cur = coalesce(cand[0], cand[1], num_nodes)
+    return cur
+
+
+def k_hop_graph(graph, num_hops: int, add_edge_features_to_khop: bool = False):
+    """compute_k_hop_graph (torch_graph.py:57-105): the graph with its k-hop edge_index, optionally with fresh
+    [pos_i - pos_j, distance] edge features."""
+    if num_hops == 1:
+        return graph
+    n = graph.x.shape[0] if graph.x is not None else graph.pos.shape[0]
+    out = graph.clone() if hasattr(graph, "clone") else graph
+    out.edge_index = k_hop_edge_index(graph.edge_index, num_hops, n)
+    if add_edge_features_to_khop:
+        out.edge_attr = edge_features(out.pos, out.edge_index)
+    return out
+
+
 def edge_features(pos: torch.Tensor, edge_index: torch.Tensor, out: Optional[torch.Tensor] = None, col: int = 0) -> torch.Tensor:
     """[pos[row] - pos[col], ||pos[col] - pos[row]||] per edge (fp32, dim + 1 columns), optionally written into columns
     [col, col + dim + 1) of an existing [E, >=] buffer."""

@@ -389,6 +389,9 @@ int gp_colsum(const float* src, int32_t ld, int32_t rows, int32_t cols, int32_t 
  *                             int32) = number of unordered pairs; gp_world_pairs_fill writes both directions of every
  *                             pair (2 * num_pairs entries).  workspace: gp_world_pairs_workspace_bytes(num_nodes)
  *   gp_add_noise            : x[r, col_start:col_end] += noise[r, :] * scale where x[r, node_type_col] == normal_type
+ *   gp_khop_candidates      : one hop of compute_k_hop_edge_index (graphphysics/utils/torch_graph.py:14-54): for every entry (i, j)
+ *                             of adj_k the candidates (i, j) and (i, l), l in adj[j] (a self loop is written as (i, j) again), at
+ *                             offsets[e] = exclusive prefix sum of 1 + deg_adj(col); gp_coalesce_* then gives adj_k + adj_k . adj
  * --------------------------------------------------------------------------------------------- */
 int gp_cell_edge_candidates(const int64_t* cells, int64_t n_cells, int32_t verts_per_cell, int32_t cell_major, int64_t* cand_row,
                             int64_t* cand_col, void* stream);
@@ -404,6 +407,8 @@ int gp_world_pairs_count(const float* pos, int32_t ld_pos, const float* node_typ
                          int32_t normal_type, int32_t obstacle_type, void* workspace, int32_t* num_pairs, void* stream);
 int gp_world_pairs_fill(const float* pos, int32_t ld_pos, const float* node_type, int32_t ld_type, int32_t num_nodes, double radius,
                         int32_t obstacle_type, void* workspace, int64_t* out_row, int64_t* out_col, void* stream);
+int gp_khop_candidates(const int64_t* rowk, const int64_t* colk, int64_t num_entries, const int64_t* adj_rowptr, const int64_t* adj_col,
+                       const int64_t* offsets, int64_t* cand_row, int64_t* cand_col, void* stream);
 int gp_add_noise(float* x, int32_t ld, int32_t rows, int32_t col_start, int32_t col_end, int32_t node_type_col, int32_t normal_type,
                  const float* noise, float scale, void* stream);
 

@@ -200,3 +200,38 @@ def test_graph_construction_edge_cases():
     g4 = P.add_world_edges(Data(x=_t(x), edge_index=g.edge_index.clone()), 0, 3, 3, radius=10.0)
     ref = O.world_edges(g.edge_index.cpu().numpy(), pos, x[:, 3].astype(np.int64), 6, 10.0)
     assert np.array_equal(g4.edge_index.cpu().numpy(), ref) and g4.edge_index.shape[1] > 12
+
+
+@pytest.mark.parametrize("hops", [1, 2, 3])
+def test_k_hop_edges_bit_exact(hops):
+    """compute_k_hop_edge_index (graphphysics/utils/torch_graph.py:14-54) on the device: bit-exact against the oracle's sparse
+    matrix powers; 32 638 edges at two hops on the reference's cylinder mesh (tests/graphphysics/dataset/test_xdmfdataset.py)."""
+    from graphphysics_b200.preprocessing import k_hop_edge_index, k_hop_graph
+    from graphphysics_b200.graph import Data
+    from oracle import gp_oracle as O
+    c = np.load(os.path.join(G, "cylinder_mesh.npz"))
+    ei = O.face_to_edge(c["triangles"], 1923)
+    got = k_hop_edge_index(_t(ei), hops, 1923)
+    ref = O.khop_edges(ei, 1923, hops)
+    assert got.dtype == torch.int64 and np.array_equal(got.cpu().numpy(), ref)
+    if hops == 2:
+        assert got.shape[1] == 32638
+        g = k_hop_graph(Data(x=torch.zeros(1923, 1, device="cuda"), pos=_t(c["points"][:, :2].astype(np.float32)), edge_index=_t(ei)), 2, True)
+        assert tuple(g.edge_attr.shape) == (32638, 3)
+        np.testing.assert_array_equal(g.edge_attr.cpu().numpy(), O.edge_features(c["points"][:, :2].astype(np.float32), ref))
+
+
+def test_k_hop_edge_cases():
+    from graphphysics_b200.preprocessing import k_hop_edge_index
+    from oracle import gp_oracle as O
+    # a path 0-1-2-3 plus an isolated node, duplicate entries and a self loop in the input
+    ei = np.array([[0, 1, 1, 2, 2, 3, 1, 2], [1, 0, 2, 1, 3, 2, 2, 2]])
+    for hops in (1, 2, 3, 4):
+        got = k_hop_edge_index(_t(ei), hops, 5).cpu().numpy()
+        ref = O.khop_edges(ei, 5, hops) if hops > 1 else np.unique(ei[0] * 5 + ei[1])
+        if hops == 1:
+            assert np.array_equal(got[0] * 5 + got[1], ref)          # coalesced input, self loop kept (the reference's adj.indices())
+        else:
+            assert np.array_equal(got, ref), hops
+    empty = k_hop_edge_index(torch.zeros((2, 0), dtype=torch.int64, device="cuda"), 3, 4)
+    assert tuple(empty.shape) == (2, 0)
