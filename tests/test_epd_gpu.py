@@ -185,3 +185,31 @@ def test_epd_edge_case_graphs(n_nodes, n_edges, hidden):
     assert all(torch.isfinite(g).all() for g in grads.values())
     if n_edges == 0:                                            # no message ever reaches the edge MLPs
         assert float(grads["processor_list.0.edge_block.6.weight"].abs().max()) == 0.0
+
+
+def test_side_stream_scheduling_does_not_change_results(monkeypatch):
+    """The engine runs the per-layer gradient reduction, the receiver-side fix-up and the node encoder on side streams
+    (GP_B200_SIDE_REDUCE, default on).  Same kernels, same order of every sum: output and gradients are bit-identical to the
+    single-stream schedule (the captured-graph form of the same schedule is what tests/test_trainer_gpu.py replays)."""
+    from graphphysics_b200.graph import Data
+    from graphphysics_b200.models.processors import EncodeProcessDecode
+    from graphphysics_b200.synthetic import cylinder_flow_batch
+    dev = torch.device("cuda:0")
+    b = cylinder_flow_batch(4, seed=3).to(dev)
+    torch.manual_seed(0)
+    x, Gm = torch.randn(b.x.shape[0], 11, device=dev), torch.randn(b.x.shape[0], 2, device=dev)
+    res = {}
+    for side in ("0", "1"):
+        monkeypatch.setenv("GP_B200_SIDE_REDUCE", side)
+        torch.manual_seed(1)
+        m = EncodeProcessDecode(4, 11, 3, 2, hidden_size=128).to(dev)
+        assert m.engine._side_reduce == (side == "1")
+        outs = []
+        for _ in range(2):                       # twice: the partial-gradient sets alternate between layers and steps
+            out = m(Data(x=x, edge_index=b.edge_index, edge_attr=b.edge_attr))
+            (out * Gm).sum().backward()
+            outs.append((out.detach().clone(), m.engine.gflat.clone()))
+            m.zero_grad(set_to_none=True)
+        res[side] = outs
+    for (o0, g0), (o1, g1) in zip(res["0"], res["1"]):
+        assert torch.equal(o0, o1) and torch.equal(g0, g1)
