@@ -165,11 +165,6 @@ __global__ void __launch_bounds__(BwdCfg<H>::NT, 1) mlp_bwd_kernel(const gp_mlp_
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    // everything above is independent of the previous kernel in the stream (parameters only); from here on
-    // its outputs are read, and the next kernel may start its own prologue
-    pdl_wait();
-    pdl_launch_dependents();
-
     const uint32_t tmem = tmem_slot;
     const uint32_t tlane = tmem_addr(tmem, (row >> 5) * 32, 0);
     const uint32_t ain_s = smem_u32(ain), ha_s = smem_u32(ha), db_s = smem_u32(db), qb_s = smem_u32(qb);
@@ -239,7 +234,47 @@ __global__ void __launch_bounds__(BwdCfg<H>::NT, 1) mlp_bwd_kernel(const gp_mlp_
             i0n = (MODE == 2 || p.idx0) ? __ldg(p.idx0 + r) : r;
         }
     };
-    if ((int)blockIdx.x < n_tiles) load_idx(blockIdx.x);
+    // everything the P0 of the tile starting at row Rn will ask for goes to L2 (bulk tiles by the copy engine, gathered
+    // rows one prefetch per 128-byte line; row ids from the last load_idx), so that P0 waits on L2 only
+    auto prefetch_inputs = [&](int Rn) {
+        if (warp == 0 && elect_one()) {
+            if (t_ain) for (int b = 0; b < (ka + 63) >> 6; ++b) tma_prefetch_2d(&maps.ain, b * 64, Rn);
+            if (t_db) for (int b = 0; b < (nb + 63) >> 6; ++b) tma_prefetch_2d(&maps.db, b * 64, Rn);
+            if (t_gy) for (int b = 0; b < (H + 63) >> 6; ++b) tma_prefetch_2d(&maps.gy, b * 64, Rn);
+            if (t_res) for (int b = 0; b < (ka + 63) >> 6; ++b) tma_prefetch_2d(&maps.resid, b * 64, Rn);
+            if (t_ha) for (int b = 0; b < (H + 63) >> 6; ++b) tma_prefetch_2d(&maps.ha, b * 64, Rn);
+        }
+#pragma unroll
+        for (int j = 0; j < CPT; ++j) {
+            const int i = tid + j * NT;
+            if ((i & 7) == 0) {         // chunk 0 of a 128-byte line
+                if (has_init)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(p.init + (size_t)ridx[j] * p.ld_init + soff + (i % KC) * 8));
+                if (du_smem && f_gather && f_gbf) {
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(p.gy_gather_bf16 + (size_t)gidx[j] * H + (i % KC) * 8));
+                } else if (du_smem && f_gather) {       // fp32 rows: two lines per 8-chunk group
+                    const float* gp_ = p.gy_gather + (size_t)gidx[j] * H + (i % KC) * 8;
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(gp_));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(gp_ + 32));
+                }
+            }
+        }
+        if (MODE == 3)      // the tile's fp32 gradient rows: 512 lines, one per thread
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.gy_f32 + (size_t)min(Rn + (tid >> 2), p.rows - 1) * p.ld_gy + (tid & 3) * 32));
+        if (has_init && stage1 && tid < 128)
+            for (int c = 0; c < H; c += 64)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(p.init + (size_t)i0n * p.ld_init + p.init_off0 + c));
+    };
+    if ((int)blockIdx.x < n_tiles) {
+        // the first tile of this CTA: ids and L2 prefetch before the wait below -- these requests overlap the tail of the
+        // previous kernel (what it is still writing reaches L2 anyway: a prefetched line is never stale there)
+        load_idx(blockIdx.x);
+        prefetch_inputs((int)blockIdx.x << 7);
+    }
+    // everything above is independent of the previous kernel in the stream (parameters, graph layout, prefetches); from here
+    // on its outputs are read, and the next kernel may start its own prologue
+    pdl_wait();
+    pdl_launch_dependents();
     BWD_STAMP(16);        // ns from kernel entry: prologue done (weights staged, previous kernel finished)
     bool first = true;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, first = false) {
@@ -418,33 +453,7 @@ __global__ void __launch_bounds__(BwdCfg<H>::NT, 1) mlp_bwd_kernel(const gp_mlp_
             // copy engine, gathered rows one prefetch per 128-byte line), so that P0 waits on L2 only
             const int Rn = (tile + (int)gridDim.x) << 7;
             load_idx(tile + gridDim.x);
-            if (warp == 0 && elect_one()) {
-                if (t_ain) for (int b = 0; b < (ka + 63) >> 6; ++b) tma_prefetch_2d(&maps.ain, b * 64, Rn);
-                if (t_db) for (int b = 0; b < (nb + 63) >> 6; ++b) tma_prefetch_2d(&maps.db, b * 64, Rn);
-                if (t_gy) for (int b = 0; b < (H + 63) >> 6; ++b) tma_prefetch_2d(&maps.gy, b * 64, Rn);
-                if (t_res) for (int b = 0; b < (ka + 63) >> 6; ++b) tma_prefetch_2d(&maps.resid, b * 64, Rn);
-                if (t_ha) for (int b = 0; b < (H + 63) >> 6; ++b) tma_prefetch_2d(&maps.ha, b * 64, Rn);
-            }
-#pragma unroll
-            for (int j = 0; j < CPT; ++j) {
-                const int i = tid + j * NT;
-                if ((i & 7) == 0) {         // chunk 0 of a 128-byte line
-                    if (has_init)
-                        asm volatile("prefetch.global.L2 [%0];" ::"l"(p.init + (size_t)ridx[j] * p.ld_init + soff + (i % KC) * 8));
-                    if (du_smem && f_gather && f_gbf) {
-                        asm volatile("prefetch.global.L2 [%0];" ::"l"(p.gy_gather_bf16 + (size_t)gidx[j] * H + (i % KC) * 8));
-                    } else if (du_smem && f_gather) {       // fp32 rows: two lines per 8-chunk group
-                        const float* gp_ = p.gy_gather + (size_t)gidx[j] * H + (i % KC) * 8;
-                        asm volatile("prefetch.global.L2 [%0];" ::"l"(gp_));
-                        asm volatile("prefetch.global.L2 [%0];" ::"l"(gp_ + 32));
-                    }
-                }
-            }
-            if (MODE == 3)      // the next tile's fp32 gradient rows: 512 lines, one per thread
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(p.gy_f32 + (size_t)min(Rn + (tid >> 2), p.rows - 1) * p.ld_gy + (tid & 3) * 32));
-            if (has_init && stage1 && tid < 128)
-                for (int c = 0; c < H; c += 64)
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(p.init + (size_t)i0n * p.ld_init + p.init_off0 + c));
+            prefetch_inputs(Rn);
         }
         if (!ha_given) wait_mma();
         tick(3);      // P1 MMA

@@ -124,6 +124,16 @@ __global__ void __launch_bounds__(kSlotThreads * NG, 1) mlp_fwd_kernel(const gp_
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    if (kNode) {
+        // node update: the pre-activation rows (P) and the residual rows (x) of this slot's first tile are older than the
+        // previous kernel: pull them into L2 while it finishes (every CTA runs only ~4 tiles; the first used to start cold)
+        const int tile0_ = blockIdx.x * NG + g;
+        if (tile0_ < ((p.rows + 127) >> 7) && t < 256) {
+            const int r = min((tile0_ << 7) + (t >> 1), p.rows - 1);
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.init + (size_t)r * p.ld_init + p.init_off0 + (t & 1) * 64));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.resid + (size_t)r * p.ld_out + (t & 1) * 64));
+        }
+    }
     // everything above is independent of the previous kernel in the stream (parameters only); from here on
     // its outputs are read, and the next kernel may start its own prologue
     pdl_wait();
