@@ -38,6 +38,18 @@ __global__ void __launch_bounds__(256, 1) linear_bwd_kernel(const gp_linear_bwd_
     uint8_t* xbuf = smem + off;
     float* stg = reinterpret_cast<float*>(abuf);                 // reused after the MMAs have read abuf
 
+    // the first tile of this CTA: x is forward data (cold), the incoming dX rows are older than the previous kernels --
+    // both go to L2 while the weights are staged (a CTA runs ~4 tiles)
+    if ((int)blockIdx.x < ((p.rows + 127) >> 7)) {
+        const int R0_ = (int)blockIdx.x << 7;
+        if ((maps.use & 1u) && warp == 0 && elect_one())
+            for (int b = 0; b < (H + 63) >> 6; ++b) tma_prefetch_2d(&maps.x, b * 64, R0_);
+        if (p.dx_in) {
+            constexpr int LPR = (H * 4 / 128) > 0 ? H * 4 / 128 : 1;
+            for (int i = tid; i < 128 * LPR; i += 256)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(p.dx_in + (size_t)min(R0_ + i / LPR, p.rows - 1) * H + (i % LPR) * 32));
+        }
+    }
     stage_weight(w_t, p.w, wrows, H);
     cp_async_commit();
     if (tid == 0) {
