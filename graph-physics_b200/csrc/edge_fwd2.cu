@@ -301,6 +301,15 @@ edge_fwd2_kernel(const gp_mlp_fwd_args p, const __grid_constant__ Fwd2Maps maps)
     const uint32_t tmem_base = B.tmem_slot;
     cluster_sync_all();               // both CTAs' weights, barriers and TMEM exist before any cross-CTA traffic
     tc_fence_after();
+    // the first e tile of each slot is older than the previous kernel (it wrote P): into L2 before the wait
+    if (tid < 2) {
+        const int q0 = cid * 2 + tid;
+        if (q0 < n_pairs) {
+            const int R0_ = (2 * q0 + (int)rank) << 7;
+            tma_prefetch_2d(&maps.e, 0, R0_);
+            tma_prefetch_2d(&maps.e, 64, R0_);
+        }
+    }
     pdl_wait();
     pdl_launch_dependents();
 
