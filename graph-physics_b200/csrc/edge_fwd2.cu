@@ -156,13 +156,6 @@ __device__ __forceinline__ void tma_gather4(uint32_t smem_dst, const void* tmap,
 }
 __device__ __forceinline__ void named_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
-__device__ __forceinline__ void tmem_st1(uint32_t taddr, uint32_t v) {
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(taddr), "r"(v) : "memory");
-}
-__device__ __forceinline__ void tmem_ld2(uint32_t taddr, uint32_t& a, uint32_t& b) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0,%1}, [%2];" : "=r"(a), "=r"(b) : "r"(taddr) : "memory");
-}
-
 // Segment sum of one (32-row sub-tile, column pair) unit of the bf16 tile `buf` -- the partition, the summation order
 // and the output convention of tile_segment_sum<128, 256> (tile_util.cuh; complete segments -> seg_out_bf16 rounded
 // once, pieces cut by the sub-tile -> seg_bnd for gp_seg_fixup_bf16), but straight-line: the row loop is unrolled
