@@ -22,6 +22,7 @@ fp32.  terms = 3 (precision="tight") splits every fp32 operand into three bf16 t
 from __future__ import annotations
 
 import ctypes as C
+import math
 from typing import Optional
 
 import torch
@@ -390,6 +391,47 @@ def attention_branch(x, norm_scale, att, g, add_resid: bool, terms: int = 1, pos
     return _AttentionBranch.apply(x, norm_scale, att.q_proj.weight, att.q_proj.bias, att.k_proj.weight, att.k_proj.bias,
                                   att.v_proj.weight, att.v_proj.bias, att.proj.weight, att.proj.bias, wg, bg, add_resid, g, att.num_heads,
                                   terms, rope)
+
+
+class SparseAttention:
+    """What `return_attention=True` hands back (the reference returns the dgl SparseMatrix of the softmax, layers.py:509-517,
+    680-683): `val` [E, heads] in the order of the caller's edge_index, `row` / `col` = edge_index[0] / edge_index[1]."""
+
+    def __init__(self, row: torch.Tensor, col: torch.Tensor, val: torch.Tensor, num_nodes: int):
+        self.row, self.col, self.val, self.shape = row, col, val, (num_nodes, num_nodes)
+
+    def coo(self):
+        return self.row, self.col
+
+
+@torch.no_grad()
+def attention_weights(att, x, norm_scale, g, terms: int = 1, pos=None) -> SparseAttention:
+    """softmax_j(q_i . k_j / sqrt(head_dim)) per stored entry (i, j) and head -- the attention matrix of `att` for input x
+    (normalised first when `norm_scale` is given).  A diagnostic beside the fused path (which never materialises these
+    values): projections on gp_gemm, RoPE by its kernel, the E x heads softmax with torch indexing in fp32."""
+    x = _f32(x)
+    n = norm_fwd(x, norm_scale, None, out_bf16=False) if norm_scale is not None else x
+    heads, d = att.num_heads, att.head_dim
+    q = lin_fwd(n, att.q_proj.weight, att.q_proj.bias, terms=terms)
+    k = lin_fwd(n, att.k_proj.weight, att.k_proj.bias, terms=terms)
+    if pos is not None and att.m > 0:
+        p_ = pos[:, :att.pos_dimension].float().contiguous()
+        _rope_nodes_(q, p_, d, heads, int(att.m), float(att.rope_base), False)
+        _rope_nodes_(k, p_, d, heads, int(att.m), float(att.rope_base), False)
+    row, col = g.src.long(), g.dst.long()                  # receiver-sorted positions; rows of the matrix = edge_index[0]
+    E, N = row.numel(), n.shape[0]
+    s = (q[row].view(E, d, heads) * k[col].view(E, d, heads)).sum(1) / math.sqrt(d)
+    idx = row[:, None].expand(E, heads)
+    mx = torch.full((N, heads), -float("inf"), dtype=s.dtype, device=s.device).scatter_reduce(0, idx, s, reduce="amax", include_self=True)
+    pexp = torch.exp(s - mx[row])
+    den = torch.zeros((N, heads), dtype=s.dtype, device=s.device).index_add_(0, row, pexp)
+    a = pexp / den[row]
+    perm = g.perm_dst64
+    val = torch.empty_like(a)
+    val[perm] = a                                          # back to the caller's edge order
+    r0 = torch.empty_like(row); c0 = torch.empty_like(col)
+    r0[perm] = row; c0[perm] = col
+    return SparseAttention(r0, c0, val, N)
 
 
 class _GatedBranch(torch.autograd.Function):

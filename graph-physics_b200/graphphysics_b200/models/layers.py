@@ -309,10 +309,11 @@ class Attention(nn.Module):
 
     def forward(self, x: torch.Tensor, adj, pos: Optional[torch.Tensor] = None, return_attention: bool = False):
         from .. import dense
-        if return_attention:
-            raise NotImplementedError("return_attention=True is not supported (attention weights are never materialised)")
-        return dense.attention_branch(x, None, self, self._graph(x, adj), add_resid=False,
-                                      terms=3 if self.precision == "tight" else 1, pos=self._rope_pos(pos))
+        g, terms = self._graph(x, adj), 3 if self.precision == "tight" else 1
+        out = dense.attention_branch(x, None, self, g, add_resid=False, terms=terms, pos=self._rope_pos(pos))
+        if return_attention:          # (out, attn) like layers.py:680-697; attn is computed beside the fused path
+            return out, dense.attention_weights(self, x, None, g, terms=terms, pos=self._rope_pos(pos))
+        return out
 
     def _rope_pos(self, pos):
         if not self.use_rope_embeddings:
@@ -353,14 +354,17 @@ class Transformer(nn.Module):
         GEMMs, the CSR attention kernel and three row-wise kernels; both residual adds ride in a GEMM epilogue.  Two
         autograd nodes (dense.attention_branch, dense.gated_branch) with hand-written backwards."""
         from .. import dense
-        if return_attention:
-            raise NotImplementedError("return_attention=True is not supported (attention weights are never materialised)")
         terms = 3 if self.precision == "tight" else 1
+        attn = None
+        if return_attention:          # layers.py:795-801: the attention matrix of this block's input
+            attn = dense.attention_weights(self.attention, x, self.norm1.scale, self.attention._graph(x, adj), terms=terms,
+                                           pos=self.attention._rope_pos(pos))
         x = dense.attention_branch(x, self.norm1.scale, self.attention, self.attention._graph(x, adj), add_resid=True, terms=terms,
                                    pos=self.attention._rope_pos(pos))
         # the double norm: Transformer.norm2, then build_gated_mlp's own leading RMSNorm (layers.py:252-278)
-        return dense.gated_branch(x, self.norm2.scale, self.gated_mlp[0].scale, self.gated_mlp[1], self.gated_mlp[2],
-                                  add_resid=True, terms=terms, act=self.gated_mlp[1].act)
+        x = dense.gated_branch(x, self.norm2.scale, self.gated_mlp[0].scale, self.gated_mlp[1], self.gated_mlp[2],
+                               add_resid=True, terms=terms, act=self.gated_mlp[1].act)
+        return (x, attn) if return_attention else x
 
 
 class TemporalAttention(nn.Module):

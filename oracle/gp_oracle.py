@@ -198,6 +198,18 @@ def sparse_attention(q, k, v, row, col, num_nodes: int):
     return y
 
 
+def attention_values(q, k, row, col, num_nodes: int):
+    """scaled_query_key_softmax on the DGL branch (layers.py:493-522): the values of the sparse softmax, one row per stored
+    entry (in the order of row / col) and one column per head -- what return_attention=True exposes as attn.val."""
+    d = q.shape[1]
+    s = (q[row] / math.sqrt(d) * k[col]).sum(dim=1)
+    smax = torch.full((num_nodes, s.shape[1]), -float("inf"), dtype=s.dtype)
+    smax = smax.scatter_reduce(0, row[:, None].expand_as(s), s, reduce="amax", include_self=True)
+    p = torch.exp(s - smax[row])
+    den = torch.zeros((num_nodes, s.shape[1]), dtype=s.dtype).index_add_(0, row, p)
+    return p / den[row]
+
+
 def attention(x, row, col, sd, prefix: str, num_heads: int, mode: Optional[str] = None):
     """Attention.forward (layers.py:637-697), no RoPE / gate."""
     N, H = x.shape

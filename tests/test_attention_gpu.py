@@ -101,3 +101,44 @@ def test_transformer_training_steps_run_through_trainer():
     losses = [float(tr.training_step(batch)) for _ in range(8)]
     assert all(np.isfinite(losses)) and losses[-1] < losses[0], losses
     assert not torch.equal(p0, tr.engine.flat.data)
+
+
+@pytest.mark.parametrize("rope", [False, True])
+def test_return_attention_matches_oracle(rope):
+    """Attention / Transformer .forward(..., return_attention=True) (layers.py:680-697, 795-801): the output is the fused
+    path's, the attention values (E x heads, caller's edge order) match the oracle's sparse softmax and sum to one per row."""
+    from graphphysics_b200.models.layers import Transformer
+    from oracle import gp_oracle as O
+    dev = torch.device("cuda:0")
+    torch.manual_seed(5)
+    N, H, heads = 300, 64, 4
+    rng = np.random.default_rng(0)
+    key = np.unique(rng.integers(0, N, 4000) * N + rng.integers(0, N, 4000))
+    ei = torch.from_numpy(np.stack([key // N, key % N]))
+    ei = ei[:, torch.randperm(ei.shape[1])]                      # not sorted: the values must follow the caller's order
+    blk = Transformer(H, H, heads, use_rope_embeddings=rope, pos_dimension=2).to(dev)
+    blk.set_precision("tight")
+    x = torch.randn(N, H, device=dev)
+    pos = torch.rand(N, 2, device=dev)
+    with torch.no_grad():
+        plain = blk(x, ei.to(dev), pos=pos)
+        out, attn = blk(x, ei.to(dev), pos=pos, return_attention=True)
+        a_out, a_attn = blk.attention(x, ei.to(dev), pos=pos, return_attention=True)
+    assert torch.equal(out, plain)
+    assert tuple(attn.val.shape) == (ei.shape[1], heads) and torch.equal(attn.row.cpu(), ei[0]) and torch.equal(attn.col.cpu(), ei[1])
+    sums = torch.zeros(N, heads, device=dev).index_add_(0, ei[0].to(dev), attn.val)
+    has = torch.zeros(N, device=dev).index_add_(0, ei[0].to(dev), torch.ones(ei.shape[1], device=dev)) > 0
+    assert torch.allclose(sums[has], torch.ones_like(sums[has]), atol=1e-5)
+    # oracle: the same projections in fp64
+    sd = {k: v.detach().double().cpu() for k, v in blk.state_dict().items()}
+    xd = x.double().cpu()
+    n1 = O.rms_norm(xd, sd["norm1.scale"])
+    d = H // heads
+    q = O.linear(n1, sd["attention.q_proj.weight"], sd["attention.q_proj.bias"], None).reshape(N, d, heads)
+    k = O.linear(n1, sd["attention.k_proj.weight"], sd["attention.k_proj.bias"], None).reshape(N, d, heads)
+    if rope:
+        q, k = O.rope_nodes(q, k, pos.double().cpu(), sd["attention.rope_inv_freq"])
+    ref = O.attention_values(q, k, ei[0], ei[1], N)
+    assert float((attn.val.double().cpu() - ref).abs().max()) < 2e-5
+    # the bare Attention module normalises nothing: a different matrix, same shape, rows summing to one
+    assert tuple(a_attn.val.shape) == (ei.shape[1], heads) and a_out.shape == x.shape
