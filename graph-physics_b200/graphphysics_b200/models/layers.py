@@ -193,9 +193,9 @@ class GraphNetBlock(nn.Module):
         self.use_gated_mlp, self.use_rope, self.use_gate = use_gated_mlp, use_rope, use_gate
         self.rope_axes, self.rope_base = rope_axes, rope_base
         self.act = "silu" if use_silu_activation() else "relu"
-        self.variant = use_rope or use_gated_mlp or use_gate or self.act != "relu"
-        if not self.variant and (nb_of_layers != 4 or not layer_norm):
-            raise NotImplementedError("the fused kernels implement the 4-layer, RMS-normalised MLP the reference uses")
+        # the fused kernels implement the 4-layer, RMS-normalised MLP every shipped configuration uses; any other depth, or
+        # no norm, takes the general path like the flags do
+        self.variant = use_rope or use_gated_mlp or use_gate or self.act != "relu" or nb_of_layers != 4 or not layer_norm
         if use_gated_mlp:
             self.edge_block = build_gated_mlp(in_size=3 * hidden_size, hidden_size=hidden_size, out_size=hidden_size)
             self.node_block = build_gated_mlp(in_size=2 * hidden_size, hidden_size=hidden_size, out_size=hidden_size)

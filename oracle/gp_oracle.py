@@ -585,7 +585,8 @@ def rope_rel(x_src, delta_pos, axes: int, base: float = 10000.0):
 
 
 def graph_net_block_variant(x, e, src, dst, sd, prefix: str, *, act: str = "relu", gated_mlp: bool = False, gate: bool = False,
-                            rope_axes: int = 0, rope_base: float = 10000.0, pos=None, phi=None, mode: Optional[str] = None):
+                            rope_axes: int = 0, rope_base: float = 10000.0, pos=None, phi=None, mode: Optional[str] = None,
+                            nb_layers: int = 4, layer_norm: bool = True):
     """GraphNetBlock.forward with its constructor flags (layers.py:989-1102).  Kernel mode (`mode="bf16"`): GEMM operands
     and the gradients entering them rounded to bf16, everything else in the working precision -- the arithmetic of
     graphphysics_b200/variants.py."""
@@ -596,7 +597,7 @@ def graph_net_block_variant(x, e, src, dst, sd, prefix: str, *, act: str = "relu
     if gated_mlp:
         e_upd = gated_mlp_seq(cat, sd, f"{prefix}.edge_block", "silu" if act == "silu" else "gelu", mode)
     else:
-        e_upd = dense_mlp_act(cat, sd, f"{prefix}.edge_block", act, mode)
+        e_upd = dense_mlp_act(cat, sd, f"{prefix}.edge_block", act, mode, layer_norm, nb_layers)
     agg = torch.zeros_like(x).index_add_(0, dst, e_upd)
     if gate:
         logits = linear(x, sd[f"{prefix}.gate_proj.weight"], sd[f"{prefix}.gate_proj.bias"], mode)
@@ -607,18 +608,19 @@ def graph_net_block_variant(x, e, src, dst, sd, prefix: str, *, act: str = "relu
     if gated_mlp:
         x_upd = gated_mlp_seq(cat_n, sd, f"{prefix}.node_block", "silu" if act == "silu" else "gelu", mode)
     else:
-        x_upd = dense_mlp_act(cat_n, sd, f"{prefix}.node_block", act, mode)
+        x_upd = dense_mlp_act(cat_n, sd, f"{prefix}.node_block", act, mode, layer_norm, nb_layers)
     return x + x_upd, e + e_upd
 
 
-def dense_mlp_act(x, sd, prefix: str, act: str = "relu", mode: Optional[str] = None, layer_norm: bool = True):
-    """build_mlp with a selectable activation, one GEMM per Linear (hidden activations are MMA operands)."""
+def dense_mlp_act(x, sd, prefix: str, act: str = "relu", mode: Optional[str] = None, layer_norm: bool = True, nb_layers: int = 4):
+    """build_mlp (layers.py:163-210) with a selectable activation and depth, one GEMM per Linear (hidden activations are
+    MMA operands): Linear, act, ..., Linear [, RMSNorm] -- the norm is module 2 * nb_layers - 1 of the Sequential."""
     h = x
-    for i in range(4):
+    for i in range(nb_layers):
         h = linear(h, sd[f"{prefix}.{2 * i}.weight"], sd[f"{prefix}.{2 * i}.bias"], mode)
-        if i < 3:
+        if i < nb_layers - 1:
             h = _ACT[act](h)
-    return rms_norm(h, sd[f"{prefix}.7.scale"]) if layer_norm else h
+    return rms_norm(h, sd[f"{prefix}.{2 * nb_layers - 1}.scale"]) if layer_norm else h
 
 
 def temporal_attention(h_prev, h_pred, row, col, sd, prefix: str, num_heads: int = 4, use_gate: bool = True, mode: Optional[str] = None):

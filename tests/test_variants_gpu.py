@@ -162,3 +162,29 @@ def test_variant_path_edge_case_graphs(n_nodes, n_edges):
     assert l2_rel(out, ref) < 3e-3, l2_rel(out, ref)
     (out * G_.to(DEV)).sum().backward()
     assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in m.parameters())
+
+
+@pytest.mark.parametrize("nb,norm", [(3, False), (5, True), (2, True)])
+def test_graph_net_block_other_depths(nb, norm):
+    """GraphNetBlock(nb_of_layers != 4) / layer_norm=False (constructor arguments of layers.py:896-987 that no shipped
+    configuration uses): the general path, tight mode, against the oracle in fp64 -- outputs and parameter gradients."""
+    from graphphysics_b200.models.layers import GraphNetBlock
+    from oracle import gp_oracle as O
+    z = np.load(os.path.join(G, "variants.npz"))
+    ei = torch.from_numpy(z["edge_index"])
+    N, H = z["x_epd"].shape[0], 32
+    torch.manual_seed(nb)
+    blk = GraphNetBlock(H, nb_of_layers=nb, layer_norm=norm)
+    blk.precision = "tight"
+    assert blk.variant and len([m for m in blk.edge_block if isinstance(m, torch.nn.Linear)]) == nb
+    x, e = torch.randn(N, H), torch.randn(ei.shape[1], H)
+    Gx, Ge = torch.randn(N, H), torch.randn(ei.shape[1], H)
+    sd = {"b." + k: v.detach().double().requires_grad_(True) for k, v in blk.state_dict().items()}
+    rx, re = O.graph_net_block_variant(x.double(), e.double(), ei[0], ei[1], sd, "b", nb_layers=nb, layer_norm=norm)
+    ((rx * Gx.double()).sum() + (re * Ge.double()).sum()).backward()
+    blk = blk.to(DEV)
+    ox, oe = blk(x.to(DEV), ei.to(DEV), e.to(DEV))
+    ((ox * Gx.to(DEV)).sum() + (oe * Ge.to(DEV)).sum()).backward()
+    assert l2_rel(ox, rx) < 1e-3 and l2_rel(oe, re) < 1e-3
+    for k, p in blk.named_parameters():
+        assert l2_rel(p.grad, sd["b." + k].grad) < 1e-3, k
