@@ -229,3 +229,30 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert line["impl"] == "reference" and line["value"] > 0
     assert line["cpu_baseline"]["kind"] == ("reference" if staged else "port")      # the reference's own modules when staged
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+
+
+def test_get_preprocessing_and_loss_from_the_json_configs():
+    """parse_parameters.get_preprocessing / get_loss / get_gradient_method (parse_parameters.py:24-78, 300-341) on the
+    reference's own training configs: the transform pipeline in the reference's order (noise second, world edges for the
+    plate), L2Loss for the configurations of the path."""
+    import json
+    from graphphysics_b200.training.parse_parameters import get_gradient_method, get_loss, get_preprocessing
+    from graphphysics_b200.utils.loss import L2Loss
+    cfgs = json.load(open(os.path.join(ROOT, "tests", "golden", "training_configs.json")))
+    # the `transformations` sections of training_config/cylinder.json and plate.json, verbatim
+    cfgs["cylinder"]["transformations"] = {"preprocessing": {"noise": 0.02, "noise_index_start": [0], "noise_index_end": [2], "masking": 0},
+                                           "world_pos_parameters": {"use": False, "world_pos_index_start": 0, "world_pos_index_end": 3}}
+    cfgs["plate"]["transformations"] = {"preprocessing": {"noise": 0.003, "noise_index_start": [0], "noise_index_end": [3], "masking": 0},
+                                        "world_pos_parameters": {"use": True, "world_pos_index_start": 0, "world_pos_index_end": 3}}
+    names = lambda pre: [getattr(t, "func", t).__name__ for t in pre.transforms]
+    cyl = get_preprocessing(cfgs["cylinder"], torch.device("cpu"))
+    assert names(cyl) == ["face_to_edge", "add_noise", "_apply"]
+    assert cyl.transforms[1].keywords["noise_scale"] == cfgs["cylinder"]["transformations"]["preprocessing"]["noise"]
+    assert names(get_preprocessing(cfgs["cylinder"], torch.device("cpu"), remove_noise=True)) == ["face_to_edge", "_apply"]
+    assert names(get_preprocessing(cfgs["cylinder"], torch.device("cpu"), use_edge_feature=False, remove_noise=True)) == ["face_to_edge"]
+    plate = get_preprocessing(cfgs["plate"], torch.device("cpu"))
+    assert names(plate) == ["add_obstacles_next_pos", "add_noise", "face_to_edge", "add_world_edges", "_apply"]
+    loss, name = get_loss(cfgs["cylinder"])
+    assert isinstance(loss, L2Loss) and name == "L2LOSS" and get_gradient_method(cfgs["cylinder"]) is None
+    with pytest.raises(NotImplementedError):
+        get_loss({"loss": {"type": ["l2loss", "divergenceloss"], "weights": [1.0, 0.1]}})
