@@ -40,6 +40,41 @@ class Data:
 Batch = Data
 
 
+def collate(graphs) -> Data:
+    """The union graph of a list of graphs, as PyG's DataLoader collate builds it: tensors whose first
+    dimension is the node or edge count are concatenated on dim 0, `edge_index` / `face` / `tetra` on dim 1 with the node
+    offset of their graph added, plus `batch` (graph id per node) and `ptr` (node offsets).  Other tensor attributes are
+    stacked when every graph has them with the same shape, non-tensor attributes are gathered into a list.  The model code
+    treats the result as one graph (a block-diagonal adjacency)."""
+    graphs = list(graphs)
+    if not graphs:
+        raise ValueError("collate needs at least one graph")
+    keys = [k for k in graphs[0].__dict__.keys() if all(getattr(g, k) is not None for g in graphs)]
+    sizes = [int(g.x.shape[0]) if g.x is not None else int(g.pos.shape[0]) for g in graphs]
+    offs = [0]
+    for n in sizes:
+        offs.append(offs[-1] + n)
+    out = {}
+    for k in keys:
+        vals = [getattr(g, k) for g in graphs]
+        if not all(torch.is_tensor(v) for v in vals):
+            out[k] = vals
+        elif k in ("edge_index", "face", "tetra"):
+            out[k] = torch.cat([v + o for v, o in zip(vals, offs)], dim=1)
+        elif all(v.dim() >= 1 for v in vals) and all(v.shape[1:] == vals[0].shape[1:] for v in vals) and (
+                all(v.shape[0] == n for v, n in zip(vals, sizes)) or
+                ("edge_index" in keys and all(v.shape[0] == g.edge_index.shape[1] for v, g in zip(vals, graphs)))):
+            out[k] = torch.cat(vals, dim=0)
+        elif all(v.shape == vals[0].shape for v in vals):
+            out[k] = torch.stack(vals, dim=0)
+        else:
+            out[k] = vals
+    dev = graphs[0].x.device if graphs[0].x is not None else graphs[0].pos.device
+    out["batch"] = torch.cat([torch.full((n,), i, dtype=torch.long, device=dev) for i, n in enumerate(sizes)])
+    out["ptr"] = torch.tensor(offs, dtype=torch.long, device=dev)
+    return Data(**out)
+
+
 class GraphCSR:
     """Receiver-sorted edge layout of one topology (all int32, on the device of edge_index).
 

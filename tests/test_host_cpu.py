@@ -256,3 +256,23 @@ def test_get_preprocessing_and_loss_from_the_json_configs():
     assert isinstance(loss, L2Loss) and name == "L2LOSS" and get_gradient_method(cfgs["cylinder"]) is None
     with pytest.raises(NotImplementedError):
         get_loss({"loss": {"type": ["l2loss", "divergenceloss"], "weights": [1.0, 0.1]}})
+
+
+def test_collate_builds_the_union_graph_like_pyg():
+    """graph.collate: node / edge tensors concatenated, edge_index and face shifted by the node offsets, batch and ptr
+    vectors -- the block-diagonal union graph PyG's DataLoader hands to the reference's training step."""
+    from graphphysics_b200.graph import Data, collate
+    g1 = Data(x=torch.arange(6.).view(3, 2), y=torch.ones(3, 2), pos=torch.zeros(3, 2), edge_index=torch.tensor([[0, 1, 2], [1, 2, 0]]),
+              edge_attr=torch.arange(9.).view(3, 3), face=torch.tensor([[0], [1], [2]]), traj_index=torch.tensor(4), name="a")
+    g2 = Data(x=torch.arange(8.).view(4, 2) + 10, y=torch.zeros(4, 2), pos=torch.ones(4, 2),
+              edge_index=torch.tensor([[0, 3], [3, 0]]), edge_attr=torch.ones(2, 3), face=torch.tensor([[0, 1], [1, 2], [3, 3]]),
+              traj_index=torch.tensor(7), name="b")
+    u = collate([g1, g2])
+    assert u.x.shape == (7, 2) and u.y.shape == (7, 2) and u.pos.shape == (7, 2) and u.edge_attr.shape == (5, 3)
+    assert torch.equal(u.edge_index, torch.tensor([[0, 1, 2, 3, 6], [1, 2, 0, 6, 3]]))
+    assert torch.equal(u.face, torch.tensor([[0, 3, 4], [1, 4, 5], [2, 6, 6]]))
+    assert torch.equal(u.batch, torch.tensor([0, 0, 0, 1, 1, 1, 1])) and torch.equal(u.ptr, torch.tensor([0, 3, 7]))
+    assert torch.equal(u.traj_index, torch.tensor([4, 7])) and u.name == ["a", "b"]
+    assert torch.equal(u.x[3:], g2.x) and u.num_nodes == 7
+    one = collate([g1])
+    assert torch.equal(one.edge_index, g1.edge_index) and torch.equal(one.batch, torch.zeros(3, dtype=torch.long))
