@@ -33,7 +33,7 @@ class Trainer:
     def __init__(self, parameters: Dict[str, Any], learning_rate: float, num_steps: int, warmup: int,
                  device: torch.device, masks: Sequence[int] = (NodeType.NORMAL, NodeType.OUTFLOW),
                  gradient_clip_val: float = 1.0, weight_decay: float = 1e-4, betas=(0.9, 0.95), eps: float = 1e-8,
-                 process_group=None, seed: Optional[int] = None, inject_noise: bool = False):
+                 process_group=None, seed: Optional[int] = None, inject_noise: bool = False, accumulate_grad_batches: int = 1):
         if seed is not None:
             torch.manual_seed(seed)
         self.param = parameters
@@ -58,6 +58,10 @@ class Trainer:
         # 17 NCCL kernels queue behind them and then delay the next compute kernel.  Off by default.
         self.overlap_allreduce = os.environ.get("GP_B200_OVERLAP_ALLREDUCE", "0") == "1"
         self.step_index = 0
+        # Trainer(accumulate_grad_batches=k) of the reference (train.py:70, 289): the loss of each of k consecutive batches is
+        # scaled by 1 / k, the gradients add up, clip + AdamW + the LR schedule advance on every k-th call
+        self.accumulate = max(int(accumulate_grad_batches), 1)
+        self._micro, self._gacc = 0, None
         # EPD on the fused kernels: engine-driven forward/backward, no autograd tape (precision="tight" and the
         # Transformer run under autograd over flat parameter / gradient buffers)
         self.fused = (hasattr(type(self.processor), "engine") and getattr(self.processor, "precision", "bf16") == "bf16"
@@ -198,12 +202,23 @@ class Trainer:
             for v in batch.__dict__.values():           # the side stream allocated these tensors
                 if torch.is_tensor(v):
                     v.record_stream(torch.cuda.current_stream(self.device))
-        step = self._partitioned_step if self._part is not None else self._training_step_eager
+        last = True                                     # this call ends an accumulation window (always, without accumulation)
+        if self.accumulate > 1:
+            if self._part is not None:
+                raise NotImplementedError("accumulate_grad_batches > 1 is not available in node-partition mode")
+            if self._gacc is None:
+                self._gacc = torch.zeros_like(self.engine.gflat)
+            self._micro += 1
+            last = self._micro % self.accumulate == 0
+        if self._part is not None:
+            step = self._partitioned_step
+        else:
+            step = lambda b: self._training_step_eager(b, last)
         if not self.use_cuda_graph:
             return step(batch)
         from ..graph import Data, no_csr_cache
         fields = [k for k in ("x", "y", "pos", "edge_index", "edge_attr") if getattr(batch, k) is not None]
-        key = tuple((k, tuple(getattr(batch, k).shape), getattr(batch, k).dtype) for k in fields)
+        key = tuple((k, tuple(getattr(batch, k).shape), getattr(batch, k).dtype) for k in fields) + (last,)
         entry = self._graphs.get(key)
         if entry is None:
             static = Data(**{k: torch.empty_like(getattr(batch, k), device=self.device) for k in fields})
@@ -220,17 +235,32 @@ class Trainer:
             mode = "thread_local" if self.pg is not None else "global"
             with no_csr_cache(), torch.cuda.graph(graph, capture_error_mode=mode):
                 step(static)
-            self.step_index -= 1                        # the capture pass enqueued nothing; undo its host-side count
+            if last:
+                self.step_index -= 1                    # the capture pass enqueued nothing; undo its host-side count
             self._graphs[key] = (graph, static, fields)
             return self._loss[0]
         graph, static, fields = entry
         for k in fields:
             getattr(static, k).copy_(getattr(batch, k), non_blocking=True)
         graph.replay()
-        self.step_index += 1
+        if last:
+            self.step_index += 1
         return self._loss[0]
 
-    def _training_step_eager(self, batch) -> torch.Tensor:
+    def _accumulated(self, last: bool) -> bool:
+        """Gradient accumulation: add this batch's gradient / k to the window's sum; on the window's last batch put the sum
+        back into the gradient buffer.  Returns whether the optimizer runs now."""
+        if self.accumulate == 1:
+            return True
+        eng = self.engine
+        self._gacc.add_(eng.gflat, alpha=1.0 / self.accumulate)
+        if not last:
+            return False
+        eng.gflat.copy_(self._gacc)
+        self._gacc.zero_()
+        return True
+
+    def _training_step_eager(self, batch, last: bool = True) -> torch.Tensor:
         sim, eng = self.model, self.engine
         sim.train()
         if not batch.x.is_cuda:
@@ -252,7 +282,7 @@ class Trainer:
             out, _, ctx = eng.forward(graph.x, graph.edge_attr, g, save=True)
             d_out = torch.empty_like(out)
             ops.masked_mse(out, target.contiguous(), mask, self._loss, d_out)
-            if self.pg is not None and self.overlap_allreduce:
+            if self.pg is not None and self.overlap_allreduce and self.accumulate == 1:
                 # the gradient slice of every layer is all-reduced (NCCL's own stream) as soon as that layer's backward
                 # has written it, under the backward of the earlier layers; only the encoders' slice is exposed
                 import torch.distributed as dist
@@ -271,6 +301,8 @@ class Trainer:
             d_out = torch.empty_like(out)
             ops.masked_mse(out.detach().contiguous(), target.contiguous(), mask, self._loss, d_out)
             out.backward(d_out)                                        # gradients land in the flat buffer
+        if not self._accumulated(last):
+            return self._loss[0]
         if self.pg is not None:
             from ..dist.ddp import allreduce_mean_
             allreduce_mean_(eng.gflat, self.pg)

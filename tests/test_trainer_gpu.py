@@ -172,3 +172,38 @@ def test_checkpointed_training_is_bit_identical_and_smaller():
     assert torch.equal(res[True][0], res[False][0])
     assert all(torch.equal(res[True][1][k], res[False][1][k]) for k in res[False][1])
     assert res[True][2] < 0.7 * res[False][2], (res[True][2], res[False][2])
+
+
+@pytest.mark.parametrize("graphed", [False, True])
+def test_gradient_accumulation_matches_lightning_semantics(graphed):
+    """Trainer(accumulate_grad_batches=2) (train.py:70, 289): each batch's loss counts 1/2, the optimizer, the clip and the
+    LR schedule advance on every second call.  With the online normalisers frozen (they would otherwise move inside a
+    window), feeding the same batch twice must land exactly where one plain step on it lands (g/2 + g/2 = g) -- bit for bit,
+    eagerly and replayed."""
+    from graphphysics_b200.training.loop import Trainer
+    dev = torch.device("cuda:0")
+    b0, b1 = _batch(0).to(dev), _batch(1).to(dev)
+    warm = Trainer(copy.deepcopy(CFG), learning_rate=1e-3, num_steps=50, warmup=4, device=dev, seed=0)
+    for b in (b0, b1):
+        warm.training_step(b)
+    stats = {k: v.clone() for k, v in warm.model.state_dict().items() if "_normalizer" in k}
+
+    def make(k):
+        tr = Trainer(copy.deepcopy(CFG), learning_rate=1e-3, num_steps=50, warmup=4, device=dev, seed=0, accumulate_grad_batches=k)
+        tr.model.load_state_dict(stats, strict=False)
+        for n in (tr.model._output_normalizer, tr.model._node_normalizer, tr.model._edge_normalizer):
+            n._max_accumulations, n._host_calls = 0, 0            # frozen statistics
+        tr.enable_cuda_graph(graphed)
+        return tr
+
+    plain, acc = make(1), make(2)
+    before = acc.engine.flat.data.clone()
+    for b in (b0, b1, b0):                       # three optimizer steps
+        plain.training_step(b)
+    for i, b in enumerate((b0, b0, b1, b1, b0, b0)):
+        acc.training_step(b)
+        if i == 0:
+            assert torch.equal(acc.engine.flat.data, before) and acc.step_index == 0      # no update inside the window
+    assert acc.step_index == plain.step_index == 3
+    assert torch.equal(acc.engine.flat.data, plain.engine.flat.data)
+    assert torch.equal(acc.exp_avg, plain.exp_avg) and torch.equal(acc.exp_avg_sq, plain.exp_avg_sq)
