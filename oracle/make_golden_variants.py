@@ -78,6 +78,15 @@ def main():
         m = processors.EncodeTransformDecode(2, 23, 3, hidden_size=64, num_heads=4, **case["kw"])
         out = m(Data(x=x_etd, edge_index=ei_t, pos=pos_t))
         (out * g_etd).sum().backward()
+        if name in ("etd_gated_attention", "etd_rope"):
+            # return_attention=True of the first block (layers.py:795-801): the values of the sparse softmax, in edge order
+            import dgl.sparse as dglsp
+            with torch.no_grad():
+                h0 = m.nodes_encoder(x_etd)
+                adj = dglsp.spmatrix(indices=ei_t, shape=(N, N))
+                _, attn = m.processor_list[0](h0, adj, pos=pos_t, return_attention=True)
+            store[f"{name}/h0"] = h0.numpy()
+            store[f"{name}/attn0"] = attn.val.numpy()
         store[f"{name}/out"] = out.detach().numpy()
         for k, v in m.state_dict().items():
             store[f"{name}/sd/{k}"] = v.detach().numpy()

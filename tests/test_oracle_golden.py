@@ -252,3 +252,26 @@ def test_oracle_variant_flags_against_reference_golden():
             if shared and k.endswith("attention.q_proj.weight"):       # one Parameter behind q / k / v: its gradient is the sum
                 got = got + sd[k.replace("q_proj", "k_proj")].grad + sd[k.replace("q_proj", "v_proj")].grad
             assert l2_rel(got, torch.from_numpy(g)) < 2e-4, (name, k)
+
+
+def test_oracle_attention_values_against_reference_golden():
+    """return_attention=True (layers.py:493-522, 680-683, 795-801): the oracle's sparse-softmax values equal attn.val of the
+    UNMODIFIED reference's first Transformer block, in the caller's edge order, with and without RoPE
+    (tests/golden/variants.npz, oracle/make_golden_variants.py)."""
+    from oracle import gp_oracle as O
+    z = np.load(os.path.join(G, "variants.npz"))
+    ei, pos = torch.from_numpy(z["edge_index"]), torch.from_numpy(z["pos"]).double()
+    for name, rope in (("etd_gated_attention", False), ("etd_rope", True)):
+        sd = {k[len(name) + 4:]: torch.from_numpy(z[k]).double() for k in z.files if k.startswith(name + "/sd/")}
+        h0 = torch.from_numpy(z[name + "/h0"]).double()
+        N, H, heads = h0.shape[0], h0.shape[1], 4
+        d = H // heads
+        p = "processor_list.0"
+        n1 = O.rms_norm(h0, sd[f"{p}.norm1.scale"])
+        q = O.linear(n1, sd[f"{p}.attention.q_proj.weight"], sd[f"{p}.attention.q_proj.bias"], None).reshape(N, d, heads)
+        k = O.linear(n1, sd[f"{p}.attention.k_proj.weight"], sd[f"{p}.attention.k_proj.bias"], None).reshape(N, d, heads)
+        if rope:
+            q, k = O.rope_nodes(q, k, pos, sd[f"{p}.attention.rope_inv_freq"])
+        got = O.attention_values(q, k, ei[0], ei[1], N)
+        ref = torch.from_numpy(z[name + "/attn0"]).double()
+        assert got.shape == ref.shape and float((got - ref).abs().max()) < 2e-6, name

@@ -188,3 +188,19 @@ def test_graph_net_block_other_depths(nb, norm):
     assert l2_rel(ox, rx) < 1e-3 and l2_rel(oe, re) < 1e-3
     for k, p in blk.named_parameters():
         assert l2_rel(p.grad, sd["b." + k].grad) < 1e-3, k
+
+
+@pytest.mark.parametrize("name", ["etd_gated_attention", "etd_rope"])
+def test_return_attention_matches_reference_golden(name):
+    """Transformer.forward(..., return_attention=True): attn.val of the UNMODIFIED reference's first block (golden) vs the
+    values this implementation returns, tight mode, in the caller's edge order."""
+    z = np.load(os.path.join(G, "variants.npz"))
+    sd, _ = _load(z, name)
+    m = _build("etd", name, "tight")
+    m.load_state_dict(sd)
+    m = m.to(DEV)
+    t = lambda k: torch.from_numpy(z[k]).to(DEV)
+    with torch.no_grad():
+        _, attn = m.processor_list[0](t(name + "/h0"), t("edge_index"), pos=t("pos"), return_attention=True)
+    ref = t(name + "/attn0")
+    assert attn.val.shape == ref.shape and float((attn.val - ref).abs().max()) < 1e-4
