@@ -276,3 +276,28 @@ def test_collate_builds_the_union_graph_like_pyg():
     assert torch.equal(u.x[3:], g2.x) and u.num_nodes == 7
     one = collate([g1])
     assert torch.equal(one.edge_index, g1.edge_index) and torch.equal(one.batch, torch.zeros(3, dtype=torch.long))
+
+
+def test_committed_bench_lines_follow_the_contract():
+    """The bench lines kept under profiles/ (what `python bench.py [--gpus N]` printed on the B200 box) carry every key of
+    the benchmark contract, with consistent values."""
+    import json
+    for n in (1, 2, 4, 8):
+        path = os.path.join(ROOT, "profiles", f"r02_bench_{n}gpu.json")
+        d = json.loads(open(path).read().strip().splitlines()[-1])
+        for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+                  "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline"):
+            assert k in d, (n, k)
+        assert d["n_gpus"] == n and d["higher_is_better"] is True and d["scaling"] == "weak" and d["vs_baseline"] is None
+        assert "workload" in d["config"] and "model" not in d["config"]
+        assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(d["e2e"]) and d["e2e"]["h2d_bytes_per_step"] > 0
+        r = d["roofline"]
+        assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(r) and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+        assert d["gpu_launches"] > 0 and not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+        # value = directed edges x MP layers x ranks / step time
+        edges = d["config"]["directed_edges_per_gpu"] * d["config"]["mp_layers"] * n
+        assert abs(d["value"] - edges / (d["ms_per_step"] * 1e-3)) / d["value"] < 1e-6
+        if n == 1:
+            assert {"value", "unit", "cores", "kind", "sample"} <= set(d["cpu_baseline"]) and d["cpu_baseline"]["kind"] == "reference"
+        else:
+            assert d["partition"]["scaling"] == "strong" and d["partition"]["n_gpus"] == n
