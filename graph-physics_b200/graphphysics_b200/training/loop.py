@@ -33,7 +33,8 @@ class Trainer:
     def __init__(self, parameters: Dict[str, Any], learning_rate: float, num_steps: int, warmup: int,
                  device: torch.device, masks: Sequence[int] = (NodeType.NORMAL, NodeType.OUTFLOW),
                  gradient_clip_val: float = 1.0, weight_decay: float = 1e-4, betas=(0.9, 0.95), eps: float = 1e-8,
-                 process_group=None, seed: Optional[int] = None, inject_noise: bool = False, accumulate_grad_batches: int = 1):
+                 process_group=None, seed: Optional[int] = None, inject_noise: bool = False, accumulate_grad_batches: int = 1,
+                 use_previous_data: bool = False, previous_data_start: Optional[int] = None, previous_data_end: Optional[int] = None):
         if seed is not None:
             torch.manual_seed(seed)
         self.param = parameters
@@ -60,6 +61,13 @@ class Trainer:
         self.step_index = 0
         # Trainer(accumulate_grad_batches=k) of the reference (train.py:70, 289): the loss of each of k consecutive batches is
         # scaled by 1 / k, the gradients add up, clip + AdamW + the LR schedule advance on every k-th call
+        # use_previous_data (lightning_module.py:49-51, 383-401): the roll-out also feeds the last predicted increment
+        # (prediction - current value) back into the columns [previous_data_start, previous_data_end) of x
+        self.use_previous_data = bool(use_previous_data)
+        self.previous_data_start, self.previous_data_end = previous_data_start, previous_data_end
+        if self.use_previous_data and (previous_data_start is None or previous_data_end is None):
+            raise ValueError("use_previous_data=True needs previous_data_start and previous_data_end")
+        self._last_previous = None
         self.accumulate = max(int(accumulate_grad_batches), 1)
         self._micro, self._gacc = 0, None
         # EPD on the fused kernels: engine-driven forward/backward, no autograd tape (precision="tight" and the
@@ -319,16 +327,22 @@ class Trainer:
 
     # ------------------------------------------------------------------ roll-out
     @torch.no_grad()
-    def make_prediction(self, batch, last_prediction):
-        """_make_prediction (lightning_module.py:375-409), `use_previous_data` off."""
+    def make_prediction(self, batch, last_prediction, last_previous_data_prediction=None):
+        """_make_prediction (lightning_module.py:375-409).  With use_previous_data the increment of this step
+        (prediction - current value) is left in `self._last_previous` for the next call."""
         sim = self.model
         sim.eval()
         batch = batch.clone()
+        a, b = sim.output_index_start, sim.output_index_end
         if last_prediction is not None:
-            batch.x[:, sim.output_index_start:sim.output_index_end] = last_prediction
+            batch.x[:, a:b] = last_prediction
+            if self.use_previous_data and last_previous_data_prediction is not None:
+                batch.x[:, self.previous_data_start:self.previous_data_end] = last_previous_data_prediction
         mask = build_mask(self.param, batch)
         _, _, predicted = sim(batch)
         predicted = torch.where(mask[:, None], batch.y, predicted)       # ground truth on the boundary nodes (no host sync)
+        if self.use_previous_data:
+            self._last_previous = predicted - batch.x[:, a:b]
         return batch, predicted
 
     @torch.no_grad()
@@ -349,25 +363,30 @@ class Trainer:
                 getattr(static, k).copy_(getattr(first, k), non_blocking=True)
             last = static.x[:, a:b].clone()
             pred = torch.empty_like(static.y)
+            prev = static.x[:, self.previous_data_start:self.previous_data_end].clone() if self.use_previous_data else None
 
             def step():
-                _, p = self.make_prediction(static, last)
+                _, p = self.make_prediction(static, last, prev)
                 pred.copy_(p)
                 last.copy_(p)
+                if prev is not None:
+                    prev.copy_(self._last_previous)
 
             with no_csr_cache():
                 step()                                  # eager once: allocations, shared-memory attributes
             graph = torch.cuda.CUDAGraph()
             with no_csr_cache(), torch.cuda.graph(graph):
                 step()
-            entry = self._rollout_graphs[key] = (graph, static, last, pred, fields)
-        graph, static, last, pred, fields = entry
+            entry = self._rollout_graphs[key] = (graph, static, last, pred, fields, prev)
+        graph, static, last, pred, fields, prev = entry
         preds = []
         for i, fr in enumerate(frames):
             for k in fields:
                 getattr(static, k).copy_(getattr(fr, k), non_blocking=True)
             if i == 0:
                 last.copy_(static.x[:, a:b])            # first frame: its own input (overwriting it changes nothing)
+                if prev is not None:
+                    prev.copy_(static.x[:, self.previous_data_start:self.previous_data_end])
             graph.replay()
             preds.append(pred.clone())
         return preds
@@ -381,10 +400,11 @@ class Trainer:
             preds = self._rollout_graphed(frames)
             targets = [fr.y.to(self.device) for fr in frames]
         else:
-            last, preds, targets = None, [], []
+            last, last_prev, preds, targets = None, None, [], []
             for fr in frames:
                 fr = fr.to(self.device) if not fr.x.is_cuda else fr
-                _, last = self.make_prediction(fr, last)
+                _, last = self.make_prediction(fr, last, last_prev)
+                last_prev = self._last_previous if self.use_previous_data else None
                 preds.append(last)
                 targets.append(fr.y)
         p, t = torch.cat(preds), torch.cat(targets)

@@ -163,3 +163,54 @@ def test_graphed_rollout_equals_eager_rollout():
     for a, b, c in zip(eager["predictions"], graphed["predictions"], again["predictions"]):
         assert torch.equal(a, b) and torch.equal(a, c)
     assert eager["val_all_rollout_rmse"] == graphed["val_all_rollout_rmse"] == again["val_all_rollout_rmse"]
+
+
+def test_rollout_with_previous_data():
+    """use_previous_data (lightning_module.py:49-51, 383-401): the roll-out writes the last predicted increment into the
+    columns [previous_data_start, previous_data_end) of the next frame.  Checked against the reference's loop written out
+    with the Simulator, eagerly and under graph replay (bit-identical)."""
+    from graphphysics_b200.graph import Data
+    from graphphysics_b200.training.loop import Trainer, build_mask
+    dev = torch.device("cuda:0")
+    z = np.load(os.path.join(G, "rollout.npz"))
+    cfg = {"model": {"type": "epd", "message_passing_num": 2, "hidden_size": 64, "node_input_size": 4, "output_size": 2,
+                     "edge_input_size": 3},
+           "index": {"feature_index_start": 0, "feature_index_end": 4, "output_index_start": 0, "output_index_end": 2,
+                     "node_type_index": 4}}
+    torch.manual_seed(0)
+    tr = Trainer(cfg, learning_rate=1e-3, num_steps=10, warmup=2, device=dev, use_previous_data=True, previous_data_start=2,
+                 previous_data_end=4)
+    ei, ea, pos = (torch.from_numpy(z[k]).to(dev) for k in ("edge_index", "edge_attr", "pos"))
+    frames = []
+    for x, y in zip(z["frames"], z["ys"]):
+        x = torch.from_numpy(x)
+        x6 = torch.cat([x[:, :2], 0.1 * torch.randn(x.shape[0], 2), x[:, 2:]], 1)          # [vx, vy, pvx, pvy, node_type, time]
+        frames.append(Data(x=x6.to(dev), y=torch.from_numpy(y).to(dev), pos=pos, edge_index=ei, edge_attr=ea))
+    tr.training_step(frames[0])                      # non-trivial normaliser statistics
+    # the reference's loop (lightning_module.py:375-409, 451-489)
+    sim = tr.model
+    sim.eval()
+    last = last_prev = None
+    want = []
+    with torch.no_grad():
+        for fr in frames:
+            b = fr.clone()
+            if last is not None:
+                b.x[:, 0:2] = last
+                b.x[:, 2:4] = last_prev
+            mask = build_mask(cfg, b)
+            cur = b.x[:, 0:2]
+            _, _, pred = sim(b)
+            pred[mask] = b.y[mask]
+            last, last_prev = pred, pred - cur
+            want.append(pred)
+    eager = tr.rollout(frames)
+    tr.enable_cuda_graph(True)
+    graphed = tr.rollout(frames)
+    for w, a, b in zip(want, eager["predictions"], graphed["predictions"]):
+        assert torch.equal(w, a) and torch.equal(a, b)
+    # the option matters: without it the later frames differ
+    tr.use_previous_data = False
+    tr.enable_cuda_graph(False)
+    plain = tr.rollout(frames)
+    assert torch.equal(plain["predictions"][0], want[0]) and not torch.equal(plain["predictions"][2], want[2])
